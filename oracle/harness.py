@@ -1,0 +1,393 @@
+"""TEST INFRASTRUCTURE ONLY -- deterministic replay harness for the UNMODIFIED reference.
+
+Nothing under `oracle/` is product code.  Only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s cpu_baseline / `--impl reference` leg may import it, and only as the checker.
+
+What it does:
+  * puts `oracle/shims` (shapely/geopy/matplotlib/descartes stand-ins) and the reference's own
+    directories on sys.path in the order the reference needs
+    ([shims, /root/reference/path_planning, /root/reference]) and imports the unmodified
+    `rrt_dubins`, `cost`, `catalina`, `motion_plan_state` modules;
+  * replaces `rrt_dubins.random` by a player of a PRE-GENERATED uniform stream
+    (`random.uniform(a, b)` is `a + (b - a) * random()` in CPython, Lib/random.py) and
+    `rrt_dubins.time` by a fake clock that turns the wall-clock budget of
+    `RRT.exploring` (/root/reference/path_planning/rrt_dubins.py:107-118) into an exact budget of
+    I steer calls;
+  * records, per loop iteration, the parent index, the accept flag and the new node.
+
+`/root/reference` only exists in the build container; on the GPU box the committed fixtures under
+tests/golden/ (written by oracle/make_golden.py from this harness) are used instead.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("AUVRRT_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SHIMS = os.path.join(_HERE, "shims")
+
+_REF_MODULE_NAMES = [
+    "rrt_dubins", "cost", "catalina", "motion_plan_state", "sharkOccupancyGrid", "sharkEstimate",
+    "path_planning", "path_planning.sharkOccupancyGrid", "shapely", "shapely.geometry",
+    "shapely.ops", "shapely.wkt", "geopy", "geopy.distance", "matplotlib", "matplotlib.pyplot",
+    "matplotlib.cm", "matplotlib.patches", "matplotlib.collections", "matplotlib.path",
+    "descartes",
+]
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "path_planning", "rrt_dubins.py"))
+
+
+_ref_cache = None
+
+
+def load_reference():
+    """Import the unmodified reference modules; return a namespace holding them.
+
+    The modules are removed from sys.modules again (and whatever was there before is put back) so
+    that the product's drop-in modules of the same names (`rrt_dubins`, `cost`, ...) can live in
+    the same process.
+    """
+    global _ref_cache
+    if _ref_cache is not None:
+        return _ref_cache
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    saved_mods = {n: sys.modules.pop(n) for n in _REF_MODULE_NAMES if n in sys.modules}
+    saved_path = list(sys.path)
+    sys.path[:0] = [SHIMS, os.path.join(REFERENCE_ROOT, "path_planning"), REFERENCE_ROOT]
+    try:
+        import rrt_dubins  # noqa
+        import cost  # noqa
+        import catalina  # noqa
+        import motion_plan_state  # noqa
+        import shapely.geometry as shp  # noqa
+        ns = types.SimpleNamespace(
+            rrt_dubins=rrt_dubins, cost=cost, catalina=catalina,
+            motion_plan_state=motion_plan_state, shapely_geometry=shp,
+            RRT=rrt_dubins.RRT, MPS=motion_plan_state.Motion_plan_state,
+            Polygon=shp.Polygon, Point=shp.Point)
+    finally:
+        sys.path[:] = saved_path
+        for n in _REF_MODULE_NAMES:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved_mods)
+    _ref_cache = ns
+    return ns
+
+
+# ---------------------------------------------------------------------------------------------
+# The pre-generated sample sequence: counter-based SplitMix64 stream.
+# u_k(seed) is a pure function of (seed, k), so the GPU can evaluate any position without state
+# and numpy can pre-generate the same doubles for the reference.  (Restated independently of the
+# product's csrc/rng.cuh; tests check both agree.)
+# ---------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+_GOLDEN = 0x9E3779B97F4A7C15
+
+
+def _mix64(z: int) -> int:
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def stream_key(seed: int) -> int:
+    return _mix64(((seed + 1) * _GOLDEN) & _M64)
+
+
+def stream_bits(seed: int, k: int) -> int:
+    return _mix64((stream_key(seed) + (k + 1) * _GOLDEN) & _M64)
+
+
+def stream_u53(seed: int, k: int) -> float:
+    return (stream_bits(seed, k) >> 11) * (2.0 ** -53)
+
+
+def stream_u24(seed: int, k: int) -> float:
+    """The fp32 build's uniform: top 24 bits, exactly representable in fp32, in [0, 1)."""
+    return (stream_bits(seed, k) >> 40) * (2.0 ** -24)
+
+
+def stream_block(seed: int, start: int, n: int, bits24: bool = False) -> np.ndarray:
+    """Vectorised u_k for k in [start, start+n) as float64."""
+    with np.errstate(over="ignore"):
+        key = np.uint64(stream_key(seed))
+        k = np.arange(start + 1, start + n + 1, dtype=np.uint64)
+        z = key + k * np.uint64(_GOLDEN)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    if bits24:
+        return (z >> np.uint64(40)).astype(np.float64) * (2.0 ** -24)
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
+
+
+class StreamPlayer:
+    """Stands in for the `random` module inside the reference: plays u_0, u_1, ..."""
+
+    def __init__(self, seed=None, values=None, bits24=False):
+        self.seed = seed
+        self.values = None if values is None else np.asarray(values, dtype=np.float64)
+        self.bits24 = bits24
+        self.pos = 0
+        self._block = None
+        self._block_start = 0
+
+    def random(self) -> float:
+        k = self.pos
+        self.pos += 1
+        if self.values is not None:
+            return float(self.values[k])
+        if self._block is None or not (self._block_start <= k < self._block_start + len(self._block)):
+            self._block_start = k
+            self._block = stream_block(self.seed, k, 4096, self.bits24)
+        return float(self._block[k - self._block_start])
+
+    def uniform(self, a, b):
+        return a + (b - a) * self.random()
+
+
+class RecordingRandom:
+    """Wraps Python's own Mersenne Twister and records every u it hands out."""
+
+    def __init__(self, seed):
+        import random as _r
+        self._r = _r.Random(seed)
+        self.log = []
+
+    def random(self):
+        u = self._r.random()
+        self.log.append(u)
+        return u
+
+    def uniform(self, a, b):
+        return a + (b - a) * self.random()
+
+
+class BudgetClock:
+    """`time` stand-in: time() is 0.0 until `budget` steer calls have completed, then +inf."""
+
+    def __init__(self, budget):
+        self.budget = budget
+        self.done = 0
+
+    def time(self):
+        return 0.0 if self.done < self.budget else float("inf")
+
+    def sleep(self, _):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------
+# World model
+# ---------------------------------------------------------------------------------------------
+def clip_polygon_to_rect(pts, x0, y0, x1, y1):
+    """Sutherland-Hodgman clip of polygon `pts` against the axis-aligned rectangle."""
+    def clip(poly, inside, intersect):
+        out = []
+        n = len(poly)
+        for i in range(n):
+            cur, prv = poly[i], poly[i - 1]
+            ci, pi = inside(cur), inside(prv)
+            if ci:
+                if not pi:
+                    out.append(intersect(prv, cur))
+                out.append(cur)
+            elif pi:
+                out.append(intersect(prv, cur))
+        return out
+
+    def ix(xc):
+        return lambda p, q: (xc, p[1] + (q[1] - p[1]) * (xc - p[0]) / (q[0] - p[0]))
+
+    def iy(yc):
+        return lambda p, q: (p[0] + (q[0] - p[0]) * (yc - p[1]) / (q[1] - p[1]), yc)
+
+    poly = list(pts)
+    for inside, inter in ((lambda p: p[0] >= x0, ix(x0)), (lambda p: p[0] <= x1, ix(x1)),
+                          (lambda p: p[1] >= y0, iy(y0)), (lambda p: p[1] <= y1, iy(y1))):
+        if not poly:
+            break
+        poly = clip(poly, inside, inter)
+    return poly
+
+
+def polygon_area(pts):
+    a = 0.0
+    for i in range(len(pts)):
+        x0, y0 = pts[i - 1]
+        x1, y1 = pts[i]
+        a += x0 * y1 - x1 * y0
+    return 0.5 * a
+
+
+def lattice_cells(boundary_pts, cell_size=10.0, min_area=1e-9):
+    """Cell bounds of the 10 m lattice clipped to the boundary polygon, COLUMN-MAJOR order.
+
+    Stand-in for `splitCell` (/root/reference/path_planning/sharkOccupancyGrid.py:376-393), which
+    needs shapely.ops.split.  Same lattice (anchored at the polygon's minx/miny); each cell's
+    `.bounds` is the bounding box of the clipped piece, as shapely would report.  The ORDER in which
+    GEOS emits the pieces cannot be known here (parity unpinned), so the
+    order is defined as: columns by increasing x, then rows by increasing y.
+    """
+    xs = [p[0] for p in boundary_pts]
+    ys = [p[1] for p in boundary_pts]
+    minx, miny, maxx, maxy = min(xs), min(ys), max(xs), max(ys)
+    cells = []
+    nx = int(math.ceil((maxx - minx) / cell_size))
+    ny = int(math.ceil((maxy - miny) / cell_size))
+    for i in range(nx):
+        for j in range(ny):
+            x0, y0 = minx + i * cell_size, miny + j * cell_size
+            piece = clip_polygon_to_rect(boundary_pts, x0, y0, x0 + cell_size, y0 + cell_size)
+            if len(piece) >= 3 and abs(polygon_area(piece)) > min_area:
+                px = [p[0] for p in piece]
+                py = [p[1] for p in piece]
+                cells.append((min(px), min(py), max(px), max(py)))
+    return cells
+
+
+class Cell:
+    """Object with `.bounds`, the only attribute the hot path reads from `cell_list` entries."""
+
+    def __init__(self, bounds):
+        self.bounds = tuple(float(b) for b in bounds)
+
+
+def catalina_world(ref=None):
+    """Cartesian Catalina map computed by the reference's own catalina.create_environs
+    (/root/reference/path_planning/catalina.py:32-65) on top of the Vincenty shim."""
+    ref = ref or load_reference()
+    cat = ref.catalina
+    env = cat.create_environs(cat.OBSTACLES, cat.BOUNDARIES, cat.BOATS, cat.HABITATS)
+    obstacles = env[0] + env[2]
+    boundary_pts = [(float(m.x), float(m.y)) for m in env[1]]
+    habitats = env[3]
+    return {
+        "circles": [[float(o.x), float(o.y), float(o.size)] for o in obstacles],
+        "boundary": [list(p) for p in boundary_pts],
+        "habitats": [[float(h.x), float(h.y), float(h.size)] for h in habitats],
+        "cells": [list(c) for c in lattice_cells(boundary_pts, 10.0)],
+    }
+
+
+def world_objects(ref, world, grid_csv=None, grid=None):
+    """Turn a world dict into the reference's own argument objects."""
+    MPS = ref.MPS
+    obstacles = [MPS(c[0], c[1], size=c[2]) for c in world["circles"]]
+    habitats = [MPS(h[0], h[1], size=h[2]) for h in world["habitats"]]
+    poly = ref.Polygon([tuple(p) for p in world["boundary"]])
+    cells = [Cell(c) for c in world["cells"]]
+    if grid_csv is not None:
+        shark = ref.rrt_dubins.createSharkGrid(grid_csv, cells)
+    elif grid is not None:
+        shark = {}
+        for (t0, t1), probs in grid:
+            shark[(t0, t1)] = {cells[i].bounds: float(p) for i, p in enumerate(probs)}
+    else:
+        shark = {}
+    return obstacles, poly, habitats, cells, shark
+
+
+def shark_arrays(shark, cells):
+    """{(t0,t1): {bounds: p}} -> (bins [T,2], probs [T,C]) in dict order."""
+    bins = np.array([[k[0], k[1]] for k in shark.keys()], dtype=np.float64).reshape(-1, 2)
+    probs = np.zeros((len(shark), len(cells)), dtype=np.float64)
+    for ti, grid in enumerate(shark.values()):
+        for ci, c in enumerate(cells):
+            if c.bounds in grid:
+                probs[ti, ci] = grid[c.bounds]
+    return bins, probs
+
+
+# ---------------------------------------------------------------------------------------------
+# Traced runs of the unmodified planner
+# ---------------------------------------------------------------------------------------------
+def traced_exploring(ref, rrt, initial, habitats, *, iterations, rng, bin_interval=5, v=2,
+                     shark_interval=50, traj_time_stamp=True, max_plan_time=10.0,
+                     max_traj_time=500.0, plan_time=True, weights=(-3, -3, -4),
+                     plot_interval=0.5):
+    """Run RRT.exploring (/root/reference/path_planning/rrt_dubins.py:92-176) for exactly
+    `iterations` steer calls on the injected uniform stream `rng`; return (result, trace).
+
+    trace: dict of arrays, one row per steer call:
+      parent  index into mps_list of the node steer started from
+      safe    check_collision result (True = safe, i.e. node accepted)
+      nwp     len(new.path) (waypoints incl. path[0] = parent)
+      leaf    (x, y, theta, traj_time_stamp, length) of the new node
+      upos    stream position before the iteration's first draw
+    plus  cost_evals: list of (iteration, cost_total) for every cost evaluation, and
+          best_iter: iteration whose node became the final optimum.
+    """
+    mod = ref.rrt_dubins
+    clock = BudgetClock(iterations)
+    saved = (mod.random, mod.time, mod.habitat_shark_cost_func)
+    tr = {"parent": [], "safe": [], "nwp": [], "leaf": [], "upos": []}
+    cost_evals = []
+    index_of = {}
+
+    orig_steer = rrt.steer
+    orig_cc = rrt.check_collision
+    state = {"upos": 0}
+
+    def steer(mps, *a, **k):
+        if not index_of:
+            pass
+        for i in range(len(index_of), len(rrt.mps_list)):
+            index_of[id(rrt.mps_list[i])] = i
+        tr["parent"].append(index_of[id(mps)])
+        new = orig_steer(mps, *a, **k)
+        tr["nwp"].append(len(new.path))
+        tr["leaf"].append((new.x, new.y, new.theta, new.traj_time_stamp, new.length))
+        return new
+
+    def check_collision(mps, obstacles):
+        r = orig_cc(mps, obstacles)
+        tr["safe"].append(bool(r))
+        tr["upos"].append(state["upos"])
+        state["upos"] = getattr(rng, "pos", len(getattr(rng, "log", ())))
+        clock.done += 1
+        return r
+
+    def cost_spy(path, t, habitats_, grid, w):
+        c = saved[2](path, t, habitats_, grid, w)
+        cost_evals.append((len(tr["parent"]) - 1, c[0], c[1][0], c[1][1], c[1][2], len(path)))
+        return c
+
+    rrt.steer = steer
+    rrt.check_collision = check_collision
+    mod.random, mod.time, mod.habitat_shark_cost_func = rng, clock, cost_spy
+    try:
+        try:
+            res = rrt.exploring(initial, habitats, plot_interval, bin_interval, v, shark_interval,
+                                traj_time_stamp=traj_time_stamp, max_plan_time=max_plan_time,
+                                max_traj_time=max_traj_time, plan_time=plan_time,
+                                weights=list(weights))
+        except TypeError:
+            res = None  # no node reached the horizon: opt_path is None (rrt_dubins.py:174)
+    finally:
+        mod.random, mod.time, mod.habitat_shark_cost_func = saved
+        del rrt.steer, rrt.check_collision
+    trace = {
+        "parent": np.array(tr["parent"], dtype=np.int32),
+        "safe": np.array(tr["safe"], dtype=np.uint8),
+        "nwp": np.array(tr["nwp"], dtype=np.int32),
+        "leaf": np.array(tr["leaf"], dtype=np.float64).reshape(-1, 5),
+        "upos": np.array(tr["upos"], dtype=np.int64),
+        "cost_evals": np.array(cost_evals, dtype=np.float64).reshape(-1, 6),
+        "n_uniforms": getattr(rng, "pos", len(getattr(rng, "log", ()))),
+    }
+    return res, trace
+
+
+def path_to_array(path):
+    """list[Motion_plan_state] -> [n, 6] (x, y, theta, v, traj_time_stamp, length)."""
+    return np.array([[p.x, p.y, p.theta, p.v, p.traj_time_stamp, p.length] for p in path],
+                    dtype=np.float64).reshape(-1, 6)
