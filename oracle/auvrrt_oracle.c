@@ -1,0 +1,653 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- fp64 CPU restatement ("oracle") of the RRT planning hot path of
+ * hmc-lair-shark-tracking/auv-sim.  NOT product code: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference leg may load it, as the checker or the CPU baseline.
+ *
+ * Every function cites the reference lines it restates (paths relative to /root/reference).
+ * The reference is CPython: floats are IEEE doubles, `a ** 2` is libm pow(a, 2.0), math.sin/cos/
+ * sqrt/atan2 are libm, random.uniform(a, b) is `a + (b - a) * random()`.  This file is compiled
+ * with -ffp-contract=off and calls the same libm, so it is expected to agree with the reference
+ * BIT FOR BIT; tests/test_oracle_golden.py pins it against tests/golden/ (outputs of the
+ * unmodified reference under oracle/harness.py).
+ *
+ * Parity status: PINNED for nn / arc steer / collision / cost / exploring (golden vectors from
+ * the reference itself).  PARITY UNPINNED for the six-word Dubins solver (orc_dubins_*): the
+ * reference only hints at it in a commented-out call into the third-party PyPI `dubins` module
+ * (path_planning/rrt_dubins.py:238-251; module absent, unpinned); it restates the published
+ * Shkel & Lumelsky normalised formulation and is validated by closure/symmetry properties.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <pthread.h>
+#include <unistd.h>
+
+#define ORC_OK 0
+#define ORC_NO_PATH 1      /* TypeError: opt_path is None (rrt_dubins.py:174) */
+#define ORC_ZERO_DIV 2     /* ZeroDivisionError (rrt_dubins.py:270, :281) */
+#define ORC_KEY_ERROR 3    /* KeyError / IndexError when uniform() returns its end point (:123-126) */
+#define ORC_STREAM_END 4   /* explicit uniform stream exhausted */
+
+typedef struct {
+    int K; const double *circles;   /* [K][3] x, y, size, in obstacle_list order */
+    int E; const double *poly;      /* [E][2] boundary polygon vertices (open ring) */
+    int H; const double *habitats;  /* [H][3] x, y, size */
+    int T; const double *bins;      /* [T][2] shark-grid time bins in dict order */
+    int C; const double *cells;     /* [C][4] minx, miny, maxx, maxy in dict order */
+    const double *probs;            /* [T][C] */
+} orc_world_t;
+
+/* ---------------------------------------------------------------- uniform stream ----------- */
+typedef struct {
+    const double *ext; int64_t n_ext;   /* explicit pre-generated stream, or NULL */
+    uint64_t key; int bits24;           /* else: counter-based SplitMix64 stream */
+    int64_t pos; int exhausted;
+} orc_stream_t;
+
+static uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+uint64_t orc_stream_key(uint64_t seed) { return mix64((seed + 1) * 0x9E3779B97F4A7C15ULL); }
+double orc_stream_u(uint64_t seed, int64_t k, int bits24) {
+    uint64_t z = mix64(orc_stream_key(seed) + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ULL);
+    return bits24 ? (double)(z >> 40) * 0x1.0p-24 : (double)(z >> 11) * 0x1.0p-53;
+}
+static double next_u(orc_stream_t *s) {
+    int64_t k = s->pos++;
+    if (s->ext) {
+        if (k >= s->n_ext) { s->exhausted = 1; return 0.5; }
+        return s->ext[k];
+    }
+    uint64_t z = mix64(s->key + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ULL);
+    return s->bits24 ? (double)(z >> 40) * 0x1.0p-24 : (double)(z >> 11) * 0x1.0p-53;
+}
+/* random.uniform(a, b): CPython Lib/random.py */
+static double uniform(orc_stream_t *s, double a, double b) { return a + (b - a) * next_u(s); }
+
+
+/* ---------------------------------------------------------------- tiny parallel-for -------- */
+/* pthreads, dynamic chunks off an atomic counter (no OpenMP runtime needed on the GPU box). */
+typedef void (*orc_body_t)(int64_t i, void *ctx);
+typedef struct { orc_body_t body; void *ctx; int64_t n, chunk; int64_t next; } orc_pf_t;
+static void *orc_pf_worker(void *arg) {
+    orc_pf_t *pf = (orc_pf_t *)arg;
+    for (;;) {
+        int64_t b = __atomic_fetch_add(&pf->next, pf->chunk, __ATOMIC_RELAXED);
+        if (b >= pf->n) break;
+        int64_t e = b + pf->chunk < pf->n ? b + pf->chunk : pf->n;
+        for (int64_t i = b; i < e; i++) pf->body(i, pf->ctx);
+    }
+    return NULL;
+}
+int orc_num_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+static void orc_parallel_for(int64_t n, int64_t chunk, int nthreads, orc_body_t body, void *ctx) {
+    if (nthreads <= 0) nthreads = orc_num_threads();
+    if (nthreads > 256) nthreads = 256;
+    orc_pf_t pf = {body, ctx, n, chunk > 0 ? chunk : 1, 0};
+    if (nthreads == 1) { orc_pf_worker(&pf); return; }
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < nthreads; t++) if (pthread_create(&th[started], NULL, orc_pf_worker, &pf) == 0) started++;
+    if (started == 0) orc_pf_worker(&pf);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
+
+/* ---------------------------------------------------------------- get_closest_mps ---------- */
+/* path_planning/rrt_dubins.py:505-513 with get_distance_angle :558-564: strict <, seeded with
+ * index 0, compares sqrt(dx**2 + dy**2). */
+int orc_nn(const double *tx, const double *ty, int n, double qx, double qy) {
+    int best = 0;
+    double dx = qx - tx[0], dy = qy - ty[0];
+    double min_dist = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+    for (int i = 0; i < n; i++) {
+        dx = qx - tx[i]; dy = qy - ty[i];
+        double d = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+        if (d < min_dist) { min_dist = d; best = i; }
+    }
+    return best;
+}
+void orc_nn_batch(const double *tx, const double *ty, int n, const double *q, int nq, int *out) {
+    for (int k = 0; k < nq; k++) out[k] = orc_nn(tx, ty, n, q[2 * k], q[2 * k + 1]);
+}
+
+/* ---------------------------------------------------------------- RRT.steer (arc rollout) -- */
+/* path_planning/rrt_dubins.py:252-295.  parent/leaf = (x, y, theta, traj_time_stamp, length);
+ * wp rows = (x, y, theta, v, traj_time_stamp, length) for the APPENDED waypoints (path[1:]). */
+typedef struct { double dist_to_end, diff_max, freq, min_dist, velocity; } orc_steer_params_t;
+
+int orc_steer_arc(const double parent[5], orc_stream_t *rng, const orc_steer_params_t *p,
+                  double leaf[5], double *wp, int *nwp) {
+    double x = parent[0], y = parent[1], th = parent[2], t = parent[3], len = parent[4];
+    int n = 0, status = ORC_OK;
+    double n_expand = floor(uniform(rng, 0.0, p->freq) / 1.0);                      /* :259-260 */
+    for (int i = 0; i < (int)n_expand; i++) {
+        double dist = uniform(rng, 0.0, p->dist_to_end);                            /* :264 */
+        double diff = uniform(rng, -p->diff_max, p->diff_max);                      /* :265 */
+        if (fabs(dist) > fabs(diff)) {                                              /* :266 */
+            double s1 = dist + diff, s2 = dist - diff;
+            double den = -s1 + s2;
+            if (den == 0.0) { status = ORC_ZERO_DIV; break; }
+            double radius = (s1 + s2) / den;                                        /* :270 */
+            if (2.0 * radius == 0.0) { status = ORC_ZERO_DIV; break; }
+            double phi = (s1 + s2) / (2.0 * radius);                                /* :271 */
+            double ori = th;
+            th += phi;                                                              /* :274 */
+            double dx = radius * (sin(th) - sin(ori));                              /* :275 */
+            double dy = radius * (-cos(th) + cos(ori));                             /* :276 */
+            x += dx; y += dy;
+            double vt = uniform(rng, 0.0, 2.0 * p->velocity);                       /* :279 */
+            double movement = sqrt(pow(dx, 2.0) + pow(dy, 2.0));                    /* :280 */
+            if (vt == 0.0) { status = ORC_ZERO_DIV; break; }
+            t += movement / vt;                                                     /* :281 */
+            len += movement;
+            if (movement >= p->min_dist) {                                          /* :283 */
+                double *w = wp + 6 * n++;
+                w[0] = x; w[1] = y; w[2] = th; w[3] = vt; w[4] = t; w[5] = len;
+            }
+        }
+    }
+    leaf[0] = x; leaf[1] = y; leaf[2] = th; leaf[3] = t; leaf[4] = len;
+    *nwp = n;
+    if (rng->exhausted) status = ORC_STREAM_END;
+    return status;
+}
+
+/* steer on an explicit uniform array (golden replay); returns status, *nused = uniforms eaten */
+int orc_steer_arc_ext(const double parent[5], const double *u, int64_t nu,
+                      const orc_steer_params_t *p, double leaf[5], double *wp, int *nwp,
+                      int64_t *nused) {
+    orc_stream_t s = {u, nu, 0, 0, 0, 0};
+    int st = orc_steer_arc(parent, &s, p, leaf, wp, nwp);
+    *nused = s.pos;
+    return st;
+}
+
+/* ---------------------------------------------------------------- exact point-in-polygon --- */
+/* shapely Point.within(Polygon) (rrt_dubins.py:544-547): strictly interior, boundary excluded,
+ * decided with exact orientation predicates (GEOS).  Float filter + exact expansion fallback. */
+static void two_sum(double a, double b, double *s, double *e) {
+    double x = a + b, bv = x - a, av = x - bv;
+    *s = x; *e = (a - av) + (b - bv);
+}
+static int grow_expansion(int n, double *e, double b) {
+    double h[40]; int m = 0; double q = b;
+    for (int i = 0; i < n; i++) {
+        double s, err; two_sum(q, e[i], &s, &err);
+        if (err != 0.0) h[m++] = err;
+        q = s;
+    }
+    if (q != 0.0 || m == 0) h[m++] = q;
+    memcpy(e, h, sizeof(double) * (size_t)m);
+    return m;
+}
+/* sign of (ax-cx)(by-cy) - (ay-cy)(bx-cx), exactly */
+int orc_orient2d(double ax, double ay, double bx, double by, double cx, double cy) {
+    double detl = (ax - cx) * (by - cy), detr = (ay - cy) * (bx - cx), det = detl - detr, detsum;
+    if (detl > 0.0) { if (detr <= 0.0) return (det > 0) - (det < 0); detsum = detl + detr; }
+    else if (detl < 0.0) { if (detr >= 0.0) return (det > 0) - (det < 0); detsum = -detl - detr; }
+    else detsum = fabs(detr);
+    const double errbound = (3.0 + 16.0 * 0x1.0p-53) * 0x1.0p-53;
+    if (fabs(det) > errbound * detsum) return (det > 0) - (det < 0);
+    /* det = ax*by - ax*cy - cx*by - ay*bx + ay*cx + cy*bx  (the cx*cy terms cancel) */
+    const double pa[6] = {ax, -ax, -cx, -ay, ay, cy};
+    const double pb[6] = {by, cy, by, bx, cx, bx};
+    double e[40]; int n = 0;
+    for (int i = 0; i < 6; i++) {
+        double hi = pa[i] * pb[i], lo = fma(pa[i], pb[i], -hi);
+        n = grow_expansion(n, e, lo);
+        n = grow_expansion(n, e, hi);
+    }
+    double top = e[n - 1];
+    return (top > 0) - (top < 0);
+}
+/* +1 strictly inside, 0 on the boundary, -1 outside */
+int orc_point_in_polygon(const double *poly, int E, double px, double py) {
+    int inside = 0;
+    for (int i = 0; i < E; i++) {
+        double ax = poly[2 * i], ay = poly[2 * i + 1];
+        int j = (i + 1) % E;
+        double bx = poly[2 * j], by = poly[2 * j + 1];
+        if (px == ax && py == ay) return 0;
+        if (ay == py && by == py) {
+            if (fmin(ax, bx) <= px && px <= fmax(ax, bx)) return 0;
+            continue;
+        }
+        if ((ay > py) != (by > py)) {
+            int s = orc_orient2d(ax, ay, bx, by, px, py);
+            if (s == 0) return 0;
+            if ((s > 0) == (by > ay)) inside = !inside;
+        }
+    }
+    return inside ? 1 : -1;
+}
+
+/* ---------------------------------------------------------------- RRT.check_collision ------ */
+/* path_planning/rrt_dubins.py:530-549.  pts = mps.path as [n][2].  dList is NEVER reset between
+ * obstacles (:535-542), so obstacle k is tested against the running minimum over obstacles 0..k.
+ * Returns 1 = safe (True), 0 = collision / outside. */
+int orc_check_collision(const double *pts, int n, const orc_world_t *w) {
+    double running = INFINITY;
+    for (int k = 0; k < w->K; k++) {
+        double ox = w->circles[3 * k], oy = w->circles[3 * k + 1], sz = w->circles[3 * k + 2];
+        for (int i = 0; i < n; i++) {
+            double dx = pts[2 * i] - ox, dy = pts[2 * i + 1] - oy;
+            double d = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+            if (d < running) running = d;
+        }
+        if (n == 0) return -1; /* min([]) raises ValueError in the reference */
+        if (running <= sz) return 0;
+    }
+    for (int i = 0; i < n; i++)
+        if (orc_point_in_polygon(w->poly, w->E, pts[2 * i], pts[2 * i + 1]) <= 0) return 0;
+    return 1;
+}
+/* check_collision_obstacle (:551-556): one point, per-obstacle test, no running minimum */
+int orc_check_collision_obstacle(double x, double y, const orc_world_t *w) {
+    for (int k = 0; k < w->K; k++) {
+        double dx = x - w->circles[3 * k], dy = y - w->circles[3 * k + 1];
+        if (sqrt(pow(dx, 2.0) + pow(dy, 2.0)) <= w->circles[3 * k + 2]) return 0;
+    }
+    return 1;
+}
+
+/* ---------------------------------------------------------------- habitat_shark_cost_func -- */
+/* builtin sum() over [c0, c1, c2] as CPython >= 3.12 evaluates it (Python/bltinmodule.c,
+ * builtin_sum_impl): the int start 0 absorbs c0 exactly, then the float fast path adds the rest
+ * with Neumaier-compensated summation and folds the compensation in at the end.  (CPython < 3.12
+ * would give ((0 + c0) + c1) + c2; the build and GPU-box interpreter is 3.12.3.) */
+static double py312_sum3(double c0, double c1, double c2) {
+    double f = 0.0 + c0, c = 0.0;
+    const double xs[2] = {c1, c2};
+    for (int i = 0; i < 2; i++) {
+        double x = xs[i], t = f + x;
+        if (fabs(f) >= fabs(x)) c += (f - t) + x; else c += (x - t) + f;
+        f = t;
+    }
+    if (c != 0.0 && isfinite(c)) f += c;
+    return f;
+}
+
+/* path_planning/cost.py:145-207.  pts = [n][3] (x, y, traj_time_stamp) in the order the caller
+ * passes the path.  bin_mask (may be NULL) selects the bins the planner kept
+ * (rrt_dubins.py:161-166).  out = [sum, c0, c1, c2].  The cell test reproduces the reference's
+ * typo `mps.x <= cell_bound[3]` (cost.py:182). */
+void orc_cost(const double *pts, int n, double total_traj_time, const orc_world_t *w,
+              const uint8_t *bin_mask, const double weight[3], double out[4]) {
+    double w1 = weight[0], w2 = weight[1], w3 = weight[2];
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    uint8_t *visited = (uint8_t *)calloc((size_t)(w->H > 0 ? w->H : 1), 1);
+    for (int i = 0; i < n; i++) {
+        double x = pts[3 * i], y = pts[3 * i + 1], t = pts[3 * i + 2];
+        int tb = -1;
+        for (int b = 0; b < w->T; b++) {
+            if (bin_mask && !bin_mask[b]) continue;
+            if (t >= w->bins[2 * b] && t <= w->bins[2 * b + 1]) { tb = b; break; }
+        }
+        if (tb < 0) continue;                                                  /* cost.py:178-179 */
+        for (int c = 0; c < w->C; c++) {
+            const double *cb = w->cells + 4 * c;
+            if (x >= cb[0] && x <= cb[2] && y >= cb[1] && x <= cb[3]) {           /* cost.py:182 */
+                c2 += w3 * w->probs[(size_t)tb * w->C + c];
+                break;
+            }
+        }
+        for (int h = 0; h < w->H; h++) {
+            double dx = w->habitats[3 * h] - x, dy = w->habitats[3 * h + 1] - y;
+            double dist = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+            if (dist <= w->habitats[3 * h + 2]) { visited[h] = 1; c1 += w2; break; }
+        }
+    }
+    if (total_traj_time > 0) { c1 = c1 / total_traj_time; c2 = c2 / total_traj_time; }
+    int count = 0;
+    for (int h = 0; h < w->H; h++) count += visited[h];
+    if (w->H != 0) c0 = w1 * count / w->H;
+    free(visited);
+    out[1] = c0; out[2] = c1; out[3] = c2;
+    out[0] = py312_sum3(c0, c1, c2);                                          /* sum(cost) */
+}
+
+/* habitat_shark_cost_point (cost.py:209-241): `visited[i] == True` is a comparison, not an
+ * assignment (:234), so visited never changes.  AUV grid = row `tb` of probs. */
+double orc_cost_point(double x, double y, const orc_world_t *w, const uint8_t *visited, int tb,
+                      const double weight[3]) {
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    for (int h = 0; h < w->H; h++) {
+        double dx = w->habitats[3 * h] - x, dy = w->habitats[3 * h + 1] - y;
+        if (sqrt(pow(dx, 2.0) + pow(dy, 2.0)) <= w->habitats[3 * h + 2]) {
+            if (!visited[h]) c0 += weight[0] / w->H;
+            c1 += weight[1] / w->H;
+        }
+    }
+    for (int c = 0; c < w->C; c++) {
+        const double *cb = w->cells + 4 * c;
+        if (x >= cb[0] && x <= cb[2] && y >= cb[1] && x <= cb[3]) {
+            c2 += weight[2] * w->probs[(size_t)tb * w->C + c];
+            break;
+        }
+    }
+    return py312_sum3(c0, c1, c2);
+}
+
+/* ---------------------------------------------------------------- RRT.exploring ------------ */
+typedef struct {
+    int iterations;          /* budget: number of steer calls */
+    int mode;                /* 0: traj_time_stamp and plan_time (time-bin pick, :122-127)
+                                1: plan_time False (get_random_mps + get_closest_mps, :136-139) */
+    double bin_interval, v, max_traj_time;
+    double dist_to_end, diff_max, freq, min_dist;   /* RRT.__init__ defaults 2, .5, 30; 0.5 (:141) */
+    double weights[3];
+} orc_plan_params_t;
+
+typedef struct {
+    /* per steer call (caller allocates `iterations` rows; any pointer may be NULL) */
+    int32_t *parent; uint8_t *safe; int32_t *nwp; double *leaf; int64_t *upos;
+    double *cost_evals; int32_t n_cost_evals;   /* rows: iter, sum, c0, c1, c2, len(path) */
+    int32_t best_iter, best_node, n_nodes; int64_t n_uniforms;
+    double result[5];                           /* path length, sum, c0, c1, c2 */
+    double *path; int32_t path_cap, n_path;     /* best path root->leaf, rows (x,y,theta,v,t,len) */
+    int64_t n_waypoints_total;                  /* sum over steer calls of len(new.path) */
+} orc_trace_t;
+
+typedef struct { double x, y, th, v, t, len; } wp_t;
+typedef struct { wp_t s; int parent; int npath; int path_off; } node_t;
+typedef struct { int *v; int n, cap; } ilist_t;
+
+static void il_push(ilist_t *l, int x) {
+    if (l->n == l->cap) { l->cap = l->cap ? 2 * l->cap : 8; l->v = (int *)realloc(l->v, sizeof(int) * (size_t)l->cap); }
+    l->v[l->n++] = x;
+}
+/* Python float `//` (Objects/floatobject.c float_floor_div / float_divmod) */
+static double py_floordiv(double vx, double wx) {
+    double mod = fmod(vx, wx), div = (vx - mod) / wx, fd;
+    if (mod) { if ((wx < 0) != (mod < 0)) { mod += wx; div -= 1.0; } }
+    if (div) { fd = floor(div); if (div - fd > 0.5) fd += 1.0; }
+    else fd = copysign(0.0, vx / wx);
+    return fd;
+}
+
+/* generate_final_course (:321-331): [leaf] + reversed(leaf.path) + reversed(parent.path) + ... */
+static int final_course(const node_t *nodes, const wp_t *wps, int leaf, wp_t *out) {
+    int n = 0, cur = leaf;
+    out[n++] = nodes[leaf].s;
+    while (nodes[cur].parent >= 0) {
+        for (int k = nodes[cur].npath - 1; k >= 0; k--) out[n++] = wps[nodes[cur].path_off + k];
+        out[n++] = nodes[nodes[cur].parent].s;           /* path[0] is the parent node object */
+        cur = nodes[cur].parent;
+    }
+    return n;
+}
+
+int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng,
+                  const orc_plan_params_t *p, orc_trace_t *out) {
+    const int I = p->iterations;
+    node_t *nodes = (node_t *)malloc(sizeof(node_t) * (size_t)(I + 1));
+    wp_t *wps = (wp_t *)malloc(sizeof(wp_t) * (size_t)I * 30 + sizeof(wp_t));
+    wp_t *course = (wp_t *)malloc(sizeof(wp_t) * ((size_t)I * 31 + 2));
+    double *cpts = (double *)malloc(sizeof(double) * 3 * ((size_t)I * 31 + 2));
+    uint8_t *bin_mask = (uint8_t *)malloc((size_t)(w->T > 0 ? w->T : 1));
+    int n_nodes = 0, n_wps = 0, status = ORC_OK;
+    nodes[n_nodes++] = (node_t){{start[0], start[1], start[2], 0.0, start[3], start[4]}, -1, 0, 0};
+
+    int time_expand = (int)ceil(p->max_traj_time / p->bin_interval);               /* :111 */
+    ilist_t *bins = (ilist_t *)calloc((size_t)time_expand + 2, sizeof(ilist_t));
+    il_push(&bins[1], 0);                                                          /* :114 */
+
+    double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+    for (int i = 0; i < w->E; i++) {
+        minx = fmin(minx, w->poly[2 * i]); maxx = fmax(maxx, w->poly[2 * i]);
+        miny = fmin(miny, w->poly[2 * i + 1]); maxy = fmax(maxy, w->poly[2 * i + 1]);
+    }
+    orc_steer_params_t sp = {p->dist_to_end, p->diff_max, p->freq, p->min_dist, p->v};
+    double opt_cost[4] = {INFINITY, 0, 0, 0}, opt_len = 0.0;
+    int opt_node = -1, opt_iter = -1;
+    out->n_cost_evals = 0; out->n_waypoints_total = 0;
+    int it = 0;
+    int64_t upos0 = 0;   /* stream position after the previous steer call's iteration */
+    int64_t guard = 0, guard_max = 64LL * I + 1024;
+    double pts_buf[2 * 31];
+    while (it < I && guard++ < guard_max) {
+        int parent;
+        if (p->mode == 0) {
+            int ran_bin = (int)uniform(rng, 1.0, (double)(time_expand + 1));       /* :123 */
+            if (ran_bin > time_expand) { status = ORC_KEY_ERROR; break; }
+            while (bins[ran_bin].n == 0) {
+                ran_bin = (int)uniform(rng, 1.0, (double)(time_expand + 1));       /* :125 */
+                if (ran_bin > time_expand || rng->exhausted) break;
+            }
+            if (ran_bin > time_expand) { status = ORC_KEY_ERROR; break; }
+            if (rng->exhausted) { status = ORC_STREAM_END; break; }
+            int ran_index = (int)uniform(rng, 0.0, (double)bins[ran_bin].n);       /* :126 */
+            if (ran_index >= bins[ran_bin].n) { status = ORC_KEY_ERROR; break; }
+            parent = bins[ran_bin].v[ran_index];
+        } else {
+            double rx = uniform(rng, minx, maxx);                                  /* :336-339 */
+            double ry = uniform(rng, miny, maxy);
+            (void)uniform(rng, -M_PI, M_PI);
+            (void)uniform(rng, 0.0, 15.0);
+            int best = 0;                                                          /* :505-513 */
+            double dx = rx - nodes[0].s.x, dy = ry - nodes[0].s.y;
+            double md = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+            for (int i = 0; i < n_nodes; i++) {
+                dx = rx - nodes[i].s.x; dy = ry - nodes[i].s.y;
+                double d = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+                if (d < md) { md = d; best = i; }
+            }
+            parent = best;
+            if (nodes[parent].s.t > p->max_traj_time) continue;                    /* :138-139 */
+        }
+        /* steer (:141) */
+        double par[5] = {nodes[parent].s.x, nodes[parent].s.y, nodes[parent].s.th, nodes[parent].s.t, nodes[parent].s.len};
+        double leaf[5]; int nwp;
+        int st = orc_steer_arc(par, rng, &sp, leaf, (double *)(wps + n_wps), &nwp);
+        if (st != ORC_OK) { status = st; break; }
+        /* check_collision over path = [parent] + appended (:143) */
+        pts_buf[0] = par[0]; pts_buf[1] = par[1];
+        for (int k = 0; k < nwp; k++) { pts_buf[2 * k + 2] = wps[n_wps + k].x; pts_buf[2 * k + 3] = wps[n_wps + k].y; }
+        int safe = orc_check_collision(pts_buf, nwp + 1, w);
+        if (out->parent) out->parent[it] = parent;
+        if (out->safe) out->safe[it] = (uint8_t)safe;
+        if (out->nwp) out->nwp[it] = nwp + 1;
+        if (out->leaf) memcpy(out->leaf + 5 * (size_t)it, leaf, sizeof(double) * 5);
+        if (out->upos) out->upos[it] = upos0;
+        out->n_waypoints_total += nwp + 1;
+        if (safe) {
+            int id = n_nodes++;
+            nodes[id] = (node_t){{leaf[0], leaf[1], leaf[2], 0.0, leaf[3], leaf[4]}, parent, nwp, n_wps};
+            n_wps += nwp;
+            /* time-bin insert (:147-151) */
+            double fd = py_floordiv(leaf[3], p->bin_interval);
+            double curr_bin = (fd + 1.0) * p->bin_interval;
+            double fidx = fd + 1.0;
+            if (curr_bin > p->max_traj_time) {
+                if (fidx >= 1.0 && fidx <= (double)time_expand) {      /* resets a live key */
+                    int bi = (int)fidx;
+                    if (bi * p->bin_interval == curr_bin) { bins[bi].n = 0; il_push(&bins[bi], id); }
+                }
+            } else {
+                if (!(fidx >= 1.0 && fidx <= (double)time_expand)) { status = ORC_KEY_ERROR; break; }
+                il_push(&bins[(int)fidx], id);
+            }
+            if (leaf[3] >= p->max_traj_time - 30) {                                /* :158 */
+                int n = final_course(nodes, wps, id, course);
+                double t0 = start[3], t1 = leaf[3];
+                for (int b = 0; b < w->T; b++) {                                   /* :164-166 */
+                    double b0 = w->bins[2 * b], b1 = w->bins[2 * b + 1];
+                    bin_mask[b] = (uint8_t)((t0 >= b0 && t0 <= b1) || (b0 >= t0 && b1 <= t1) || (t1 >= b0 && t1 <= b1));
+                }
+                for (int k = 0; k < n; k++) { cpts[3 * k] = course[k].x; cpts[3 * k + 1] = course[k].y; cpts[3 * k + 2] = course[k].t; }
+                double c[4];
+                orc_cost(cpts, n, leaf[3], w, bin_mask, p->weights, c);            /* :168 */
+                if (out->cost_evals) {
+                    double *r = out->cost_evals + 6 * (size_t)out->n_cost_evals;
+                    r[0] = it; r[1] = c[0]; r[2] = c[1]; r[3] = c[2]; r[4] = c[3]; r[5] = n;
+                }
+                out->n_cost_evals++;
+                if (c[0] < opt_cost[0]) {                                          /* :169 */
+                    memcpy(opt_cost, c, sizeof(c)); opt_len = leaf[4]; opt_node = id; opt_iter = it;
+                }
+            }
+        }
+        it++;
+        upos0 = rng->pos;
+        if (rng->exhausted) { status = ORC_STREAM_END; break; }
+    }
+    out->n_nodes = n_nodes; out->n_uniforms = rng->pos;
+    out->best_iter = opt_iter; out->best_node = opt_node; out->n_path = 0;
+    if (status == ORC_OK && opt_node < 0) status = ORC_NO_PATH;
+    if (opt_node >= 0) {
+        out->result[0] = opt_len; memcpy(out->result + 1, opt_cost, sizeof(opt_cost));
+        int n = final_course(nodes, wps, opt_node, course);
+        out->n_path = n;
+        if (out->path) for (int k = 0; k < n && k < out->path_cap; k++)            /* :174 reverse */
+            memcpy(out->path + 6 * (size_t)k, &course[n - 1 - k], sizeof(wp_t));
+    }
+    for (int i = 0; i < time_expand + 2; i++) free(bins[i].v);
+    free(bins); free(nodes); free(wps); free(course); free(cpts); free(bin_mask);
+    return status;
+}
+
+/* Many independent queries (configs 2/5), OpenMP over queries: the CPU baseline.
+ * starts [Q][5]; seeds [Q]; out_result [Q][5]; out_counts [Q][3] = nodes, cost evals, waypoints */
+typedef struct {
+    const orc_world_t *w; const double *starts; const uint64_t *seeds; const orc_plan_params_t *p;
+    int bits24; double *out_result; int64_t *out_counts; int32_t *out_status;
+} orc_eb_t;
+static void orc_eb_body(int64_t q, void *vc) {
+    orc_eb_t *c = (orc_eb_t *)vc;
+    orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[q]), c->bits24, 0, 0};
+    orc_trace_t tr; memset(&tr, 0, sizeof(tr));
+    int st = orc_exploring(c->w, c->starts + 5 * (size_t)q, &rng, c->p, &tr);
+    if (c->out_status) c->out_status[q] = st;
+    if (c->out_result) memcpy(c->out_result + 5 * (size_t)q, tr.result, sizeof(double) * 5);
+    if (c->out_counts) { c->out_counts[3 * q] = tr.n_nodes; c->out_counts[3 * q + 1] = tr.n_cost_evals; c->out_counts[3 * q + 2] = tr.n_waypoints_total; }
+}
+int orc_exploring_batch(const orc_world_t *w, const double *starts, const uint64_t *seeds, int Q,
+                        const orc_plan_params_t *p, int bits24, double *out_result,
+                        int64_t *out_counts, int32_t *out_status, int nthreads) {
+    orc_eb_t c = {w, starts, seeds, p, bits24, out_result, out_counts, out_status};
+    orc_parallel_for(Q, 1, nthreads, orc_eb_body, &c);
+    return 0;
+}
+/* ---------------------------------------------------------------- Dubins six-word steer ---- */
+/* PARITY UNPINNED (see file header).  Words in evaluation order LSL, LSR, RSL, RSR, RLR, LRL;
+ * strict < on t+p+q so the first word wins ties. */
+static double mod2pi(double t) { return t - 2.0 * M_PI * floor(t / (2.0 * M_PI)); }
+
+static int dubins_word(int word, double alpha, double beta, double d, double o[3]) {
+    double sa = sin(alpha), sb = sin(beta), ca = cos(alpha), cb = cos(beta), cab = cos(alpha - beta);
+    double d2 = d * d, p2, p, t0, w;
+    switch (word) {
+    case 0: p2 = 2 + d2 - 2 * cab + 2 * d * (sa - sb); if (p2 < 0) return 0;
+        t0 = atan2(cb - ca, d + sa - sb); o[0] = mod2pi(t0 - alpha); o[1] = sqrt(p2); o[2] = mod2pi(beta - t0); return 1;
+    case 1: p2 = -2 + d2 + 2 * cab + 2 * d * (sa + sb); if (p2 < 0) return 0;
+        p = sqrt(p2); t0 = atan2(-ca - cb, d + sa + sb) - atan2(-2.0, p);
+        o[0] = mod2pi(t0 - alpha); o[1] = p; o[2] = mod2pi(t0 - mod2pi(beta)); return 1;
+    case 2: p2 = -2 + d2 + 2 * cab - 2 * d * (sa + sb); if (p2 < 0) return 0;
+        p = sqrt(p2); t0 = atan2(ca + cb, d - sa - sb) - atan2(2.0, p);
+        o[0] = mod2pi(alpha - t0); o[1] = p; o[2] = mod2pi(beta - t0); return 1;
+    case 3: p2 = 2 + d2 - 2 * cab + 2 * d * (sb - sa); if (p2 < 0) return 0;
+        t0 = atan2(ca - cb, d - sa + sb); o[0] = mod2pi(alpha - t0); o[1] = sqrt(p2); o[2] = mod2pi(t0 - beta); return 1;
+    case 4: w = (6. - d2 + 2 * cab + 2 * d * (sa - sb)) / 8.; if (fabs(w) > 1) return 0;
+        t0 = atan2(ca - cb, d - sa + sb); p = mod2pi(2 * M_PI - acos(w));
+        o[0] = mod2pi(alpha - t0 + mod2pi(p / 2.)); o[1] = p; o[2] = mod2pi(alpha - beta - o[0] + mod2pi(p)); return 1;
+    default: w = (6. - d2 + 2 * cab + 2 * d * (sb - sa)) / 8.; if (fabs(w) > 1) return 0;
+        t0 = atan2(ca - cb, d + sa - sb); p = mod2pi(2 * M_PI - acos(w));
+        o[0] = mod2pi(-alpha - t0 + p / 2.); o[1] = p; o[2] = mod2pi(mod2pi(beta) - alpha - o[0] + mod2pi(p)); return 1;
+    }
+}
+/* returns the word id (0..5) or -1; params = (t, p, q) in units of rho; *length = rho (t+p+q) */
+int orc_dubins_shortest(const double q0[3], const double q1[3], double rho, double params[3],
+                        double *length, double all_len[6]) {
+    double dx = q1[0] - q0[0], dy = q1[1] - q0[1], D = sqrt(dx * dx + dy * dy), d = D / rho;
+    double th = d > 0 ? mod2pi(atan2(dy, dx)) : 0.0;
+    double alpha = mod2pi(q0[2] - th), beta = mod2pi(q1[2] - th);
+    int best = -1; double bestc = INFINITY;
+    for (int wd = 0; wd < 6; wd++) {
+        double o[3];
+        if (all_len) all_len[wd] = -1.0;
+        if (!dubins_word(wd, alpha, beta, d, o)) continue;
+        double c = o[0] + o[1] + o[2];
+        if (all_len) all_len[wd] = c * rho;
+        if (c < bestc) { bestc = c; best = wd; params[0] = o[0]; params[1] = o[1]; params[2] = o[2]; }
+    }
+    *length = best >= 0 ? bestc * rho : INFINITY;
+    return best;
+}
+static const char DUBINS_SEG[6][3] = {{'L','S','L'},{'L','S','R'},{'R','S','L'},{'R','S','R'},{'R','L','R'},{'L','R','L'}};
+static void dubins_segment(double t, const double qi[3], char type, double qt[3]) {
+    double st = sin(qi[2]), ct = cos(qi[2]);
+    if (type == 'L') { qt[0] = sin(qi[2] + t) - st; qt[1] = -cos(qi[2] + t) + ct; qt[2] = t; }
+    else if (type == 'R') { qt[0] = -sin(qi[2] - t) + st; qt[1] = cos(qi[2] - t) - ct; qt[2] = -t; }
+    else { qt[0] = ct * t; qt[1] = st * t; qt[2] = 0.0; }
+    qt[0] += qi[0]; qt[1] += qi[1]; qt[2] += qi[2];
+}
+/* configuration at arclength s along the path */
+void orc_dubins_sample(const double q0[3], double rho, int word, const double params[3], double s,
+                       double q[3]) {
+    double tp = s / rho, qi[3] = {0.0, 0.0, q0[2]}, a[3], b[3];
+    const char *ty = DUBINS_SEG[word];
+    dubins_segment(params[0], qi, ty[0], a);
+    dubins_segment(params[1], a, ty[1], b);
+    if (tp < params[0]) dubins_segment(tp, qi, ty[0], q);
+    else if (tp < params[0] + params[1]) dubins_segment(tp - params[0], a, ty[1], q);
+    else dubins_segment(tp - params[0] - params[1], b, ty[2], q);
+    q[0] = q[0] * rho + q0[0]; q[1] = q[1] * rho + q0[1]; q[2] = mod2pi(q[2]);
+}
+/* One Dubins edge of the config-4 micro-bench: W waypoints = samples at s = k L/(W-1),
+ * k = 0..W-2, then q1 itself (the commented block appends to_mps, rrt_dubins.py:248);
+ * then check_collision on those points.  wp [W][3].  Returns safe flag; fills word/length. */
+int orc_edge_dubins(const orc_world_t *w, const double q0[3], const double q1[3], double rho, int W,
+                    double *wp, int *word, double params[3], double *length) {
+    double pts[2 * 64];
+    *word = orc_dubins_shortest(q0, q1, rho, params, length, NULL);
+    if (*word < 0 || W > 64) return 0;
+    double step = *length / (double)(W - 1);
+    for (int k = 0; k < W - 1; k++) orc_dubins_sample(q0, rho, *word, params, (double)k * step, wp + 3 * k);
+    memcpy(wp + 3 * (W - 1), q1, sizeof(double) * 3);
+    for (int k = 0; k < W; k++) { pts[2 * k] = wp[3 * k]; pts[2 * k + 1] = wp[3 * k + 1]; }
+    return orc_check_collision(pts, W, w);
+}
+typedef struct {
+    const orc_world_t *w; const double *q0, *q1; double rho; int W; uint8_t *safe, *word; double *length;
+} orc_db_t;
+static void orc_db_body(int64_t i, void *vc) {
+    orc_db_t *c = (orc_db_t *)vc;
+    double wp[3 * 64], prm[3], len; int wd;
+    int s = orc_edge_dubins(c->w, c->q0 + 3 * i, c->q1 + 3 * i, c->rho, c->W, wp, &wd, prm, &len);
+    if (c->safe) c->safe[i] = (uint8_t)s;
+    if (c->word) c->word[i] = (uint8_t)wd;
+    if (c->length) c->length[i] = len;
+}
+void orc_edges_dubins_batch(const orc_world_t *w, const double *q0, const double *q1, int64_t n,
+                            double rho, int W, uint8_t *safe, uint8_t *word, double *length,
+                            int nthreads) {
+    orc_db_t c = {w, q0, q1, rho, W, safe, word, length};
+    orc_parallel_for(n, 256, nthreads, orc_db_body, &c);
+}
+/* arc-steer edges on the counter stream: edge i uses stream seed seeds[i] from position 0 */
+typedef struct {
+    const orc_world_t *w; const double *parents; const uint64_t *seeds; const orc_steer_params_t *sp;
+    int bits24; uint8_t *safe; int32_t *nwp_out; double *leaf_out;
+} orc_ab_t;
+static void orc_ab_body(int64_t i, void *vc) {
+    orc_ab_t *c = (orc_ab_t *)vc;
+    orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[i]), c->bits24, 0, 0};
+    double leaf[5], wp[6 * 32], pts[2 * 32]; int nwp;
+    orc_steer_arc(c->parents + 5 * i, &rng, c->sp, leaf, wp, &nwp);
+    pts[0] = c->parents[5 * i]; pts[1] = c->parents[5 * i + 1];
+    for (int k = 0; k < nwp; k++) { pts[2 * k + 2] = wp[6 * k]; pts[2 * k + 3] = wp[6 * k + 1]; }
+    int s = orc_check_collision(pts, nwp + 1, c->w);
+    if (c->safe) c->safe[i] = (uint8_t)s;
+    if (c->nwp_out) c->nwp_out[i] = nwp + 1;
+    if (c->leaf_out) memcpy(c->leaf_out + 5 * i, leaf, sizeof(leaf));
+}
+void orc_edges_arc_batch(const orc_world_t *w, const double *parents, const uint64_t *seeds,
+                         int64_t n, const orc_steer_params_t *sp, int bits24, uint8_t *safe,
+                         int32_t *nwp_out, double *leaf_out, int nthreads) {
+    orc_ab_t c = {w, parents, seeds, sp, bits24, safe, nwp_out, leaf_out};
+    orc_parallel_for(n, 256, nthreads, orc_ab_body, &c);
+}
