@@ -1,0 +1,287 @@
+// edge.cuh -- one candidate edge, evaluated cooperatively by a group of G lanes:
+//   RRT.steer, the random-arc rollout   (/root/reference/path_planning/rrt_dubins.py:252-295)
+//   RRT.check_collision                  (rrt_dubins.py:530-549)
+//   the per-waypoint part of cost.habitat_shark_cost_func (/root/reference/path_planning/cost.py:171-191)
+//
+// Lane k of the group owns arc primitive k of the current chunk of G primitives.
+// The reference consumes its uniforms serially and data-dependently (2 per primitive, a 3rd only if
+// abs(dist) > abs(diff), rrt_dubins.py:264-279).  Here every lane hashes its own stream positions,
+// the per-position step (2 or 3) goes to shared memory, and log2(G) rounds of pointer doubling give
+// each lane the stream offset of its primitive.  theta/x/y/time/length are then prefix sums over
+// the lanes: shuffle scans in the fast build, the reference's exact serial order in the fp64
+// verification build.
+#pragma once
+#include "geom.cuh"
+
+namespace auv {
+
+template <typename R> struct SteerParams {
+    R d2e, dmax, neg_dmax, freq, min_dist, two_vel;
+};
+
+template <int G> struct Log2 { static const int v = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : 1; };
+
+// per-group shared-memory scratch
+template <typename R, int G> struct GroupScratch {
+    R us[3 * G];                          // window of uniforms starting at the chunk's offset
+    R wx[G + 1], wy[G + 1];               // waypoint coordinates for the circle lanes (slot G: parent)
+    unsigned char jmp[Log2<G>::v][3 * G + 4];
+};
+
+template <typename R> struct EdgeOut {
+    R x, y, th, t, len;       // the new node (leaf of the edge)
+    int nwp;                  // len(new.path): appended waypoints + 1 (path[0] = parent)
+    int n_exp;                // primitives drawn
+    uint32_t ctr;             // stream position after the edge
+    int status;
+    bool safe;                // check_collision result
+    // cost contributions (only if DO_COST): sums over the APPENDED waypoints ...
+    R s2; uint32_t cnt; uint64_t mask;
+    // ... and of the new node's own state (valid iff leaf_moved; else identical to the parent's)
+    R self_s2; int self_hab; bool leaf_moved;
+};
+
+// sin(h)/h for the fast build (|h| = |diff|/2 <= diff_max/2)
+__device__ __forceinline__ float sinc_small(float h) {
+    float z = h * h;
+    if (z > 0.25f) return __fdividef(sinf(h), h);
+    // 1 - z/6 + z^2/120 - z^3/5040 + z^4/362880     (|err| < 2e-9 for |h| <= 0.5)
+    float p = fmaf(z, 2.7557319e-6f, -1.9841270e-4f);
+    p = fmaf(z, p, 8.3333333e-3f);
+    p = fmaf(z, p, -1.6666667e-1f);
+    return fmaf(z, p, 1.0f);
+}
+
+// wp_out rows: (x, y, theta, v, traj_time_stamp, length)
+template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP>
+__device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &sc, const EnvView<R> &env,
+                                          const Stream<R> &rng, uint32_t ctr, const SteerParams<R> &sp,
+                                          R px, R py, R pth, R pt, R plen, R w3, int n_hab,
+                                          R *wp_out, int wp_cap, EdgeOut<R> &out) {
+    typedef typename Policy<R>::A A;
+    const bool VERIFY = Policy<R>::VERIFY;
+    const int LOG = Log2<G>::v;
+    int exhausted = 0;
+
+    // n_expand = floor(uniform(0, freq) / 1)                                   rrt_dubins.py:259-260
+    R u0 = rng.u(ctr, &exhausted);
+    ctr += 1;
+    int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, u0));
+    out.n_exp = n_exp;
+    out.status = 0;
+
+    // carries (group-uniform)
+    R cth = pth, cx = px, cy = py, ct = pt, clen = plen;
+    R csin = 0, ccos = 0;
+    if (VERIFY) A::sincos(pth, &csin, &ccos);
+    int nwp = 1;
+    bool hit = false, outside = false, zero_div = false, moved = false;
+    R acc_s2 = 0; uint32_t acc_cnt = 0; uint64_t acc_mask = 0;
+    R self_s2 = 0; int self_hab = -1;
+
+    if (DO_COLLIDE) {
+        // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
+        if (g.gl == 0) { sc.wx[G] = px; sc.wy[G] = py; }
+        bool pin = point_within<R>(env, px, py);
+        outside = !pin;
+    }
+
+    for (int base = 0; base < n_exp; base += G) {
+        const int nact = min(G, n_exp - base);          // active primitives in this chunk
+        // ---- 1. window of uniforms, one hash per lane per round
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            int s = g.gl + G * r;
+            sc.us[s] = (s < 3 * nact) ? rng.u(ctr + (uint32_t)s, &exhausted) : (R)0;
+        }
+        g.sync();
+        // ---- 2. stream offset of every primitive: pointer doubling over step(s) in {2, 3}
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            int s = g.gl + G * r;
+            int nx = 3 * G;
+            if (s <= 3 * G - 3) {
+                R dist = uniform_ab<R>((R)0, sp.d2e, sc.us[s]);
+                R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, sc.us[s + 1]);
+                nx = s + 2 + (A::fabs(dist) > A::fabs(diff) ? 1 : 0);
+                if (nx > 3 * G) nx = 3 * G;
+            }
+            sc.jmp[0][s] = (unsigned char)nx;
+        }
+        if (g.gl == 0) {
+#pragma unroll
+            for (int d = 0; d < LOG; d++) sc.jmp[d][3 * G] = (unsigned char)(3 * G);
+        }
+        g.sync();
+#pragma unroll
+        for (int d = 1; d < LOG; d++) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                int s = g.gl + G * r;
+                sc.jmp[d][s] = sc.jmp[d - 1][sc.jmp[d - 1][s]];
+            }
+            g.sync();
+        }
+        int o = 0;
+#pragma unroll
+        for (int d = 0; d < LOG; d++)
+            if ((g.gl >> d) & 1) o = sc.jmp[d][o];
+        const bool act = g.gl < nact;
+        // ---- 3. this lane's primitive                                          rrt_dubins.py:264-284
+        R dist = 0, diff = 0, vt = 1;
+        bool valid = false;
+        if (act) {
+            dist = uniform_ab<R>((R)0, sp.d2e, sc.us[o]);
+            diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, sc.us[o + 1]);
+            valid = A::fabs(dist) > A::fabs(diff);
+            if (valid) vt = uniform_ab<R>((R)0, sp.two_vel, sc.us[o + 2]);
+        }
+        // offset just past the chunk's last active primitive
+        int o_end = g.bcast(o + 2 + (valid ? 1 : 0), nact - 1);
+        ctr += (uint32_t)o_end;
+
+        R phi = 0, radius = 0, chord = 0;
+        if (valid) {
+            if (VERIFY) {
+                R s1 = A::add(dist, diff), s2 = A::sub(dist, diff);
+                R den = A::add(-s1, s2);
+                R num = A::add(s1, s2);
+                if (den == (R)0) zero_div = true;
+                radius = A::div(num, den);                                     // :270
+                R r2 = A::mul((R)2, radius);
+                if (r2 == (R)0) zero_div = true;
+                phi = A::div(num, r2);                                         // :271
+            } else {
+                if (diff == (R)0) zero_div = true;
+                phi = -diff;                       // (s1+s2)/(2*radius) with radius = -dist/diff
+                chord = dist * sinc_small((float)diff * 0.5f);
+            }
+            if (vt == (R)0) zero_div = true;
+        }
+        // theta: inclusive running sum                                           :274
+        R th;
+        if (VERIFY) th = (R)grp_scan_serial<G>(g, (double)phi, (double)cth);
+        else th = grp_scan_incl<G>(g, phi) + cth;
+        R dx = 0, dy = 0, movement = 0, dt = 0;
+        if (VERIFY) {
+            R s1v, c1v;
+            A::sincos(th, &s1v, &c1v);
+            R s0v = g.up(s1v, 1), c0v = g.up(c1v, 1);
+            if (g.gl == 0) { s0v = csin; c0v = ccos; }
+            if (valid) {
+                dx = A::mul(radius, A::sub(s1v, s0v));                         // :275
+                dy = A::mul(radius, A::add(-c1v, c0v));                        // :276
+                movement = A::sqrt(A::sq2(dx, dy));                            // :280
+                dt = A::div(movement, vt);                                     // :281
+            }
+            csin = g.bcast(s1v, G - 1); ccos = g.bcast(c1v, G - 1);
+        } else {
+            if (valid) {
+                R sm, cm;
+                A::sincos(th - (R)0.5 * phi, &sm, &cm);       // heading at the middle of the arc
+                dx = chord * cm; dy = chord * sm;
+                movement = chord;
+                dt = A::div(movement, vt);
+            }
+        }
+        R x, y, t, len;
+        if (VERIFY) {
+            x = (R)grp_scan_serial<G>(g, (double)dx, (double)cx);
+            y = (R)grp_scan_serial<G>(g, (double)dy, (double)cy);
+            t = (R)grp_scan_serial<G>(g, (double)dt, (double)ct);
+            len = (R)grp_scan_serial<G>(g, (double)movement, (double)clen);
+        } else {
+            x = grp_scan_incl<G>(g, dx) + cx;
+            y = grp_scan_incl<G>(g, dy) + cy;
+            t = grp_scan_incl<G>(g, dt) + ct;
+            len = grp_scan_incl<G>(g, movement) + clen;
+        }
+        const bool is_wp = valid && (movement >= sp.min_dist);                  // :283
+        const unsigned wpm = g.ballot(is_wp);
+        const unsigned vm = g.ballot(valid);
+        if (vm) moved = true;
+        const int last_valid = vm ? 31 - __clz(vm) : -1;   // lane whose state is the chunk's end state
+
+        if (WRITE_WP) {
+            if (is_wp) {
+                int row = nwp - 1 + __popc(wpm & ((1u << g.gl) - 1u));
+                if (row < wp_cap) {
+                    R *w = wp_out + 6 * (size_t)row;
+                    w[0] = x; w[1] = y; w[2] = th; w[3] = vt; w[4] = t; w[5] = len;
+                }
+            }
+        }
+        if (DO_COLLIDE) {
+            // polygon: lane = waypoint
+            bool in = true;
+            if (is_wp) in = point_within<R>(env, x, y);
+            if (g.ballot(!in)) outside = true;
+            // circles: lane = circle, waypoints broadcast through shared memory
+            if (env.K > 0) {
+                if (is_wp) { int slot = __popc(wpm & ((1u << g.gl) - 1u)); sc.wx[slot] = x; sc.wy[slot] = y; }
+                g.sync();
+                const int nw = __popc(wpm);
+                bool h = false;
+                for (int k = g.gl; k < env.K; k += G) {
+                    R ccx = env.cx[k], ccy = env.cy[k];
+                    R q = A::inf();
+                    if (base == 0) q = A::sq2(A::sub(sc.wx[G], ccx), A::sub(sc.wy[G], ccy));
+                    for (int j = 0; j < nw; j++) {
+                        R qq = A::sq2(A::sub(sc.wx[j], ccx), A::sub(sc.wy[j], ccy));
+                        q = qq < q ? qq : q;
+                    }
+                    if (VERIFY) h = h || (A::sqrt(q) <= env.creff[k]);
+                    else h = h || (q <= env.creff2[k]);
+                }
+                if (g.ballot(h)) hit = true;
+                g.sync();
+            }
+        }
+        if (DO_COST) {
+            // lane = waypoint; the lane holding the chunk's end state also evaluates it as the
+            // (provisional) leaf state
+            const bool need = is_wp || (g.gl == last_valid);
+            Contrib c; c.bin = -1; c.cell = -1; c.hab = -1;
+            if (need) c = point_contrib<R>(env, x, y, t, 0xffffffffu, n_hab);
+            R ps2 = (R)0;
+            if (c.bin >= 0 && c.cell >= 0) ps2 = A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]);
+            const bool counts = is_wp && c.bin >= 0;
+            acc_s2 += grp_sum<G>(g, counts ? ps2 : (R)0);
+            unsigned hm = g.ballot(counts && c.hab >= 0);
+            acc_cnt += __popc(hm);
+            // visited-habitat set: OR of (1 << hab) over counting lanes
+            unsigned long long mbits = (counts && c.hab >= 0) ? (1ull << c.hab) : 0ull;
+#pragma unroll
+            for (int m = G / 2; m > 0; m >>= 1) mbits |= g.xorv(mbits, m);
+            acc_mask |= mbits;
+            if (last_valid >= 0) {
+                self_s2 = g.bcast((c.bin >= 0) ? ps2 : (R)0, last_valid);
+                self_hab = g.bcast((c.bin >= 0) ? c.hab : -1, last_valid);
+            }
+        }
+        nwp += __popc(wpm);
+        // carries for the next chunk = state of lane G-1 (invalid/inactive lanes add zero)
+        cth = g.bcast(th, G - 1); cx = g.bcast(x, G - 1); cy = g.bcast(y, G - 1);
+        ct = g.bcast(t, G - 1); clen = g.bcast(len, G - 1);
+        g.sync();      // scratch (us / wx / wy / jmp) is rewritten by the next chunk
+        if (g.ballot(zero_div)) { out.status = 2; break; }
+    }
+    if (DO_COLLIDE && n_exp == 0 && env.K > 0) {
+        // the path is [parent] alone: test it against the circles
+        bool h = false;
+        for (int k = g.gl; k < env.K; k += G) {
+            R q = A::sq2(A::sub(px, env.cx[k]), A::sub(py, env.cy[k]));
+            if (VERIFY) h = h || (A::sqrt(q) <= env.creff[k]);
+            else h = h || (q <= env.creff2[k]);
+        }
+        if (g.ballot(h)) hit = true;
+    }
+    if (g.ballot(exhausted != 0)) out.status = 4;
+    out.x = cx; out.y = cy; out.th = cth; out.t = ct; out.len = clen;
+    out.nwp = nwp; out.ctr = ctr;
+    out.safe = !(hit || outside);
+    out.s2 = acc_s2; out.cnt = acc_cnt; out.mask = acc_mask;
+    out.self_s2 = self_s2; out.self_hab = self_hab; out.leaf_moved = moved;
+}
+
+}  // namespace auv

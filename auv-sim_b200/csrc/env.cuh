@@ -1,0 +1,125 @@
+// env.cuh -- the world model in HBM and its shared-memory staging.
+//
+// Layout in HBM (one blob per precision, built once by auvrrt_env_create):
+//   EnvHeader | circles SoA (cx, cy, r, r_eff, r_eff^2) | polygon (px, py) | habitats SoA |
+//   time bins (b0, b1) | cell index (breakpoints, piece offsets, candidates) | probs [T][C]
+// Everything up to `hot_bytes` is copied into shared memory by ONE TMA bulk copy
+// (cp.async.bulk.shared::cluster.global, completion on an mbarrier) at kernel start; the
+// probability table follows it into shared memory too when it fits, else it is read from L2.
+//
+// Semantics preserved from the reference:
+//  * r_eff[j] = max_{k >= j} r[k].  RRT.check_collision never resets dList between obstacles
+//    (rrt_dubins.py:535-542), so it reports a collision iff  exists k: min_{j<=k} m_j <= r_k
+//    <=> exists j: m_j <= max_{k>=j} r_k.  The running-minimum quirk is therefore EXACTLY an
+//    inflation of circle j to the suffix maximum of the radii, in obstacle order.
+//  * cell index: cost.py:181-184 scans the cell dict in order and takes the first cell with
+//    x>=c0 and x<=c2 and y>=c1 and x<=c3 (sic).  The x-conditions say x in [c0, min(c2,c3)].
+//    The breakpoints {c0, min(c2,c3)} cut the x axis into points and open intervals ("pieces") on
+//    which the set of x-admissible cells is constant; within a piece, a cell can only be the
+//    first match if its c1 is strictly below the c1 of every earlier admissible cell, so each
+//    piece keeps that strictly decreasing candidate list.  First candidate with c1 <= y wins.
+#pragma once
+#include "common.cuh"
+
+namespace auv {
+
+struct EnvHeader {
+    int K, E, H, T, C, NB, NP, NCAND;
+    int convex;        // +1: convex CCW, -1: convex CW, 0: general simple polygon
+    int hot_bytes;     // bytes [0, hot_bytes) are staged in shared memory
+    int total_bytes;
+    int off_cx, off_cy, off_cr, off_creff, off_creff2;
+    int off_px, off_py;
+    int off_hx, off_hy, off_hr, off_hr2;
+    int off_b0, off_b1;
+    int off_brk, off_piece, off_c1, off_cell;
+    int off_probs;
+    int pad_[3];
+    double bbox[4];    // minx, miny, maxx, maxy of the polygon (Polygon.bounds, rrt_dubins.py:334)
+};
+static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignment of the arrays");
+
+template <typename R> struct EnvView {
+    int K, E, H, T, C, NB, NP, convex;
+    R minx, miny, maxx, maxy;
+    const R *cx, *cy, *cr, *creff, *creff2;
+    const R *px, *py;
+    const R *hx, *hy, *hr, *hr2;
+    const R *b0, *b1;
+    const R *brk;
+    const int *piece;
+    const R *c1;
+    const int *cell;
+    const R *probs;
+
+    __device__ __forceinline__ void bind(const unsigned char *hot, const unsigned char *probs_base) {
+        const EnvHeader *h = (const EnvHeader *)hot;
+        K = h->K; E = h->E; H = h->H; T = h->T; C = h->C; NB = h->NB; NP = h->NP; convex = h->convex;
+        minx = (R)h->bbox[0]; miny = (R)h->bbox[1]; maxx = (R)h->bbox[2]; maxy = (R)h->bbox[3];
+        cx = (const R *)(hot + h->off_cx); cy = (const R *)(hot + h->off_cy);
+        cr = (const R *)(hot + h->off_cr); creff = (const R *)(hot + h->off_creff);
+        creff2 = (const R *)(hot + h->off_creff2);
+        px = (const R *)(hot + h->off_px); py = (const R *)(hot + h->off_py);
+        hx = (const R *)(hot + h->off_hx); hy = (const R *)(hot + h->off_hy);
+        hr = (const R *)(hot + h->off_hr); hr2 = (const R *)(hot + h->off_hr2);
+        b0 = (const R *)(hot + h->off_b0); b1 = (const R *)(hot + h->off_b1);
+        brk = (const R *)(hot + h->off_brk); piece = (const int *)(hot + h->off_piece);
+        c1 = (const R *)(hot + h->off_c1); cell = (const int *)(hot + h->off_cell);
+        probs = (const R *)(probs_base + h->off_probs);
+    }
+};
+
+// ---- TMA bulk staging -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// Stage `bytes` (multiple of 16) of the blob into shared memory.  One elected thread arms the
+// mbarrier with the byte count and issues the bulk copies (<= 64 KiB each); everybody waits.
+// Must be called by all threads of the CTA.
+__device__ __forceinline__ void stage_env_tma(unsigned char *smem_dst, const unsigned char *blob,
+                                              int bytes, uint64_t *bar) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)bytes);
+        for (int o = 0; o < bytes; o += 65536) {
+            int n = bytes - o < 65536 ? bytes - o : 65536;
+            tma_bulk_g2s(smem_dst + o, blob + o, (uint32_t)n, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+// bytes of dynamic shared memory a kernel needs for the env given a budget
+struct EnvStagePlan { int bytes; int probs_staged; };
+
+}  // namespace auv

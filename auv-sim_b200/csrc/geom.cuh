@@ -1,0 +1,144 @@
+// geom.cuh -- point-in-polygon, circle collision, per-point cost contribution (device).
+#pragma once
+#include "env.cuh"
+
+namespace auv {
+
+// ---------------------------------------------------------------- exact orientation (fp64)
+// Sign of (ax-cx)(by-cy) - (ay-cy)(bx-cx).  Float filter with Shewchuk's error bound; when it is
+// inconclusive the six exact products are summed as a non-overlapping expansion.  This is what
+// "Point.within" needs to be decided exactly (rrt_dubins.py:544-547 via GEOS).
+__device__ __forceinline__ void two_sum_d(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    double bv = __dsub_rn(s, a), av = __dsub_rn(s, bv);
+    e = __dadd_rn(__dsub_rn(a, av), __dsub_rn(b, bv));
+}
+static __device__ __noinline__ int orient2d_exact_slow(double ax, double ay, double bx, double by, double cx, double cy) {
+    const double pa[6] = {ax, -ax, -cx, -ay, ay, cy};
+    const double pb[6] = {by, cy, by, bx, cx, bx};
+    double e[16];
+    int n = 0;
+    for (int i = 0; i < 6; i++) {
+        double hi = __dmul_rn(pa[i], pb[i]);
+        double lo = fma(pa[i], pb[i], -hi);
+        for (int pass = 0; pass < 2; pass++) {
+            double q = pass == 0 ? lo : hi;
+            int m = 0;
+            for (int k = 0; k < n; k++) {
+                double s, err;
+                two_sum_d(q, e[k], s, err);
+                if (err != 0.0) e[m++] = err;
+                q = s;
+            }
+            if (q != 0.0 || m == 0) e[m++] = q;
+            n = m;
+        }
+    }
+    double top = e[n - 1];
+    return (top > 0.0) - (top < 0.0);
+}
+__device__ __forceinline__ int orient2d(double ax, double ay, double bx, double by, double cx, double cy) {
+    double detl = __dmul_rn(__dsub_rn(ax, cx), __dsub_rn(by, cy));
+    double detr = __dmul_rn(__dsub_rn(ay, cy), __dsub_rn(bx, cx));
+    double det = __dsub_rn(detl, detr), detsum;
+    if (detl > 0.0) { if (detr <= 0.0) return (det > 0.0) - (det < 0.0); detsum = detl + detr; }
+    else if (detl < 0.0) { if (detr >= 0.0) return (det > 0.0) - (det < 0.0); detsum = -detl - detr; }
+    else detsum = fabs(detr);
+    const double errbound = (3.0 + 16.0 * 0x1.0p-53) * 0x1.0p-53;
+    if (fabs(det) > errbound * detsum) return (det > 0.0) - (det < 0.0);
+    return orient2d_exact_slow(ax, ay, bx, by, cx, cy);
+}
+__device__ __forceinline__ int orient2d(float ax, float ay, float bx, float by, float cx, float cy) {
+    float det = (ax - cx) * (by - cy) - (ay - cy) * (bx - cx);
+    return (det > 0.f) - (det < 0.f);
+}
+
+// strictly inside the boundary polygon?  (boundary points are NOT within)
+template <typename R> __device__ __forceinline__ bool point_within(const EnvView<R> &env, R px, R py) {
+    if (!Policy<R>::VERIFY && env.convex != 0) {
+        // convex ring: strictly inside <=> strictly on the interior side of every edge
+        bool in = true;
+        R ax = env.px[env.E - 1], ay = env.py[env.E - 1];
+        for (int i = 0; i < env.E; i++) {
+            R bx = env.px[i], by = env.py[i];
+            R det = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+            in = in && (env.convex > 0 ? det > (R)0 : det < (R)0);
+            ax = bx; ay = by;
+        }
+        return in && env.E >= 3;
+    }
+    bool inside = false;
+    bool boundary = false;
+    for (int i = 0; i < env.E; i++) {
+        int j = i + 1 == env.E ? 0 : i + 1;
+        R ax = env.px[i], ay = env.py[i], bx = env.px[j], by = env.py[j];
+        if (px == ax && py == ay) boundary = true;
+        if (ay == py && by == py) {
+            if (fmin(ax, bx) <= px && px <= fmax(ax, bx)) boundary = true;
+            continue;
+        }
+        if ((ay > py) != (by > py)) {
+            int s = orient2d(ax, ay, bx, by, px, py);
+            if (s == 0) boundary = true;
+            if ((s > 0) == (by > ay)) inside = !inside;
+        }
+    }
+    return inside && !boundary;
+}
+
+// does the point hit any (inflated, see env.cuh) circle?   thread-level, all circles
+template <typename R> __device__ __forceinline__ bool point_hits_circles(const EnvView<R> &env, R x, R y) {
+    typedef typename Policy<R>::A A;
+    bool hit = false;
+    for (int k = 0; k < env.K; k++) {
+        R q = A::sq2(A::sub(x, env.cx[k]), A::sub(y, env.cy[k]));
+        if (Policy<R>::VERIFY) hit = hit || (A::sqrt(q) <= env.creff[k]);
+        else hit = hit || (q <= env.creff2[k]);
+    }
+    return hit;
+}
+
+// ---------------------------------------------------------------- cost contribution of a point
+// One iteration of the `for mps in path` loop of habitat_shark_cost_func (cost.py:171-191).
+struct Contrib {
+    int bin;      // first shark-grid bin containing t, -1: none (the point is skipped, cost.py:178)
+    int cell;     // first matching cell, -1: none
+    int hab;      // first habitat containing the point, -1: none
+};
+
+template <typename R>
+__device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
+    if (env.NB == 0 || !(x >= env.brk[0]) || !(x <= env.brk[env.NB - 1])) return -1;
+    int lo = 0, hi = env.NB - 1;            // largest i with brk[i] <= x
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (env.brk[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    int p = 2 * lo + (x == env.brk[lo] ? 0 : 1);
+    int b = env.piece[p], e = env.piece[p + 1];
+    for (int k = b; k < e; k++)
+        if (env.c1[k] <= y) return env.cell[k];
+    return -1;
+}
+
+template <typename R>
+__device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y, R t,
+                                                 unsigned bin_mask, int n_hab) {
+    typedef typename Policy<R>::A A;
+    Contrib c;
+    c.bin = -1; c.cell = -1; c.hab = -1;
+    for (int b = 0; b < env.T; b++) {
+        if (b < 32 && !((bin_mask >> b) & 1u)) continue;
+        if (t >= env.b0[b] && t <= env.b1[b]) { c.bin = b; break; }
+    }
+    if (c.bin < 0) return c;
+    c.cell = find_cell(env, x, y);
+    for (int h = 0; h < n_hab; h++) {
+        R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
+        bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
+        if (in) { c.hab = h; break; }
+    }
+    return c;
+}
+
+}  // namespace auv

@@ -1,0 +1,504 @@
+// plan.cu -- RRT.exploring (/root/reference/path_planning/rrt_dubins.py:92-176) for thousands of
+// independent planning queries: one group of G lanes grows one tree.
+//
+// Persistent kernel: the grid is sized to the machine (148 SMs x resident CTAs), every lane group
+// owns one tree workspace in HBM and pulls queries off an atomic counter, so memory is
+// O(resident groups), not O(queries).  Per query the kernel keeps, in the group's workspace,
+//   * the tree as SoA arrays (x, y, theta, t, length | parent, stream position of the edge |
+//     cost prefix sums) -- coalesced for the nearest-node scan,
+//   * the reference's time bins (rrt_dubins.py:110-114,147-151) as per-bin chains of 32-entry
+//     chunks, so "the idx-th node of bin b" is one chunk walk.
+// Waypoints are never stored: an edge is a pure function of (parent state, stream position), so
+// the optimal path is re-created at the end from the chain of stream positions (also what the
+// multi-GPU gather ships instead of paths).
+//
+// Cost is incremental: habitat_shark_cost_func (cost.py:145-207) is a sum
+// over the waypoints of generate_final_course (rrt_dubins.py:321-331) plus a visited-habitat set, so
+// every node stores the sums over its root chain; a candidate leaf costs O(1).  For a parentless
+// `initial` the planner's bin filter (rrt_dubins.py:161-166) never changes a waypoint's first-match
+// bin (every waypoint time lies in [t_initial, t_leaf]).  Totals equal the reference's up to
+// summation order (fp64: <= 1e-12 relative).
+#include "launch.h"
+
+namespace auv {
+
+#define AUV_LAUNCH_CHECK2()                                                                 \
+    do {                                                                                    \
+        g_launches++;                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess)                                                              \
+            return set_err(AUVRRT_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,         \
+                           cudaGetErrorString(e_));                                         \
+    } while (0)
+
+static const int PLAN_THREADS = 256;
+
+template <typename R> struct PlanP {
+    int I, mode, nb, chain_cap, path_cap, trace, cap, nchunks;
+    R bin_interval, max_traj, horizon, w1, w2, w3;
+    SteerParams<R> sp;
+};
+
+struct WsLayout {
+    size_t slot_bytes;
+    size_t x, y, th, t, len, s2, self_s2, ctr, parent, cnt, mask, self_hab, pool, next, head, tail, count;
+};
+
+template <typename R> static WsLayout make_layout(int cap, int nb, int nchunks) {
+    WsLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~(size_t)127; return r; };
+    L.x = take(sizeof(R) * cap); L.y = take(sizeof(R) * cap); L.th = take(sizeof(R) * cap);
+    L.t = take(sizeof(R) * cap); L.len = take(sizeof(R) * cap); L.s2 = take(sizeof(R) * cap);
+    L.self_s2 = take(sizeof(R) * cap);
+    L.ctr = take(4 * (size_t)cap); L.parent = take(4 * (size_t)cap); L.cnt = take(4 * (size_t)cap);
+    L.mask = take(8 * (size_t)cap); L.self_hab = take(4 * (size_t)cap);
+    L.pool = take(4 * 32 * (size_t)nchunks); L.next = take(4 * (size_t)nchunks);
+    L.head = take(4 * (size_t)(nb + 2)); L.tail = take(4 * (size_t)(nb + 2)); L.count = take(4 * (size_t)(nb + 2));
+    L.slot_bytes = o;
+    return L;
+}
+
+template <typename R> struct Tree {
+    R *x, *y, *th, *t, *len, *s2, *self_s2;
+    uint32_t *ctr; int *parent; uint32_t *cnt; unsigned long long *mask; int *self_hab;
+    int *pool, *next, *head, *tail, *count;
+    __device__ __forceinline__ void bind(unsigned char *b, const WsLayout &L) {
+        x = (R *)(b + L.x); y = (R *)(b + L.y); th = (R *)(b + L.th); t = (R *)(b + L.t); len = (R *)(b + L.len);
+        s2 = (R *)(b + L.s2); self_s2 = (R *)(b + L.self_s2);
+        ctr = (uint32_t *)(b + L.ctr); parent = (int *)(b + L.parent); cnt = (uint32_t *)(b + L.cnt);
+        mask = (unsigned long long *)(b + L.mask); self_hab = (int *)(b + L.self_hab);
+        pool = (int *)(b + L.pool); next = (int *)(b + L.next);
+        head = (int *)(b + L.head); tail = (int *)(b + L.tail); count = (int *)(b + L.count);
+    }
+};
+
+// builtin sum([c0, c1, c2]) as CPython >= 3.12 evaluates it (Neumaier-compensated float fast path)
+template <typename R> __device__ __forceinline__ R py_sum3p(R c0, R c1, R c2) {
+    typedef typename Policy<R>::A A;
+    R f = A::add((R)0, c0), c = (R)0;
+    R xs[2] = {c1, c2};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        R x = xs[i], t = A::add(f, x);
+        if (A::fabs(f) >= A::fabs(x)) c = A::add(c, A::add(A::sub(f, t), x));
+        else c = A::add(c, A::add(A::sub(x, t), f));
+        f = t;
+    }
+    if (c != (R)0 && isfinite(c)) f = A::add(f, c);
+    return f;
+}
+
+template <typename R, int G>
+__global__ void __launch_bounds__(PLAN_THREADS, 2)
+k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
+       const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
+       auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
+    typedef typename Policy<R>::A A;
+    const bool VERIFY = Policy<R>::VERIFY;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ GroupScratch<R, G> scratch[PLAN_THREADS / G];
+    EnvView<R> env;
+    {
+        if (stage_mode == 0) env.bind(blob, blob);
+        else {
+            uint64_t *bar = (uint64_t *)smem;
+            stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
+            env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
+        }
+    }
+    Grp<G> g;
+    GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
+    const int slot = blockIdx.x * (PLAN_THREADS / G) + threadIdx.x / G;
+    Tree<R> T;
+    T.bind(ws + (size_t)slot * L.slot_bytes, L);
+
+    for (;;) {
+        long long q = 0;
+        if (g.gl == 0) q = (long long)atomicAdd(qcounter, 1ull);
+        q = g.bcast(q, 0);
+        if (q >= Q) break;
+
+        Stream<R> rng;
+        rng.key = stream_key(seeds[q]); rng.ext = nullptr; rng.n_ext = 0;
+        const R sx = starts[5 * q], sy = starts[5 * q + 1], sth = starts[5 * q + 2], st = starts[5 * q + 3],
+                slen = starts[5 * q + 4];
+        // ---- init: mps_list = [initial]; time_bin[bin_interval] = [initial]        rrt_dubins.py:105-114
+        for (int b = g.gl; b < P.nb + 2; b += G) T.count[b] = 0;
+        if (g.gl == 0) {
+            T.x[0] = sx; T.y[0] = sy; T.th[0] = sth; T.t[0] = st; T.len[0] = slen;
+            T.parent[0] = -1; T.ctr[0] = 0; T.s2[0] = (R)0; T.cnt[0] = 0; T.mask[0] = 0ull;
+            Contrib c = point_contrib<R>(env, sx, sy, st, 0xffffffffu, env.H);
+            T.self_s2[0] = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+            T.self_hab[0] = c.bin >= 0 ? c.hab : -1;
+        }
+        g.sync();
+        if (g.gl == 0) { T.head[1] = 0; T.tail[1] = 0; T.count[1] = 1; T.pool[0] = 0; T.next[0] = -1; }
+        g.sync();
+        int n_nodes = 1, n_chunks = 1;
+        uint32_t ctr = 0, upos_mark = 0;
+        int status = AUVRRT_ST_OK;
+        int best_node = -1, best_iter = -1, n_cost_evals = 0;
+        long long n_waypoints = 0, n_prims = 0;
+        R best_c[4] = {A::inf(), 0, 0, 0}, best_len = 0, best_t = 0;
+        int it = 0;
+        long long guard = 0;
+        const long long guard_max = 64LL * P.I + 1024;
+
+        while (it < P.I && guard++ < guard_max) {
+            int parent;
+            int dummy_ex = 0;
+            if (P.mode == 0) {
+                // ---- pick a random non-empty time bin, then a random node in it           :122-127
+                int ran_bin = 0, bincnt = 0;
+                bool kerr = false;
+                for (;;) {
+                    R u = rng.u(ctr + (uint32_t)g.gl, &dummy_ex);
+                    int rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), u);
+                    bool ke = rb > P.nb || rb < 1;
+                    int cn = ke ? 0 : T.count[rb];
+                    unsigned m = g.ballot(ke || cn > 0);
+                    if (m) {
+                        int f = __ffs(m) - 1;
+                        ran_bin = g.bcast(rb, f); bincnt = g.bcast(cn, f); kerr = g.bcast(ke ? 1 : 0, f) != 0;
+                        ctr += (uint32_t)f + 1u;
+                        break;
+                    }
+                    ctr += G;
+                }
+                if (kerr) { status = AUVRRT_ST_KEY_ERROR; break; }
+                R u = rng.u(ctr, &dummy_ex);
+                ctr += 1;
+                int idx = (int)uniform_ab<R>((R)0, (R)bincnt, u);
+                if (idx >= bincnt) { status = AUVRRT_ST_KEY_ERROR; break; }
+                int ch = T.head[ran_bin];
+                for (int hop = idx >> 5; hop > 0; hop--) ch = T.next[ch];
+                parent = T.pool[ch * 32 + (idx & 31)];
+            } else {
+                // ---- get_random_mps (:333-343) + get_closest_mps (:505-513)
+                R rx = uniform_ab<R>(env.minx, env.maxx, rng.u(ctr, &dummy_ex));
+                R ry = uniform_ab<R>(env.miny, env.maxy, rng.u(ctr + 1, &dummy_ex));
+                ctr += 4;     // theta and size are drawn and never used
+                R bq = A::inf(), bs = A::inf();
+                int bi = 0x7fffffff;
+                for (int i = g.gl; i < n_nodes; i += G) {
+                    R qq = A::sq2(A::sub(rx, T.x[i]), A::sub(ry, T.y[i]));
+                    if (qq < bq) {
+                        if (VERIFY) { R s = A::sqrt(qq); if (s < bs) { bs = s; bi = i; } }
+                        else { bs = qq; bi = i; }
+                        bq = qq;
+                    }
+                }
+#pragma unroll
+                for (int m = G / 2; m > 0; m >>= 1) {
+                    R os = g.xorv(bs, m);
+                    int oi = g.xorv(bi, m);
+                    if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                }
+                parent = bi;
+                if (T.t[parent] > P.max_traj) continue;                                    // :138-139
+            }
+            // ---- steer + check_collision + per-waypoint cost                              :141-143
+            const R ppx = T.x[parent], ppy = T.y[parent], ppth = T.th[parent], ppt = T.t[parent], pplen = T.len[parent];
+            const uint32_t ctr0 = ctr;
+            EdgeOut<R> o;
+            eval_edge<R, G, true, true, false>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
+                                               nullptr, 0, o);
+            ctr = o.ctr;
+            n_waypoints += o.nwp; n_prims += o.n_exp;
+            if (P.trace && g.gl == 0) {
+                size_t r = (size_t)q * P.I + it;
+                tr.parent[r] = parent; tr.safe[r] = o.safe ? 1 : 0; tr.nwp[r] = o.nwp; tr.upos[r] = upos_mark;
+                R *lf = (R *)tr.leaf + 5 * r;
+                lf[0] = o.x; lf[1] = o.y; lf[2] = o.th; lf[3] = o.t; lf[4] = o.len;
+            }
+            if (o.status != 0) { status = o.status; break; }
+            if (o.safe) {
+                const int id = n_nodes++;                                                  // :144-145
+                R pre_s2 = 0, self_s2n = 0;
+                uint32_t pre_cnt = 0; unsigned long long pre_mask = 0; int self_habn = -1;
+                if (g.gl == 0) {
+                    const int ph = T.self_hab[parent];
+                    pre_s2 = A::add(A::add(T.s2[parent], T.self_s2[parent]), o.s2);
+                    pre_cnt = T.cnt[parent] + (ph >= 0 ? 1u : 0u) + o.cnt;
+                    pre_mask = T.mask[parent] | (ph >= 0 ? (1ull << ph) : 0ull) | o.mask;
+                    self_s2n = o.leaf_moved ? o.self_s2 : T.self_s2[parent];
+                    self_habn = o.leaf_moved ? o.self_hab : ph;
+                    T.x[id] = o.x; T.y[id] = o.y; T.th[id] = o.th; T.t[id] = o.t; T.len[id] = o.len;
+                    T.parent[id] = parent; T.ctr[id] = ctr0;
+                    T.s2[id] = pre_s2; T.cnt[id] = pre_cnt; T.mask[id] = pre_mask;
+                    T.self_s2[id] = self_s2n; T.self_hab[id] = self_habn;
+                }
+                // ---- time-bin insert (decision is group-uniform, lane 0 writes)            :147-151
+                {
+                    R fd = floordiv_pos<R>(o.t, P.bin_interval);
+                    R fidx = fd + (R)1;
+                    R curr_bin = A::mul(fidx, P.bin_interval);
+                    int bidx = -1; bool reset = false;
+                    if (curr_bin > P.max_traj) {
+                        // `self.time_bin[curr_bin] = []` re-creates the key; only reachable if it is a live one
+                        if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; }
+                    } else {
+                        if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else status = AUVRRT_ST_KEY_ERROR;
+                    }
+                    if (bidx >= 0) {
+                        const int c_old = T.count[bidx];
+                        const bool reuse_head = reset && c_old > 0;
+                        const int c = reset ? 0 : c_old;
+                        const bool alloc = ((c & 31) == 0) && !reuse_head;
+                        const int nc = n_chunks;
+                        if (alloc) n_chunks++;
+                        if (g.gl == 0) {
+                            if (reuse_head) T.tail[bidx] = T.head[bidx];
+                            if (alloc) {
+                                T.next[nc] = -1;
+                                if (c == 0) T.head[bidx] = nc; else T.next[T.tail[bidx]] = nc;
+                                T.tail[bidx] = nc;
+                            }
+                            T.pool[T.tail[bidx] * 32 + (c & 31)] = id;
+                            T.count[bidx] = c + 1;
+                        }
+                    }
+                }
+                status = g.bcast(status, 0);
+                if (status != AUVRRT_ST_OK) break;
+                // ---- candidate leaf: cost of the path root -> new node                    :158-171
+                if (o.t >= P.horizon) {
+                    R tot_s2 = 0, c0 = 0, c1 = 0, c2 = 0, total = 0;
+                    if (g.gl == 0) {
+                        uint32_t cnt = pre_cnt + (self_habn >= 0 ? 1u : 0u);
+                        unsigned long long mk = pre_mask | (self_habn >= 0 ? (1ull << self_habn) : 0ull);
+                        tot_s2 = A::add(pre_s2, self_s2n);
+                        c1 = A::mul(P.w2, (R)cnt);
+                        c2 = tot_s2;
+                        if (o.t > (R)0) { c1 = A::div(c1, o.t); c2 = A::div(c2, o.t); }        // cost.py:194-196
+                        if (env.H != 0) c0 = A::div(A::mul(P.w1, (R)__popcll(mk)), (R)env.H);  // cost.py:204-205
+                        total = py_sum3p<R>(c0, c1, c2);
+                    }
+                    total = g.bcast(total, 0);
+                    n_cost_evals++;
+                    if (total < best_c[0]) {                                               // :169 strict <
+                        best_c[0] = total; best_c[1] = g.bcast(c0, 0); best_c[2] = g.bcast(c1, 0);
+                        best_c[3] = g.bcast(c2, 0);
+                        best_node = id; best_iter = it; best_len = o.len; best_t = o.t;
+                    }
+                }
+                g.sync();
+            }
+            it++;
+            upos_mark = ctr;
+        }
+        if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
+        // ---- optimal path: chain of stream positions, optional waypoints             :174-176, :321-331
+        int depth = 0, n_path = 0;
+        if (best_node >= 0) {
+            for (int n = best_node; T.parent[n] >= 0; n = T.parent[n]) depth++;
+            uint32_t *chain = chain_out ? chain_out + (size_t)q * P.chain_cap : nullptr;
+            if (depth > P.chain_cap && chain) { if (status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW; }
+            if (chain && g.gl == 0) {
+                int n = best_node;
+                for (int k = depth - 1; k >= 0; k--) { if (k < P.chain_cap) chain[k] = (uint32_t)n; n = T.parent[n]; }
+            }
+            g.sync();
+            if (path_out && P.path_cap > 0 && chain && depth <= P.chain_cap) {
+                R *rows = path_out + (size_t)q * P.path_cap * 6;
+                for (int e = 0; e < depth; e++) {
+                    const int id = (int)chain[e], par = T.parent[id];
+                    if (g.gl == 0 && n_path < P.path_cap) {
+                        R *w = rows + 6 * (size_t)n_path;
+                        w[0] = T.x[par]; w[1] = T.y[par]; w[2] = T.th[par]; w[3] = (R)0; w[4] = T.t[par]; w[5] = T.len[par];
+                    }
+                    n_path++;
+                    EdgeOut<R> o;
+                    int room = P.path_cap - n_path; if (room < 0) room = 0;
+                    eval_edge<R, G, false, false, true>(g, sc, env, rng, T.ctr[id], P.sp, T.x[par], T.y[par], T.th[par],
+                                                        T.t[par], T.len[par], (R)0, 0,
+                                                        rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0), room, o);
+                    n_path += o.nwp - 1;
+                }
+                if (g.gl == 0 && n_path < P.path_cap) {
+                    R *w = rows + 6 * (size_t)n_path;
+                    w[0] = T.x[best_node]; w[1] = T.y[best_node]; w[2] = T.th[best_node]; w[3] = (R)0;
+                    w[4] = T.t[best_node]; w[5] = T.len[best_node];
+                }
+                n_path++;
+                if (n_path > P.path_cap && status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW;
+            }
+            g.sync();
+            if (chain && g.gl == 0)
+                for (int k = 0; k < depth && k < P.chain_cap; k++) chain[k] = T.ctr[chain[k]];
+        }
+        if (g.gl == 0) {
+            auvrrt_plan_record_t rec;
+            rec.status = status; rec.n_nodes = n_nodes; rec.best_node = best_node; rec.best_iter = best_iter;
+            rec.depth = depth; rec.n_path = n_path; rec.n_cost_evals = n_cost_evals;
+            rec.n_waypoints = (int32_t)n_waypoints; rec.n_uniforms = (long long)ctr; rec.n_primitives = n_prims;
+            rec.cost[0] = best_node >= 0 ? (double)best_c[0] : 0.0; rec.cost[1] = (double)best_c[1];
+            rec.cost[2] = (double)best_c[2]; rec.cost[3] = (double)best_c[3];
+            rec.path_length = (double)best_len; rec.t_leaf = (double)best_t;
+            records[q] = rec;
+        }
+        g.sync();
+    }
+}
+
+// ---- re-create paths from (start, seed, chain of stream positions): no tree needed ------------
+template <typename R, int G>
+__global__ void __launch_bounds__(128)
+k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds, const uint32_t *chain,
+              const int32_t *depth, long long Q, PlanP<R> P, R *path_out, int32_t *n_path_out) {
+    __shared__ GroupScratch<R, G> scratch[128 / G];
+    EnvView<R> env;
+    env.bind(blob, blob);
+    Grp<G> g;
+    GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
+    const long long groups = (long long)gridDim.x * (128 / G);
+    for (long long q = blockIdx.x * (long long)(128 / G) + threadIdx.x / G; q < Q; q += groups) {
+        Stream<R> rng;
+        rng.key = stream_key(seeds[q]); rng.ext = nullptr; rng.n_ext = 0;
+        R x = starts[5 * q], y = starts[5 * q + 1], th = starts[5 * q + 2], t = starts[5 * q + 3], len = starts[5 * q + 4];
+        R *rows = path_out + (size_t)q * P.path_cap * 6;
+        int n_path = 0;
+        const int d = depth[q];
+        for (int e = 0; e < d; e++) {
+            if (g.gl == 0 && n_path < P.path_cap) {
+                R *w = rows + 6 * (size_t)n_path;
+                w[0] = x; w[1] = y; w[2] = th; w[3] = (R)0; w[4] = t; w[5] = len;
+            }
+            n_path++;
+            EdgeOut<R> o;
+            int room = P.path_cap - n_path; if (room < 0) room = 0;
+            eval_edge<R, G, false, false, true>(g, sc, env, rng, chain[(size_t)q * P.chain_cap + e], P.sp, x, y, th, t,
+                                                len, (R)0, 0, rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0),
+                                                room, o);
+            n_path += o.nwp - 1;
+            x = o.x; y = o.y; th = o.th; t = o.t; len = o.len;
+        }
+        if (d >= 0) {
+            if (g.gl == 0 && n_path < P.path_cap) {
+                R *w = rows + 6 * (size_t)n_path;
+                w[0] = x; w[1] = y; w[2] = th; w[3] = (R)0; w[4] = t; w[5] = len;
+            }
+            n_path++;
+        }
+        if (g.gl == 0) n_path_out[q] = n_path;
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+template <typename R> static int make_planp(const auvrrt_env *env, const auvrrt_plan_params_t *p, PlanP<R> *out) {
+    if (p->iterations < 1) return set_err(AUVRRT_ERR_ARG, "plan: iterations must be >= 1");
+    if (p->mode != 0 && p->mode != 1) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0 or 1");
+    if (!(p->bin_interval > 0) || !(p->max_traj_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: bin_interval and max_traj_time must be > 0");
+    if (env->H > 64) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 64 habitats");
+    double nbd = ceil(p->max_traj_time / p->bin_interval);                      // rrt_dubins.py:111
+    if (nbd > 1e6) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 1e6 time bins");
+    PlanP<R> P;
+    P.I = p->iterations; P.mode = p->mode; P.nb = (int)nbd;
+    P.chain_cap = p->chain_cap > 0 ? p->chain_cap : 1; P.path_cap = p->path_cap; P.trace = p->trace;
+    P.cap = P.I + 1; P.nchunks = P.nb + P.cap / 32 + 4;
+    P.bin_interval = (R)p->bin_interval; P.max_traj = (R)p->max_traj_time;
+    P.horizon = (R)(p->max_traj_time - 30);                                     // :158
+    P.w1 = (R)p->weights[0]; P.w2 = (R)p->weights[1]; P.w3 = (R)p->weights[2];
+    double sp[5] = {p->dist_to_end, p->diff_max, p->freq, p->min_dist, p->v};
+    P.sp = make_steer_params<R>(sp);
+    *out = P;
+    return AUVRRT_OK;
+}
+
+template <typename R, int G> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
+    EnvBlob<R> b = env_blob<R>(env);
+    int budget = 110 * 1024;     // leaves room for 2 CTAs per SM
+    int sm = 16, mode = 0;
+    if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
+    else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
+    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    int per_sm = 0;
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G>, PLAN_THREADS, sm));
+    if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan: kernel does not fit on an SM (smem %d)", sm);
+    int nsm = 0, dev = 0;
+    AUV_CUDA(cudaGetDevice(&dev));
+    AUV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    *grid = nsm * per_sm; *smem = sm; *stage_mode = mode;
+    return AUVRRT_OK;
+}
+
+template <typename R, int G>
+static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
+                         const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
+                         auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
+                         cudaStream_t s, int64_t *need_bytes) {
+    PlanP<R> P;
+    int rc = make_planp<R>(env, p, &P);
+    if (rc) return rc;
+    int grid, smem, mode;
+    rc = plan_geometry<R, G>(env, &grid, &smem, &mode);
+    if (rc) return rc;
+    WsLayout L = make_layout<R>(P.cap, P.nb, P.nchunks);
+    const int gpc = PLAN_THREADS / G;
+    int64_t need = 256 + (int64_t)grid * gpc * (int64_t)L.slot_bytes;
+    if (need_bytes) { *need_bytes = need; return AUVRRT_OK; }
+    if (Q <= 0) return AUVRRT_OK;
+    if (workspace_bytes < need) return set_err(AUVRRT_ERR_ARG, "plan: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    if (P.trace && !trace) return set_err(AUVRRT_ERR_ARG, "plan: trace requested without trace buffers");
+    int64_t blocks = (Q + gpc - 1) / gpc;
+    if (blocks < grid) grid = (int)blocks;
+    AUV_CUDA(cudaMemsetAsync(workspace, 0, 256, s));
+    auvrrt_plan_trace_t tr;
+    if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
+    EnvBlob<R> b = env_blob<R>(env);
+    k_plan<R, G><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+                                                  (unsigned char *)workspace + 256, (unsigned long long *)workspace,
+                                                  records, chain, path, tr);
+    AUV_LAUNCH_CHECK2();
+    return AUVRRT_OK;
+}
+
+template <typename R>
+int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
+                const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
+                auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
+                cudaStream_t s) {
+    int G = p->group ? p->group : 32;
+    if (G == 32) return launch_plan_g<R, 32>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, nullptr);
+    if (G == 16) return launch_plan_g<R, 16>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, nullptr);
+    if (G == 8) return launch_plan_g<R, 8>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, nullptr);
+    return set_err(AUVRRT_ERR_ARG, "plan: group must be 32, 16 or 8");
+}
+template <typename R>
+int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p) {
+    int64_t need = -1;
+    int G = p->group ? p->group : 32, rc;
+    if (G == 32) rc = launch_plan_g<R, 32>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
+    else if (G == 16) rc = launch_plan_g<R, 16>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
+    else if (G == 8) rc = launch_plan_g<R, 8>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
+    else { set_err(AUVRRT_ERR_ARG, "plan: group must be 32, 16 or 8"); return -1; }
+    return rc ? -1 : need;
+}
+template int launch_plan<float>(const auvrrt_env *, const float *, const uint64_t *, int64_t, const auvrrt_plan_params_t *,
+                                void *, int64_t, auvrrt_plan_record_t *, uint32_t *, float *, const auvrrt_plan_trace_t *, cudaStream_t);
+template int launch_plan<double>(const auvrrt_env *, const double *, const uint64_t *, int64_t, const auvrrt_plan_params_t *,
+                                 void *, int64_t, auvrrt_plan_record_t *, uint32_t *, double *, const auvrrt_plan_trace_t *, cudaStream_t);
+template int64_t plan_workspace_bytes<float>(const auvrrt_env *, const auvrrt_plan_params_t *);
+template int64_t plan_workspace_bytes<double>(const auvrrt_env *, const auvrrt_plan_params_t *);
+
+template <typename R>
+int launch_materialize(const auvrrt_env *env, const R *starts, const uint64_t *seeds, const uint32_t *chain,
+                       const int32_t *depth, int64_t Q, const auvrrt_plan_params_t *p, R *path, int32_t *n_path,
+                       cudaStream_t s) {
+    if (Q <= 0) return AUVRRT_OK;
+    PlanP<R> P;
+    int rc = make_planp<R>(env, p, &P);
+    if (rc) return rc;
+    int64_t blocks = (Q + 3) / 4;
+    if (blocks > AUV_SMS * 8) blocks = AUV_SMS * 8;
+    k_materialize<R, 32><<<(unsigned)blocks, 128, 0, s>>>(env_blob<R>(env).blob, starts, seeds, chain, depth, (long long)Q, P, path, n_path);
+    AUV_LAUNCH_CHECK2();
+    return AUVRRT_OK;
+}
+template int launch_materialize<float>(const auvrrt_env *, const float *, const uint64_t *, const uint32_t *, const int32_t *,
+                                       int64_t, const auvrrt_plan_params_t *, float *, int32_t *, cudaStream_t);
+template int launch_materialize<double>(const auvrrt_env *, const double *, const uint64_t *, const uint32_t *, const int32_t *,
+                                        int64_t, const auvrrt_plan_params_t *, double *, int32_t *, cudaStream_t);
+
+}  // namespace auv

@@ -1,0 +1,212 @@
+/*
+ * auvrrt.h -- C ABI of libauvrrt.so, the B200 (sm_100a) implementation of the RRT planning inner
+ * loop of hmc-lair-shark-tracking/auv-sim.
+ *
+ * The reference has no FFI of its own: its boundary is the Python surface of
+ * path_planning/rrt_dubins.py (class RRT) and path_planning/cost.py.  Each entry point below names
+ * the reference function it replaces (file:line under /root/reference); INTEGRATION.md shows the
+ * ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types; every function returns an int status
+ *     (AUVRRT_OK == 0) and auvrrt_last_error() returns a thread-local message for the last failure.
+ *   - `precision`: AUVRRT_F32 = fast build (fp32 arithmetic, tolerance 1e-5 relative vs the fp64
+ *     reference), AUVRRT_F64 = verification build (fp64, no FMA contraction, the reference's
+ *     operation order; indices / booleans match the reference exactly).
+ *   - Functions without a suffix take HOST buffers (always double / int32 / uint8 / uint64) and do
+ *     their own host<->device copies on an internal stream.  Functions ending in `_dev` take DEVICE
+ *     pointers whose floating type is float (AUVRRT_F32) or double (AUVRRT_F64) plus a cudaStream_t
+ *     passed as void*; they enqueue work and return without synchronising.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry fails with
+ *     AUVRRT_ERR_CUDA.
+ */
+#ifndef AUVRRT_H
+#define AUVRRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUVRRT_OK 0
+#define AUVRRT_ERR_ARG 1
+#define AUVRRT_ERR_CUDA 2
+#define AUVRRT_ERR_UNSUPPORTED 3
+
+#define AUVRRT_F32 0
+#define AUVRRT_F64 1
+
+/* per-query / per-edge status codes, mirroring the reference's uncaught exceptions */
+#define AUVRRT_ST_OK 0
+#define AUVRRT_ST_NO_PATH 1     /* TypeError at rrt_dubins.py:174 (opt_path is None) */
+#define AUVRRT_ST_ZERO_DIV 2    /* ZeroDivisionError at rrt_dubins.py:270 / :281 */
+#define AUVRRT_ST_KEY_ERROR 3   /* KeyError / IndexError at rrt_dubins.py:123-127 */
+#define AUVRRT_ST_STREAM_END 4  /* explicit uniform stream exhausted */
+#define AUVRRT_ST_OVERFLOW 5    /* a fixed-size output (chain / path) was too small */
+
+typedef struct auvrrt_env auvrrt_env_t;
+
+const char *auvrrt_last_error(void);
+/* number of CUDA devices visible, 0 if none (never an error) */
+int auvrrt_device_count(void);
+/* kernels this library launched in this process since load (bench.py's gpu_launches) */
+int64_t auvrrt_launch_count(void);
+
+/* ---- world model ---------------------------------------------------------------------------
+ * Replaces the Python objects RRT.__init__ keeps (rrt_dubins.py:26-49): obstacle circles in
+ * obstacle_list order, the boundary polygon ring, habitats (cost.py:145), and the shark grid
+ * {(t0,t1): {cell.bounds: p}} (createSharkGrid, rrt_dubins.py:612-630) flattened to
+ * bins[T][2], cells[C][4] (minx,miny,maxx,maxy, dict order), probs[T][C].  Any count may be 0. */
+int auvrrt_env_create(const double *circles, int K, const double *poly, int E,
+                      const double *habitats, int H, const double *bins, int T,
+                      const double *cells, int C, const double *probs, int device,
+                      auvrrt_env_t **out);
+void auvrrt_env_destroy(auvrrt_env_t *env);
+
+/* ---- RRT.get_closest_mps (rrt_dubins.py:505-513) ---------------------------------------------
+ * nq queries against one tree of n nodes (SoA x[], y[]); strict <, lowest index wins ties;
+ * compares sqrt(dx*dx + dy*dy) exactly as the reference does. */
+int auvrrt_nn(const double *tree_x, const double *tree_y, int64_t n, const double *qx,
+              const double *qy, int nq, int precision, int device, int32_t *out_idx);
+int auvrrt_nn_dev(const void *tree_x, const void *tree_y, int64_t n, const void *qx, const void *qy,
+                  int nq, int precision, void *scratch, int64_t scratch_bytes, int32_t *out_idx,
+                  void *stream);
+int64_t auvrrt_nn_scratch_bytes(int nq);
+
+/* ---- RRT.steer, the random-arc rollout (rrt_dubins.py:237-295) --------------------------------
+ * params = {dist_to_end, diff_max, freq, min_dist, velocity}.  Edge i starts at
+ * parents[i] = (x, y, theta, traj_time_stamp, length) and consumes uniforms
+ * u[uoff[i] .. uoff[i+1]) in the reference's order.
+ * Outputs: leaf[i] (same 5 fields), counts[i] = len(new.path) (parent included),
+ * waypoints[i][k] = (x, y, theta, v, traj_time_stamp, length) for k < counts[i]-1 (wp_cap rows per
+ * edge), used[i] = uniforms consumed, status[i]. */
+int auvrrt_steer_arc(const double *parents, int64_t n, const double *u, const int64_t *uoff,
+                     const double params[5], int precision, int device, double *leaf,
+                     int32_t *counts, double *waypoints, int wp_cap, int32_t *used,
+                     int32_t *status);
+
+/* ---- six-word Dubins steer (named by the north star; rrt_dubins.py:238-251 is a commented-out
+ * call into the absent PyPI `dubins` module -> parity unpinned) -----------------
+ * from/to = (x, y, theta); word in evaluation order LSL=0, LSR, RSL, RSR, RLR, LRL (255 = none);
+ * seg = (t, p, q) in units of rho; length = rho (t+p+q); waypoints[i][k], k < W: samples at
+ * s = k * length/(W-1) for k < W-1, then `to` itself. */
+int auvrrt_steer_dubins(const double *from, const double *to, int64_t n, double rho, int W,
+                        int precision, int device, uint8_t *word, double *seg, double *length,
+                        double *waypoints);
+
+/* ---- RRT.check_collision (rrt_dubins.py:530-549), True(1) = safe -----------------------------
+ * Path i = points[off[i] .. off[i+1]) as (x, y).  Reproduces the running-minimum quirk
+ * (:535-542) and strict-interior Point.within (:544-547, exact predicate in AUVRRT_F64).
+ * An empty path with K > 0 raises ValueError in the reference: out_safe = 255. */
+int auvrrt_collide(const auvrrt_env_t *env, const double *points, const int64_t *off, int64_t n,
+                   int precision, uint8_t *out_safe);
+/* check_collision_obstacle (rrt_dubins.py:551-556): single points, per-obstacle test */
+int auvrrt_collide_points(const auvrrt_env_t *env, const double *points, int64_t n, int precision,
+                          uint8_t *out_safe);
+
+/* ---- cost.habitat_shark_cost_func (cost.py:145-207) ------------------------------------------
+ * Path i = points[off[i] .. off[i+1]) as (x, y, traj_time_stamp) in the caller's order;
+ * out[i] = (sum, c0, c1, c2).  bin_mask (T bytes, may be NULL) selects shark-grid bins
+ * (the planner's filter, rrt_dubins.py:161-166).  n_habitats < 0 means all of env's habitats,
+ * otherwise only the first n_habitats. */
+int auvrrt_cost(const auvrrt_env_t *env, const double *points, const int64_t *off, int64_t n,
+                const double *t_total, const double weights[3], const uint8_t *bin_mask,
+                int n_habitats, int precision, double *out);
+/* cost.habitat_shark_cost_point (cost.py:209-241): visited[H] bytes, time-bin row tb */
+int auvrrt_cost_point(const auvrrt_env_t *env, const double *points, int64_t n,
+                      const uint8_t *visited, int tb, const double weights[3], int precision,
+                      double *out_sum);
+
+/* ---- fused edge evaluation: steer + collide (+ cost), the config-4 micro-benchmark -----------
+ * Dubins edges: one (from, to) pair per edge, W waypoints each.  Arc edges: edge i consumes the
+ * counter stream of seed seeds[i] from position 0 (see auvrrt_stream_u).  out_cost (may be NULL)
+ * = cost of the edge's waypoints alone, (sum, c0, c1, c2) with total time = last waypoint time. */
+int auvrrt_edges_dubins_dev(const auvrrt_env_t *env, const void *from, const void *to, int64_t n,
+                            double rho, int W, int precision, uint8_t *out_safe, uint8_t *out_word,
+                            void *out_length, void *stream);
+int auvrrt_edges_arc_dev(const auvrrt_env_t *env, const void *parents, const uint64_t *seeds,
+                         int64_t n, const double params[5], int precision, uint8_t *out_safe,
+                         int32_t *out_counts, void *out_leaf, void *stream);
+int auvrrt_edges_dubins(const auvrrt_env_t *env, const double *from, const double *to, int64_t n,
+                        double rho, int W, int precision, uint8_t *out_safe, uint8_t *out_word,
+                        double *out_length);
+int auvrrt_edges_arc(const auvrrt_env_t *env, const double *parents, const uint64_t *seeds,
+                     int64_t n, const double params[5], int precision, uint8_t *out_safe,
+                     int32_t *out_counts, double *out_leaf);
+
+/* ---- the pre-generated sample sequence ------------------------------------------------------
+ * u_k(seed): counter-based SplitMix64 stream; 53-bit doubles, or the top 24 bits (bits24 != 0,
+ * what the AUVRRT_F32 build consumes).  Host-side evaluation for callers that replay it. */
+double auvrrt_stream_u(uint64_t seed, int64_t k, int bits24);
+
+/* ---- RRT.exploring (rrt_dubins.py:92-176): batched independent planning queries --------------*/
+typedef struct {
+    int32_t iterations;      /* budget: steer calls per query (replaces the wall-clock budget) */
+    int32_t mode;            /* 0: traj_time_stamp & plan_time (time-bin pick, :122-127)
+                                1: plan_time False (get_random_mps + get_closest_mps, :136-139) */
+    double bin_interval, v, max_traj_time;
+    double dist_to_end, diff_max, freq, min_dist;   /* RRT.__init__ defaults 2, 0.5, 30; 0.5 (:141) */
+    double weights[3];
+    int32_t chain_cap;       /* max tree depth recorded per query (<= 255) */
+    int32_t path_cap;        /* rows per query in out_path (0: no paths) */
+    int32_t trace;           /* != 0: fill the per-iteration trace arrays (parity tests) */
+    int32_t group;           /* lanes cooperating on one tree: 32 (default when 0), 16 or 8 */
+} auvrrt_plan_params_t;
+
+/* one fixed-size record per query: the unit the multi-GPU gather moves */
+typedef struct {
+    int32_t status;          /* AUVRRT_ST_* */
+    int32_t n_nodes;         /* len(mps_list) */
+    int32_t best_node;       /* index into the tree of the optimal leaf, -1 if none */
+    int32_t best_iter;       /* steer call that created it */
+    int32_t depth;           /* edges from the root to best_node */
+    int32_t n_path;          /* waypoints on the optimal path (len(path)) */
+    int32_t n_cost_evals;    /* candidate leaves evaluated (t >= max_traj_time - 30) */
+    int32_t n_waypoints;     /* sum of len(new.path) over all steer calls */
+    int64_t n_uniforms;      /* stream positions consumed */
+    int64_t n_primitives;    /* arc primitives drawn */
+    double cost[4];          /* sum, c0, c1, c2 of the optimal path */
+    double path_length;      /* "path length" of the result dict */
+    double t_leaf;           /* traj_time_stamp of the optimal leaf */
+} auvrrt_plan_record_t;
+
+/* optional per-iteration trace, each [Q][iterations] (parity tests only) */
+typedef struct {
+    int32_t *parent; uint8_t *safe; int32_t *nwp; double *leaf /* [Q][I][5] */; int64_t *upos;
+} auvrrt_plan_trace_t;
+
+/* starts[Q][5] = (x, y, theta, traj_time_stamp, length); seeds[Q];
+ * out_chain[Q][chain_cap]: stream positions of the steer calls root->leaf along the optimal path
+ * (enough to re-create it with auvrrt_materialize); out_path[Q][path_cap][6] =
+ * (x, y, theta, v, traj_time_stamp, length) in root->leaf order, i.e. result["path"][0]. */
+int auvrrt_plan_batch(const auvrrt_env_t *env, const double *starts, const uint64_t *seeds,
+                      int64_t Q, const auvrrt_plan_params_t *params, int precision,
+                      auvrrt_plan_record_t *out_records, uint32_t *out_chain, double *out_path,
+                      const auvrrt_plan_trace_t *trace);
+/* device-resident variant: starts are float[Q][5] (F32) or double[Q][5] (F64); records / chain /
+ * path / trace are device pointers (path rows in the precision's floating type; trace.leaf too).
+ * workspace from auvrrt_plan_workspace_bytes(); nothing is synchronised. */
+int64_t auvrrt_plan_workspace_bytes(const auvrrt_env_t *env, const auvrrt_plan_params_t *params,
+                                    int precision);
+int auvrrt_plan_batch_dev(const auvrrt_env_t *env, const void *starts, const uint64_t *seeds,
+                          int64_t Q, const auvrrt_plan_params_t *params, int precision,
+                          void *workspace, int64_t workspace_bytes,
+                          auvrrt_plan_record_t *out_records, uint32_t *out_chain, void *out_path,
+                          const auvrrt_plan_trace_t *trace, void *stream);
+
+/* re-create optimal paths from (start, seed, chain) records, e.g. for the few winners after the
+ * multi-GPU gather.  Same row layout as out_path. */
+int auvrrt_materialize(const auvrrt_env_t *env, const double *starts, const uint64_t *seeds,
+                       const uint32_t *chain, const int32_t *depth, int64_t Q,
+                       const auvrrt_plan_params_t *params, int precision, double *out_path,
+                       int32_t *out_n_path);
+
+/* FP32 FFMA issue-rate calibration kernel for the roofline denominator: runs `iters` dependent
+ * FFMA chains on every lane of a full grid and returns achieved FLOP/s (FMA = 2). */
+int auvrrt_calibrate_fp32(int device, int iters, double *out_flops, double *out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUVRRT_H */

@@ -1,0 +1,423 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libauvrrt.so host-buffer entry points),
+against the fp64 oracle and the golden vectors produced by the unmodified reference.
+
+Bars (BASELINE.json north_star): indices, Dubins words and booleans bit-exact in the fp64
+verification build; lengths / waypoints / costs within 1e-5 relative in the fp32 fast build (the
+tolerance is written at each assert).  fp64 floats are compared at 1e-9: CUDA's sin/cos are within
+1-2 ulp of glibc's, not bit-identical.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402  (the checker)
+
+RTOL32 = 1e-5      # fp32 fast build, relative (absolute floor 1e-5 * map scale of 1 m .. 500 m below)
+TOL64 = 1e-9
+
+
+@pytest.fixture(scope="module")
+def api():
+    import auvrrt
+    assert auvrrt.api.device_count() > 0, "no CUDA device"
+    return auvrrt.api
+
+
+@pytest.fixture(scope="module")
+def env(api, catalina_map, shark_grid):
+    bins, probs = shark_grid
+    return api.Env.from_map(catalina_map, bins, probs)
+
+
+@pytest.fixture(scope="module")
+def oworld(catalina_map, shark_grid):
+    bins, probs = shark_grid
+    return orc.OracleWorld.from_map(catalina_map, bins, probs)
+
+
+def close(a, b, rtol, scale=1.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), scale))
+
+
+# ------------------------------------------------------------------------------------ stream
+def test_stream_matches_oracle(api):
+    for seed in (0, 7, 2**33 + 5):
+        for k in (0, 1, 1000, 2**31 + 3):
+            assert api.stream_u(seed, k) == orc.stream_u(seed, k)
+            assert api.stream_u(seed, k, True) == orc.stream_u(seed, k, True)
+
+
+# ------------------------------------------------------------------------------------ steer (arc)
+def test_steer_arc_f64_golden(api, golden_dir):
+    z = np.load(os.path.join(golden_dir, "steer_arc.npz"))
+    n = len(z["parents"])
+    for v in np.unique(z["velocity"]):
+        sel = np.where(z["velocity"] == v)[0]
+        us = [z["u"][z["uoff"][i]:z["uoff"][i + 1]] for i in sel]
+        uoff = np.concatenate([[0], np.cumsum([len(u) for u in us])])
+        params = list(z["params"]) + [v]
+        leaf, counts, wp, used, status = api.steer_arc(z["parents"][sel], np.concatenate(us), uoff, params, "f64")
+        assert np.all(status == 0)
+        assert np.array_equal(counts, z["nwp"][sel])                   # len(new.path): exact
+        assert np.array_equal(used, np.diff(uoff))                     # uniforms consumed: exact
+        assert close(leaf, z["leaf"][sel], TOL64)
+        for j, i in enumerate(sel):
+            ref = z["wp"][z["woff"][i]:z["woff"][i + 1]]
+            assert close(wp[j, :len(ref)], ref, TOL64)
+    assert n == 1500
+
+
+def test_steer_arc_f32_vs_oracle(api):
+    rs = np.random.RandomState(3)
+    n = 2000
+    parents = np.stack([rs.uniform(-450, 80, n), rs.uniform(-150, 190, n), rs.uniform(-12, 12, n),
+                        rs.uniform(0, 480, n), rs.uniform(0, 900, n)], 1).astype(np.float32).astype(np.float64)
+    us, want_leaf, want_wp, want_n = [], [], [], []
+    for i in range(n):
+        u = np.array([orc.stream_u(5000 + i, k, True) for k in range(100)])
+        st, leaf, wp, used = orc.steer_arc(parents[i], u, 2.0, 0.5, 30.0, 0.5, 2.0)
+        assert st == 0
+        us.append(u[:used]); want_leaf.append(leaf); want_wp.append(wp); want_n.append(len(wp) + 1)
+    uoff = np.concatenate([[0], np.cumsum([len(u) for u in us])])
+    leaf, counts, wp, used, status = api.steer_arc(parents, np.concatenate(us), uoff, [2.0, 0.5, 30.0, 0.5, 2.0], "f32")
+    assert np.all(status == 0) and np.array_equal(used, np.diff(uoff))
+    # `movement >= min_dist` can flip for a movement within fp32 rounding of 0.5: allow those only
+    flips = np.where(counts != np.array(want_n))[0]
+    assert len(flips) <= 2
+    ok = np.setdiff1d(np.arange(n), flips)
+    want_leaf = np.array(want_leaf)
+    # positions relative to the map scale (coordinates up to ~500 m), time/length relative to value
+    assert close(leaf[ok][:, :2], want_leaf[ok][:, :2], RTOL32, scale=100.0)
+    assert close(leaf[ok][:, 2], want_leaf[ok][:, 2], RTOL32, scale=1.0)
+    assert close(leaf[ok][:, 3:], want_leaf[ok][:, 3:], RTOL32, scale=1.0)
+    for i in ok[:400]:
+        w = want_wp[i]
+        assert close(wp[i, :len(w), :2], w[:, :2], RTOL32, scale=100.0)
+        assert close(wp[i, :len(w), 2:], w[:, 2:], RTOL32, scale=1.0)
+
+
+# ------------------------------------------------------------------------------------ collision
+def _golden_paths(z):
+    return [np.vstack([z["parents"][i][None, :2], z["wp"][z["woff"][i]:z["woff"][i + 1], :2]])
+            for i in range(len(z["parents"]))]
+
+
+def test_collision_f64_golden_both_orders(api, golden_dir, catalina_map):
+    z = np.load(os.path.join(golden_dir, "steer_arc.npz"))
+    paths = _golden_paths(z)
+    fwd = api.Env.from_map(catalina_map, with_cells=False)
+    rev = api.Env.from_map(dict(catalina_map, circles=list(reversed(catalina_map["circles"]))), with_cells=False)
+    assert np.array_equal(api.collide(fwd, paths, "f64"), z["safe_fwd"])
+    assert np.array_equal(api.collide(rev, paths, "f64"), z["safe_rev"])      # running-min quirk
+    # fast build: same booleans except points within fp32 rounding of a circle / the boundary
+    assert np.mean(api.collide(fwd, paths, "f32") != z["safe_fwd"]) < 0.005
+
+
+def test_collision_f64_hand_cases(api, golden_dir):
+    with open(os.path.join(golden_dir, "collision_hand.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        e = api.Env(circles=c["circles"], boundary=c["boundary"])
+        got = api.collide(e, [np.array(c["points"])], "f64")[0]
+        assert bool(got) == c["safe"], c
+        e.close()
+
+
+def test_collision_empty_and_ragged(api, catalina_map):
+    e = api.Env.from_map(catalina_map, with_cells=False)
+    out = api.collide(e, [np.zeros((0, 2)), np.array([[-200.0, 0.0]]), np.array([[-200.0, 0.0]] * 70)], "f64")
+    assert list(out) == [255, 1, 1]
+    pts = np.array([[-200.0, 0.0], [9.4, -3.2], [1e4, 1e4]])
+    want = [orc.check_collision_obstacle(p[0], p[1], orc.OracleWorld.from_map(catalina_map)) for p in pts]
+    assert list(api.collide_points(e, pts, "f64")) == want
+
+
+# ------------------------------------------------------------------------------------ cost
+def test_cost_f64_golden_bit_exact(api, golden_dir, catalina_map, shark_grid):
+    bins, probs = shark_grid
+    z = np.load(os.path.join(golden_dir, "cost.npz"))
+    e = api.Env.from_map(catalina_map, bins, probs)
+    for i in range(len(z["t_total"])):
+        pts = z["pts"][z["off"][i]:z["off"][i + 1]]
+        out = api.cost(e, [pts], [z["t_total"][i]], z["weights"][i], n_habitats=int(z["n_hab"][i]), precision="f64")[0]
+        assert np.array_equal(out, z["out"][i]), (i, out, z["out"][i])
+        out32 = api.cost(e, [pts], [z["t_total"][i]], z["weights"][i], n_habitats=int(z["n_hab"][i]), precision="f32")[0]
+        assert close(out32, z["out"][i], 1e-4, scale=1.0)      # fp32 sums over ~200 waypoints
+
+
+def test_cost_f64_hand_cases(api, golden_dir):
+    with open(os.path.join(golden_dir, "cost_hand.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        bins = [g[0] for g in c["grid"]]
+        cells = [cb for cb, _ in c["grid"][0][1]] if c["grid"] else []
+        probs = [[p for _, p in g[1]] for g in c["grid"]] if c["grid"] else None
+        e = api.Env(habitats=c["habitats"], bins=bins, cells=cells, probs=probs)
+        out = api.cost(e, [np.array(c["points"], dtype=np.float64).reshape(-1, 3)], [c["t_total"]], c["weights"],
+                       precision="f64")[0]
+        assert np.array_equal(out, np.array(c["out"], dtype=np.float64)), (c, out)
+        e.close()
+
+
+def test_cost_random_cells_vs_oracle(api):
+    """arbitrary overlapping / unordered cells: the piece/candidate index must reproduce the
+    reference's first-match-in-dict-order scan, typo included."""
+    rs = np.random.RandomState(11)
+    for trial in range(6):
+        C_ = 40
+        lo = rs.uniform(0, 80, (C_, 2))
+        cells = np.concatenate([lo, lo + rs.uniform(1, 40, (C_, 2))], 1)
+        cells = np.round(cells * 2) / 2               # many shared edges -> exact ties
+        bins = [[0, 50], [50, 100], [120, 150]]
+        probs = rs.uniform(0, 1, (3, C_))
+        habs = np.concatenate([rs.uniform(0, 100, (5, 2)), rs.uniform(5, 30, (5, 1))], 1)
+        pts = np.concatenate([np.round(rs.uniform(0, 110, (300, 2)) * 2) / 2, rs.uniform(0, 160, (300, 1))], 1)
+        pts[:20, 2] = [0, 50, 100, 120, 150, 110] * 3 + [50, 50]
+        ow = orc.OracleWorld(habitats=habs, bins=bins, cells=cells, probs=probs)
+        e = api.Env(habitats=habs, bins=bins, cells=cells, probs=probs)
+        for w in ([-3, -3, -4], [0.1, 0.7, 1.3]):
+            want = orc.cost(pts, 77.0, ow, w)
+            got = api.cost(e, [pts], [77.0], w, precision="f64")[0]
+            assert np.array_equal(got, want), (trial, got, want)
+            singles = api.cost(e, [pts[i:i + 1] for i in range(60)], [1.0] * 60, w, precision="f64")
+            for i in range(60):
+                assert np.array_equal(singles[i], orc.cost(pts[i:i + 1], 1.0, ow, w))
+        vis = [1, 0, 0, 1, 0]
+        got = api.cost_point(e, pts[:50, :2], vis, 1, [-3, -3, -4], "f64")
+        want = [orc.cost_point(p[0], p[1], ow, vis, 1, [-3, -3, -4]) for p in pts[:50]]
+        assert np.array_equal(got, np.array(want))
+        e.close()
+
+
+# ------------------------------------------------------------------------------------ nearest node
+def test_nn_golden_exact(api, golden_dir):
+    z = np.load(os.path.join(golden_dir, "nn.npz"))
+    for i in range(int(z["n"])):
+        tree, qs, idx = z["tree%d" % i], z["q%d" % i], z["idx%d" % i]
+        assert np.array_equal(api.nn(tree, qs, "f64"), idx)
+        t32 = tree.astype(np.float32).astype(np.float64)
+        q32 = qs.astype(np.float32).astype(np.float64)
+        want = np.array([orc.nn(t32, q) for q in q32])
+        assert np.array_equal(api.nn(t32, q32, "f32"), want)      # exact indices in the fast build too
+
+
+def test_nn_large_tree_properties(api):
+    rs = np.random.RandomState(5)
+    n = 3_000_001
+    tree = rs.uniform(-500, 500, (n, 2))
+    qs = rs.uniform(-500, 500, (5, 2))
+    got = api.nn(tree, qs, "f64")
+    for q, g in zip(qs, got):
+        d = np.sqrt((tree[:, 0] - q[0]) ** 2 + (tree[:, 1] - q[1]) ** 2)
+        assert g == int(np.argmin(d))
+    tree[:] = tree[0]                                    # all nodes identical: lowest index wins
+    assert list(api.nn(tree, qs, "f64")) == [0] * 5
+
+
+# ------------------------------------------------------------------------------------ Dubins
+def _dubins_cases(n, seed=1):
+    rs = np.random.RandomState(seed)
+    q0 = np.stack([rs.uniform(-400, 50, n), rs.uniform(-100, 150, n), rs.uniform(-np.pi, np.pi, n)], 1)
+    r = rs.choice([0.5, 3.0, 10.0, 40.0], n)
+    q1 = np.stack([q0[:, 0] + rs.uniform(-1, 1, n) * r, q0[:, 1] + rs.uniform(-1, 1, n) * r,
+                   rs.uniform(-np.pi, np.pi, n)], 1)
+    return q0, q1
+
+
+def test_dubins_f64_vs_oracle_and_closure(api):
+    q0, q1 = _dubins_cases(4000)
+    W = 12
+    for rho in (1.0, 2.5):
+        word, seg, length, wp = api.steer_dubins(q0, q1, rho, W, "f64")
+        for i in range(len(q0)):
+            wd, prm, ln, al = orc.dubins_shortest(q0[i], q1[i], rho)
+            alt = np.sort(al[al >= 0])
+            near_tie = len(alt) > 1 and alt[1] - alt[0] < 1e-9 * max(1.0, alt[0])
+            assert word[i] == wd or near_tie                      # chosen word: exact
+            assert abs(length[i] - ln) <= TOL64 * max(1.0, ln)
+            if not near_tie:
+                assert close(seg[i], prm, 1e-7, scale=1.0)        # atan2/acos conditioning near 0 / 2pi
+            end = orc.dubins_sample(q0[i], rho, int(word[i]), seg[i], length[i] * (1 - 1e-12))
+            assert np.hypot(end[0] - q1[i, 0], end[1] - q1[i, 1]) < 1e-6      # closure at s = L
+            assert length[i] >= np.hypot(*(q1[i, :2] - q0[i, :2])) - 1e-9     # L >= Euclidean distance
+            assert np.allclose(wp[i, 0, :2], q0[i, :2], atol=1e-9) and np.array_equal(wp[i, -1], q1[i])
+        # waypoints against the oracle's sampler
+        for i in range(0, len(q0), 40):
+            step = length[i] / (W - 1)
+            for k in range(W - 1):
+                ref = orc.dubins_sample(q0[i], rho, int(word[i]), seg[i], k * step)
+                assert np.hypot(*(wp[i, k, :2] - ref[:2])) < 1e-7
+
+
+def test_dubins_mirror_symmetry_and_degenerate(api):
+    q0, q1 = _dubins_cases(2000, seed=9)
+    word, seg, length, _ = api.steer_dubins(q0, q1, 1.0, 0, "f64")
+    m0, m1 = q0 * [1, -1, -1], q1 * [1, -1, -1]                 # reflect y, negate headings
+    wordm, _, lengthm, _ = api.steer_dubins(m0, m1, 1.0, 0, "f64")
+    swap = {0: 3, 3: 0, 1: 2, 2: 1, 4: 5, 5: 4}                   # L <-> R
+    assert close(lengthm, length, 1e-9)
+    agree = np.mean([swap[int(w)] == int(wm) for w, wm in zip(word, wordm)])
+    assert agree > 0.995                                          # only exact ties may differ
+    w, s, ln, _ = api.steer_dubins([[1.0, 2.0, 0.3]], [[1.0, 2.0, 0.3]], 1.0, 0, "f64")
+    assert ln[0] == 0.0 and w[0] == 0
+
+
+def test_dubins_f32_vs_f64(api):
+    q0, q1 = _dubins_cases(4000, seed=4)
+    q0 = q0.astype(np.float32).astype(np.float64); q1 = q1.astype(np.float32).astype(np.float64)
+    w64, s64, l64, wp64 = api.steer_dubins(q0, q1, 1.0, 20, "f64")
+    w32, s32, l32, wp32 = api.steer_dubins(q0, q1, 1.0, 20, "f32")
+    same = w64 == w32
+    assert same.mean() > 0.99
+    # fp32 conditioning: d = D/rho up to ~60, p^2 = d^2 + O(d) -> relative 1e-5 needs care near
+    # infeasibility boundaries; the bar is 1e-5 relative on lengths for matching words
+    assert np.mean(np.abs(l32[same] - l64[same]) <= RTOL32 * np.maximum(l64[same], 1.0)) > 0.995
+    assert np.max(np.abs(l32[same] - l64[same]) / np.maximum(l64[same], 1.0)) < 1e-3
+
+
+# ------------------------------------------------------------------------------------ fused edges
+def test_edges_dubins_vs_oracle(api):
+    rs = np.random.RandomState(2)
+    K = 500
+    circles = np.stack([rs.uniform(-467, 82, K), rs.uniform(-153, 191, K), rs.uniform(1, 5, K)], 1)
+    boundary = [[-467.4, 85.6], [-359.1, 191.2], [82.4, -8.7], [-56.7, -153.5], [-336.0, -39.8]]
+    e = api.Env(circles=circles, boundary=boundary)
+    ow = orc.OracleWorld(circles=circles, boundary=boundary)
+    n = 20000
+    q0 = np.stack([rs.uniform(-400, 50, n), rs.uniform(-100, 120, n), rs.uniform(-np.pi, np.pi, n)], 1)
+    ang = rs.uniform(-np.pi, np.pi, n); dist = rs.uniform(2, 40, n)
+    q1 = np.stack([q0[:, 0] + dist * np.cos(ang), q0[:, 1] + dist * np.sin(ang), rs.uniform(-np.pi, np.pi, n)], 1)
+    want_safe, want_word, want_len = orc.edges_dubins_batch(ow, q0, q1, 1.0, 20)
+    safe, word, length = api.edges_dubins(e, q0, q1, 1.0, 20, "f64")
+    assert np.mean(word != want_word) < 1e-3 and close(length, want_len, TOL64)
+    assert np.array_equal(safe[word == want_word], want_safe[word == want_word])        # booleans exact
+    q0f, q1f = q0.astype(np.float32).astype(np.float64), q1.astype(np.float32).astype(np.float64)
+    want_safe, want_word, want_len = orc.edges_dubins_batch(ow, q0f, q1f, 1.0, 20)
+    safe, word, length = api.edges_dubins(e, q0f, q1f, 1.0, 20, "f32")
+    assert np.mean(word != want_word) < 0.01
+    assert np.mean(safe != want_safe) < 0.01
+    assert 0.05 < want_safe.mean() < 0.95
+
+
+def test_edges_arc_vs_oracle(api, env, oworld):
+    rs = np.random.RandomState(8)
+    n = 20000
+    parents = np.stack([rs.uniform(-300, -100, n), rs.uniform(-60, 100, n), rs.uniform(-6, 6, n),
+                        rs.uniform(0, 400, n), rs.uniform(0, 500, n)], 1)
+    seeds = np.arange(n) + 77
+    want_safe, want_nwp, want_leaf = orc.edges_arc_batch(oworld, parents, seeds, velocity=2.0)
+    safe, counts, leaf = api.edges_arc(env, parents, seeds, [2.0, 0.5, 30.0, 0.5, 2.0], "f64")
+    assert np.array_equal(safe, want_safe) and np.array_equal(counts, want_nwp)
+    assert close(leaf, want_leaf, TOL64)
+    p32 = parents.astype(np.float32).astype(np.float64)
+    want_safe, want_nwp, want_leaf = orc.edges_arc_batch(oworld, p32, seeds, velocity=2.0, bits24=True)
+    safe, counts, leaf = api.edges_arc(env, p32, seeds, [2.0, 0.5, 30.0, 0.5, 2.0], "f32")
+    assert np.mean(safe != want_safe) < 0.002 and np.mean(counts != want_nwp) < 0.002
+    ok = counts == want_nwp
+    assert close(leaf[ok][:, :2], want_leaf[ok][:, :2], RTOL32, scale=100.0)
+    assert close(leaf[ok][:, 2:], want_leaf[ok][:, 2:], RTOL32, scale=1.0)
+
+
+# ------------------------------------------------------------------------------------ planner
+def test_exploring_f64_traces_match_reference(api, env, exploring_golden):
+    z, meta = exploring_golden
+    for mode in ("A", "B"):
+        for iters in sorted({m["iterations"] for m in meta if m["mode"] == mode}):
+            ms = [m for m in meta if m["mode"] == mode and m["iterations"] == iters]
+            starts = np.array([[m["start"][0], m["start"][1], 0.0, 0.0, 0.0] for m in ms])
+            seeds = [m["seed"] for m in ms]
+            pp = api.plan_params(iters, mode=0 if mode == "A" else 1, trace=True, path_cap=1024, chain_cap=96)
+            r = api.plan_batch(env, starts, seeds, pp, "f64")
+            for j, m in enumerate(ms):
+                tag = m["tag"]
+                rec, tr = r["records"][j], r["trace"]
+                assert rec["status"] == 0, (tag, rec)
+                assert np.array_equal(tr["parent"][j], z[tag + "_parent"]), tag      # parent indices: exact
+                assert np.array_equal(tr["safe"][j], z[tag + "_safe"]), tag          # collision booleans: exact
+                assert np.array_equal(tr["nwp"][j], z[tag + "_nwp"]), tag
+                assert np.array_equal(tr["upos"][j], z[tag + "_upos"]), tag          # same sample sequence
+                assert rec["n_uniforms"] == m["n_uniforms"] and rec["n_nodes"] == m["nodes"]
+                if tag + "_leaf" in z:
+                    assert close(tr["leaf"][j], z[tag + "_leaf"], TOL64)
+                else:
+                    assert close(tr["leaf"][j][::16], z[tag + "_leaf_stride"], TOL64)
+                ce = z[tag + "_cost_evals"]
+                assert rec["n_cost_evals"] == len(ce)
+                res = z[tag + "_result"]
+                assert rec["best_iter"] == int(ce[np.argmin(ce[:, 1]), 0])            # same optimal leaf
+                assert abs(rec["path_length"] - res[0]) <= TOL64 * max(1, abs(res[0]))
+                assert close(rec["cost"], res[1:], TOL64)
+                ref_path = z[tag + "_path"]
+                assert rec["n_path"] == len(ref_path)
+                assert close(r["path"][j, :len(ref_path)], ref_path, TOL64)
+
+
+def test_materialize_equals_in_kernel_path(api, env):
+    starts = np.array([[-200.0, 0.0, 0.0, 0.0, 0.0]] * 6)
+    seeds = np.arange(6) + 100
+    for prec in ("f64", "f32"):
+        pp = api.plan_params(512, path_cap=768, chain_cap=96)
+        r = api.plan_batch(env, starts, seeds, pp, prec)
+        assert np.all(r["records"]["status"] == 0)
+        path, n_path = api.materialize(env, starts, seeds, r["chain"], r["records"]["depth"], pp, prec)
+        assert np.array_equal(n_path, r["records"]["n_path"])
+        for j in range(6):
+            assert np.array_equal(path[j, :n_path[j]], r["path"][j, :n_path[j]])
+
+
+def test_plan_f32_paths_are_valid_and_costs_consistent(api, env, oworld):
+    """fast build: every returned path must be collision-free and its cost must agree with the
+    fp64 oracle's habitat_shark_cost_func evaluated on that same path (1e-4 relative: fp32 sums)."""
+    Q = 64
+    rs = np.random.RandomState(0)
+    starts = np.zeros((Q, 5)); starts[:, 0] = rs.uniform(-260, -140, Q); starts[:, 1] = rs.uniform(-20, 60, Q)
+    pp = api.plan_params(1024, path_cap=1024, chain_cap=96)
+    r = api.plan_batch(env, starts, np.arange(Q), pp, "f32")
+    rec = r["records"]
+    assert np.all(rec["status"] == 0)
+    for j in range(Q):
+        p = r["path"][j, :rec["n_path"][j]]
+        assert np.all(np.diff(p[:, 4]) >= 0) and np.all(np.diff(p[:, 5]) >= -1e-3)      # time / length monotone
+        assert p[-1, 4] >= 470.0                                                        # reached the horizon
+        # leaf -> root order is what the planner hands to the cost function
+        want = orc.cost(p[::-1][:, [0, 1, 4]], p[-1, 4], oworld, [-3, -3, -4])
+        assert close(rec["cost"][j], want, 2e-4, scale=1.0), (j, rec["cost"][j], want)
+    # statistically the same planner as the fp64 build
+    r64 = api.plan_batch(env, starts, np.arange(Q), api.plan_params(1024), "f64")
+    assert abs(rec["n_nodes"].mean() - r64["records"]["n_nodes"].mean()) < 0.05 * r64["records"]["n_nodes"].mean()
+    assert abs(rec["cost"][:, 0].mean() - r64["records"]["cost"][:, 0].mean()) < 0.25
+
+
+def test_plan_groups_16_and_8_match_32(api, env):
+    starts = np.array([[-200.0, 0.0, 0.0, 0.0, 0.0]] * 5)
+    seeds = np.arange(5)
+    base = api.plan_batch(env, starts, seeds, api.plan_params(300, trace=True), "f64")
+    for G in (16, 8):
+        r = api.plan_batch(env, starts, seeds, api.plan_params(300, trace=True, group=G), "f64")
+        for k in ("parent", "safe", "nwp", "upos"):
+            assert np.array_equal(r["trace"][k], base["trace"][k]), (G, k)
+        assert np.array_equal(r["records"]["cost"], base["records"]["cost"])
+
+
+def test_plan_full_size_properties(api, env):
+    """BASELINE config 2 at full size (4096 queries x 2048 iterations, fp32): size-independent checks."""
+    Q = 4096
+    rs = np.random.RandomState(1)
+    starts = np.zeros((Q, 5)); starts[:, 0] = rs.uniform(-260, -140, Q); starts[:, 1] = rs.uniform(-20, 60, Q)
+    pp = api.plan_params(2048)
+    r = api.plan_batch(env, starts, np.arange(Q), pp, "f32")
+    rec = r["records"]
+    assert np.all(rec["status"] == 0)
+    assert np.all(rec["n_nodes"] <= 2049) and np.all(rec["n_nodes"] > 1000)
+    assert np.all(rec["t_leaf"] >= 470.0) and np.all(rec["cost"][:, 0] < 0)
+    assert np.all(rec["best_node"] < rec["n_nodes"])
+    # determinism: the same seeds give the same plans, in any batch position
+    sub = np.array([5, 77, 4000])
+    r2 = api.plan_batch(env, starts[sub], sub, pp, "f32")
+    assert np.array_equal(r2["records"]["cost"], rec["cost"][sub])
+    assert np.array_equal(r2["chain"], r["chain"][sub])
