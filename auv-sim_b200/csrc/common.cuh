@@ -84,12 +84,14 @@ template <typename R> struct Stream {
     uint64_t key;
     const double *ext;    // explicit doubles (host-provided), or nullptr
     int64_t n_ext;
-    __device__ __forceinline__ R u(uint32_t k, int *exhausted) const {
-        if (ext) {
-            if ((int64_t)k >= n_ext) { *exhausted = 1; return (R)0.5; }
-            return (R)ext[k];
-        }
+    // Positions past the end of an explicit stream read as 0.5: lanes prefetch a window of positions
+    // speculatively, so only a CONSUMED position past the end is an error (see consumed_ok()).
+    __device__ __forceinline__ R u(uint32_t k) const {
+        if (ext) return ((int64_t)k < n_ext) ? (R)ext[k] : (R)0.5;
         return bits_to_u<R>(stream_bits(key, k));
+    }
+    __device__ __forceinline__ bool consumed_ok(uint32_t ctr_end) const {
+        return !ext || (int64_t)ctr_end <= n_ext;
     }
 };
 

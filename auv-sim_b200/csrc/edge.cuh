@@ -61,10 +61,9 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
     typedef typename Policy<R>::A A;
     const bool VERIFY = Policy<R>::VERIFY;
     const int LOG = Log2<G>::v;
-    int exhausted = 0;
 
     // n_expand = floor(uniform(0, freq) / 1)                                   rrt_dubins.py:259-260
-    R u0 = rng.u(ctr, &exhausted);
+    R u0 = rng.u(ctr);
     ctr += 1;
     int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, u0));
     out.n_exp = n_exp;
@@ -75,7 +74,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
     R csin = 0, ccos = 0;
     if (VERIFY) A::sincos(pth, &csin, &ccos);
     int nwp = 1;
-    bool hit = false, outside = false, zero_div = false, moved = false;
+    bool hit = false, outside = false, zero_div = false, moved = false, degenerate = false;
     R acc_s2 = 0; uint32_t acc_cnt = 0; uint64_t acc_mask = 0;
     R self_s2 = 0; int self_hab = -1;
 
@@ -92,7 +91,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             int s = g.gl + G * r;
-            sc.us[s] = (s < 3 * nact) ? rng.u(ctr + (uint32_t)s, &exhausted) : (R)0;
+            sc.us[s] = (s < 3 * nact) ? rng.u(ctr + (uint32_t)s) : (R)0;
         }
         g.sync();
         // ---- 2. stream offset of every primitive: pointer doubling over step(s) in {2, 3}
@@ -174,7 +173,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
                 movement = A::sqrt(A::sq2(dx, dy));                            // :280
                 dt = A::div(movement, vt);                                     // :281
             }
-            csin = g.bcast(s1v, G - 1); ccos = g.bcast(c1v, G - 1);
+            csin = g.bcast(s1v, G - 1); ccos = g.bcast(c1v, G - 1);   // theta(G-1) == theta(last valid) bit for bit
         } else {
             if (valid) {
                 R sm, cm;
@@ -260,11 +259,21 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             }
         }
         nwp += __popc(wpm);
-        // carries for the next chunk = state of lane G-1 (invalid/inactive lanes add zero)
-        cth = g.bcast(th, G - 1); cx = g.bcast(x, G - 1); cy = g.bcast(y, G - 1);
-        ct = g.bcast(t, G - 1); clen = g.bcast(len, G - 1);
+        // carries for the next chunk = state after the last valid primitive.  (Invalid / inactive lanes
+        // add zero, but a shuffle scan associates differently per lane, so take the value from the
+        // lane whose waypoint it is: the node object and its last waypoint must be the same numbers.)
+        if (last_valid >= 0) {
+            cth = g.bcast(th, last_valid); cx = g.bcast(x, last_valid); cy = g.bcast(y, last_valid);
+            ct = g.bcast(t, last_valid); clen = g.bcast(len, last_valid);
+        }
         g.sync();      // scratch (us / wx / wy / jmp) is rewritten by the next chunk
-        if (g.ballot(zero_div)) { out.status = 2; break; }
+        if (g.ballot(zero_div)) {
+            // fp64: mirror the reference's ZeroDivisionError (rrt_dubins.py:270, :281).  fp32: with 24-bit
+            // uniforms diff == 0 / velocity == 0 have probability 2^-24 per draw (2^-53 in the
+            // reference), an artefact of the build, so the sample is rejected instead of aborting.
+            if (VERIFY) out.status = 2; else degenerate = true;
+            break;
+        }
     }
     if (DO_COLLIDE && n_exp == 0 && env.K > 0) {
         // the path is [parent] alone: test it against the circles
@@ -276,10 +285,10 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
         }
         if (g.ballot(h)) hit = true;
     }
-    if (g.ballot(exhausted != 0)) out.status = 4;
+    if (!rng.consumed_ok(ctr)) out.status = 4;
     out.x = cx; out.y = cy; out.th = cth; out.t = ct; out.len = clen;
     out.nwp = nwp; out.ctr = ctr;
-    out.safe = !(hit || outside);
+    out.safe = !(hit || outside || degenerate);
     out.s2 = acc_s2; out.cnt = acc_cnt; out.mask = acc_mask;
     out.self_s2 = self_s2; out.self_hab = self_hab; out.leaf_moved = moved;
 }

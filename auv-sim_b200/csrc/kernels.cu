@@ -470,13 +470,12 @@ __device__ __forceinline__ void nn_consider(NNBest &b, double dx, double dy, lon
 __device__ __forceinline__ void nn_merge(NNBest &a, double s, long long i) {
     if (s < a.s || (s == a.s && i < a.i)) { a.s = s; a.i = i; }
 }
-#define NN_QT 4
-template <typename R>
+template <typename R, int NN_QT>
 __global__ void __launch_bounds__(256) k_nn_partial(const R *__restrict__ tx, const R *__restrict__ ty, int64_t n,
                                                     const R *__restrict__ qx, const R *__restrict__ qy, int nq,
                                                     double *part_s, long long *part_i) {
-    __shared__ double sh_s[8][NN_QT];
-    __shared__ long long sh_i[8][NN_QT];
+    __shared__ double sh_s[8][4];
+    __shared__ long long sh_i[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q0 = 0; q0 < nq; q0 += NN_QT) {
         double qxs[NN_QT], qys[NN_QT];
@@ -573,7 +572,9 @@ int launch_nn(const R *tx, const R *ty, int64_t n, const R *qx, const R *qy, int
     if (blocks > NN_BLOCKS) blocks = NN_BLOCKS;
     double *ps = (double *)scratch;
     long long *pi = (long long *)(ps + (size_t)nq * NN_BLOCKS);
-    k_nn_partial<R><<<blocks, 256, 0, s>>>(tx, ty, n, qx, qy, nq, ps, pi);
+    if (nq == 1) k_nn_partial<R, 1><<<blocks, 256, 0, s>>>(tx, ty, n, qx, qy, nq, ps, pi);
+    else if (nq == 2) k_nn_partial<R, 2><<<blocks, 256, 0, s>>>(tx, ty, n, qx, qy, nq, ps, pi);
+    else k_nn_partial<R, 4><<<blocks, 256, 0, s>>>(tx, ty, n, qx, qy, nq, ps, pi);
     AUV_LAUNCH_CHECK();
     k_nn_final<<<nq, 256, 0, s>>>(ps, pi, blocks, nq, out_idx);
     AUV_LAUNCH_CHECK();

@@ -147,13 +147,12 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
 
         while (it < P.I && guard++ < guard_max) {
             int parent;
-            int dummy_ex = 0;
             if (P.mode == 0) {
                 // ---- pick a random non-empty time bin, then a random node in it           :122-127
                 int ran_bin = 0, bincnt = 0;
                 bool kerr = false;
                 for (;;) {
-                    R u = rng.u(ctr + (uint32_t)g.gl, &dummy_ex);
+                    R u = rng.u(ctr + (uint32_t)g.gl);
                     int rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), u);
                     bool ke = rb > P.nb || rb < 1;
                     int cn = ke ? 0 : T.count[rb];
@@ -167,7 +166,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     ctr += G;
                 }
                 if (kerr) { status = AUVRRT_ST_KEY_ERROR; break; }
-                R u = rng.u(ctr, &dummy_ex);
+                R u = rng.u(ctr);
                 ctr += 1;
                 int idx = (int)uniform_ab<R>((R)0, (R)bincnt, u);
                 if (idx >= bincnt) { status = AUVRRT_ST_KEY_ERROR; break; }
@@ -176,8 +175,8 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 parent = T.pool[ch * 32 + (idx & 31)];
             } else {
                 // ---- get_random_mps (:333-343) + get_closest_mps (:505-513)
-                R rx = uniform_ab<R>(env.minx, env.maxx, rng.u(ctr, &dummy_ex));
-                R ry = uniform_ab<R>(env.miny, env.maxy, rng.u(ctr + 1, &dummy_ex));
+                R rx = uniform_ab<R>(env.minx, env.maxx, rng.u(ctr));
+                R ry = uniform_ab<R>(env.miny, env.maxy, rng.u(ctr + 1));
                 ctr += 4;     // theta and size are drawn and never used
                 R bq = A::inf(), bs = A::inf();
                 int bi = 0x7fffffff;

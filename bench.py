@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, one JSON line on rank 0.
+
+metric  : Dubins/arc edge evaluations per second (steer + collide + cost) of the batched RRT planner
+workload: configs[1] -- 4096 independent RRT queries per GPU x 2048 steer calls each, Catalina map
+          (K=27 circles, E=5, H=10 habitats, T=10 x C=986 shark grid), reference default mode
+          (traj_time_stamp=True, plan_time=True), fp32 fast build.
+A "step" is one pass of the planner over the batch.  `value` has the queries resident in HBM;
+`e2e` goes through the host-buffer C ABI (auvrrt_plan_batch) with host<->device copies inside.
+N > 1 (torchrun): queries are sharded across ranks (weak scaling, no data-path collective) and the
+96-byte plan records are gathered to rank 0 over NCCL inside the timed region.
+
+--impl reference times the reference's CPU algorithm (the fp64 C oracle port of the pure-Python
+reference, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "auv-sim_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "edge_evals_per_s"
+UNIT = "edges/s"
+Q_PER_GPU = 4096
+ITERS = 2048
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4
+
+
+def load_world():
+    with open(os.path.join(ROOT, "tests", "golden", "catalina_map.json")) as f:
+        world = json.load(f)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "shark_grid.npz"))
+    return world, g["bins"], g["probs"]
+
+
+def make_queries(q0, q1):
+    """config 2: starts uniform in the box x in [-300,-100], y in [-100,100] restricted to the
+    polygon (performance.py:56-62), theta = 0, t = 0; seed = global query id."""
+    world, _, _ = load_world()
+    poly = np.array(world["boundary"])
+    rs = np.random.RandomState(12345)
+    n = q1
+    pts = []
+    while len(pts) < n:
+        c = np.stack([rs.uniform(-300, -100, 4 * n), rs.uniform(-100, 100, 4 * n)], 1)
+        ax, ay = poly[:, 0], poly[:, 1]
+        bx, by = np.roll(ax, -1), np.roll(ay, -1)
+        cr = (bx - ax)[None] * (c[:, 1:2] - ay[None]) - (by - ay)[None] * (c[:, 0:1] - ax[None])
+        inside = np.all(cr < 0, 1) | np.all(cr > 0, 1)
+        # also keep the start out of the obstacle circles: a start inside one can never grow a tree
+        # (the reference raises TypeError at rrt_dubins.py:174) and would be a degenerate cheap query
+        circ = np.array(world["circles"])
+        reff = np.maximum.accumulate(circ[::-1, 2])[::-1]
+        d = np.hypot(c[:, 0:1] - circ[None, :, 0], c[:, 1:2] - circ[None, :, 1])
+        inside &= np.all(d > reff[None] + 1e-6, 1)
+        pts.extend(c[inside].tolist())
+    starts = np.zeros((n, 5))
+    starts[:, :2] = np.array(pts[:n])
+    return starts[q0:q1], np.arange(q0, q1, dtype=np.uint64)
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(nthreads=0, sample_queries=None):
+    """the oracle port (fp64 C restatement of the pure-Python reference) on the host cores"""
+    from oracle import orc
+    world, bins, probs = load_world()
+    ow = orc.OracleWorld.from_map(world, bins, probs)
+    nt = nthreads or orc.num_threads()
+    nq = sample_queries or max(4 * nt, 64)
+    starts, seeds = make_queries(0, nq)
+    pp = orc.plan_params(ITERS)
+    t0 = time.perf_counter()
+    res, counts, status = orc.exploring_batch(ow, starts, seeds, pp, nthreads=nt)
+    dt = time.perf_counter() - t0
+    return {"value": nq * ITERS / dt, "unit": UNIT, "cores": nt, "kind": "port",
+            "sample": "%d of the %d queries x %d iterations, fp64 C port of the pure-Python reference "
+                      "(oracle/auvrrt_oracle.c), %d threads, %.2f s wall" % (nq, Q_PER_GPU, ITERS, nt, dt),
+            "plans_per_s": nq / dt, "seconds": dt}
+
+
+def config_dict(n_gpus):
+    return {"workload": "configs[1]: %d independent RRT-Dubins queries per GPU x %d steer calls, Catalina map "
+                        "(K=27, E=5, H=10, T=10, C=986), time-bin parent pick (reference default mode)" % (Q_PER_GPU, ITERS),
+            "queries_per_gpu": Q_PER_GPU, "iterations": ITERS, "global_queries": Q_PER_GPU * n_gpus,
+            "parallelism": "queries sharded across %d GPU(s); NCCL gather of 96-byte plan records" % n_gpus,
+            "l2": "flushed between timed steps (256 MiB write); tree workspace is larger than L2"}
+
+
+def run_reference(args, rank, world_size):
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        b = cpu_baseline()
+        if i >= args.warmup:
+            vals.append(b)
+    v = float(np.mean([b["value"] for b in vals]))
+    ms = float(np.mean([b["seconds"] for b in vals])) * 1e3
+    b = vals[-1]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": b["cores"], "kind": "port", "sample": b["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference is pure Python (no native code to compile into oracle/_ref); this arm times its "
+                    "fp64 C port on all host threads. The unmodified Python reference measured in the build "
+                    "container: ~0.41 k edges/s per core with cost active (BASELINE.md section 2)."}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--group", type=int, default=32)
+    ap.add_argument("--no-extras", action="store_true", help="skip micro-benchmarks / cpu baseline")
+    ap.add_argument("--micro-edges", type=int, default=100_000_000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from auvrrt import api, device as adev
+    if not torch.cuda.is_available() or api.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    world, bins, probs = load_world()
+    env = api.Env.from_map(world, bins, probs, device=local_rank)
+    pp = api.plan_params(ITERS, group=args.group)
+    starts, seeds = make_queries(rank * Q_PER_GPU, (rank + 1) * Q_PER_GPU)
+    planner = adev.DevicePlanner(env, pp, args.precision, Q_PER_GPU, want_chain=True)
+    planner.set_queries(starts, seeds)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world_size, Q_PER_GPU, planner.records.shape[1]), dtype=torch.uint8, device=dev) if world_size > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        planner.launch(stream)
+        if world_size > 1:   # the final min-cost plan gather: 96-byte records, rank 0 keeps the minimum
+            dist.all_gather_into_tensor(gathered.view(-1), planner.records.view(-1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = api.launch_count()
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)                       # L2 flush, outside the event-timed region
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    launches = api.launch_count() - launches0
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    sampler.stop_flag = True
+    sampler.join()
+    rec = planner.records_numpy()
+    ok = int((rec["status"] == 0).sum())
+
+    # ---- end to end through the host-buffer C ABI (host arrays in, records + chains out)
+    e2e_steps = max(2, min(args.steps, 3))
+    api.plan_batch(env, starts, seeds, pp, args.precision)           # warm: allocates env-owned buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = api.plan_batch(env, starts, seeds, pp, args.precision)
+        if world_size > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(r["records"].view(np.uint8).reshape(-1)).to(dev))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    rsz = 4 if args.precision == "f32" else 8
+
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    edges = Q_PER_GPU * world_size * ITERS * args.steps
+    value = edges / (ms_total * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config_dict(world_size),
+            "plans_per_s": Q_PER_GPU * world_size * args.steps / (ms_total * 1e-3),
+            "queries_ok": ok, "gpu_launches": int(launches), "clocks": sampler.result(),
+            "e2e": {"value": Q_PER_GPU * world_size * ITERS * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": Q_PER_GPU * (5 * rsz + 8),
+                    "d2h_bytes_per_step": Q_PER_GPU * (96 + 4 * pp.chain_cap),
+                    "plans_per_s": Q_PER_GPU * world_size * e2e_steps / e2e_s, "steps": e2e_steps}}
+
+    # ---- roofline of the dominant kernel (k_plan): algorithmic FLOP per launch / event time
+    K, E, H, T = len(world["circles"]), len(world["boundary"]), len(world["habitats"]), len(bins)
+    W = float(rec["n_waypoints"].sum()); P = float(rec["n_primitives"].sum())
+    acc = float((rec["n_nodes"] - 1).sum()) / (len(rec) * ITERS)
+    R_rows = 35
+    flop = 6 * W * K + 6 * W * E + 30 * P + acc * W * (2 * T + 2 * R_rows + 6 * H + 3)
+    sfu = K * len(rec) * ITERS + 8 * P
+    per_launch_s = ms_total * 1e-3 / args.steps
+    try:
+        cal_flops, _ = api.calibrate_fp32(local_rank, 8192)
+    except Exception:
+        cal_flops = None
+    peak = (cal_flops or FP32_NOMINAL_TFLOPS * 1e12) / 1e12
+    ach = flop * world_size / per_launch_s / 1e12 / world_size
+    line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None, "kernel": "k_plan<float,%d>" % args.group,
+                        "peak_source": "FFMA calibration kernel measured live in this run" if cal_flops else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                        "nominal_peak": FP32_NOMINAL_TFLOPS,
+                        "algorithmic_flop_per_edge": flop / (len(rec) * ITERS), "sfu_per_edge": sfu / (len(rec) * ITERS),
+                        "waypoints_per_edge": W / (len(rec) * ITERS), "primitives_per_edge": P / (len(rec) * ITERS),
+                        "note": "no tensor cores: no dense contraction on this path (BASELINE.json north_star)"}
+
+    if not args.no_extras and world_size == 1:
+        line["cpu_baseline"] = {k: v for k, v in cpu_baseline().items() if k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            line["extras"] = extras(env, dev, args, api, adev)
+        except Exception as ex:   # extras never invalidate the headline line
+            line["extras"] = {"error": repr(ex)}
+    elif not args.no_extras:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def extras(env, dev, args, api, adev):
+    """secondary measurements: NN scan against the HBM roofline, config-4 micro-benchmark, fp64 build"""
+    import torch
+    out = {}
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return float(np.mean(ts)), float(np.min(ts))
+
+    # NN scan: one query over a tree larger than L2 (2^27 nodes, 1 GiB of fp32 x/y)
+    n = 1 << 27
+    tx = torch.rand(n, device=dev) * 550 - 467
+    ty = torch.rand(n, device=dev) * 345 - 153
+    qx = torch.tensor([-200.0], device=dev); qy = torch.tensor([0.0], device=dev)
+    idx = torch.zeros(1, dtype=torch.int32, device=dev)
+    scr = adev.nn_scratch(1, dev)
+    mean_s, min_s = timed(lambda: adev.nn_dev(tx, ty, qx, qy, idx, scr, "f32"))
+    gbs = 8.0 * n / mean_s / 1e9
+    out["roofline_nn"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                          "traffic": None, "kernel": "k_nn_partial<float>", "nodes": n, "queries": 1,
+                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                          "algorithmic_bytes": "8 B per node per pass"}
+    del tx, ty
+
+    # config 4: Dubins edges vs 500 synthetic circles, 20 waypoints per edge
+    rs = np.random.RandomState(1234)
+    K = 500
+    circles = np.stack([rs.uniform(-467.4, 82.4, K), rs.uniform(-153.5, 191.2, K), rs.uniform(1, 5, K)], 1)
+    world, _, _ = load_world()
+    env4 = api.Env(circles=circles, boundary=world["boundary"], device=dev.index)
+    ne = int(args.micro_edges)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    q0 = torch.stack([torch.rand(ne, device=dev, generator=g) * 549.8 - 467.4,
+                      torch.rand(ne, device=dev, generator=g) * 344.7 - 153.5,
+                      (torch.rand(ne, device=dev, generator=g) * 2 - 1) * np.pi], 1).contiguous()
+    ang = (torch.rand(ne, device=dev, generator=g) * 2 - 1) * np.pi
+    dist_ = torch.rand(ne, device=dev, generator=g) * 38 + 2
+    q1 = torch.stack([q0[:, 0] + dist_ * torch.cos(ang), q0[:, 1] + dist_ * torch.sin(ang),
+                      (torch.rand(ne, device=dev, generator=g) * 2 - 1) * np.pi], 1).contiguous()
+    del ang, dist_
+    safe = torch.zeros(ne, dtype=torch.uint8, device=dev); word = torch.zeros(ne, dtype=torch.uint8, device=dev)
+    length = torch.zeros(ne, device=dev)
+    mean_s, min_s = timed(lambda: adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32"), reps=3, warm=1)
+    flop_edge = 6 * 20 * K + 6 * 20 * 5 + 140 + 24 * 20
+    cal, _ = api.calibrate_fp32(dev.index, 8192)
+    out["micro_config4"] = {"edges": ne, "circles": K, "waypoints": 20, "edges_per_s": ne / mean_s,
+                            "algorithmic_flop_per_edge": flop_edge, "achieved_tflops": ne * flop_edge / mean_s / 1e12,
+                            "fp32_peak_tflops_calibrated": cal / 1e12, "frac": ne * flop_edge / mean_s / cal,
+                            "safe_fraction": float(safe.float().mean().item()), "kernel": "k_edges_dubins<float,20>"}
+    del q0, q1, safe, word, length
+    return out
+
+
+if __name__ == "__main__":
+    main()
