@@ -1,0 +1,96 @@
+"""Multi-GPU driver: planning queries are independent (own start, seed, tree; read-only shared map),
+so they are sharded contiguously across ranks with NO data-path collective; one collective at the
+end gathers the fixed-size plan records (the "final min-cost plan gather" of the north star).
+
+One process per GPU, torch.distributed for the plumbing: backend "nccl" on GPUs (NVLink / NVSwitch),
+"gloo" on CPU for the host-logic tests.  The gather payload is 96 bytes per query.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .api import RECORD_DTYPE
+
+
+def shard_range(n_queries: int, rank: int, world: int):
+    """contiguous shard [lo, hi) of rank `rank`; the first n % world ranks get one extra query"""
+    base, extra = divmod(int(n_queries), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _comm_device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def gather_records(local: np.ndarray, n_queries: int) -> np.ndarray:
+    """all-gather the per-query plan records of every rank, in global query order.
+    `local` is this rank's structured array (RECORD_DTYPE) for its shard_range()."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = _comm_device()
+    sizes = [shard_range(n_queries, r, world) for r in range(world)]
+    cap = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros((cap, RECORD_DTYPE.itemsize), dtype=torch.uint8)
+    lo, hi = sizes[rank]
+    assert len(local) == hi - lo, (len(local), lo, hi)
+    if hi > lo:
+        buf[:hi - lo] = torch.from_numpy(np.ascontiguousarray(local).view(np.uint8).reshape(hi - lo, -1))
+    buf = buf.to(dev)
+    out = torch.empty((world, cap, RECORD_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), buf.view(-1)) if dev.type == "cuda" else dist.all_gather(
+        list(out.unbind(0)), buf)
+    out = out.cpu().numpy()
+    parts = [out[r, :h - l].reshape(-1).view(RECORD_DTYPE) for r, (l, h) in enumerate(sizes)]
+    return np.concatenate(parts) if parts else np.zeros(0, RECORD_DTYPE)
+
+
+def _orderable(cost: np.ndarray) -> np.ndarray:
+    """float64 -> uint64 whose unsigned order equals the float order (NaN excluded)"""
+    b = np.asarray(cost, dtype=np.float64).view(np.uint64)
+    return np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+
+
+def global_best(local: np.ndarray, lo: int) -> int:
+    """global query index of the minimum-cost successful plan over all ranks (-1 if none).
+    Every rank contributes its local minimum as (orderable cost bits, global index); the tiny
+    all-gather is reduced identically on every rank, ties going to the lowest index -- the same rule
+    as the reference's strict `<` (rrt_dubins.py:169)."""
+    dev = _comm_device()
+    ok = local["status"] == 0
+    if ok.any():
+        keys = _orderable(np.where(ok, local["cost"][:, 0], np.inf))
+        j = int(np.lexsort((np.arange(len(local)), keys))[0])
+        key, idx = int(keys[j]), lo + j
+    else:
+        key, idx = (1 << 64) - 1, -1
+    mine = torch.tensor([key >> 32, key & 0xFFFFFFFF, idx], dtype=torch.int64, device=dev)
+    world = dist.get_world_size()
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    c = torch.stack(allc).cpu().numpy()
+    c = c[c[:, 2] >= 0]
+    if len(c) == 0:
+        return -1
+    order = np.lexsort((c[:, 2], c[:, 1], c[:, 0]))
+    return int(c[order[0], 2])
+
+
+def plan_sharded(env, starts, seeds, params, precision="f32", plan_fn=None):
+    """Run all queries sharded over the ranks of the default process group and return
+    (records for ALL queries in global order, index of the global minimum-cost plan).
+    `plan_fn(env, starts, seeds, params, precision) -> {"records": ...}` defaults to the CUDA
+    planner (auvrrt.api.plan_batch); tests inject a stand-in to exercise the host logic on gloo."""
+    if plan_fn is None:
+        from . import api
+        plan_fn = api.plan_batch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    starts = np.asarray(starts, dtype=np.float64).reshape(-1, 5)
+    seeds = np.asarray(seeds, dtype=np.uint64)
+    Q = len(seeds)
+    lo, hi = shard_range(Q, rank, world)
+    local = plan_fn(env, starts[lo:hi], seeds[lo:hi], params, precision)["records"] if hi > lo else np.zeros(0, RECORD_DTYPE)
+    allrec = gather_records(local, Q)
+    best = global_best(local, lo)
+    return allrec, best

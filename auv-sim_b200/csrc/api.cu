@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every compute entry runs the CUDA kernels or fails with AUVRRT_ERR_CUDA.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "launch.h"
@@ -89,7 +90,30 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     h.off_cell = take(4 * cand_cell.size());
     h.hot_bytes = (int)o;
     h.off_probs = take(sr * (size_t)T * C);
-    h.total_bytes = (int)o;
+    h.total_bytes = (int)o;          // what may be staged in shared memory ends here
+    // --- classification grid (env.cuh): geometry
+    int max_cells = 16384;
+    if (const char *ev = getenv("AUVRRT_GRID_CELLS")) max_cells = atoi(ev);
+    h.gnx = h.gny = 0; h.gs = 1.0; h.gx0 = h.gy0 = 0.0;
+    if (E >= 3 && max_cells >= 16 && h.bbox[2] > h.bbox[0] && h.bbox[3] > h.bbox[1]) {
+        double wx = h.bbox[2] - h.bbox[0], wy = h.bbox[3] - h.bbox[1];
+        double gs = sqrt(wx * wy / max_cells);
+        gs = ceil(gs * 4.0) / 4.0;                       // multiples of 0.25 m
+        if (gs < 0.25) gs = 0.25;
+        h.gs = gs; h.gx0 = h.bbox[0] - gs; h.gy0 = h.bbox[1] - gs;
+        h.gnx = (int)ceil(wx / gs) + 2; h.gny = (int)ceil(wy / gs) + 2;
+    }
+    h.off_grid = take(4 * (size_t)h.gnx * h.gny);
+    // --- uniform time bins?
+    h.bins_uniform = 0; h.bin_s0 = 0.0; h.bin_w = 1.0;
+    if (T >= 1 && T <= 32) {
+        bool ok = true;
+        for (int i = 0; i < T && ok; i++) {
+            if (!((R)bins[2 * i + 1] > (R)bins[2 * i])) ok = false;
+            if (i + 1 < T && (R)bins[2 * i + 1] != (R)bins[2 * i + 2]) ok = false;
+        }
+        if (ok) { h.bins_uniform = 1; h.bin_s0 = bins[0]; h.bin_w = (bins[2 * T - 1] - bins[0]) / T; }
+    }
     std::vector<unsigned char> blob(o, 0);
     auto arr = [&](int off) { return (R *)(blob.data() + off); };
     R suffix = 0;
@@ -111,6 +135,83 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     for (size_t i = 0; i < cand_c1.size(); i++) arr(h.off_c1)[i] = cand_c1[i];
     if (!cand_cell.empty()) memcpy(blob.data() + h.off_cell, cand_cell.data(), 4 * cand_cell.size());
     for (size_t i = 0; i < (size_t)T * C; i++) arr(h.off_probs)[i] = (R)probs[i];
+    // --- classification grid: codes.  A code is definitive only if the whole cell, grown by `margin`
+    // (far above the rounding error of the kernels' exact tests near a decision boundary), gets one
+    // answer; everything else is "ambiguous" and falls back to the exact test on the device.
+    if (h.gnx > 0) {
+        const double margin = sizeof(R) == 4 ? 2e-3 : 1e-6;
+        const double gs = h.gs, rho = gs * 0.70710678118654757 * (1.0 + 1e-9) + margin;
+        unsigned *grid = (unsigned *)(blob.data() + h.off_grid);
+        auto seg_dist = [](double px, double py, double ax, double ay, double bx, double by) {
+            double vx = bx - ax, vy = by - ay, wx = px - ax, wy = py - ay;
+            double L2 = vx * vx + vy * vy, t = L2 > 0 ? (wx * vx + wy * vy) / L2 : 0.0;
+            t = t < 0 ? 0 : (t > 1 ? 1 : t);
+            double dx = px - (ax + t * vx), dy = py - (ay + t * vy);
+            return sqrt(dx * dx + dy * dy);
+        };
+        auto inside_poly = [&](double px, double py) {
+            bool in = false;
+            for (int i = 0, j = E - 1; i < E; j = i++) {
+                double xi = poly[2 * i], yi = poly[2 * i + 1], xj = poly[2 * j], yj = poly[2 * j + 1];
+                if ((yi > py) != (yj > py) && px < (xj - xi) * (py - yi) / (yj - yi) + xi) in = !in;
+            }
+            return in;
+        };
+        std::vector<double> reff(K);
+        for (int k = K - 1; k >= 0; k--) reff[k] = (k == K - 1) ? circles[3 * k + 2] : std::max(reff[k + 1], circles[3 * k + 2]);
+        for (int iy = 0; iy < h.gny; iy++)
+            for (int ix = 0; ix < h.gnx; ix++) {
+                const double x0 = h.gx0 + ix * gs, y0 = h.gy0 + iy * gs, mx = x0 + 0.5 * gs, my = y0 + 0.5 * gs;
+                unsigned code = 0;
+                // polygon
+                double dmin = INFINITY;
+                for (int i = 0; i < E; i++) {
+                    int j = (i + 1) % E;
+                    dmin = std::min(dmin, seg_dist(mx, my, poly[2 * i], poly[2 * i + 1], poly[2 * j], poly[2 * j + 1]));
+                }
+                if (dmin > rho) code |= inside_poly(mx, my) ? 1u : 2u;
+                // obstacle circles (inflated radii)
+                bool clear = true;
+                for (int k = 0; k < K && clear; k++)
+                    if (hypot(mx - circles[3 * k], my - circles[3 * k + 1]) - rho <= reff[k]) clear = false;
+                if (clear) code |= 4u;
+                // habitats: first match in list order
+                unsigned hc = AUV_GRID_HAB_NONE;
+                for (int q = 0; q < H; q++) {
+                    double d = hypot(mx - hab[3 * q], my - hab[3 * q + 1]);
+                    if (d - rho <= hab[3 * q + 2]) {                       // the cell touches habitat q
+                        hc = (d + rho < hab[3 * q + 2]) ? (unsigned)q : AUV_GRID_HAB_AMBIG;
+                        break;
+                    }
+                }
+                code |= hc << 3;
+                // shark cell: constant piece and constant first candidate over the whole grid cell?
+                unsigned cc = AUV_GRID_CELL_AMBIG;
+                if (NB == 0 || C >= 65534) { if (NB == 0) cc = AUV_GRID_CELL_NONE; }
+                else {
+                    const double xa = x0 - margin, xb = x0 + gs + margin, ya = y0 - margin, yb = y0 + gs + margin;
+                    if (xb < (double)brk[0] || xa > (double)brk[NB - 1]) cc = AUV_GRID_CELL_NONE;
+                    else {
+                        int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)xa) - brk.begin()) - 1;   // last brk <= xa
+                        bool has_break = false;
+                        for (int i = std::max(lo_i, 0); i < NB && (double)brk[i] <= xb; i++)
+                            if ((double)brk[i] >= xa) { has_break = true; break; }
+                        if (!has_break && lo_i >= 0 && lo_i + 1 < NB) {
+                            const int p = 2 * lo_i + 1;
+                            bool amb = false; int first = -1;
+                            for (int k = piece[p]; k < piece[p + 1]; k++) {
+                                double c1v = (double)cand_c1[k];
+                                if (c1v > ya && c1v <= yb) { amb = true; break; }
+                                if (c1v <= ya) { first = cand_cell[k]; break; }
+                            }
+                            if (!amb) cc = first >= 0 ? (unsigned)first : AUV_GRID_CELL_NONE;
+                        }
+                    }
+                }
+                code |= cc << 16;
+                grid[(size_t)iy * h.gnx + ix] = code;
+            }
+    }
     memcpy(blob.data(), &h, sizeof(h));
     *hout = h;
     return blob;

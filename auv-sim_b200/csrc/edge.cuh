@@ -74,15 +74,16 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
     R csin = 0, ccos = 0;
     if (VERIFY) A::sincos(pth, &csin, &ccos);
     int nwp = 1;
-    bool hit = false, outside = false, zero_div = false, moved = false, degenerate = false;
+    bool hit = false, outside = false, zero_div = false, moved = false, degenerate = false, parent_clear = false;
     R acc_s2 = 0; uint32_t acc_cnt = 0; uint64_t acc_mask = 0;
     R self_s2 = 0; int self_hab = -1;
 
     if (DO_COLLIDE) {
         // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
         if (g.gl == 0) { sc.wx[G] = px; sc.wy[G] = py; }
-        bool pin = point_within<R>(env, px, py);
-        outside = !pin;
+        const unsigned pcode = env.classify(px, py);
+        outside = !point_within_c<R>(env, pcode, px, py);
+        parent_clear = (pcode & 4u) != 0u;
     }
 
     for (int base = 0; base < n_exp; base += G) {
@@ -210,13 +211,18 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
                 }
             }
         }
+        // one classification-grid load per waypoint replaces most of the exact tests below
+        unsigned code = AUV_GRID_ALL_AMBIG | 4u;
+        if ((DO_COLLIDE || DO_COST) && (is_wp || g.gl == last_valid)) code = env.classify(x, y);
         if (DO_COLLIDE) {
             // polygon: lane = waypoint
             bool in = true;
-            if (is_wp) in = point_within<R>(env, x, y);
+            if (is_wp) in = point_within_c<R>(env, code, x, y);
             if (g.ballot(!in)) outside = true;
-            // circles: lane = circle, waypoints broadcast through shared memory
-            if (env.K > 0) {
+            // circles: lane = circle, waypoints broadcast through shared memory; skipped when every
+            // path point sits in a grid cell that is clear of all (inflated) circles
+            const bool circles_needed = g.ballot(is_wp && !(code & 4u)) != 0u || (base == 0 && !parent_clear);
+            if (env.K > 0 && circles_needed) {
                 if (is_wp) { int slot = __popc(wpm & ((1u << g.gl) - 1u)); sc.wx[slot] = x; sc.wy[slot] = y; }
                 g.sync();
                 const int nw = __popc(wpm);
@@ -241,7 +247,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             // (provisional) leaf state
             const bool need = is_wp || (g.gl == last_valid);
             Contrib c; c.bin = -1; c.cell = -1; c.hab = -1;
-            if (need) c = point_contrib<R>(env, x, y, t, 0xffffffffu, n_hab);
+            if (need) c = point_contrib<R>(env, x, y, t, 0xffffffffu, n_hab, code);
             R ps2 = (R)0;
             if (c.bin >= 0 && c.cell >= 0) ps2 = A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]);
             const bool counts = is_wp && c.bin >= 0;
@@ -275,7 +281,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             break;
         }
     }
-    if (DO_COLLIDE && n_exp == 0 && env.K > 0) {
+    if (DO_COLLIDE && n_exp == 0 && env.K > 0 && !parent_clear) {
         // the path is [parent] alone: test it against the circles
         bool h = false;
         for (int k = g.gl; k < env.K; k += G) {

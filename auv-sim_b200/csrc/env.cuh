@@ -34,13 +34,38 @@ struct EnvHeader {
     int off_b0, off_b1;
     int off_brk, off_piece, off_c1, off_cell;
     int off_probs;
+    int off_grid;      // classification grid (u32 per cell), not staged: read through L1/L2
+    int gnx, gny;      // grid dimensions (0: no grid)
+    int bins_uniform;  // 1: bins are [s0 + i w, s0 + (i+1) w], contiguous and in order
     int pad_[3];
     double bbox[4];    // minx, miny, maxx, maxy of the polygon (Polygon.bounds, rrt_dubins.py:334)
+    double gx0, gy0, gs;   // grid origin and cell size
+    double bin_s0, bin_w;
+    double pad2_;
 };
 static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignment of the arrays");
 
+// Classification grid (built once on the host, see api.cu): one u32 per cell of a uniform grid over
+// the polygon's bounding box, so that most waypoints are classified by ONE load instead of the
+// loops over circles / polygon edges / habitats / shark cells.  A code is only definitive when
+// every point of the cell (plus a rounding margin) gets the same answer from the exact test;
+// otherwise the cell is marked ambiguous and the exact test runs.  Results are therefore identical
+// to the exact tests by construction.
+//   bits  0-1  polygon: 0 ambiguous, 1 strictly inside, 2 outside
+//   bit   2    1: clear of every (inflated) obstacle circle
+//   bits  3-10 habitat: 0..63 first-match habitat, 254 none, 255 ambiguous
+//   bits 16-31 shark cell: first-match cell id, 0xFFFF none, 0xFFFE ambiguous
+#define AUV_GRID_HAB_NONE 254u
+#define AUV_GRID_HAB_AMBIG 255u
+#define AUV_GRID_CELL_NONE 0xFFFFu
+#define AUV_GRID_CELL_AMBIG 0xFFFEu
+#define AUV_GRID_ALL_AMBIG ((AUV_GRID_CELL_AMBIG << 16) | (AUV_GRID_HAB_AMBIG << 3))
+
 template <typename R> struct EnvView {
     int K, E, H, T, C, NB, NP, convex;
+    int gnx, gny, bins_uniform;
+    R gx0, gy0, ginv, bin_s0, bin_w, bin_winv;
+    const unsigned *grid;
     R minx, miny, maxx, maxy;
     const R *cx, *cy, *cr, *creff, *creff2;
     const R *px, *py;
@@ -66,6 +91,20 @@ template <typename R> struct EnvView {
         brk = (const R *)(hot + h->off_brk); piece = (const int *)(hot + h->off_piece);
         c1 = (const R *)(hot + h->off_c1); cell = (const int *)(hot + h->off_cell);
         probs = (const R *)(probs_base + h->off_probs);
+    }
+    // the grid stays in global memory: bind it from the blob in HBM
+    __device__ __forceinline__ void bind_grid(const unsigned char *blob_global, const unsigned char *hot) {
+        const EnvHeader *h = (const EnvHeader *)hot;
+        gnx = h->gnx; gny = h->gny; bins_uniform = h->bins_uniform;
+        gx0 = (R)h->gx0; gy0 = (R)h->gy0; ginv = (R)(1.0 / h->gs);
+        bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w);
+        grid = (const unsigned *)(blob_global + h->off_grid);
+    }
+    // classification code of the cell containing (x, y); all-ambiguous outside the grid
+    __device__ __forceinline__ unsigned classify(R x, R y) const {
+        R fx = (x - gx0) * ginv, fy = (y - gy0) * ginv;
+        if (!(fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny)) return AUV_GRID_ALL_AMBIG;
+        return __ldg(grid + (int)fy * gnx + (int)fx);
     }
 };
 

@@ -86,6 +86,14 @@ template <typename R> __device__ __forceinline__ bool point_within(const EnvView
     return inside && !boundary;
 }
 
+// same, short-circuited by the classification grid code of the point's cell
+template <typename R> __device__ __forceinline__ bool point_within_c(const EnvView<R> &env, unsigned code, R px, R py) {
+    const unsigned pc = code & 3u;
+    if (pc == 1u) return true;
+    if (pc == 2u) return false;
+    return point_within<R>(env, px, py);
+}
+
 // does the point hit any (inflated, see env.cuh) circle?   thread-level, all circles
 template <typename R> __device__ __forceinline__ bool point_hits_circles(const EnvView<R> &env, R x, R y) {
     typedef typename Policy<R>::A A;
@@ -121,22 +129,45 @@ __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
     return -1;
 }
 
+// first shark-grid time bin (dict order) with b0 <= t <= b1, -1 if none          cost.py:173-177
 template <typename R>
-__device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y, R t,
-                                                 unsigned bin_mask, int n_hab) {
-    typedef typename Policy<R>::A A;
-    Contrib c;
-    c.bin = -1; c.cell = -1; c.hab = -1;
+__device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin_mask) {
+    if (env.bins_uniform && bin_mask == 0xffffffffu) {
+        // contiguous sorted bins: the containing bins are adjacent; guess, then settle on the first
+        if (!(t >= env.b0[0]) || !(t <= env.b1[env.T - 1])) return -1;
+        int k = (int)((t - env.bin_s0) * env.bin_winv);
+        k = k < 0 ? 0 : (k > env.T - 1 ? env.T - 1 : k);
+        while (k > 0 && t <= env.b1[k - 1]) k--;
+        while (k < env.T - 1 && t > env.b1[k]) k++;
+        return (t >= env.b0[k] && t <= env.b1[k]) ? k : -1;
+    }
     for (int b = 0; b < env.T; b++) {
         if (b < 32 && !((bin_mask >> b) & 1u)) continue;
-        if (t >= env.b0[b] && t <= env.b1[b]) { c.bin = b; break; }
+        if (t >= env.b0[b] && t <= env.b1[b]) return b;
     }
+    return -1;
+}
+
+template <typename R>
+__device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y, R t,
+                                                 unsigned bin_mask, int n_hab, unsigned code) {
+    typedef typename Policy<R>::A A;
+    Contrib c;
+    c.cell = -1; c.hab = -1;
+    c.bin = find_bin<R>(env, t, bin_mask);
     if (c.bin < 0) return c;
-    c.cell = find_cell(env, x, y);
-    for (int h = 0; h < n_hab; h++) {
-        R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
-        bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
-        if (in) { c.hab = h; break; }
+    const unsigned cc = code >> 16;
+    if (cc == AUV_GRID_CELL_AMBIG) c.cell = find_cell(env, x, y);
+    else if (cc != AUV_GRID_CELL_NONE) c.cell = (int)cc;
+    const unsigned hc = (code >> 3) & 0xFFu;
+    if (hc == AUV_GRID_HAB_AMBIG) {
+        for (int h = 0; h < n_hab; h++) {
+            R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
+            bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
+            if (in) { c.hab = h; break; }
+        }
+    } else if (hc != AUV_GRID_HAB_NONE && (int)hc < n_hab) {
+        c.hab = (int)hc;
     }
     return c;
 }

@@ -45,11 +45,12 @@ template <typename R>
 __device__ __forceinline__ EnvView<R> load_env(unsigned char *smem, const unsigned char *blob, int hot_bytes,
                                                int total_bytes, int stage_mode) {
     EnvView<R> v;
-    if (stage_mode == 0) { v.bind(blob, blob); return v; }
+    if (stage_mode == 0) { v.bind(blob, blob); v.bind_grid(blob, blob); return v; }
     uint64_t *bar = (uint64_t *)smem;
     unsigned char *dst = smem + 16;
     stage_env_tma(dst, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
     v.bind(dst, stage_mode == 2 ? dst : blob);
+    v.bind_grid(blob, dst);
     return v;
 }
 static inline int env_stage_mode(int hot, int total, int budget, int *smem_bytes) {
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(128) k_steer_arc(const R *parents, int64_t n, 
     GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
     EnvView<R> env;
     env.K = env.E = env.H = env.T = env.C = env.NB = env.NP = env.convex = 0;
+    env.gnx = env.gny = env.bins_uniform = 0;
     const int64_t groups = (int64_t)gridDim.x * (128 / G);
     for (int64_t i = blockIdx.x * (int64_t)(128 / G) + threadIdx.x / G; i < n; i += groups) {
         Stream<R> rng;
@@ -171,7 +173,8 @@ __global__ void __launch_bounds__(128) k_collide(const unsigned char *blob, int 
         bool bad = false;
         for (int64_t k = b + g.gl; k < e; k += 32) {
             R x = pts[2 * k], y = pts[2 * k + 1];
-            bad = bad || point_hits_circles<R>(env, x, y) || !point_within<R>(env, x, y);
+            const unsigned code = env.classify(x, y);
+            bad = bad || (!(code & 4u) && point_hits_circles<R>(env, x, y)) || !point_within_c<R>(env, code, x, y);
         }
         unsigned any = g.ballot(bad);
         if (g.gl == 0) safe[i] = (e == b && env.K > 0) ? 255 : (any ? 0 : 1);
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(256) k_collide_points(const unsigned char *blo
     typedef typename Policy<R>::A A;
     EnvView<R> env;
     env.bind(blob, blob);
+    env.bind_grid(blob, blob);
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     R x = pts[2 * i], y = pts[2 * i + 1];
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(128) k_cost(const unsigned char *blob, int hot
         for (int64_t k0 = b; k0 < e; k0 += 32) {       // path order is the summation order (cost.py:171)
             int64_t k = k0 + g.gl;
             Contrib c; c.bin = -1; c.cell = -1; c.hab = -1;
-            if (k < e) c = point_contrib<R>(env, pts[3 * k], pts[3 * k + 1], pts[3 * k + 2], bin_mask, n_hab);
+            if (k < e) c = point_contrib<R>(env, pts[3 * k], pts[3 * k + 1], pts[3 * k + 2], bin_mask, n_hab,
+                                             env.classify(pts[3 * k], pts[3 * k + 1]));
             R v2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
             R v1 = (c.bin >= 0 && c.hab >= 0) ? w2 : (R)0;
             if (VERIFY) {
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(256) k_cost_point(const unsigned char *blob, c
     typedef typename Policy<R>::A A;
     EnvView<R> env;
     env.bind(blob, blob);
+    env.bind_grid(blob, blob);
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     R x = pts[2 * i], y = pts[2 * i + 1], c0 = 0, c1 = 0, c2 = 0;
@@ -486,24 +492,40 @@ __global__ void __launch_bounds__(256) k_nn_partial(const R *__restrict__ tx, co
             qxs[j] = (double)qx[qi]; qys[j] = (double)qy[qi];
             best[j].s = __longlong_as_double(0x7ff0000000000000LL); best[j].q = best[j].s; best[j].i = 0x7fffffffffffffffLL;
         }
-        // 4 consecutive nodes per thread per step (one 16-byte load per array in fp32)
+        // 4 consecutive nodes per thread per 16-byte load (fp32), NN_UNROLL independent loads per
+        // array in flight per thread: the scan is HBM-bound, so memory-level parallelism is what counts
         const int64_t n4 = n / 4;
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += stride) {
-            R xs[4], ys[4];
-            if (sizeof(R) == 4) {
-                float4 a = __ldg((const float4 *)tx + v), b = __ldg((const float4 *)ty + v);
-                xs[0] = a.x; xs[1] = a.y; xs[2] = a.z; xs[3] = a.w; ys[0] = b.x; ys[1] = b.y; ys[2] = b.z; ys[3] = b.w;
-            } else {
-                double2 a0 = __ldg((const double2 *)tx + 2 * v), a1 = __ldg((const double2 *)tx + 2 * v + 1);
-                double2 b0 = __ldg((const double2 *)ty + 2 * v), b1 = __ldg((const double2 *)ty + 2 * v + 1);
-                xs[0] = a0.x; xs[1] = a0.y; xs[2] = a1.x; xs[3] = a1.y; ys[0] = b0.x; ys[1] = b0.y; ys[2] = b1.x; ys[3] = b1.y;
+        const int NN_UNROLL = 4;
+        for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < n4; v0 += stride * NN_UNROLL) {
+            R xs[NN_UNROLL][4], ys[NN_UNROLL][4];
+#pragma unroll
+            for (int u = 0; u < NN_UNROLL; u++) {
+                const int64_t v = v0 + u * stride;
+                if (v < n4) {
+                    if (sizeof(R) == 4) {
+                        float4 a = __ldcs((const float4 *)tx + v), b = __ldcs((const float4 *)ty + v);
+                        xs[u][0] = a.x; xs[u][1] = a.y; xs[u][2] = a.z; xs[u][3] = a.w;
+                        ys[u][0] = b.x; ys[u][1] = b.y; ys[u][2] = b.z; ys[u][3] = b.w;
+                    } else {
+                        double2 a0 = __ldcs((const double2 *)tx + 2 * v), a1 = __ldcs((const double2 *)tx + 2 * v + 1);
+                        double2 b0 = __ldcs((const double2 *)ty + 2 * v), b1 = __ldcs((const double2 *)ty + 2 * v + 1);
+                        xs[u][0] = a0.x; xs[u][1] = a0.y; xs[u][2] = a1.x; xs[u][3] = a1.y;
+                        ys[u][0] = b0.x; ys[u][1] = b0.y; ys[u][2] = b1.x; ys[u][3] = b1.y;
+                    }
+                }
             }
 #pragma unroll
-            for (int e = 0; e < 4; e++)
+            for (int u = 0; u < NN_UNROLL; u++) {
+                const int64_t v = v0 + u * stride;
+                if (v < n4) {
 #pragma unroll
-                for (int j = 0; j < NN_QT; j++)
-                    nn_consider(best[j], __dsub_rn(qxs[j], (double)xs[e]), __dsub_rn(qys[j], (double)ys[e]), 4 * v + e);
+                    for (int e = 0; e < 4; e++)
+#pragma unroll
+                        for (int j = 0; j < NN_QT; j++)
+                            nn_consider(best[j], __dsub_rn(qxs[j], (double)xs[u][e]), __dsub_rn(qys[j], (double)ys[u][e]), 4 * v + e);
+                }
+            }
         }
         if (blockIdx.x == 0 && threadIdx.x < (int)(n - 4 * n4)) {     // tail
             int64_t i = 4 * n4 + threadIdx.x;

@@ -100,11 +100,12 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     __shared__ GroupScratch<R, G> scratch[PLAN_THREADS / G];
     EnvView<R> env;
     {
-        if (stage_mode == 0) env.bind(blob, blob);
+        if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
         else {
             uint64_t *bar = (uint64_t *)smem;
             stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
             env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
+            env.bind_grid(blob, smem + 16);
         }
     }
     Grp<G> g;
@@ -128,7 +129,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         if (g.gl == 0) {
             T.x[0] = sx; T.y[0] = sy; T.th[0] = sth; T.t[0] = st; T.len[0] = slen;
             T.parent[0] = -1; T.ctr[0] = 0; T.s2[0] = (R)0; T.cnt[0] = 0; T.mask[0] = 0ull;
-            Contrib c = point_contrib<R>(env, sx, sy, st, 0xffffffffu, env.H);
+            Contrib c = point_contrib<R>(env, sx, sy, st, 0xffffffffu, env.H, env.classify(sx, sy));
             T.self_s2[0] = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
             T.self_hab[0] = c.bin >= 0 ? c.hab : -1;
         }
@@ -349,6 +350,7 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
     __shared__ GroupScratch<R, G> scratch[128 / G];
     EnvView<R> env;
     env.bind(blob, blob);
+    env.bind_grid(blob, blob);
     Grp<G> g;
     GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
     const long long groups = (long long)gridDim.x * (128 / G);

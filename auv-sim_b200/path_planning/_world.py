@@ -1,0 +1,82 @@
+"""Host-side marshalling shared by the drop-in modules: Python objects -> flat arrays -> auvrrt.Env."""
+import os
+import sys
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+from auvrrt import api  # noqa: E402
+
+
+def circles_of(objs):
+    return np.array([[float(o.x), float(o.y), float(o.size)] for o in objs], dtype=np.float64).reshape(-1, 3)
+
+
+def ring_of(boundary):
+    """vertices of a shapely-like Polygon (`.exterior.xy` / `.exterior.coords`), a list of (x, y), or a
+    list of objects with .x/.y; the closing vertex is dropped"""
+    if boundary is None:
+        return np.zeros((0, 2))
+    if hasattr(boundary, "exterior"):
+        ext = boundary.exterior
+        if hasattr(ext, "xy"):
+            xs, ys = ext.xy
+            pts = list(zip(list(xs), list(ys)))
+        else:
+            pts = [tuple(c[:2]) for c in ext.coords]
+    else:
+        pts = [(p.x, p.y) if hasattr(p, "x") else (p[0], p[1]) for p in boundary]
+    pts = [(float(a), float(b)) for a, b in pts]
+    if len(pts) > 1 and pts[0] == pts[-1]:
+        pts = pts[:-1]
+    return np.array(pts, dtype=np.float64).reshape(-1, 2)
+
+
+def grid_of(shark_dict):
+    """{(t0, t1): {cell_bounds: p}} -> bins[T,2], cells[C,4], probs[T,C].
+
+    The cost function scans each bin's dict in insertion order and takes the first matching cell
+    (cost.py:181-184), so that order is part of the data: all bins must list the same cells in the
+    same order (createSharkGrid, rrt_dubins.py:612-630, guarantees it)."""
+    if not shark_dict:
+        return np.zeros((0, 2)), np.zeros((0, 4)), np.zeros((0, 0))
+    bins = np.array([[float(k[0]), float(k[1])] for k in shark_dict.keys()], dtype=np.float64)
+    first = next(iter(shark_dict.values()))
+    keys = list(first.keys())
+    cells = np.array([[float(v) for v in k] for k in keys], dtype=np.float64).reshape(-1, 4)
+    probs = np.zeros((len(bins), len(keys)))
+    for i, g in enumerate(shark_dict.values()):
+        if len(g) != len(keys) or (g is not first and list(g.keys()) != keys):
+            raise NotImplementedError("shark grid bins must list the same cells in the same order")
+        probs[i] = np.fromiter((float(p) for p in g.values()), dtype=np.float64, count=len(keys))
+    return bins, cells, probs
+
+
+class EnvCache:
+    """auvrrt.Env handles keyed by the content of their inputs (small LRU)."""
+
+    def __init__(self, cap=8):
+        self.cap, self.items = cap, []
+
+    def get(self, circles, ring, habitats, grid_id, grid_arrays_fn, device=0):
+        key = (circles.tobytes(), ring.tobytes(), habitats.tobytes(), grid_id, device)
+        for k, env in self.items:
+            if k == key:
+                return env
+        bins, cells, probs = grid_arrays_fn()
+        env = api.Env(circles, ring, habitats, bins, cells, probs, device=device)
+        self.items.append((key, env))
+        if len(self.items) > self.cap:
+            _, old = self.items.pop(0)
+            old.close()
+        return env
+
+
+def grid_fingerprint(shark_dict):
+    if not shark_dict:
+        return None
+    first = next(iter(shark_dict.values()))
+    return (id(shark_dict), len(shark_dict), len(first), tuple(shark_dict.keys()))
