@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libauvrrt.so")
+LIB_PATH = os.environ.get("AUVRRT_LIB") or os.path.join(HERE, "libauvrrt.so")
 
 F32, F64 = 0, 1
 ST_OK, ST_NO_PATH, ST_ZERO_DIV, ST_KEY_ERROR, ST_STREAM_END, ST_OVERFLOW = range(6)

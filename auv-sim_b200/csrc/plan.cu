@@ -32,6 +32,9 @@ namespace auv {
     } while (0)
 
 static const int PLAN_THREADS = 256;
+#ifndef AUV_PLAN_MINB
+#define AUV_PLAN_MINB 2      // resident CTAs per SM the register allocation targets
+#endif
 
 template <typename R> struct PlanP {
     int I, mode, nb, chain_cap, path_cap, trace, cap, nchunks;
@@ -90,7 +93,7 @@ template <typename R> __device__ __forceinline__ R py_sum3p(R c0, R c1, R c2) {
 }
 
 template <typename R, int G>
-__global__ void __launch_bounds__(PLAN_THREADS, 2)
+__global__ void __launch_bounds__(PLAN_THREADS, AUV_PLAN_MINB)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
@@ -327,6 +330,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             g.sync();
             if (chain && g.gl == 0)
                 for (int k = 0; k < depth && k < P.chain_cap; k++) chain[k] = T.ctr[chain[k]];
+            if (chain) for (int k = depth + g.gl; k < P.chain_cap; k += G) chain[k] = 0u;
         }
         if (g.gl == 0) {
             auvrrt_plan_record_t rec;
