@@ -45,7 +45,7 @@ EXPORTS = [
     "auvrrt_env_destroy", "auvrrt_nn", "auvrrt_nn_dev", "auvrrt_nn_scratch_bytes", "auvrrt_steer_arc",
     "auvrrt_steer_dubins", "auvrrt_collide", "auvrrt_collide_points", "auvrrt_cost",
     "auvrrt_cost_point", "auvrrt_edges_dubins_dev", "auvrrt_edges_arc_dev", "auvrrt_edges_dubins",
-    "auvrrt_edges_arc", "auvrrt_stream_u", "auvrrt_plan_batch", "auvrrt_plan_workspace_bytes",
+    "auvrrt_edges_arc", "auvrrt_stream_u", "auvrrt_plan_batch", "auvrrt_plan_workspace_bytes", "auvrrt_plan_workspace_bytes_q",
     "auvrrt_plan_batch_dev", "auvrrt_materialize", "auvrrt_calibrate_fp32",
 ]
 
@@ -94,6 +94,8 @@ def lib():
                                     C.POINTER(PlanRecord), _u32p, _dp, C.POINTER(PlanTrace)]
     L.auvrrt_plan_workspace_bytes.restype = C.c_int64
     L.auvrrt_plan_workspace_bytes.argtypes = [vp, C.POINTER(PlanParams), C.c_int]
+    L.auvrrt_plan_workspace_bytes_q.restype = C.c_int64
+    L.auvrrt_plan_workspace_bytes_q.argtypes = [vp, C.POINTER(PlanParams), C.c_int, C.c_int64]
     L.auvrrt_plan_batch_dev.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(PlanParams), C.c_int, vp, C.c_int64,
                                         vp, vp, vp, C.POINTER(PlanTrace), vp]
     L.auvrrt_materialize.argtypes = [vp, _dp, _u64p, _u32p, _i32p, C.c_int64, C.POINTER(PlanParams), C.c_int,

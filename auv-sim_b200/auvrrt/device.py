@@ -36,7 +36,7 @@ class DevicePlanner:
         self.env, self.params, self.prec = env, params, _prec(precision)
         self.dev = torch.device("cuda", env.device)
         self.rdtype = _rdtype(precision)
-        wsb = lib().auvrrt_plan_workspace_bytes(env.handle, C.byref(params), self.prec)
+        wsb = lib().auvrrt_plan_workspace_bytes_q(env.handle, C.byref(params), self.prec, int(max_queries))
         if wsb < 0:
             raise _lib.AuvrrtError(lib().auvrrt_last_error().decode())
         self.workspace = torch.empty(int(wsb), dtype=torch.uint8, device=self.dev)

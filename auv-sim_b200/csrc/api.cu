@@ -88,6 +88,14 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     h.off_b0 = take(sr * T); h.off_b1 = take(sr * T);
     h.off_brk = take(sr * NB); h.off_piece = take(4 * (size_t)(NP + 1)); h.off_c1 = take(sr * cand_c1.size());
     h.off_cell = take(4 * cand_cell.size());
+    // x-bucket table over the breakpoints (find_cell): ~4 buckets per breakpoint, at most 4096
+    h.nxb = 0; h.xb0 = 0.0; h.xbw = 1.0;
+    if (NB >= 2 && NB < 65535 && (double)brk[NB - 1] > (double)brk[0]) {
+        h.nxb = std::min(4096, std::max(16, 4 * NB));
+        h.xb0 = (double)brk[0];
+        h.xbw = ((double)brk[NB - 1] - (double)brk[0]) / h.nxb * (1.0 + 1e-12);
+    }
+    h.off_xb = take(2 * (size_t)h.nxb);
     h.hot_bytes = (int)o;
     h.off_probs = take(sr * (size_t)T * C);
     h.total_bytes = (int)o;          // what may be staged in shared memory ends here
@@ -103,7 +111,7 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         h.gs = gs; h.gx0 = h.bbox[0] - gs; h.gy0 = h.bbox[1] - gs;
         h.gnx = (int)ceil(wx / gs) + 2; h.gny = (int)ceil(wy / gs) + 2;
     }
-    h.off_grid = take(4 * (size_t)h.gnx * h.gny);
+    h.off_grid = take(12 * (size_t)h.gnx * h.gny);
     // --- uniform time bins?
     h.bins_uniform = 0; h.bin_s0 = 0.0; h.bin_w = 1.0;
     if (T >= 1 && T <= 32) {
@@ -131,6 +139,14 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     }
     for (int i = 0; i < T; i++) { arr(h.off_b0)[i] = (R)bins[2 * i]; arr(h.off_b1)[i] = (R)bins[2 * i + 1]; }
     for (int i = 0; i < NB; i++) arr(h.off_brk)[i] = brk[i];
+    {
+        unsigned short *xb = (unsigned short *)(blob.data() + h.off_xb);
+        for (int b = 0; b < h.nxb; b++) {
+            double left = h.xb0 + b * h.xbw;
+            int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)left) - brk.begin()) - 1;
+            xb[b] = (unsigned short)std::max(lo_i, 0);      // the device walks +-1 from here: any start is exact
+        }
+    }
     memcpy(blob.data() + h.off_piece, piece.data(), 4 * piece.size());
     for (size_t i = 0; i < cand_c1.size(); i++) arr(h.off_c1)[i] = cand_c1[i];
     if (!cand_cell.empty()) memcpy(blob.data() + h.off_cell, cand_cell.data(), 4 * cand_cell.size());
@@ -162,39 +178,77 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         for (int iy = 0; iy < h.gny; iy++)
             for (int ix = 0; ix < h.gnx; ix++) {
                 const double x0 = h.gx0 + ix * gs, y0 = h.gy0 + iy * gs, mx = x0 + 0.5 * gs, my = y0 + 0.5 * gs;
-                unsigned code = 0;
-                // polygon
+                unsigned code = 0, w1 = 0x3FFFFFFFu, w2 = 0x0FFFFFFFu;
+                // polygon: definitive if no edge comes within rho of the centre; else (convex ring) the
+                // edges whose supporting line does
                 double dmin = INFINITY;
+                int ne = 0, ecand[2] = {0x1F, 0x1F};
+                bool efull = (h.convex == 0) || E > 31;
                 for (int i = 0; i < E; i++) {
                     int j = (i + 1) % E;
-                    dmin = std::min(dmin, seg_dist(mx, my, poly[2 * i], poly[2 * i + 1], poly[2 * j], poly[2 * j + 1]));
+                    double d = seg_dist(mx, my, poly[2 * i], poly[2 * i + 1], poly[2 * j], poly[2 * j + 1]);
+                    dmin = std::min(dmin, d);
+                    // distance to the supporting LINE decides whether the half-plane test is constant on the cell
+                    double vx = poly[2 * j] - poly[2 * i], vy = poly[2 * j + 1] - poly[2 * i + 1], L = hypot(vx, vy);
+                    double dl = L > 0 ? fabs(vx * (my - poly[2 * i + 1]) - vy * (mx - poly[2 * i])) / L : 0.0;
+                    if (dl <= rho) { if (ne < 2) ecand[ne] = i; ne++; }
                 }
                 if (dmin > rho) code |= inside_poly(mx, my) ? 1u : 2u;
-                // obstacle circles (inflated radii)
-                bool clear = true;
-                for (int k = 0; k < K && clear; k++)
-                    if (hypot(mx - circles[3 * k], my - circles[3 * k + 1]) - rho <= reff[k]) clear = false;
-                if (clear) code |= 4u;
+                else {
+                    // ambiguous w.r.t. the boundary.  For a convex ring the point is inside iff it is on the
+                    // inner side of EVERY edge; edges farther than rho (as lines) have a constant side on the
+                    // cell, so if any of those is the outer side the cell is outside, else only the
+                    // candidates remain to be tested.
+                    bool outer_const = false;
+                    if (h.convex != 0)
+                        for (int i = 0; i < E; i++) {
+                            int j = (i + 1) % E;
+                            double vx = poly[2 * j] - poly[2 * i], vy = poly[2 * j + 1] - poly[2 * i + 1], L = hypot(vx, vy);
+                            double cr = vx * (my - poly[2 * i + 1]) - vy * (mx - poly[2 * i]);
+                            double dl = L > 0 ? fabs(cr) / L : 0.0;
+                            if (dl > rho && ((h.convex > 0 && cr < 0) || (h.convex < 0 && cr > 0))) outer_const = true;
+                        }
+                    if (outer_const) code |= 2u;
+                    else if (efull || ne > 2) code |= AUV_GRID_POLY_FULL;
+                    else w2 = (w2 & ~(0x3FFu << 18)) | ((unsigned)ecand[0] << 18) | ((unsigned)ecand[1] << 23);
+                }
+                // obstacle circles (inflated radii): candidates = circles a point of the cell can hit
+                int nc = 0; unsigned cc3[3] = {0x3FF, 0x3FF, 0x3FF};
+                for (int k = 0; k < K; k++)
+                    if (hypot(mx - circles[3 * k], my - circles[3 * k + 1]) - rho <= reff[k]) { if (nc < 3) cc3[nc] = (unsigned)k; nc++; }
+                if (nc == 0) code |= 4u;
+                else if (nc > 3 || K > 1022) code |= AUV_GRID_CIRC_MANY;
+                else w1 = cc3[0] | (cc3[1] << 10) | (cc3[2] << 20);
                 // habitats: first match in list order
                 unsigned hc = AUV_GRID_HAB_NONE;
+                int nh = 0; unsigned hh3[3] = {0x3F, 0x3F, 0x3F};
+                bool hmany = false;
                 for (int q = 0; q < H; q++) {
                     double d = hypot(mx - hab[3 * q], my - hab[3 * q + 1]);
                     if (d - rho <= hab[3 * q + 2]) {                       // the cell touches habitat q
-                        hc = (d + rho < hab[3 * q + 2]) ? (unsigned)q : AUV_GRID_HAB_AMBIG;
-                        break;
+                        const bool covers = d + rho < hab[3 * q + 2];
+                        if (nh == 0 && covers) { hc = (unsigned)q; break; }    // definitive
+                        hc = AUV_GRID_HAB_AMBIG;
+                        if (nh < 3) hh3[nh] = (unsigned)q; else hmany = true;
+                        nh++;
+                        if (covers) break;                                 // later habitats can never be first
                     }
                 }
                 code |= hc << 3;
+                if (hc == AUV_GRID_HAB_AMBIG) {
+                    if (hmany || H > 62) code |= AUV_GRID_HAB_MANY;
+                    else w2 = (w2 & ~0x3FFFFu) | hh3[0] | (hh3[1] << 6) | (hh3[2] << 12);
+                }
                 // shark cell: constant piece and constant first candidate over the whole grid cell?
                 unsigned cc = AUV_GRID_CELL_AMBIG;
                 if (NB == 0 || C >= 65534) { if (NB == 0) cc = AUV_GRID_CELL_NONE; }
                 else {
-                    const double xa = x0 - margin, xb = x0 + gs + margin, ya = y0 - margin, yb = y0 + gs + margin;
-                    if (xb < (double)brk[0] || xa > (double)brk[NB - 1]) cc = AUV_GRID_CELL_NONE;
+                    const double xa = x0 - margin, xb_ = x0 + gs + margin, ya = y0 - margin, yb = y0 + gs + margin;
+                    if (xb_ < (double)brk[0] || xa > (double)brk[NB - 1]) cc = AUV_GRID_CELL_NONE;
                     else {
                         int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)xa) - brk.begin()) - 1;   // last brk <= xa
                         bool has_break = false;
-                        for (int i = std::max(lo_i, 0); i < NB && (double)brk[i] <= xb; i++)
+                        for (int i = std::max(lo_i, 0); i < NB && (double)brk[i] <= xb_; i++)
                             if ((double)brk[i] >= xa) { has_break = true; break; }
                         if (!has_break && lo_i >= 0 && lo_i + 1 < NB) {
                             const int p = 2 * lo_i + 1;
@@ -209,7 +263,9 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
                     }
                 }
                 code |= cc << 16;
-                grid[(size_t)iy * h.gnx + ix] = code;
+                grid[3 * ((size_t)iy * h.gnx + ix)] = code;
+                grid[3 * ((size_t)iy * h.gnx + ix) + 1] = w1;
+                grid[3 * ((size_t)iy * h.gnx + ix) + 2] = w2;
             }
     }
     memcpy(blob.data(), &h, sizeof(h));
@@ -603,7 +659,12 @@ extern "C" int auvrrt_edges_arc(const auvrrt_env_t *env, const double *parents, 
 extern "C" int64_t auvrrt_plan_workspace_bytes(const auvrrt_env_t *env, const auvrrt_plan_params_t *params, int precision) {
     if (!env || !params || check_precision(precision)) return -1;
     if (need_device(env->device)) return -1;
-    return precision == AUVRRT_F32 ? plan_workspace_bytes<float>(env, params) : plan_workspace_bytes<double>(env, params);
+    return precision == AUVRRT_F32 ? plan_workspace_bytes<float>(env, params, 0) : plan_workspace_bytes<double>(env, params, 0);
+}
+extern "C" int64_t auvrrt_plan_workspace_bytes_q(const auvrrt_env_t *env, const auvrrt_plan_params_t *params, int precision, int64_t Q) {
+    if (!env || !params || check_precision(precision)) return -1;
+    if (need_device(env->device)) return -1;
+    return precision == AUVRRT_F32 ? plan_workspace_bytes<float>(env, params, Q) : plan_workspace_bytes<double>(env, params, Q);
 }
 extern "C" int auvrrt_plan_batch_dev(const auvrrt_env_t *env, const void *starts, const uint64_t *seeds, int64_t Q,
                                      const auvrrt_plan_params_t *params, int precision, void *workspace,
@@ -625,7 +686,7 @@ static int plan_host(auvrrt_env *env, const double *starts, const uint64_t *seed
                      const auvrrt_plan_trace_t *trace) {
     cudaStream_t s = env->stream;
     const int I = p->iterations;
-    int64_t wsb = plan_workspace_bytes<R>(env, p);
+    int64_t wsb = plan_workspace_bytes<R>(env, p, Q);
     if (wsb < 0) return AUVRRT_ERR_CUDA;
     void *ws, *dstart, *dseed, *drec, *dchain = nullptr, *dpath = nullptr, *dtrace = nullptr;
     AUV_TRY(env_dev_scratch(env, 0, (size_t)wsb, &ws));
@@ -635,6 +696,8 @@ static int plan_host(auvrrt_env *env, const double *starts, const uint64_t *seed
     const int ccap = p->chain_cap > 0 ? p->chain_cap : 1;
     if (chain) AUV_TRY(env_dev_scratch(env, 4, 4 * (size_t)Q * ccap, &dchain));
     // in-kernel path materialisation walks the chain, so paths need a chain buffer
+    if (path && p->path_cap > 0 && p->group == 1)
+        return set_err(AUVRRT_ERR_UNSUPPORTED, "plan_batch: group 1 (thread per tree) writes no paths; use auvrrt_materialize");
     if (path && p->path_cap > 0) {
         AUV_TRY(env_dev_scratch(env, 4, 4 * (size_t)Q * ccap, &dchain));
         AUV_TRY(env_dev_scratch(env, 5, sizeof(R) * 6 * (size_t)Q * p->path_cap, &dpath));

@@ -74,16 +74,18 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
     R csin = 0, ccos = 0;
     if (VERIFY) A::sincos(pth, &csin, &ccos);
     int nwp = 1;
-    bool hit = false, outside = false, zero_div = false, moved = false, degenerate = false, parent_clear = false;
+    bool hit = false, outside = false, zero_div = false, moved = false, degenerate = false, parent_clear = false, parent_many = false;
     R acc_s2 = 0; uint32_t acc_cnt = 0; uint64_t acc_mask = 0;
     R self_s2 = 0; int self_hab = -1;
 
     if (DO_COLLIDE) {
         // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
         if (g.gl == 0) { sc.wx[G] = px; sc.wy[G] = py; }
-        const unsigned pcode = env.classify(px, py);
-        outside = !point_within_c<R>(env, pcode, px, py);
-        parent_clear = (pcode & 4u) != 0u;
+        const Cls pcl = env.classify(px, py);
+        outside = !point_within_c<R>(env, pcl, px, py);
+        parent_clear = (pcl.code & 4u) != 0u;
+        parent_many = (pcl.code & AUV_GRID_CIRC_MANY) != 0u;
+        if (!parent_clear && !parent_many) hit = point_hits_circles_c<R>(env, pcl, px, py);
     }
 
     for (int base = 0; base < n_exp; base += G) {
@@ -212,16 +214,21 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             }
         }
         // one classification-grid load per waypoint replaces most of the exact tests below
-        unsigned code = AUV_GRID_ALL_AMBIG | 4u;
-        if ((DO_COLLIDE || DO_COST) && (is_wp || g.gl == last_valid)) code = env.classify(x, y);
+        Cls cl; cl.code = AUV_GRID_ALL_AMBIG | 4u; cl.idx = -1;
+        if ((DO_COLLIDE || DO_COST) && (is_wp || g.gl == last_valid)) cl = env.classify(x, y);
         if (DO_COLLIDE) {
-            // polygon: lane = waypoint
-            bool in = true;
-            if (is_wp) in = point_within_c<R>(env, code, x, y);
+            // lane = waypoint: polygon and the cell's candidate circles
+            bool in = true, h1 = false;
+            if (is_wp) {
+                in = point_within_c<R>(env, cl, x, y);
+                if (!(cl.code & AUV_GRID_CIRC_MANY)) h1 = point_hits_circles_c<R>(env, cl, x, y);
+            }
             if (g.ballot(!in)) outside = true;
-            // circles: lane = circle, waypoints broadcast through shared memory; skipped when every
-            // path point sits in a grid cell that is clear of all (inflated) circles
-            const bool circles_needed = g.ballot(is_wp && !(code & 4u)) != 0u || (base == 0 && !parent_clear);
+            if (g.ballot(h1)) hit = true;
+            // cells with more than 3 candidate circles (or points outside the grid): lane = circle over
+            // all circles, waypoints broadcast through shared memory
+            const bool circles_needed = g.ballot(is_wp && !(cl.code & 4u) && (cl.code & AUV_GRID_CIRC_MANY)) != 0u ||
+                                        (base == 0 && !parent_clear && parent_many);
             if (env.K > 0 && circles_needed) {
                 if (is_wp) { int slot = __popc(wpm & ((1u << g.gl) - 1u)); sc.wx[slot] = x; sc.wy[slot] = y; }
                 g.sync();
@@ -247,7 +254,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             // (provisional) leaf state
             const bool need = is_wp || (g.gl == last_valid);
             Contrib c; c.bin = -1; c.cell = -1; c.hab = -1;
-            if (need) c = point_contrib<R>(env, x, y, t, 0xffffffffu, n_hab, code);
+            if (need) c = point_contrib<R>(env, x, y, t, 0xffffffffu, n_hab, cl);
             R ps2 = (R)0;
             if (c.bin >= 0 && c.cell >= 0) ps2 = A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]);
             const bool counts = is_wp && c.bin >= 0;
@@ -281,7 +288,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             break;
         }
     }
-    if (DO_COLLIDE && n_exp == 0 && env.K > 0 && !parent_clear) {
+    if (DO_COLLIDE && n_exp == 0 && env.K > 0 && !parent_clear && parent_many) {
         // the path is [parent] alone: test it against the circles
         bool h = false;
         for (int k = g.gl; k < env.K; k += G) {

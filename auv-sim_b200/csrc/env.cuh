@@ -34,38 +34,53 @@ struct EnvHeader {
     int off_b0, off_b1;
     int off_brk, off_piece, off_c1, off_cell;
     int off_probs;
-    int off_grid;      // classification grid (u32 per cell), not staged: read through L1/L2
+    int off_xb;        // x-bucket table for the shark-cell pieces (u16 per bucket), staged
+    int nxb;           // number of x buckets (0: none)
+    int off_grid;      // classification grid (3 x u32 per cell), not staged: read through L1/L2
     int gnx, gny;      // grid dimensions (0: no grid)
     int bins_uniform;  // 1: bins are [s0 + i w, s0 + (i+1) w], contiguous and in order
-    int pad_[3];
+    int pad_[1];
     double bbox[4];    // minx, miny, maxx, maxy of the polygon (Polygon.bounds, rrt_dubins.py:334)
     double gx0, gy0, gs;   // grid origin and cell size
     double bin_s0, bin_w;
+    double xb0, xbw;       // x-bucket origin and width
     double pad2_;
 };
 static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignment of the arrays");
 
-// Classification grid (built once on the host, see api.cu): one u32 per cell of a uniform grid over
-// the polygon's bounding box, so that most waypoints are classified by ONE load instead of the
-// loops over circles / polygon edges / habitats / shark cells.  A code is only definitive when
-// every point of the cell (plus a rounding margin) gets the same answer from the exact test;
-// otherwise the cell is marked ambiguous and the exact test runs.  Results are therefore identical
-// to the exact tests by construction.
-//   bits  0-1  polygon: 0 ambiguous, 1 strictly inside, 2 outside
-//   bit   2    1: clear of every (inflated) obstacle circle
-//   bits  3-10 habitat: 0..63 first-match habitat, 254 none, 255 ambiguous
-//   bits 16-31 shark cell: first-match cell id, 0xFFFF none, 0xFFFE ambiguous
+// Classification grid (built once on the host, see api.cu): three u32 words per cell of a uniform
+// grid over the polygon's bounding box, so that most waypoints are classified by ONE load instead
+// of the loops over circles / polygon edges / habitats / shark cells, and the rest by a short
+// per-cell candidate list.  A code is only definitive when every point of the cell (plus a rounding
+// margin) gets the same answer from the exact test; candidate lists hold every object that can
+// decide a point of the cell.  Results are therefore identical to the exact tests by construction.
+//  word 0  bits 0-1  polygon: 0 ambiguous, 1 strictly inside, 2 outside
+//          bit  2    1: clear of every (inflated) obstacle circle
+//          bits 3-10 habitat: 0..63 first-match habitat, 254 none, 255 ambiguous
+//          bit  11   circles: more than 3 candidates -> full loop
+//          bit  12   habitats: more than 3 candidates -> full loop
+//          bit  13   polygon: convex fast path not applicable / more than 2 candidate edges -> full test
+//          bits 16-31 shark cell: first-match cell id, 0xFFFF none, 0xFFFE ambiguous
+//  word 1  three 10-bit circle indices (0x3FF = none): the only circles a point of the cell can hit
+//  word 2  bits 0-17 three 6-bit habitat indices (0x3F = none), in list order; bits 18-27 two 5-bit
+//          polygon edge indices (0x1F = none): the only edges whose half-plane is not already decided
 #define AUV_GRID_HAB_NONE 254u
 #define AUV_GRID_HAB_AMBIG 255u
 #define AUV_GRID_CELL_NONE 0xFFFFu
 #define AUV_GRID_CELL_AMBIG 0xFFFEu
-#define AUV_GRID_ALL_AMBIG ((AUV_GRID_CELL_AMBIG << 16) | (AUV_GRID_HAB_AMBIG << 3))
+#define AUV_GRID_CIRC_MANY (1u << 11)
+#define AUV_GRID_HAB_MANY (1u << 12)
+#define AUV_GRID_POLY_FULL (1u << 13)
+#define AUV_GRID_ALL_AMBIG ((AUV_GRID_CELL_AMBIG << 16) | (AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_CIRC_MANY | AUV_GRID_HAB_MANY | AUV_GRID_POLY_FULL)
+
+struct Cls { unsigned code; int idx; };   // word 0 and the cell index (-1 outside the grid)
 
 template <typename R> struct EnvView {
     int K, E, H, T, C, NB, NP, convex;
-    int gnx, gny, bins_uniform;
-    R gx0, gy0, ginv, bin_s0, bin_w, bin_winv;
+    int gnx, gny, bins_uniform, nxb;
+    R gx0, gy0, ginv, bin_s0, bin_w, bin_winv, xb0, xbinv;
     const unsigned *grid;
+    const unsigned short *xb;
     R minx, miny, maxx, maxy;
     const R *cx, *cy, *cr, *creff, *creff2;
     const R *px, *py;
@@ -95,17 +110,23 @@ template <typename R> struct EnvView {
     // the grid stays in global memory: bind it from the blob in HBM
     __device__ __forceinline__ void bind_grid(const unsigned char *blob_global, const unsigned char *hot) {
         const EnvHeader *h = (const EnvHeader *)hot;
-        gnx = h->gnx; gny = h->gny; bins_uniform = h->bins_uniform;
+        gnx = h->gnx; gny = h->gny; bins_uniform = h->bins_uniform; nxb = h->nxb;
+        xb0 = (R)h->xb0; xbinv = (R)(1.0 / h->xbw); xb = (const unsigned short *)(hot + h->off_xb);
         gx0 = (R)h->gx0; gy0 = (R)h->gy0; ginv = (R)(1.0 / h->gs);
         bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w);
         grid = (const unsigned *)(blob_global + h->off_grid);
     }
-    // classification code of the cell containing (x, y); all-ambiguous outside the grid
-    __device__ __forceinline__ unsigned classify(R x, R y) const {
+    // classification of the cell containing (x, y); all-ambiguous outside the grid
+    __device__ __forceinline__ Cls classify(R x, R y) const {
+        Cls c;
         R fx = (x - gx0) * ginv, fy = (y - gy0) * ginv;
-        if (!(fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny)) return AUV_GRID_ALL_AMBIG;
-        return __ldg(grid + (int)fy * gnx + (int)fx);
+        if (!(fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny)) { c.code = AUV_GRID_ALL_AMBIG; c.idx = -1; return c; }
+        c.idx = (int)fy * gnx + (int)fx;
+        c.code = __ldg(grid + 3 * c.idx);
+        return c;
     }
+    __device__ __forceinline__ unsigned word1(const Cls &c) const { return __ldg(grid + 3 * c.idx + 1); }
+    __device__ __forceinline__ unsigned word2(const Cls &c) const { return __ldg(grid + 3 * c.idx + 2); }
 };
 
 // ---- TMA bulk staging -------------------------------------------------------------------------

@@ -86,12 +86,26 @@ template <typename R> __device__ __forceinline__ bool point_within(const EnvView
     return inside && !boundary;
 }
 
-// same, short-circuited by the classification grid code of the point's cell
-template <typename R> __device__ __forceinline__ bool point_within_c(const EnvView<R> &env, unsigned code, R px, R py) {
-    const unsigned pc = code & 3u;
+// same, short-circuited by the classification grid: definitive code, else (fast build, convex ring)
+// only the candidate edges of the cell, else the full test
+template <typename R> __device__ __forceinline__ bool point_within_c(const EnvView<R> &env, const Cls &cl, R px, R py) {
+    const unsigned pc = cl.code & 3u;
     if (pc == 1u) return true;
     if (pc == 2u) return false;
-    return point_within<R>(env, px, py);
+    if (Policy<R>::VERIFY || (cl.code & AUV_GRID_POLY_FULL)) return point_within<R>(env, px, py);
+    const unsigned w2 = env.word2(cl);
+    bool in = true;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int i = (int)((w2 >> (18 + 5 * s)) & 0x1Fu);
+        if (i != 0x1F) {
+            const int j = i + 1 == env.E ? 0 : i + 1;
+            const R ax = env.px[i], ay = env.py[i], bx = env.px[j], by = env.py[j];
+            const R det = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+            in = in && (env.convex > 0 ? det > (R)0 : det < (R)0);
+        }
+    }
+    return in;
 }
 
 // does the point hit any (inflated, see env.cuh) circle?   thread-level, all circles
@@ -102,6 +116,25 @@ template <typename R> __device__ __forceinline__ bool point_hits_circles(const E
         R q = A::sq2(A::sub(x, env.cx[k]), A::sub(y, env.cy[k]));
         if (Policy<R>::VERIFY) hit = hit || (A::sqrt(q) <= env.creff[k]);
         else hit = hit || (q <= env.creff2[k]);
+    }
+    return hit;
+}
+
+// same through the classification grid: clear cell, else the cell's <= 3 candidate circles, else all
+template <typename R> __device__ __forceinline__ bool point_hits_circles_c(const EnvView<R> &env, const Cls &cl, R x, R y) {
+    typedef typename Policy<R>::A A;
+    if (cl.code & 4u) return false;
+    if (cl.code & AUV_GRID_CIRC_MANY) return point_hits_circles<R>(env, x, y);
+    const unsigned w1 = env.word1(cl);
+    bool hit = false;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        const int k = (int)((w1 >> (10 * s)) & 0x3FFu);
+        if (k != 0x3FF) {
+            R q = A::sq2(A::sub(x, env.cx[k]), A::sub(y, env.cy[k]));
+            if (Policy<R>::VERIFY) hit = hit || (A::sqrt(q) <= env.creff[k]);
+            else hit = hit || (q <= env.creff2[k]);
+        }
     }
     return hit;
 }
@@ -117,14 +150,26 @@ struct Contrib {
 template <typename R>
 __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
     if (env.NB == 0 || !(x >= env.brk[0]) || !(x <= env.brk[env.NB - 1])) return -1;
-    int lo = 0, hi = env.NB - 1;            // largest i with brk[i] <= x
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (env.brk[mid] <= x) lo = mid; else hi = mid - 1;
+    int lo;                                   // largest i with brk[i] <= x
+    if (env.nxb > 0) {
+        // x-bucket table: index of the last breakpoint <= the bucket's left edge (0 if none), then a
+        // short walk; exact because the walk ends on the same comparison the binary search would
+        int b = (int)((x - env.xb0) * env.xbinv);
+        b = b < 0 ? 0 : (b >= env.nxb ? env.nxb - 1 : b);
+        lo = (int)env.xb[b];
+        while (lo > 0 && env.brk[lo] > x) lo--;
+        while (lo + 1 < env.NB && env.brk[lo + 1] <= x) lo++;
+    } else {
+        lo = 0;
+        int hi = env.NB - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (env.brk[mid] <= x) lo = mid; else hi = mid - 1;
+        }
     }
     int p = 2 * lo + (x == env.brk[lo] ? 0 : 1);
-    int b = env.piece[p], e = env.piece[p + 1];
-    for (int k = b; k < e; k++)
+    int bb = env.piece[p], ee = env.piece[p + 1];
+    for (int k = bb; k < ee; k++)
         if (env.c1[k] <= y) return env.cell[k];
     return -1;
 }
@@ -150,17 +195,31 @@ __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin
 
 template <typename R>
 __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y, R t,
-                                                 unsigned bin_mask, int n_hab, unsigned code) {
+                                                 unsigned bin_mask, int n_hab, const Cls &cl) {
     typedef typename Policy<R>::A A;
     Contrib c;
     c.cell = -1; c.hab = -1;
     c.bin = find_bin<R>(env, t, bin_mask);
     if (c.bin < 0) return c;
+    const unsigned code = cl.code;
     const unsigned cc = code >> 16;
     if (cc == AUV_GRID_CELL_AMBIG) c.cell = find_cell(env, x, y);
     else if (cc != AUV_GRID_CELL_NONE) c.cell = (int)cc;
     const unsigned hc = (code >> 3) & 0xFFu;
-    if (hc == AUV_GRID_HAB_AMBIG) {
+    if (hc == AUV_GRID_HAB_AMBIG && !(code & AUV_GRID_HAB_MANY)) {
+        // the cell's candidate habitats, in list order (every habitat that touches the cell, up to
+        // and including the first that covers it)
+        const unsigned w2 = env.word2(cl);
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            const int h = (int)((w2 >> (6 * s)) & 0x3Fu);
+            if (h != 0x3F && h < n_hab && c.hab < 0) {
+                R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
+                bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
+                if (in) c.hab = h;
+            }
+        }
+    } else if (hc == AUV_GRID_HAB_AMBIG) {
         for (int h = 0; h < n_hab; h++) {
             R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
             bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);

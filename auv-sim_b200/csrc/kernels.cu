@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) k_steer_arc(const R *parents, int64_t n, 
     GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
     EnvView<R> env;
     env.K = env.E = env.H = env.T = env.C = env.NB = env.NP = env.convex = 0;
-    env.gnx = env.gny = env.bins_uniform = 0;
+    env.gnx = env.gny = env.bins_uniform = env.nxb = 0;
     const int64_t groups = (int64_t)gridDim.x * (128 / G);
     for (int64_t i = blockIdx.x * (int64_t)(128 / G) + threadIdx.x / G; i < n; i += groups) {
         Stream<R> rng;
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(128) k_collide(const unsigned char *blob, int 
         bool bad = false;
         for (int64_t k = b + g.gl; k < e; k += 32) {
             R x = pts[2 * k], y = pts[2 * k + 1];
-            const unsigned code = env.classify(x, y);
-            bad = bad || (!(code & 4u) && point_hits_circles<R>(env, x, y)) || !point_within_c<R>(env, code, x, y);
+            const Cls cl = env.classify(x, y);
+            bad = bad || point_hits_circles_c<R>(env, cl, x, y) || !point_within_c<R>(env, cl, x, y);
         }
         unsigned any = g.ballot(bad);
         if (g.gl == 0) safe[i] = (e == b && env.K > 0) ? 255 : (any ? 0 : 1);

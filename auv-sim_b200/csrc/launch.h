@@ -65,7 +65,7 @@ template <typename R> void launch_convert_back(const R *src, double *dst, int64_
 
 // ---- plan.cu
 template <typename R>
-int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p);
+int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p, int64_t Q);
 template <typename R>
 int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
                 const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,

@@ -18,7 +18,7 @@
 // `initial` the planner's bin filter (rrt_dubins.py:161-166) never changes a waypoint's first-match
 // bin (every waypoint time lies in [t_initial, t_leaf]).  Totals equal the reference's up to
 // summation order (fp64: <= 1e-12 relative).
-#include "launch.h"
+#include "plan_common.cuh"
 
 namespace auv {
 
@@ -35,12 +35,6 @@ static const int PLAN_THREADS = 256;
 #ifndef AUV_PLAN_MINB
 #define AUV_PLAN_MINB 2      // resident CTAs per SM the register allocation targets
 #endif
-
-template <typename R> struct PlanP {
-    int I, mode, nb, chain_cap, path_cap, trace, cap, nchunks;
-    R bin_interval, max_traj, horizon, w1, w2, w3;
-    SteerParams<R> sp;
-};
 
 struct WsLayout {
     size_t slot_bytes;
@@ -75,22 +69,6 @@ template <typename R> struct Tree {
         head = (int *)(b + L.head); tail = (int *)(b + L.tail); count = (int *)(b + L.count);
     }
 };
-
-// builtin sum([c0, c1, c2]) as CPython >= 3.12 evaluates it (Neumaier-compensated float fast path)
-template <typename R> __device__ __forceinline__ R py_sum3p(R c0, R c1, R c2) {
-    typedef typename Policy<R>::A A;
-    R f = A::add((R)0, c0), c = (R)0;
-    R xs[2] = {c1, c2};
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        R x = xs[i], t = A::add(f, x);
-        if (A::fabs(f) >= A::fabs(x)) c = A::add(c, A::add(A::sub(f, t), x));
-        else c = A::add(c, A::add(A::sub(x, t), f));
-        f = t;
-    }
-    if (c != (R)0 && isfinite(c)) f = A::add(f, c);
-    return f;
-}
 
 template <typename R, int G>
 __global__ void __launch_bounds__(PLAN_THREADS, AUV_PLAN_MINB)
@@ -294,6 +272,8 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
         // ---- optimal path: chain of stream positions, optional waypoints             :174-176, :321-331
         int depth = 0, n_path = 0;
+        if (best_node < 0 && chain_out)
+            for (int k = g.gl; k < P.chain_cap; k += G) chain_out[(size_t)q * P.chain_cap + k] = 0u;
         if (best_node >= 0) {
             for (int n = best_node; T.parent[n] >= 0; n = T.parent[n]) depth++;
             uint32_t *chain = chain_out ? chain_out + (size_t)q * P.chain_cap : nullptr;
@@ -391,26 +371,6 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <typename R> static int make_planp(const auvrrt_env *env, const auvrrt_plan_params_t *p, PlanP<R> *out) {
-    if (p->iterations < 1) return set_err(AUVRRT_ERR_ARG, "plan: iterations must be >= 1");
-    if (p->mode != 0 && p->mode != 1) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0 or 1");
-    if (!(p->bin_interval > 0) || !(p->max_traj_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: bin_interval and max_traj_time must be > 0");
-    if (env->H > 64) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 64 habitats");
-    double nbd = ceil(p->max_traj_time / p->bin_interval);                      // rrt_dubins.py:111
-    if (nbd > 1e6) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 1e6 time bins");
-    PlanP<R> P;
-    P.I = p->iterations; P.mode = p->mode; P.nb = (int)nbd;
-    P.chain_cap = p->chain_cap > 0 ? p->chain_cap : 1; P.path_cap = p->path_cap; P.trace = p->trace;
-    P.cap = P.I + 1; P.nchunks = P.nb + P.cap / 32 + 4;
-    P.bin_interval = (R)p->bin_interval; P.max_traj = (R)p->max_traj_time;
-    P.horizon = (R)(p->max_traj_time - 30);                                     // :158
-    P.w1 = (R)p->weights[0]; P.w2 = (R)p->weights[1]; P.w3 = (R)p->weights[2];
-    double sp[5] = {p->dist_to_end, p->diff_max, p->freq, p->min_dist, p->v};
-    P.sp = make_steer_params<R>(sp);
-    *out = P;
-    return AUVRRT_OK;
-}
-
 template <typename R, int G> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
     EnvBlob<R> b = env_blob<R>(env);
     int budget = 110 * 1024;     // leaves room for 2 CTAs per SM
@@ -465,27 +425,32 @@ int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, i
                 auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
                 cudaStream_t s) {
     int G = p->group ? p->group : 32;
+    if (G == 1) {
+        if (path && p->path_cap > 0) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: group 1 (thread per tree) writes no paths; use auvrrt_materialize");
+        return launch_plan_tpt<R>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, trace, s, nullptr);
+    }
     if (G == 32) return launch_plan_g<R, 32>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, nullptr);
     if (G == 16) return launch_plan_g<R, 16>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, nullptr);
     if (G == 8) return launch_plan_g<R, 8>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, nullptr);
-    return set_err(AUVRRT_ERR_ARG, "plan: group must be 32, 16 or 8");
+    return set_err(AUVRRT_ERR_ARG, "plan: group must be 32, 16, 8 or 1");
 }
 template <typename R>
-int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p) {
+int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p, int64_t Q) {
     int64_t need = -1;
     int G = p->group ? p->group : 32, rc;
-    if (G == 32) rc = launch_plan_g<R, 32>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
+    if (G == 1) rc = launch_plan_tpt<R>(env, nullptr, nullptr, Q, p, nullptr, 0, nullptr, nullptr, nullptr, 0, &need);
+    else if (G == 32) rc = launch_plan_g<R, 32>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
     else if (G == 16) rc = launch_plan_g<R, 16>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
     else if (G == 8) rc = launch_plan_g<R, 8>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
-    else { set_err(AUVRRT_ERR_ARG, "plan: group must be 32, 16 or 8"); return -1; }
+    else { set_err(AUVRRT_ERR_ARG, "plan: group must be 32, 16, 8 or 1"); return -1; }
     return rc ? -1 : need;
 }
 template int launch_plan<float>(const auvrrt_env *, const float *, const uint64_t *, int64_t, const auvrrt_plan_params_t *,
                                 void *, int64_t, auvrrt_plan_record_t *, uint32_t *, float *, const auvrrt_plan_trace_t *, cudaStream_t);
 template int launch_plan<double>(const auvrrt_env *, const double *, const uint64_t *, int64_t, const auvrrt_plan_params_t *,
                                  void *, int64_t, auvrrt_plan_record_t *, uint32_t *, double *, const auvrrt_plan_trace_t *, cudaStream_t);
-template int64_t plan_workspace_bytes<float>(const auvrrt_env *, const auvrrt_plan_params_t *);
-template int64_t plan_workspace_bytes<double>(const auvrrt_env *, const auvrrt_plan_params_t *);
+template int64_t plan_workspace_bytes<float>(const auvrrt_env *, const auvrrt_plan_params_t *, int64_t);
+template int64_t plan_workspace_bytes<double>(const auvrrt_env *, const auvrrt_plan_params_t *, int64_t);
 
 template <typename R>
 int launch_materialize(const auvrrt_env *env, const R *starts, const uint64_t *seeds, const uint32_t *chain,

@@ -1,0 +1,58 @@
+// plan_common.cuh -- pieces shared by the two planner kernels (plan.cu: one lane group per tree;
+// plan_tpt.cu: one thread per tree).
+#pragma once
+#include "launch.h"
+
+namespace auv {
+
+template <typename R> struct PlanP {
+    int I, mode, nb, chain_cap, path_cap, trace, cap, nchunks;
+    R bin_interval, max_traj, horizon, w1, w2, w3;
+    SteerParams<R> sp;
+};
+
+// builtin sum([c0, c1, c2]) as CPython >= 3.12 evaluates it (Neumaier-compensated float fast path)
+template <typename R> __device__ __forceinline__ R py_sum3p(R c0, R c1, R c2) {
+    typedef typename Policy<R>::A A;
+    R f = A::add((R)0, c0), c = (R)0;
+    R xs[2] = {c1, c2};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        R x = xs[i], t = A::add(f, x);
+        if (A::fabs(f) >= A::fabs(x)) c = A::add(c, A::add(A::sub(f, t), x));
+        else c = A::add(c, A::add(A::sub(x, t), f));
+        f = t;
+    }
+    if (c != (R)0 && isfinite(c)) f = A::add(f, c);
+    return f;
+}
+
+template <typename R> static inline int make_planp(const auvrrt_env *env, const auvrrt_plan_params_t *p, PlanP<R> *out) {
+    if (p->iterations < 1) return set_err(AUVRRT_ERR_ARG, "plan: iterations must be >= 1");
+    if (p->mode != 0 && p->mode != 1) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0 or 1");
+    if (!(p->bin_interval > 0) || !(p->max_traj_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: bin_interval and max_traj_time must be > 0");
+    if (env->H > 64) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 64 habitats");
+    double nbd = ceil(p->max_traj_time / p->bin_interval);                      // rrt_dubins.py:111
+    if (nbd > 1e6) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 1e6 time bins");
+    PlanP<R> P;
+    P.I = p->iterations; P.mode = p->mode; P.nb = (int)nbd;
+    P.chain_cap = p->chain_cap > 0 ? p->chain_cap : 1; P.path_cap = p->path_cap; P.trace = p->trace;
+    P.cap = P.I + 1; P.nchunks = P.nb + P.cap / 32 + 4;
+    P.bin_interval = (R)p->bin_interval; P.max_traj = (R)p->max_traj_time;
+    P.horizon = (R)(p->max_traj_time - 30);                                     // :158
+    P.w1 = (R)p->weights[0]; P.w2 = (R)p->weights[1]; P.w3 = (R)p->weights[2];
+    double sp[5] = {p->dist_to_end, p->diff_max, p->freq, p->min_dist, p->v};
+    P.sp = make_steer_params<R>(sp);
+    *out = P;
+    return AUVRRT_OK;
+}
+
+
+// thread-per-tree planner (plan_tpt.cu)
+template <typename R>
+int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
+                    const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
+                    auvrrt_plan_record_t *records, uint32_t *chain, const auvrrt_plan_trace_t *trace,
+                    cudaStream_t s, int64_t *need_bytes);
+
+}  // namespace auv

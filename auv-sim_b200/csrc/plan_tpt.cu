@@ -1,0 +1,318 @@
+// plan_tpt.cu -- RRT.exploring (/root/reference/path_planning/rrt_dubins.py:92-176), ONE THREAD PER
+// TREE: the throughput planner for very large batches of independent queries (config 5: 10^5..10^6
+// queries per GPU).
+//
+// plan.cu spends 32 lanes on one tree to shorten the latency of a single query (what matters at a
+// few thousand queries).  With >= 10^5 queries resident the machine is filled by the queries
+// themselves, so each thread simply runs the reference's serial loop for its own tree and all the
+// cooperative machinery (stream-offset resolution, scans, ballots) disappears.  Same stream, same
+// bins, same incremental cost, same statuses: in the fp64 build the traces are identical to
+// plan.cu's and to the reference's (tests/test_gpu_parity.py::test_plan_thread_per_tree_*).
+//
+// Per-tree workspace (private to the thread): AoS node rows (one 64-byte row in fp32: x,y,theta,t |
+// len,s2,self_s2,ctr | parent,cnt,self_hab | mask) and the chunked time bins of plan.cu.
+#include "plan_common.cuh"
+
+namespace auv {
+
+static const int TPT_THREADS = 128;
+
+template <typename R> struct alignas(16) NodeRow {
+    R x, y, th, t;
+    R len, s2, self_s2;
+    uint32_t ctr;
+    int parent;
+    uint32_t cnt;
+    int self_hab;
+    int pad_;
+    unsigned long long mask;
+};
+
+struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count; };
+
+template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchunks) {
+    TptLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~(size_t)127; return r; };
+    L.nodes = take(sizeof(NodeRow<R>) * (size_t)cap);
+    L.pool = take(4 * 32 * (size_t)nchunks); L.next = take(4 * (size_t)nchunks);
+    L.head = take(4 * (size_t)(nb + 2)); L.tail = take(4 * (size_t)(nb + 2)); L.count = take(4 * (size_t)(nb + 2));
+    L.slot_bytes = o;
+    return L;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(TPT_THREADS)
+k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
+           const uint64_t *seeds, long long Q, PlanP<R> P, TptLayout L, unsigned char *ws, unsigned long long *qcounter,
+           auvrrt_plan_record_t *records, uint32_t *chain_out, auvrrt_plan_trace_t tr) {
+    typedef typename Policy<R>::A A;
+    const bool VERIFY = Policy<R>::VERIFY;
+    extern __shared__ __align__(16) unsigned char smem[];
+    EnvView<R> env;
+    if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
+    else {
+        uint64_t *bar = (uint64_t *)smem;
+        stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
+        env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
+        env.bind_grid(blob, smem + 16);
+    }
+    const long long slot = (long long)blockIdx.x * TPT_THREADS + threadIdx.x;
+    unsigned char *base = ws + (size_t)slot * L.slot_bytes;
+    NodeRow<R> *nodes = (NodeRow<R> *)(base + L.nodes);
+    int *pool = (int *)(base + L.pool), *next = (int *)(base + L.next);
+    int *head = (int *)(base + L.head), *tail = (int *)(base + L.tail), *count = (int *)(base + L.count);
+    const SteerParams<R> sp = P.sp;
+
+    for (;;) {
+        const long long q = (long long)atomicAdd(qcounter, 1ull);
+        if (q >= Q) break;
+        const uint64_t key = stream_key(seeds[q]);
+        // ---- init                                                                   rrt_dubins.py:105-114
+        for (int b = 0; b < P.nb + 2; b++) count[b] = 0;
+        {
+            NodeRow<R> r0;
+            r0.x = starts[5 * q]; r0.y = starts[5 * q + 1]; r0.th = starts[5 * q + 2]; r0.t = starts[5 * q + 3];
+            r0.len = starts[5 * q + 4]; r0.s2 = (R)0; r0.ctr = 0; r0.parent = -1; r0.cnt = 0; r0.mask = 0ull; r0.pad_ = 0;
+            Contrib c = point_contrib<R>(env, r0.x, r0.y, r0.t, 0xffffffffu, env.H, env.classify(r0.x, r0.y));
+            r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+            r0.self_hab = c.bin >= 0 ? c.hab : -1;
+            nodes[0] = r0;
+        }
+        head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
+        int n_nodes = 1, n_chunks = 1, status = AUVRRT_ST_OK;
+        uint32_t ctr = 0, upos_mark = 0;
+        int best_node = -1, best_iter = -1, n_cost_evals = 0, n_waypoints = 0;
+        long long n_prims = 0;
+        R best_c0 = A::inf(), best_c1 = 0, best_c2 = 0, best_c3 = 0, best_len = 0, best_t = 0;
+        int it = 0;
+        long long guard = 0;
+        const long long guard_max = 64LL * P.I + 1024;
+
+        while (it < P.I && guard++ < guard_max) {
+            int parent;
+            if (P.mode == 0) {                                                          // :122-127
+                int rb, cn;
+                for (;;) {
+                    rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), bits_to_u<R>(stream_bits(key, ctr)));
+                    ctr++;
+                    if (rb > P.nb || rb < 1) { status = AUVRRT_ST_KEY_ERROR; break; }
+                    cn = count[rb];
+                    if (cn > 0) break;
+                }
+                if (status) break;
+                int idx = (int)uniform_ab<R>((R)0, (R)cn, bits_to_u<R>(stream_bits(key, ctr)));
+                ctr++;
+                if (idx >= cn) { status = AUVRRT_ST_KEY_ERROR; break; }
+                int ch = head[rb];
+                for (int hop = idx >> 5; hop > 0; hop--) ch = next[ch];
+                parent = pool[ch * 32 + (idx & 31)];
+            } else {                                                                    // :136-139, :505-513
+                R rx = uniform_ab<R>(env.minx, env.maxx, bits_to_u<R>(stream_bits(key, ctr)));
+                R ry = uniform_ab<R>(env.miny, env.maxy, bits_to_u<R>(stream_bits(key, ctr + 1)));
+                ctr += 4;
+                R bq = A::inf(), bs = A::inf();
+                int bi = 0;
+                for (int i = 0; i < n_nodes; i++) {
+                    R qq = A::sq2(A::sub(rx, nodes[i].x), A::sub(ry, nodes[i].y));
+                    if (qq < bq) {
+                        if (VERIFY) { R s = A::sqrt(qq); if (s < bs) { bs = s; bi = i; } }
+                        else bi = i;
+                        bq = qq;
+                    }
+                }
+                parent = bi;
+                if (nodes[parent].t > P.max_traj) continue;
+            }
+            // ---- steer (:237-295) with check_collision (:530-549) and the per-waypoint cost folded in
+            const NodeRow<R> pr = nodes[parent];
+            const uint32_t ctr0 = ctr;
+            const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, bits_to_u<R>(stream_bits(key, ctr))));
+            ctr++;
+            R x = pr.x, y = pr.y, th = pr.th, t = pr.t, len = pr.len;
+            R sin0 = 0, cos0 = 0;
+            if (VERIFY) A::sincos(th, &sin0, &cos0);
+            int nwp = 1;
+            bool bad = false, moved = false, degenerate = false;
+            R acc_s2 = 0; uint32_t acc_cnt = 0; unsigned long long acc_mask = 0;
+            R self_s2 = pr.self_s2; int self_hab = pr.self_hab;
+            bool last_is_wp = false;
+            {
+                const Cls pcl = env.classify(pr.x, pr.y);                                // path[0] = parent object
+                bad = !point_within_c<R>(env, pcl, pr.x, pr.y) || point_hits_circles_c<R>(env, pcl, pr.x, pr.y);
+            }
+            for (int k = 0; k < n_exp; k++) {
+                const R dist = uniform_ab<R>((R)0, sp.d2e, bits_to_u<R>(stream_bits(key, ctr)));
+                const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, bits_to_u<R>(stream_bits(key, ctr + 1)));
+                ctr += 2;
+                if (!(A::fabs(dist) > A::fabs(diff))) continue;
+                const R vt = uniform_ab<R>((R)0, sp.two_vel, bits_to_u<R>(stream_bits(key, ctr)));
+                ctr++;
+                R dx, dy, movement;
+                if (VERIFY) {
+                    R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
+                    if (den == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
+                    R radius = A::div(num, den), r2 = A::mul((R)2, radius);
+                    if (r2 == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
+                    th = A::add(th, A::div(num, r2));
+                    R s1v, c1v;
+                    A::sincos(th, &s1v, &c1v);
+                    dx = A::mul(radius, A::sub(s1v, sin0));
+                    dy = A::mul(radius, A::add(-c1v, cos0));
+                    sin0 = s1v; cos0 = c1v;
+                    movement = A::sqrt(A::sq2(dx, dy));
+                    if (vt == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
+                } else {
+                    if (diff == (R)0 || vt == (R)0) { degenerate = true; break; }
+                    const R phi = -diff;
+                    movement = dist * sinc_small((float)diff * 0.5f);
+                    R sm, cm;
+                    A::sincos(th + (R)0.5 * phi, &sm, &cm);
+                    th += phi;
+                    dx = movement * cm; dy = movement * sm;
+                }
+                x = A::add(x, dx); y = A::add(y, dy);
+                t = A::add(t, A::div(movement, vt));
+                len = A::add(len, movement);
+                moved = true;
+                last_is_wp = movement >= sp.min_dist;                                    // :283
+                if (last_is_wp) {
+                    nwp++;
+                    const Cls cl = env.classify(x, y);
+                    bad = bad || !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+                    Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, cl);
+                    R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+                    if (c.bin >= 0) {
+                        acc_s2 = A::add(acc_s2, ps2);
+                        if (c.hab >= 0) { acc_cnt++; acc_mask |= 1ull << c.hab; }
+                    }
+                    self_s2 = c.bin >= 0 ? ps2 : (R)0; self_hab = c.bin >= 0 ? c.hab : -1;   // provisional leaf state
+                }
+            }
+            if (status) break;
+            const bool safe = !(bad || degenerate);
+            n_waypoints += nwp; n_prims += n_exp;
+            if (P.trace) {
+                size_t r = (size_t)q * P.I + it;
+                tr.parent[r] = parent; tr.safe[r] = safe ? 1 : 0; tr.nwp[r] = nwp; tr.upos[r] = upos_mark;
+                R *lf = (R *)tr.leaf + 5 * r;
+                lf[0] = x; lf[1] = y; lf[2] = th; lf[3] = t; lf[4] = len;
+            }
+            if (safe) {
+                if (moved && !last_is_wp) {     // the leaf state is not one of the waypoints: evaluate it
+                    Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, env.classify(x, y));
+                    self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+                    self_hab = c.bin >= 0 ? c.hab : -1;
+                }
+                const int id = n_nodes++;                                               // :144-145
+                NodeRow<R> nr;
+                nr.x = x; nr.y = y; nr.th = th; nr.t = t; nr.len = len; nr.ctr = ctr0; nr.parent = parent; nr.pad_ = 0;
+                nr.s2 = A::add(A::add(pr.s2, pr.self_s2), acc_s2);
+                nr.cnt = pr.cnt + (pr.self_hab >= 0 ? 1u : 0u) + acc_cnt;
+                nr.mask = pr.mask | (pr.self_hab >= 0 ? (1ull << pr.self_hab) : 0ull) | acc_mask;
+                nr.self_s2 = self_s2; nr.self_hab = self_hab;
+                nodes[id] = nr;
+                // ---- time-bin insert                                                   :147-151
+                R fd = floordiv_pos<R>(t, P.bin_interval), fidx = fd + (R)1, curr_bin = A::mul(fidx, P.bin_interval);
+                int bidx = -1; bool reset = false;
+                if (curr_bin > P.max_traj) { if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; } }
+                else { if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else { status = AUVRRT_ST_KEY_ERROR; break; } }
+                if (bidx >= 0) {
+                    const int c_old = count[bidx];
+                    const bool reuse_head = reset && c_old > 0;
+                    const int c = reset ? 0 : c_old;
+                    if (reuse_head) tail[bidx] = head[bidx];
+                    if ((c & 31) == 0 && !reuse_head) {
+                        const int nc = n_chunks++;
+                        next[nc] = -1;
+                        if (c == 0) head[bidx] = nc; else next[tail[bidx]] = nc;
+                        tail[bidx] = nc;
+                    }
+                    pool[tail[bidx] * 32 + (c & 31)] = id;
+                    count[bidx] = c + 1;
+                }
+                if (t >= P.horizon) {                                                   // :158-171
+                    const uint32_t cnt = nr.cnt + (self_hab >= 0 ? 1u : 0u);
+                    const unsigned long long mk = nr.mask | (self_hab >= 0 ? (1ull << self_hab) : 0ull);
+                    R c1 = A::mul(P.w2, (R)cnt), c2 = A::add(nr.s2, self_s2), c0 = 0;
+                    if (t > (R)0) { c1 = A::div(c1, t); c2 = A::div(c2, t); }
+                    if (env.H != 0) c0 = A::div(A::mul(P.w1, (R)__popcll(mk)), (R)env.H);
+                    const R total = py_sum3p<R>(c0, c1, c2);
+                    n_cost_evals++;
+                    if (total < best_c0) {
+                        best_c0 = total; best_c1 = c0; best_c2 = c1; best_c3 = c2;
+                        best_node = id; best_iter = it; best_len = len; best_t = t;
+                    }
+                }
+            }
+            it++;
+            upos_mark = ctr;
+        }
+        if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
+        int depth = 0;
+        if (best_node >= 0) for (int n = best_node; nodes[n].parent >= 0; n = nodes[n].parent) depth++;
+        if (chain_out) {
+            uint32_t *chain = chain_out + (size_t)q * P.chain_cap;
+            if (depth > P.chain_cap && status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW;
+            int n = best_node;
+            for (int k = depth - 1; k >= 0; k--) { if (k < P.chain_cap) chain[k] = nodes[n].ctr; n = nodes[n].parent; }
+            for (int k = depth; k < P.chain_cap; k++) chain[k] = 0u;
+        }
+        auvrrt_plan_record_t rec;
+        rec.status = status; rec.n_nodes = n_nodes; rec.best_node = best_node; rec.best_iter = best_iter;
+        rec.depth = depth; rec.n_path = 0; rec.n_cost_evals = n_cost_evals; rec.n_waypoints = n_waypoints;
+        rec.n_uniforms = (long long)ctr; rec.n_primitives = n_prims;
+        rec.cost[0] = best_node >= 0 ? (double)best_c0 : 0.0; rec.cost[1] = (double)best_c1;
+        rec.cost[2] = (double)best_c2; rec.cost[3] = (double)best_c3;
+        rec.path_length = (double)best_len; rec.t_leaf = (double)best_t;
+        records[q] = rec;
+    }
+}
+
+template <typename R>
+int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
+                    const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
+                    auvrrt_plan_record_t *records, uint32_t *chain, const auvrrt_plan_trace_t *trace,
+                    cudaStream_t s, int64_t *need_bytes) {
+    PlanP<R> P;
+    int rc = make_planp<R>(env, p, &P);
+    if (rc) return rc;
+    EnvBlob<R> b = env_blob<R>(env);
+    int budget = 100 * 1024, sm = 16, mode = 0;
+    if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
+    else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
+    AUV_CUDA(cudaFuncSetAttribute(k_plan_tpt<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    int per_sm = 0, nsm = 0, dev = 0;
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan_tpt<R>, TPT_THREADS, sm));
+    if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan_tpt: kernel does not fit on an SM");
+    AUV_CUDA(cudaGetDevice(&dev));
+    AUV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    int grid = nsm * per_sm;
+    TptLayout L = make_tpt_layout<R>(P.cap, P.nb, P.nchunks);
+    // the workspace is sized for the full machine unless the batch (Q > 0) is smaller
+    if (Q > 0) {
+        int64_t blocks = (Q + TPT_THREADS - 1) / TPT_THREADS;
+        if (blocks < grid) grid = (int)blocks;
+    }
+    int64_t need = 256 + (int64_t)grid * TPT_THREADS * (int64_t)L.slot_bytes;
+    if (need_bytes) { *need_bytes = need; return AUVRRT_OK; }
+    if (Q <= 0) return AUVRRT_OK;
+    if (workspace_bytes < need) return set_err(AUVRRT_ERR_ARG, "plan_tpt: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    if (P.trace && !trace) return set_err(AUVRRT_ERR_ARG, "plan_tpt: trace requested without trace buffers");
+    AUV_CUDA(cudaMemsetAsync(workspace, 0, 256, s));
+    auvrrt_plan_trace_t tr;
+    if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
+    k_plan_tpt<R><<<grid, TPT_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+                                                (unsigned char *)workspace + 256, (unsigned long long *)workspace, records,
+                                                chain, tr);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(AUVRRT_ERR_CUDA, "plan_tpt launch: %s", cudaGetErrorString(e));
+    return AUVRRT_OK;
+}
+template int launch_plan_tpt<float>(const auvrrt_env *, const float *, const uint64_t *, int64_t, const auvrrt_plan_params_t *,
+                                    void *, int64_t, auvrrt_plan_record_t *, uint32_t *, const auvrrt_plan_trace_t *, cudaStream_t, int64_t *);
+template int launch_plan_tpt<double>(const auvrrt_env *, const double *, const uint64_t *, int64_t, const auvrrt_plan_params_t *,
+                                     void *, int64_t, auvrrt_plan_record_t *, uint32_t *, const auvrrt_plan_trace_t *, cudaStream_t, int64_t *);
+
+}  // namespace auv

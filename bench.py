@@ -164,7 +164,11 @@ def main():
     ap.add_argument("--group", type=int, default=32)
     ap.add_argument("--no-extras", action="store_true", help="skip micro-benchmarks / cpu baseline")
     ap.add_argument("--micro-edges", type=int, default=100_000_000)
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU (default: the configs[1] size, 4096)")
     args = ap.parse_args()
+    global Q_PER_GPU
+    if args.queries > 0:
+        Q_PER_GPU = args.queries
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -335,6 +339,23 @@ def extras(env, dev, args, api, adev):
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                           "algorithmic_bytes": "8 B per node per pass"}
     del tx, ty
+
+    # throughput planner (one thread per tree) at config-5 scale: 65536 queries resident on one GPU
+    try:
+        Qb = 65536
+        ppt = api.plan_params(ITERS, group=1)
+        st, sd = make_queries(0, Qb)
+        pl = adev.DevicePlanner(env, ppt, "f32", Qb, want_chain=True)
+        pl.set_queries(st, sd)
+        mean_s, min_s = timed(lambda: pl.launch(), reps=2, warm=1)
+        rec = pl.records_numpy()
+        out["throughput_planner_group1"] = {"queries": Qb, "iterations": ITERS, "edges_per_s": Qb * ITERS / mean_s,
+                                            "plans_per_s": Qb / mean_s, "seconds": mean_s,
+                                            "queries_ok": int((rec["status"] == 0).sum()), "kernel": "k_plan_tpt<float>"}
+        del pl
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["throughput_planner_group1"] = {"error": repr(ex)}
 
     # config 4: Dubins edges vs 500 synthetic circles, 20 waypoints per edge
     rs = np.random.RandomState(1234)

@@ -151,7 +151,8 @@ typedef struct {
     int32_t chain_cap;       /* max tree depth recorded per query (<= 255) */
     int32_t path_cap;        /* rows per query in out_path (0: no paths) */
     int32_t trace;           /* != 0: fill the per-iteration trace arrays (parity tests) */
-    int32_t group;           /* lanes cooperating on one tree: 32 (default when 0), 16 or 8 */
+    int32_t group;           /* lanes cooperating on one tree: 32 (default when 0), 16 or 8; 1 = one thread
+                                per tree, the throughput planner for >= 10^5 queries (no in-kernel paths) */
 } auvrrt_plan_params_t;
 
 /* one fixed-size record per query: the unit the multi-GPU gather moves */
@@ -189,6 +190,9 @@ int auvrrt_plan_batch(const auvrrt_env_t *env, const double *starts, const uint6
  * workspace from auvrrt_plan_workspace_bytes(); nothing is synchronised. */
 int64_t auvrrt_plan_workspace_bytes(const auvrrt_env_t *env, const auvrrt_plan_params_t *params,
                                     int precision);
+/* same, for a batch of at most Q queries (group == 1 sizes its workspace by the batch) */
+int64_t auvrrt_plan_workspace_bytes_q(const auvrrt_env_t *env, const auvrrt_plan_params_t *params,
+                                      int precision, int64_t Q);
 int auvrrt_plan_batch_dev(const auvrrt_env_t *env, const void *starts, const uint64_t *seeds,
                           int64_t Q, const auvrrt_plan_params_t *params, int precision,
                           void *workspace, int64_t workspace_bytes,

@@ -341,15 +341,22 @@ def _free_starts(oworld, n, seed, box=(-260, -140, -20, 60)):
 
 
 # ------------------------------------------------------------------------------------ planner
-def test_exploring_f64_traces_match_reference(api, env, exploring_golden):
+@pytest.mark.parametrize("group", [32, 1])
+def test_exploring_f64_traces_match_reference(api, env, exploring_golden, group):
+    """group 32: one warp per tree (plan.cu); group 1: one thread per tree (plan_tpt.cu)"""
     z, meta = exploring_golden
     for mode in ("A", "B"):
         for iters in sorted({m["iterations"] for m in meta if m["mode"] == mode}):
             ms = [m for m in meta if m["mode"] == mode and m["iterations"] == iters]
             starts = np.array([[m["start"][0], m["start"][1], 0.0, 0.0, 0.0] for m in ms])
             seeds = [m["seed"] for m in ms]
-            pp = api.plan_params(iters, mode=0 if mode == "A" else 1, trace=True, path_cap=1024, chain_cap=96)
+            pp = api.plan_params(iters, mode=0 if mode == "A" else 1, trace=True, path_cap=1024 if group == 32 else 0,
+                                 chain_cap=96, group=group)
             r = api.plan_batch(env, starts, seeds, pp, "f64")
+            if group == 1:      # the thread-per-tree planner ships chains; paths come from auvrrt_materialize
+                pp.path_cap = 1024
+                r["path"], n_path = api.materialize(env, starts, seeds, r["chain"], r["records"]["depth"], pp, "f64")
+                r["records"]["n_path"] = n_path
             for j, m in enumerate(ms):
                 tag = m["tag"]
                 rec, tr = r["records"][j], r["trace"]

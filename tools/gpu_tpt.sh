@@ -1,0 +1,13 @@
+#!/bin/bash
+python -m pytest tests/test_gpu_parity.py -q -k "traces_match" 2>&1 | tail -5
+for q in 4096 16384 65536 131072; do
+  python bench.py --steps 2 --warmup 1 --no-extras --group 1 --queries $q > /tmp/b.json 2>/tmp/b.err || tail -3 /tmp/b.err
+  python - "$q" <<'PY'
+import json, sys
+try:
+    d = json.loads(open('/tmp/b.json').read().strip().splitlines()[-1])
+    print("tpt Q", sys.argv[1], "edges/s %.4g" % d["value"], "ms/step %.2f" % d["ms_per_step"], "ok", d["queries_ok"], "e2e %.4g" % d["e2e"]["value"])
+except Exception as e:
+    print(sys.argv[1], "failed", e)
+PY
+done
