@@ -43,7 +43,15 @@ template <> struct Ar<float, false> {
     static __device__ __forceinline__ R div(R a, R b) { return __fdividef(a, b); }
     static __device__ __forceinline__ R sqrt(R a) { return sqrtf(a); }
     static __device__ __forceinline__ R sq2(R dx, R dy) { return fmaf(dy, dy, dx * dx); }
-    static __device__ __forceinline__ void sincos(R a, R *s, R *c) { sincosf(a, s, c); }
+    // fast build: two-term Cody-Waite reduction to [-pi, pi] (exact product for |a| < 2^10 * 2pi),
+    // then the MUFU sine / cosine (abs. error ~4e-7 on the reduced range): headings here are a few
+    // radians, so the error per arc primitive is < 1e-6 m, far inside the 1e-5 relative bar
+    static __device__ __forceinline__ void sincos(R a, R *s, R *c) {
+        const float k = rintf(a * 0.15915494309189535f);
+        float r = fmaf(k, -6.28318548202514648f, a);         // 2pi rounded to fp32 ...
+        r = fmaf(k, 1.74845553146951715e-7f, r);             // ... plus its rounding error
+        *s = __sinf(r); *c = __cosf(r);
+    }
     static __device__ __forceinline__ R floor(R a) { return floorf(a); }
     static __device__ __forceinline__ R fabs(R a) { return fabsf(a); }
     static __device__ __forceinline__ R fma(R a, R b, R c) { return fmaf(a, b, c); }

@@ -178,12 +178,12 @@ __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
 template <typename R>
 __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin_mask) {
     if (env.bins_uniform && bin_mask == 0xffffffffu) {
-        // contiguous sorted bins: the containing bins are adjacent; guess, then settle on the first
-        if (!(t >= env.b0[0]) || !(t <= env.b1[env.T - 1])) return -1;
+        // contiguous sorted bins: the containing bins are adjacent; guess (off by at most one), settle
+        // on the FIRST containing bin, verify with the reference's own comparisons
         int k = (int)((t - env.bin_s0) * env.bin_winv);
         k = k < 0 ? 0 : (k > env.T - 1 ? env.T - 1 : k);
-        while (k > 0 && t <= env.b1[k - 1]) k--;
-        while (k < env.T - 1 && t > env.b1[k]) k++;
+        if (k > 0 && t <= env.b1[k - 1]) k--;
+        else if (k < env.T - 1 && t > env.b1[k]) k++;
         return (t >= env.b0[k] && t <= env.b1[k]) ? k : -1;
     }
     for (int b = 0; b < env.T; b++) {

@@ -424,7 +424,9 @@ int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, i
                 const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
                 auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
                 cudaStream_t s) {
-    int G = p->group ? p->group : 32;
+    // group 0 = automatic: a warp per tree shortens the latency of a few thousand queries; from
+    // ~3x10^4 queries on, the queries themselves fill the machine and one thread per tree wins
+    int G = p->group ? p->group : ((Q >= 32768 && !(path && p->path_cap > 0)) ? 1 : 32);
     if (G == 1) {
         if (path && p->path_cap > 0) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: group 1 (thread per tree) writes no paths; use auvrrt_materialize");
         return launch_plan_tpt<R>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, trace, s, nullptr);
@@ -437,7 +439,7 @@ int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, i
 template <typename R>
 int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p, int64_t Q) {
     int64_t need = -1;
-    int G = p->group ? p->group : 32, rc;
+    int G = p->group ? p->group : (Q >= 32768 ? 1 : 32), rc;
     if (G == 1) rc = launch_plan_tpt<R>(env, nullptr, nullptr, Q, p, nullptr, 0, nullptr, nullptr, nullptr, 0, &need);
     else if (G == 32) rc = launch_plan_g<R, 32>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
     else if (G == 16) rc = launch_plan_g<R, 16>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);

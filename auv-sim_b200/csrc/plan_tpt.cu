@@ -15,7 +15,10 @@
 
 namespace auv {
 
-static const int TPT_THREADS = 128;
+static const int TPT_THREADS = 256;
+#ifndef AUV_TPT_MINB
+#define AUV_TPT_MINB 4
+#endif
 
 template <typename R> struct alignas(16) NodeRow {
     R x, y, th, t;
@@ -26,6 +29,15 @@ template <typename R> struct alignas(16) NodeRow {
     int self_hab;
     int pad_;
     unsigned long long mask;
+};
+
+// serial view of the counter stream: u_ctr, u_ctr+1, ... with the counter product kept incrementally
+template <typename R> struct SerialStream {
+    uint64_t z;        // key + (ctr) * golden: the next draw hashes z + golden
+    uint32_t ctr;
+    __device__ __forceinline__ void init(uint64_t key) { z = key; ctr = 0; }
+    __device__ __forceinline__ R next() { z += 0x9E3779B97F4A7C15ULL; ctr++; return bits_to_u<R>(mix64(z)); }
+    __device__ __forceinline__ void skip(uint32_t n) { z += (uint64_t)n * 0x9E3779B97F4A7C15ULL; ctr += n; }
 };
 
 struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count; };
@@ -42,7 +54,7 @@ template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchu
 }
 
 template <typename R>
-__global__ void __launch_bounds__(TPT_THREADS)
+__global__ void __launch_bounds__(TPT_THREADS, AUV_TPT_MINB)
 k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
            const uint64_t *seeds, long long Q, PlanP<R> P, TptLayout L, unsigned char *ws, unsigned long long *qcounter,
            auvrrt_plan_record_t *records, uint32_t *chain_out, auvrrt_plan_trace_t tr) {
@@ -67,7 +79,8 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
     for (;;) {
         const long long q = (long long)atomicAdd(qcounter, 1ull);
         if (q >= Q) break;
-        const uint64_t key = stream_key(seeds[q]);
+        SerialStream<R> rng;
+        rng.init(stream_key(seeds[q]));
         // ---- init                                                                   rrt_dubins.py:105-114
         for (int b = 0; b < P.nb + 2; b++) count[b] = 0;
         {
@@ -81,7 +94,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         }
         head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
         int n_nodes = 1, n_chunks = 1, status = AUVRRT_ST_OK;
-        uint32_t ctr = 0, upos_mark = 0;
+        uint32_t upos_mark = 0;
         int best_node = -1, best_iter = -1, n_cost_evals = 0, n_waypoints = 0;
         long long n_prims = 0;
         R best_c0 = A::inf(), best_c1 = 0, best_c2 = 0, best_c3 = 0, best_len = 0, best_t = 0;
@@ -94,23 +107,21 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
             if (P.mode == 0) {                                                          // :122-127
                 int rb, cn;
                 for (;;) {
-                    rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), bits_to_u<R>(stream_bits(key, ctr)));
-                    ctr++;
+                    rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), rng.next());
                     if (rb > P.nb || rb < 1) { status = AUVRRT_ST_KEY_ERROR; break; }
                     cn = count[rb];
                     if (cn > 0) break;
                 }
                 if (status) break;
-                int idx = (int)uniform_ab<R>((R)0, (R)cn, bits_to_u<R>(stream_bits(key, ctr)));
-                ctr++;
+                int idx = (int)uniform_ab<R>((R)0, (R)cn, rng.next());
                 if (idx >= cn) { status = AUVRRT_ST_KEY_ERROR; break; }
                 int ch = head[rb];
                 for (int hop = idx >> 5; hop > 0; hop--) ch = next[ch];
                 parent = pool[ch * 32 + (idx & 31)];
             } else {                                                                    // :136-139, :505-513
-                R rx = uniform_ab<R>(env.minx, env.maxx, bits_to_u<R>(stream_bits(key, ctr)));
-                R ry = uniform_ab<R>(env.miny, env.maxy, bits_to_u<R>(stream_bits(key, ctr + 1)));
-                ctr += 4;
+                R rx = uniform_ab<R>(env.minx, env.maxx, rng.next());
+                R ry = uniform_ab<R>(env.miny, env.maxy, rng.next());
+                rng.skip(2);                   // theta and size are drawn and never used
                 R bq = A::inf(), bs = A::inf();
                 int bi = 0;
                 for (int i = 0; i < n_nodes; i++) {
@@ -126,9 +137,8 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
             }
             // ---- steer (:237-295) with check_collision (:530-549) and the per-waypoint cost folded in
             const NodeRow<R> pr = nodes[parent];
-            const uint32_t ctr0 = ctr;
-            const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, bits_to_u<R>(stream_bits(key, ctr))));
-            ctr++;
+            const uint32_t ctr0 = rng.ctr;
+            const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
             R x = pr.x, y = pr.y, th = pr.th, t = pr.t, len = pr.len;
             R sin0 = 0, cos0 = 0;
             if (VERIFY) A::sincos(th, &sin0, &cos0);
@@ -142,12 +152,10 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 bad = !point_within_c<R>(env, pcl, pr.x, pr.y) || point_hits_circles_c<R>(env, pcl, pr.x, pr.y);
             }
             for (int k = 0; k < n_exp; k++) {
-                const R dist = uniform_ab<R>((R)0, sp.d2e, bits_to_u<R>(stream_bits(key, ctr)));
-                const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, bits_to_u<R>(stream_bits(key, ctr + 1)));
-                ctr += 2;
+                const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());
+                const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());
                 if (!(A::fabs(dist) > A::fabs(diff))) continue;
-                const R vt = uniform_ab<R>((R)0, sp.two_vel, bits_to_u<R>(stream_bits(key, ctr)));
-                ctr++;
+                const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());
                 R dx, dy, movement;
                 if (VERIFY) {
                     R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
@@ -246,7 +254,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 }
             }
             it++;
-            upos_mark = ctr;
+            upos_mark = rng.ctr;
         }
         if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
         int depth = 0;
@@ -261,7 +269,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         auvrrt_plan_record_t rec;
         rec.status = status; rec.n_nodes = n_nodes; rec.best_node = best_node; rec.best_iter = best_iter;
         rec.depth = depth; rec.n_path = 0; rec.n_cost_evals = n_cost_evals; rec.n_waypoints = n_waypoints;
-        rec.n_uniforms = (long long)ctr; rec.n_primitives = n_prims;
+        rec.n_uniforms = (long long)rng.ctr; rec.n_primitives = n_prims;
         rec.cost[0] = best_node >= 0 ? (double)best_c0 : 0.0; rec.cost[1] = (double)best_c1;
         rec.cost[2] = (double)best_c2; rec.cost[3] = (double)best_c3;
         rec.path_length = (double)best_len; rec.t_leaf = (double)best_t;

@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--group", type=int, default=32)
+    ap.add_argument("--group", type=int, default=0, help="lanes per tree: 0 auto, 32/16/8, 1 = thread per tree")
     ap.add_argument("--no-extras", action="store_true", help="skip micro-benchmarks / cpu baseline")
     ap.add_argument("--micro-edges", type=int, default=100_000_000)
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU (default: the configs[1] size, 4096)")
@@ -282,7 +282,7 @@ def main():
     peak = (cal_flops or FP32_NOMINAL_TFLOPS * 1e12) / 1e12
     ach = flop * world_size / per_launch_s / 1e12 / world_size
     line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None, "kernel": "k_plan<float,%d>" % args.group,
+                        "traffic": None, "kernel": ("k_plan_tpt<float>" if (args.group == 1 or (args.group == 0 and Q_PER_GPU >= 32768)) else "k_plan<float,%d>" % (args.group or 32)),
                         "peak_source": "FFMA calibration kernel measured live in this run" if cal_flops else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
                         "nominal_peak": FP32_NOMINAL_TFLOPS,
                         "algorithmic_flop_per_edge": flop / (len(rec) * ITERS), "sfu_per_edge": sfu / (len(rec) * ITERS),
@@ -342,16 +342,23 @@ def extras(env, dev, args, api, adev):
 
     # throughput planner (one thread per tree) at config-5 scale: 65536 queries resident on one GPU
     try:
-        Qb = 65536
+        Qb = 262144
         ppt = api.plan_params(ITERS, group=1)
         st, sd = make_queries(0, Qb)
         pl = adev.DevicePlanner(env, ppt, "f32", Qb, want_chain=True)
         pl.set_queries(st, sd)
         mean_s, min_s = timed(lambda: pl.launch(), reps=2, warm=1)
         rec = pl.records_numpy()
+        world, bins_, _ = load_world()
+        Wt, Pt = float(rec["n_waypoints"].sum()), float(rec["n_primitives"].sum())
+        acc = float((rec["n_nodes"] - 1).sum()) / (len(rec) * ITERS)
+        flop = 6 * Wt * 27 + 6 * Wt * 5 + 30 * Pt + acc * Wt * (2 * 10 + 2 * 35 + 6 * 10 + 3)
+        cal_t, _ = api.calibrate_fp32(dev.index, 8192)
         out["throughput_planner_group1"] = {"queries": Qb, "iterations": ITERS, "edges_per_s": Qb * ITERS / mean_s,
                                             "plans_per_s": Qb / mean_s, "seconds": mean_s,
-                                            "queries_ok": int((rec["status"] == 0).sum()), "kernel": "k_plan_tpt<float>"}
+                                            "queries_ok": int((rec["status"] == 0).sum()), "kernel": "k_plan_tpt<float>",
+                                            "achieved_tflops": flop / mean_s / 1e12, "frac_of_fp32_peak": flop / mean_s / cal_t,
+                                            "note": "config-5 scale on one GPU: one thread per tree"}
         del pl
         torch.cuda.empty_cache()
     except Exception as ex:
@@ -375,13 +382,21 @@ def extras(env, dev, args, api, adev):
     del ang, dist_
     safe = torch.zeros(ne, dtype=torch.uint8, device=dev); word = torch.zeros(ne, dtype=torch.uint8, device=dev)
     length = torch.zeros(ne, device=dev)
-    mean_s, min_s = timed(lambda: adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32"), reps=3, warm=1)
     flop_edge = 6 * 20 * K + 6 * 20 * 5 + 140 + 24 * 20
     cal, _ = api.calibrate_fp32(dev.index, 8192)
+    os.environ["AUVRRT_EDGES_BRUTE"] = "1"       # all-pairs kernel: the algorithmic-FLOP roofline measurement
+    mean_s, min_s = timed(lambda: adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32"), reps=3, warm=1)
+    safe_brute = safe.clone()
     out["micro_config4"] = {"edges": ne, "circles": K, "waypoints": 20, "edges_per_s": ne / mean_s,
                             "algorithmic_flop_per_edge": flop_edge, "achieved_tflops": ne * flop_edge / mean_s / 1e12,
                             "fp32_peak_tflops_calibrated": cal / 1e12, "frac": ne * flop_edge / mean_s / cal,
-                            "safe_fraction": float(safe.float().mean().item()), "kernel": "k_edges_dubins<float,20>"}
+                            "safe_fraction": float(safe.float().mean().item()), "kernel": "k_edges_dubins<float,20> (all pairs)"}
+    os.environ["AUVRRT_EDGES_BRUTE"] = "0"       # broad-phase cull through the classification grid: same booleans
+    mean_c, _ = timed(lambda: adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32"), reps=3, warm=1)
+    out["micro_config4_culled"] = {"edges": ne, "edges_per_s": ne / mean_c, "kernel": "k_edges_dubins_culled<float>",
+                                   "identical_booleans": bool(torch.equal(safe, safe_brute)),
+                                   "equivalent_all_pairs_tflops": ne * flop_edge / mean_c / 1e12,
+                                   "note": "same results as the all-pairs kernel; the grid skips circles that cannot touch a waypoint's cell"}
     del q0, q1, safe, word, length
     return out
 
