@@ -368,21 +368,59 @@ __global__ void __launch_bounds__(256) k_edges_dubins(const unsigned char *blob,
                 if (k < W - 1) smp.at(A::mul((R)k, step), wx[k], wy[k], th);
                 else { wx[k] = b[0]; wy[k] = b[1]; }       // k == W-1 is `to`; k >= W duplicates it
             }
-            bool hit = false;
-            for (int c = 0; c < env.K; c++) {
-                R ccx = env.cx[c], ccy = env.cy[c];
-                R q = A::inf();
-#pragma unroll
-                for (int k = 0; k < WT; k++) {
-                    R qq = A::sq2(A::sub(wx[k], ccx), A::sub(wy[k], ccy));
-                    q = qq < q ? qq : q;
-                }
-                if (VERIFY) hit = hit || (A::sqrt(q) <= env.creff[c]);
-                else hit = hit || (q <= env.creff2[c]);
-            }
-            bool in = true;
+            bool in = true;             // polygon first: the fast circle loop below re-centres wx / wy in place
 #pragma unroll
             for (int k = 0; k < WT; k++) in = in && point_within<R>(env, wx[k], wy[k]);
+            bool hit = false;
+            if (VERIFY) {
+                for (int c = 0; c < env.K; c++) {
+                    R ccx = env.cx[c], ccy = env.cy[c];
+                    R q = A::inf();
+#pragma unroll
+                    for (int k = 0; k < WT; k++) {
+                        R qq = A::sq2(A::sub(wx[k], ccx), A::sub(wy[k], ccy));
+                        q = qq < q ? qq : q;
+                    }
+                    hit = hit || (A::sqrt(q) <= env.creff[c]);
+                }
+            } else {
+                // fast build: |p - c|^2 = |p|^2 - 2 p.c + |c|^2 in coordinates relative to the edge's first
+                // waypoint: 2 FFMA + 1 FMNMX per (waypoint, circle) instead of 2 FADD + FMUL + FFMA + FMNMX.
+                // The expansion cancels, so a result within `guard` of the decision is re-evaluated with
+                // the direct formula (far circles never get there: their |c|^2 dwarfs r^2).
+                const R ox = wx[0], oy = wy[0];
+                R pp[WT], ppmax = (R)0;
+#pragma unroll
+                for (int k = 0; k < WT; k++) {
+                    wx[k] -= ox; wy[k] -= oy;
+                    pp[k] = fmaf(wy[k], wy[k], wx[k] * wx[k]);
+                    ppmax = fmaxf(ppmax, pp[k]);
+                }
+                for (int c = 0; c < env.K; c++) {
+                    const R cxr = env.cx[c] - ox, cyr = env.cy[c] - oy;
+                    const R cc = fmaf(cyr, cyr, cxr * cxr), m2x = (R)-2 * cxr, m2y = (R)-2 * cyr;
+                    R qa = A::inf(), qb = A::inf(), qc = A::inf(), qd4 = A::inf();    // 4 independent min chains
+#pragma unroll
+                    for (int k = 0; k < WT; k += 4) {
+                        qa = fminf(qa, fmaf(m2y, wy[k], fmaf(m2x, wx[k], pp[k])));
+                        if (k + 1 < WT) qb = fminf(qb, fmaf(m2y, wy[k + 1], fmaf(m2x, wx[k + 1], pp[k + 1])));
+                        if (k + 2 < WT) qc = fminf(qc, fmaf(m2y, wy[k + 2], fmaf(m2x, wx[k + 2], pp[k + 2])));
+                        if (k + 3 < WT) qd4 = fminf(qd4, fmaf(m2y, wy[k + 3], fmaf(m2x, wx[k + 3], pp[k + 3])));
+                    }
+                    const R q = fminf(fminf(qa, qb), fminf(qc, qd4));
+                    const R d2 = q + cc, r2 = env.creff2[c];
+                    const R guard = (R)4e-6 * (cc + ppmax);
+                    if (d2 <= r2 + guard) {
+                        if (d2 < r2 - guard) hit = true;
+                        else {                                   // too close to call: direct formula
+                            R qd = A::inf();
+#pragma unroll
+                            for (int k = 0; k < WT; k++) qd = fminf(qd, A::sq2(wx[k] - cxr, wy[k] - cyr));
+                            hit = hit || (qd <= r2);
+                        }
+                    }
+                }
+            }
             ok = !hit && in;
         }
         safe[i] = ok ? 1 : 0;
@@ -534,12 +572,14 @@ __global__ void __launch_bounds__(256) k_nn_partial(const R *__restrict__ tx, co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q0 = 0; q0 < nq; q0 += NN_QT) {
         double qxs[NN_QT], qys[NN_QT];
+        float qxf[NN_QT], qyf[NN_QT], thr[NN_QT];
         NNBest best[NN_QT];
 #pragma unroll
         for (int j = 0; j < NN_QT; j++) {
             int qi = min(q0 + j, nq - 1);
             qxs[j] = (double)qx[qi]; qys[j] = (double)qy[qi];
             best[j].s = __longlong_as_double(0x7ff0000000000000LL); best[j].q = best[j].s; best[j].i = 0x7fffffffffffffffLL;
+            qxf[j] = (float)qxs[j]; qyf[j] = (float)qys[j]; thr[j] = __int_as_float(0x7f800000);
         }
         // 4 consecutive nodes per thread per 16-byte load (fp32), NN_UNROLL independent loads per
         // array in flight per thread: the scan is HBM-bound, so memory-level parallelism is what counts
@@ -571,8 +611,20 @@ __global__ void __launch_bounds__(256) k_nn_partial(const R *__restrict__ tx, co
 #pragma unroll
                     for (int e = 0; e < 4; e++)
 #pragma unroll
-                        for (int j = 0; j < NN_QT; j++)
-                            nn_consider(best[j], __dsub_rn(qxs[j], (double)xs[u][e]), __dsub_rn(qys[j], (double)ys[u][e]), 4 * v + e);
+                        for (int j = 0; j < NN_QT; j++) {
+                            if (sizeof(R) == 4) {
+                                // fp32 filter in front of the exact fp64 evaluation: q32 is within 3e-7 relative
+                                // of the exact q, thr[j] >= 1.000001 * best exact q, so q32 > thr cannot win or tie
+                                const float fx = qxf[j] - (float)xs[u][e], fy = qyf[j] - (float)ys[u][e];
+                                const float q32 = fmaf(fy, fy, fx * fx);
+                                if (q32 <= thr[j]) {
+                                    nn_consider(best[j], __dsub_rn(qxs[j], (double)xs[u][e]), __dsub_rn(qys[j], (double)ys[u][e]), 4 * v + e);
+                                    thr[j] = __double2float_ru(best[j].q * 1.000001);
+                                }
+                            } else {
+                                nn_consider(best[j], __dsub_rn(qxs[j], (double)xs[u][e]), __dsub_rn(qys[j], (double)ys[u][e]), 4 * v + e);
+                            }
+                        }
                 }
             }
         }

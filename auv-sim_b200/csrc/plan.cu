@@ -18,6 +18,7 @@
 // `initial` the planner's bin filter (rrt_dubins.py:161-166) never changes a waypoint's first-match
 // bin (every waypoint time lies in [t_initial, t_leaf]).  Totals equal the reference's up to
 // summation order (fp64: <= 1e-12 relative).
+#include <stdlib.h>
 #include "plan_common.cuh"
 
 namespace auv {
@@ -33,7 +34,8 @@ namespace auv {
 
 static const int PLAN_THREADS = 256;
 #ifndef AUV_PLAN_MINB
-#define AUV_PLAN_MINB 2      // resident CTAs per SM the register allocation targets
+#define AUV_PLAN_MINB 4      // resident CTAs per SM the fp32 register allocation targets: 4 x 8 warps hold all
+                             // 4096 trees of config 2 in ONE wave (measured 20.5 ms vs 22.4 ms at 2)
 #endif
 
 struct WsLayout {
@@ -70,8 +72,12 @@ template <typename R> struct Tree {
     }
 };
 
-template <typename R, int G>
-__global__ void __launch_bounds__(PLAN_THREADS, AUV_PLAN_MINB)
+// BS: keep the per-bin metadata (count / head chunk / tail chunk) of the group's tree in shared
+// memory as u16 (needs <= 126 time bins and <= 65535 nodes / chunks): the rejection loop of the
+// parent pick reads count[bin] once per draw, so this takes a global round trip off every draw.
+#define AUV_BINS_SMEM 128
+template <typename R, int G, bool BS>
+__global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
@@ -79,6 +85,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     const bool VERIFY = Policy<R>::VERIFY;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ GroupScratch<R, G> scratch[PLAN_THREADS / G];
+    __shared__ unsigned short binmeta[BS ? PLAN_THREADS / G : 1][3][BS ? AUV_BINS_SMEM : 1];
     EnvView<R> env;
     {
         if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
@@ -94,6 +101,14 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     const int slot = blockIdx.x * (PLAN_THREADS / G) + threadIdx.x / G;
     Tree<R> T;
     T.bind(ws + (size_t)slot * L.slot_bytes, L);
+    unsigned short *s_count = binmeta[BS ? threadIdx.x / G : 0][0], *s_head = binmeta[BS ? threadIdx.x / G : 0][1],
+                   *s_tail = binmeta[BS ? threadIdx.x / G : 0][2];
+#define BIN_COUNT(b) (BS ? (int)s_count[b] : T.count[b])
+#define BIN_HEAD(b) (BS ? (int)s_head[b] : T.head[b])
+#define BIN_TAIL(b) (BS ? (int)s_tail[b] : T.tail[b])
+#define SET_BIN_COUNT(b, v) do { if (BS) s_count[b] = (unsigned short)(v); else T.count[b] = (v); } while (0)
+#define SET_BIN_HEAD(b, v) do { if (BS) s_head[b] = (unsigned short)(v); else T.head[b] = (v); } while (0)
+#define SET_BIN_TAIL(b, v) do { if (BS) s_tail[b] = (unsigned short)(v); else T.tail[b] = (v); } while (0)
 
     for (;;) {
         long long q = 0;
@@ -106,7 +121,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         const R sx = starts[5 * q], sy = starts[5 * q + 1], sth = starts[5 * q + 2], st = starts[5 * q + 3],
                 slen = starts[5 * q + 4];
         // ---- init: mps_list = [initial]; time_bin[bin_interval] = [initial]        rrt_dubins.py:105-114
-        for (int b = g.gl; b < P.nb + 2; b += G) T.count[b] = 0;
+        for (int b = g.gl; b < P.nb + 2; b += G) SET_BIN_COUNT(b, 0);
         if (g.gl == 0) {
             T.x[0] = sx; T.y[0] = sy; T.th[0] = sth; T.t[0] = st; T.len[0] = slen;
             T.parent[0] = -1; T.ctr[0] = 0; T.s2[0] = (R)0; T.cnt[0] = 0; T.mask[0] = 0ull;
@@ -115,7 +130,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             T.self_hab[0] = c.bin >= 0 ? c.hab : -1;
         }
         g.sync();
-        if (g.gl == 0) { T.head[1] = 0; T.tail[1] = 0; T.count[1] = 1; T.pool[0] = 0; T.next[0] = -1; }
+        if (g.gl == 0) { SET_BIN_HEAD(1, 0); SET_BIN_TAIL(1, 0); SET_BIN_COUNT(1, 1); T.pool[0] = 0; T.next[0] = -1; }
         g.sync();
         int n_nodes = 1, n_chunks = 1;
         uint32_t ctr = 0, upos_mark = 0;
@@ -137,7 +152,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     R u = rng.u(ctr + (uint32_t)g.gl);
                     int rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), u);
                     bool ke = rb > P.nb || rb < 1;
-                    int cn = ke ? 0 : T.count[rb];
+                    int cn = ke ? 0 : BIN_COUNT(rb);
                     unsigned m = g.ballot(ke || cn > 0);
                     if (m) {
                         int f = __ffs(m) - 1;
@@ -152,7 +167,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 ctr += 1;
                 int idx = (int)uniform_ab<R>((R)0, (R)bincnt, u);
                 if (idx >= bincnt) { status = AUVRRT_ST_KEY_ERROR; break; }
-                int ch = T.head[ran_bin];
+                int ch = BIN_HEAD(ran_bin);
                 for (int hop = idx >> 5; hop > 0; hop--) ch = T.next[ch];
                 parent = T.pool[ch * 32 + (idx & 31)];
             } else {
@@ -223,21 +238,22 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                         if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else status = AUVRRT_ST_KEY_ERROR;
                     }
                     if (bidx >= 0) {
-                        const int c_old = T.count[bidx];
+                        const int c_old = BIN_COUNT(bidx);
                         const bool reuse_head = reset && c_old > 0;
                         const int c = reset ? 0 : c_old;
                         const bool alloc = ((c & 31) == 0) && !reuse_head;
                         const int nc = n_chunks;
                         if (alloc) n_chunks++;
                         if (g.gl == 0) {
-                            if (reuse_head) T.tail[bidx] = T.head[bidx];
+                            int tl = reuse_head ? BIN_HEAD(bidx) : BIN_TAIL(bidx);
                             if (alloc) {
                                 T.next[nc] = -1;
-                                if (c == 0) T.head[bidx] = nc; else T.next[T.tail[bidx]] = nc;
-                                T.tail[bidx] = nc;
+                                if (c == 0) SET_BIN_HEAD(bidx, nc); else T.next[tl] = nc;
+                                tl = nc;
                             }
-                            T.pool[T.tail[bidx] * 32 + (c & 31)] = id;
-                            T.count[bidx] = c + 1;
+                            SET_BIN_TAIL(bidx, tl);
+                            T.pool[tl * 32 + (c & 31)] = id;
+                            SET_BIN_COUNT(bidx, c + 1);
                         }
                     }
                 }
@@ -371,15 +387,18 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <typename R, int G> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
+template <typename R, int G, bool BS> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
     EnvBlob<R> b = env_blob<R>(env);
-    int budget = 110 * 1024;     // leaves room for 2 CTAs per SM
+    // only the small hot part of the world model is staged in shared memory when it is tight: with 4
+    // CTAs per SM the probability table (39 KB for Catalina) is better served by the larger L1
+    int budget = sizeof(R) == 4 ? 24 * 1024 : 110 * 1024;
+    if (const char *ev = getenv("AUVRRT_PLAN_STAGE_KB")) budget = atoi(ev) * 1024;
     int sm = 16, mode = 0;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
-    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G>, PLAN_THREADS, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS>, PLAN_THREADS, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan: kernel does not fit on an SM (smem %d)", sm);
     int nsm = 0, dev = 0;
     AUV_CUDA(cudaGetDevice(&dev));
@@ -388,8 +407,8 @@ template <typename R, int G> static int plan_geometry(const auvrrt_env *env, int
     return AUVRRT_OK;
 }
 
-template <typename R, int G>
-static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
+template <typename R, int G, bool BS>
+static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
                          const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
                          auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
                          cudaStream_t s, int64_t *need_bytes) {
@@ -397,7 +416,7 @@ static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t 
     int rc = make_planp<R>(env, p, &P);
     if (rc) return rc;
     int grid, smem, mode;
-    rc = plan_geometry<R, G>(env, &grid, &smem, &mode);
+    rc = plan_geometry<R, G, BS>(env, &grid, &smem, &mode);
     if (rc) return rc;
     WsLayout L = make_layout<R>(P.cap, P.nb, P.nchunks);
     const int gpc = PLAN_THREADS / G;
@@ -412,11 +431,22 @@ static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t 
     auvrrt_plan_trace_t tr;
     if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
     EnvBlob<R> b = env_blob<R>(env);
-    k_plan<R, G><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+    k_plan<R, G, BS><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
                                                   (unsigned char *)workspace + 256, (unsigned long long *)workspace,
                                                   records, chain, path, tr);
     AUV_LAUNCH_CHECK2();
     return AUVRRT_OK;
+}
+
+template <typename R, int G>
+static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
+                         const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
+                         auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
+                         cudaStream_t s, int64_t *need_bytes) {
+    const double nb = ceil(p->max_traj_time / p->bin_interval);
+    const bool bs = nb + 2 <= AUV_BINS_SMEM && p->iterations < 65000 && !getenv("AUVRRT_PLAN_BINS_GLOBAL");
+    if (bs) return launch_plan_gb<R, G, true>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes);
+    return launch_plan_gb<R, G, false>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes);
 }
 
 template <typename R>

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""small driver for profiling the micro-kernels: python tools/micro_run.py [edges|nn] [n]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "auv-sim_b200"))
+import bench  # noqa
+from auvrrt import api, device as adev  # noqa
+
+what = sys.argv[1] if len(sys.argv) > 1 else "edges"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
+dev = torch.device("cuda", 0)
+if what == "edges":
+    rs = np.random.RandomState(1234)
+    K = 500
+    circles = np.stack([rs.uniform(-467.4, 82.4, K), rs.uniform(-153.5, 191.2, K), rs.uniform(1, 5, K)], 1)
+    world, _, _ = bench.load_world()
+    env4 = api.Env(circles=circles, boundary=world["boundary"])
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    q0 = torch.stack([torch.rand(n, device=dev, generator=g) * 549.8 - 467.4, torch.rand(n, device=dev, generator=g) * 344.7 - 153.5,
+                      (torch.rand(n, device=dev, generator=g) * 2 - 1) * np.pi], 1).contiguous()
+    ang = (torch.rand(n, device=dev, generator=g) * 2 - 1) * np.pi
+    dist_ = torch.rand(n, device=dev, generator=g) * 38 + 2
+    q1 = torch.stack([q0[:, 0] + dist_ * torch.cos(ang), q0[:, 1] + dist_ * torch.sin(ang),
+                      (torch.rand(n, device=dev, generator=g) * 2 - 1) * np.pi], 1).contiguous()
+    safe = torch.zeros(n, dtype=torch.uint8, device=dev); word = torch.zeros(n, dtype=torch.uint8, device=dev)
+    length = torch.zeros(n, device=dev)
+    for _ in range(3):
+        adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32")
+    torch.cuda.synchronize()
+else:
+    tx = torch.rand(n, device=dev) * 550 - 467; ty = torch.rand(n, device=dev) * 345 - 153
+    qx = torch.tensor([-200.0], device=dev); qy = torch.tensor([0.0], device=dev)
+    idx = torch.zeros(1, dtype=torch.int32, device=dev); scr = adev.nn_scratch(1, dev)
+    for _ in range(3):
+        adev.nn_dev(tx, ty, qx, qy, idx, scr, "f32")
+    torch.cuda.synchronize()
+print("done")
