@@ -40,18 +40,15 @@ static const int PLAN_THREADS = 256;
 
 struct WsLayout {
     size_t slot_bytes;
-    size_t x, y, th, t, len, s2, self_s2, ctr, parent, cnt, mask, self_hab, pool, next, head, tail, count;
+    size_t rows, xy, pool, next, head, tail, count;
 };
 
 template <typename R> static WsLayout make_layout(int cap, int nb, int nchunks) {
     WsLayout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~(size_t)127; return r; };
-    L.x = take(sizeof(R) * cap); L.y = take(sizeof(R) * cap); L.th = take(sizeof(R) * cap);
-    L.t = take(sizeof(R) * cap); L.len = take(sizeof(R) * cap); L.s2 = take(sizeof(R) * cap);
-    L.self_s2 = take(sizeof(R) * cap);
-    L.ctr = take(4 * (size_t)cap); L.parent = take(4 * (size_t)cap); L.cnt = take(4 * (size_t)cap);
-    L.mask = take(8 * (size_t)cap); L.self_hab = take(4 * (size_t)cap);
+    L.rows = take(sizeof(NodeRow<R>) * (size_t)cap);
+    L.xy = take(2 * sizeof(R) * (size_t)cap);                 // SoA copy of (x, y) for the nearest-node scan
     L.pool = take(4 * 32 * (size_t)nchunks); L.next = take(4 * (size_t)nchunks);
     L.head = take(4 * (size_t)(nb + 2)); L.tail = take(4 * (size_t)(nb + 2)); L.count = take(4 * (size_t)(nb + 2));
     L.slot_bytes = o;
@@ -59,14 +56,12 @@ template <typename R> static WsLayout make_layout(int cap, int nb, int nchunks) 
 }
 
 template <typename R> struct Tree {
-    R *x, *y, *th, *t, *len, *s2, *self_s2;
-    uint32_t *ctr; int *parent; uint32_t *cnt; unsigned long long *mask; int *self_hab;
+    NodeRow<R> *row;
+    R *nx, *ny;            // coalesced x[] / y[] for RRT.get_closest_mps (mode 1)
     int *pool, *next, *head, *tail, *count;
-    __device__ __forceinline__ void bind(unsigned char *b, const WsLayout &L) {
-        x = (R *)(b + L.x); y = (R *)(b + L.y); th = (R *)(b + L.th); t = (R *)(b + L.t); len = (R *)(b + L.len);
-        s2 = (R *)(b + L.s2); self_s2 = (R *)(b + L.self_s2);
-        ctr = (uint32_t *)(b + L.ctr); parent = (int *)(b + L.parent); cnt = (uint32_t *)(b + L.cnt);
-        mask = (unsigned long long *)(b + L.mask); self_hab = (int *)(b + L.self_hab);
+    __device__ __forceinline__ void bind(unsigned char *b, const WsLayout &L, int cap) {
+        row = (NodeRow<R> *)(b + L.rows);
+        nx = (R *)(b + L.xy); ny = nx + cap;
         pool = (int *)(b + L.pool); next = (int *)(b + L.next);
         head = (int *)(b + L.head); tail = (int *)(b + L.tail); count = (int *)(b + L.count);
     }
@@ -100,7 +95,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
     const int slot = blockIdx.x * (PLAN_THREADS / G) + threadIdx.x / G;
     Tree<R> T;
-    T.bind(ws + (size_t)slot * L.slot_bytes, L);
+    T.bind(ws + (size_t)slot * L.slot_bytes, L, P.cap);
     unsigned short *s_count = binmeta[BS ? threadIdx.x / G : 0][0], *s_head = binmeta[BS ? threadIdx.x / G : 0][1],
                    *s_tail = binmeta[BS ? threadIdx.x / G : 0][2];
 #define BIN_COUNT(b) (BS ? (int)s_count[b] : T.count[b])
@@ -123,11 +118,14 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         // ---- init: mps_list = [initial]; time_bin[bin_interval] = [initial]        rrt_dubins.py:105-114
         for (int b = g.gl; b < P.nb + 2; b += G) SET_BIN_COUNT(b, 0);
         if (g.gl == 0) {
-            T.x[0] = sx; T.y[0] = sy; T.th[0] = sth; T.t[0] = st; T.len[0] = slen;
-            T.parent[0] = -1; T.ctr[0] = 0; T.s2[0] = (R)0; T.cnt[0] = 0; T.mask[0] = 0ull;
+            NodeRow<R> r0;
+            r0.x = sx; r0.y = sy; r0.th = sth; r0.t = st; r0.len = slen;
+            r0.parent = -1; r0.ctr = 0; r0.s2 = (R)0; r0.cnt = 0; r0.mask = 0ull; r0.pad_ = 0;
             Contrib c = point_contrib<R>(env, sx, sy, st, 0xffffffffu, env.H, env.classify(sx, sy));
-            T.self_s2[0] = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
-            T.self_hab[0] = c.bin >= 0 ? c.hab : -1;
+            r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+            r0.self_hab = c.bin >= 0 ? c.hab : -1;
+            T.row[0] = r0;
+            if (P.mode == 1) { T.nx[0] = sx; T.ny[0] = sy; }
         }
         g.sync();
         if (g.gl == 0) { SET_BIN_HEAD(1, 0); SET_BIN_TAIL(1, 0); SET_BIN_COUNT(1, 1); T.pool[0] = 0; T.next[0] = -1; }
@@ -178,7 +176,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 R bq = A::inf(), bs = A::inf();
                 int bi = 0x7fffffff;
                 for (int i = g.gl; i < n_nodes; i += G) {
-                    R qq = A::sq2(A::sub(rx, T.x[i]), A::sub(ry, T.y[i]));
+                    R qq = A::sq2(A::sub(rx, T.nx[i]), A::sub(ry, T.ny[i]));
                     if (qq < bq) {
                         if (VERIFY) { R s = A::sqrt(qq); if (s < bs) { bs = s; bi = i; } }
                         else { bs = qq; bi = i; }
@@ -192,10 +190,11 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
                 }
                 parent = bi;
-                if (T.t[parent] > P.max_traj) continue;                                    // :138-139
+                if (T.row[parent].t > P.max_traj) continue;                               // :138-139
             }
             // ---- steer + check_collision + per-waypoint cost                              :141-143
-            const R ppx = T.x[parent], ppy = T.y[parent], ppth = T.th[parent], ppt = T.t[parent], pplen = T.len[parent];
+            const NodeRow<R> pr = T.row[parent];           // every lane reads the same row: broadcast
+            const R ppx = pr.x, ppy = pr.y, ppth = pr.th, ppt = pr.t, pplen = pr.len;
             const uint32_t ctr0 = ctr;
             EdgeOut<R> o;
             eval_edge<R, G, true, true, false>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
@@ -214,16 +213,18 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 R pre_s2 = 0, self_s2n = 0;
                 uint32_t pre_cnt = 0; unsigned long long pre_mask = 0; int self_habn = -1;
                 if (g.gl == 0) {
-                    const int ph = T.self_hab[parent];
-                    pre_s2 = A::add(A::add(T.s2[parent], T.self_s2[parent]), o.s2);
-                    pre_cnt = T.cnt[parent] + (ph >= 0 ? 1u : 0u) + o.cnt;
-                    pre_mask = T.mask[parent] | (ph >= 0 ? (1ull << ph) : 0ull) | o.mask;
-                    self_s2n = o.leaf_moved ? o.self_s2 : T.self_s2[parent];
+                    const int ph = pr.self_hab;
+                    pre_s2 = A::add(A::add(pr.s2, pr.self_s2), o.s2);
+                    pre_cnt = pr.cnt + (ph >= 0 ? 1u : 0u) + o.cnt;
+                    pre_mask = pr.mask | (ph >= 0 ? (1ull << ph) : 0ull) | o.mask;
+                    self_s2n = o.leaf_moved ? o.self_s2 : pr.self_s2;
                     self_habn = o.leaf_moved ? o.self_hab : ph;
-                    T.x[id] = o.x; T.y[id] = o.y; T.th[id] = o.th; T.t[id] = o.t; T.len[id] = o.len;
-                    T.parent[id] = parent; T.ctr[id] = ctr0;
-                    T.s2[id] = pre_s2; T.cnt[id] = pre_cnt; T.mask[id] = pre_mask;
-                    T.self_s2[id] = self_s2n; T.self_hab[id] = self_habn;
+                    NodeRow<R> nr;
+                    nr.x = o.x; nr.y = o.y; nr.th = o.th; nr.t = o.t; nr.len = o.len; nr.parent = parent; nr.ctr = ctr0;
+                    nr.s2 = pre_s2; nr.cnt = pre_cnt; nr.mask = pre_mask; nr.self_s2 = self_s2n; nr.self_hab = self_habn;
+                    nr.pad_ = 0;
+                    T.row[id] = nr;
+                    if (P.mode == 1) { T.nx[id] = o.x; T.ny[id] = o.y; }
                 }
                 // ---- time-bin insert (decision is group-uniform, lane 0 writes)            :147-151
                 {
@@ -291,41 +292,42 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         if (best_node < 0 && chain_out)
             for (int k = g.gl; k < P.chain_cap; k += G) chain_out[(size_t)q * P.chain_cap + k] = 0u;
         if (best_node >= 0) {
-            for (int n = best_node; T.parent[n] >= 0; n = T.parent[n]) depth++;
+            for (int n = best_node; T.row[n].parent >= 0; n = T.row[n].parent) depth++;
             uint32_t *chain = chain_out ? chain_out + (size_t)q * P.chain_cap : nullptr;
             if (depth > P.chain_cap && chain) { if (status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW; }
             if (chain && g.gl == 0) {
                 int n = best_node;
-                for (int k = depth - 1; k >= 0; k--) { if (k < P.chain_cap) chain[k] = (uint32_t)n; n = T.parent[n]; }
+                for (int k = depth - 1; k >= 0; k--) { if (k < P.chain_cap) chain[k] = (uint32_t)n; n = T.row[n].parent; }
             }
             g.sync();
             if (path_out && P.path_cap > 0 && chain && depth <= P.chain_cap) {
                 R *rows = path_out + (size_t)q * P.path_cap * 6;
                 for (int e = 0; e < depth; e++) {
-                    const int id = (int)chain[e], par = T.parent[id];
+                    const int id = (int)chain[e];
+                    const NodeRow<R> pn = T.row[T.row[id].parent];
                     if (g.gl == 0 && n_path < P.path_cap) {
                         R *w = rows + 6 * (size_t)n_path;
-                        w[0] = T.x[par]; w[1] = T.y[par]; w[2] = T.th[par]; w[3] = (R)0; w[4] = T.t[par]; w[5] = T.len[par];
+                        w[0] = pn.x; w[1] = pn.y; w[2] = pn.th; w[3] = (R)0; w[4] = pn.t; w[5] = pn.len;
                     }
                     n_path++;
                     EdgeOut<R> o;
                     int room = P.path_cap - n_path; if (room < 0) room = 0;
-                    eval_edge<R, G, false, false, true>(g, sc, env, rng, T.ctr[id], P.sp, T.x[par], T.y[par], T.th[par],
-                                                        T.t[par], T.len[par], (R)0, 0,
+                    eval_edge<R, G, false, false, true>(g, sc, env, rng, T.row[id].ctr, P.sp, pn.x, pn.y, pn.th,
+                                                        pn.t, pn.len, (R)0, 0,
                                                         rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0), room, o);
                     n_path += o.nwp - 1;
                 }
                 if (g.gl == 0 && n_path < P.path_cap) {
                     R *w = rows + 6 * (size_t)n_path;
-                    w[0] = T.x[best_node]; w[1] = T.y[best_node]; w[2] = T.th[best_node]; w[3] = (R)0;
-                    w[4] = T.t[best_node]; w[5] = T.len[best_node];
+                    const NodeRow<R> bn = T.row[best_node];
+                    w[0] = bn.x; w[1] = bn.y; w[2] = bn.th; w[3] = (R)0; w[4] = bn.t; w[5] = bn.len;
                 }
                 n_path++;
                 if (n_path > P.path_cap && status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW;
             }
             g.sync();
             if (chain && g.gl == 0)
-                for (int k = 0; k < depth && k < P.chain_cap; k++) chain[k] = T.ctr[chain[k]];
+                for (int k = 0; k < depth && k < P.chain_cap; k++) chain[k] = T.row[chain[k]].ctr;
             if (chain) for (int k = depth + g.gl; k < P.chain_cap; k += G) chain[k] = 0u;
         }
         if (g.gl == 0) {

@@ -48,6 +48,20 @@ template <typename R> static inline int make_planp(const auvrrt_env *env, const 
 }
 
 
+// One tree node: a 64-byte row in fp32 (x,y,theta,t | len,s2,self_s2,ctr | parent,cnt,self_hab | mask), so
+// fetching a parent and appending a node are a few 16-byte accesses to one or two sectors.
+template <typename R> struct alignas(16) NodeRow {
+    R x, y, th, t;
+    R len, s2, self_s2;
+    uint32_t ctr;
+    int parent;
+    uint32_t cnt;
+    int self_hab;
+    int pad_;
+    unsigned long long mask;
+};
+
+
 // thread-per-tree planner (plan_tpt.cu)
 template <typename R>
 int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,

@@ -20,17 +20,6 @@ static const int TPT_THREADS = 256;
 #define AUV_TPT_MINB 4
 #endif
 
-template <typename R> struct alignas(16) NodeRow {
-    R x, y, th, t;
-    R len, s2, self_s2;
-    uint32_t ctr;
-    int parent;
-    uint32_t cnt;
-    int self_hab;
-    int pad_;
-    unsigned long long mask;
-};
-
 // serial view of the counter stream: u_ctr, u_ctr+1, ... with the counter product kept incrementally
 template <typename R> struct SerialStream {
     uint64_t z;        // key + (ctr) * golden: the next draw hashes z + golden

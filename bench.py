@@ -34,6 +34,16 @@ ITERS = 2048
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4
 
 
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    (profiles/traffic.json, written from `ncu --set full` reports by tools/ncu_summary.py), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
 def load_world():
     with open(os.path.join(ROOT, "tests", "golden", "catalina_map.json")) as f:
         world = json.load(f)
@@ -112,7 +122,7 @@ def cpu_baseline(nthreads=0, sample_queries=None):
     world, bins, probs = load_world()
     ow = orc.OracleWorld.from_map(world, bins, probs)
     nt = nthreads or orc.num_threads()
-    nq = sample_queries or max(4 * nt, 64)
+    nq = sample_queries or max(32 * nt, 64)        # ~1.3 s wall, ~20-40 s of CPU work
     starts, seeds = make_queries(0, nq)
     pp = orc.plan_params(ITERS)
     t0 = time.perf_counter()
@@ -282,7 +292,7 @@ def main():
     peak = (cal_flops or FP32_NOMINAL_TFLOPS * 1e12) / 1e12
     ach = flop * world_size / per_launch_s / 1e12 / world_size
     line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None, "kernel": ("k_plan_tpt<float>" if (args.group == 1 or (args.group == 0 and Q_PER_GPU >= 32768)) else "k_plan<float,%d>" % (args.group or 32)),
+                        "traffic": ncu_traffic("k_plan_f32_g32_q4096") if (world_size == 1 and Q_PER_GPU == 4096) else None, "kernel": ("k_plan_tpt<float>" if (args.group == 1 or (args.group == 0 and Q_PER_GPU >= 32768)) else "k_plan<float,%d>" % (args.group or 32)),
                         "peak_source": "FFMA calibration kernel measured live in this run" if cal_flops else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
                         "nominal_peak": FP32_NOMINAL_TFLOPS,
                         "algorithmic_flop_per_edge": flop / (len(rec) * ITERS), "sfu_per_edge": sfu / (len(rec) * ITERS),
@@ -335,7 +345,7 @@ def extras(env, dev, args, api, adev):
     mean_s, min_s = timed(lambda: adev.nn_dev(tx, ty, qx, qy, idx, scr, "f32"))
     gbs = 8.0 * n / mean_s / 1e9
     out["roofline_nn"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                          "traffic": None, "kernel": "k_nn_partial<float>", "nodes": n, "queries": 1,
+                          "traffic": ncu_traffic("k_nn_partial_f32_n2p27"), "kernel": "k_nn_partial<float>", "nodes": n, "queries": 1,
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                           "algorithmic_bytes": "8 B per node per pass"}
     del tx, ty
