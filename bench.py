@@ -109,7 +109,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
@@ -167,7 +167,7 @@ def run_reference(args, rank, world_size):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
