@@ -384,10 +384,12 @@ static int final_course(const node_t *nodes, const wp_t *wps, int leaf, wp_t *ou
 int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng,
                   const orc_plan_params_t *p, orc_trace_t *out) {
     const int I = p->iterations;
+    const int maxp = (int)ceil(p->freq) + 2;          /* most waypoints one steer call can append */
     node_t *nodes = (node_t *)malloc(sizeof(node_t) * (size_t)(I + 1));
-    wp_t *wps = (wp_t *)malloc(sizeof(wp_t) * (size_t)I * 30 + sizeof(wp_t));
-    wp_t *course = (wp_t *)malloc(sizeof(wp_t) * ((size_t)I * 31 + 2));
-    double *cpts = (double *)malloc(sizeof(double) * 3 * ((size_t)I * 31 + 2));
+    wp_t *wps = (wp_t *)malloc(sizeof(wp_t) * ((size_t)I + 1) * (size_t)maxp);
+    wp_t *course = (wp_t *)malloc(sizeof(wp_t) * ((size_t)I * (size_t)(maxp + 1) + 2));
+    double *cpts = (double *)malloc(sizeof(double) * 3 * ((size_t)I * (size_t)(maxp + 1) + 2));
+    double *pts_buf = (double *)malloc(sizeof(double) * 2 * (size_t)(maxp + 2));
     uint8_t *bin_mask = (uint8_t *)malloc((size_t)(w->T > 0 ? w->T : 1));
     int n_nodes = 0, n_wps = 0, status = ORC_OK;
     nodes[n_nodes++] = (node_t){{start[0], start[1], start[2], 0.0, start[3], start[4]}, -1, 0, 0};
@@ -408,7 +410,6 @@ int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng
     int it = 0;
     int64_t upos0 = 0;   /* stream position after the previous steer call's iteration */
     int64_t guard = 0, guard_max = 64LL * I + 1024;
-    double pts_buf[2 * 31];
     while (it < I && guard++ < guard_max) {
         int parent;
         if (p->mode == 0) {
@@ -506,7 +507,7 @@ int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng
             memcpy(out->path + 6 * (size_t)k, &course[n - 1 - k], sizeof(wp_t));
     }
     for (int i = 0; i < time_expand + 2; i++) free(bins[i].v);
-    free(bins); free(nodes); free(wps); free(course); free(cpts); free(bin_mask);
+    free(bins); free(nodes); free(wps); free(course); free(cpts); free(bin_mask); free(pts_buf);
     return status;
 }
 
@@ -636,7 +637,9 @@ typedef struct {
 static void orc_ab_body(int64_t i, void *vc) {
     orc_ab_t *c = (orc_ab_t *)vc;
     orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[i]), c->bits24, 0, 0};
-    double leaf[5], wp[6 * 32], pts[2 * 32]; int nwp;
+    const int maxp = (int)ceil(c->sp->freq) + 2;
+    double leaf[5]; int nwp;
+    double *wp = (double *)malloc(sizeof(double) * 8 * (size_t)maxp), *pts = wp + 6 * (size_t)maxp;
     orc_steer_arc(c->parents + 5 * i, &rng, c->sp, leaf, wp, &nwp);
     pts[0] = c->parents[5 * i]; pts[1] = c->parents[5 * i + 1];
     for (int k = 0; k < nwp; k++) { pts[2 * k + 2] = wp[6 * k]; pts[2 * k + 3] = wp[6 * k + 1]; }
@@ -644,6 +647,7 @@ static void orc_ab_body(int64_t i, void *vc) {
     if (c->safe) c->safe[i] = (uint8_t)s;
     if (c->nwp_out) c->nwp_out[i] = nwp + 1;
     if (c->leaf_out) memcpy(c->leaf_out + 5 * i, leaf, sizeof(leaf));
+    free(wp);
 }
 void orc_edges_arc_batch(const orc_world_t *w, const double *parents, const uint64_t *seeds,
                          int64_t n, const orc_steer_params_t *sp, int bits24, uint8_t *safe,

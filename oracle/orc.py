@@ -140,7 +140,7 @@ def steer_arc(parent, u, dist_to_end=2.0, diff_max=0.5, freq=30.0, min_dist=0.5,
     u = _f64(u, (-1,))
     sp = SteerParams(dist_to_end, diff_max, freq, min_dist, velocity)
     leaf = np.zeros(5)
-    wp = np.zeros((32, 6))
+    wp = np.zeros((int(np.ceil(freq)) + 2, 6))
     nwp = C.c_int(0)
     nused = C.c_int64(0)
     st = lib().orc_steer_arc_ext(_p(parent), _p(u), C.c_int64(len(u)), C.byref(sp), _p(leaf), _p(wp),
