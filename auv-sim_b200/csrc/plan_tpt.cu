@@ -42,6 +42,13 @@ template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchu
     return L;
 }
 
+// Divergence control: an RRT iteration costs O(n_expand) arc primitives and n_expand is uniform in
+// [0, freq), so a warp of 32 trees would idle half its lanes in the primitive loop.  Every trip the
+// block therefore (A) lets thread i pick the parent and draw n_expand for tree slot i, (sort) orders
+// its 256 tree slots by n_expand with a shared-memory counting sort, and (B) lets thread i run the
+// steer / collide / cost / append part for the i-th slot in that order, so the lanes of a warp loop
+// over nearly the same number of primitives.  The per-tree registers that survive an iteration
+// live in shared memory (struct-of-arrays) because a different thread owns the tree every trip.
 template <typename R>
 __global__ void __launch_bounds__(TPT_THREADS, AUV_TPT_MINB)
 k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
@@ -49,7 +56,14 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
            auvrrt_plan_record_t *records, uint32_t *chain_out, auvrrt_plan_trace_t tr) {
     typedef typename Policy<R>::A A;
     const bool VERIFY = Policy<R>::VERIFY;
+    const int T = TPT_THREADS;
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned long long s_z[T];
+    __shared__ long long s_q[T], s_nprims[T];
+    __shared__ uint32_t s_ctr[T], s_upos[T];
+    __shared__ int s_nnodes[T], s_nchunks[T], s_it[T], s_status[T], s_bestnode[T], s_bestiter[T], s_ncost[T], s_nwp[T],
+        s_guard[T], s_active[T], s_parent[T], s_nexp[T], s_order[T], s_hist[64];
+    __shared__ R s_bc0[T], s_bc1[T], s_bc2[T], s_bc3[T], s_blen[T], s_bt[T];
     EnvView<R> env;
     if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
     else {
@@ -58,211 +72,271 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
         env.bind_grid(blob, smem + 16);
     }
-    const long long slot = (long long)blockIdx.x * TPT_THREADS + threadIdx.x;
-    unsigned char *base = ws + (size_t)slot * L.slot_bytes;
-    NodeRow<R> *nodes = (NodeRow<R> *)(base + L.nodes);
-    int *pool = (int *)(base + L.pool), *next = (int *)(base + L.next);
-    int *head = (int *)(base + L.head), *tail = (int *)(base + L.tail), *count = (int *)(base + L.count);
     const SteerParams<R> sp = P.sp;
+    const int tid = threadIdx.x;
+    unsigned char *block_ws = ws + (size_t)blockIdx.x * T * L.slot_bytes;
+    s_active[tid] = 0; s_q[tid] = -1; s_nexp[tid] = -2; s_order[tid] = tid;
+    bool queue_empty = false;
+    const int guard_max = 64 * P.I + 1024;
+    __syncthreads();
 
     for (;;) {
-        const long long q = (long long)atomicAdd(qcounter, 1ull);
-        if (q >= Q) break;
-        SerialStream<R> rng;
-        rng.init(stream_key(seeds[q]));
-        // ---- init                                                                   rrt_dubins.py:105-114
-        for (int b = 0; b < P.nb + 2; b++) count[b] = 0;
-        {
-            NodeRow<R> r0;
-            r0.x = starts[5 * q]; r0.y = starts[5 * q + 1]; r0.th = starts[5 * q + 2]; r0.t = starts[5 * q + 3];
-            r0.len = starts[5 * q + 4]; r0.s2 = (R)0; r0.ctr = 0; r0.parent = -1; r0.cnt = 0; r0.mask = 0ull; r0.pad_ = 0;
-            Contrib c = point_contrib<R>(env, r0.x, r0.y, r0.t, 0xffffffffu, env.H, env.classify(r0.x, r0.y));
-            r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
-            r0.self_hab = c.bin >= 0 ? c.hab : -1;
-            nodes[0] = r0;
+        // ============ phase B: thread i runs the edge of the i-th slot in n_expand order ===============
+        const int slot = s_order[tid];
+        unsigned char *base = block_ws + (size_t)slot * L.slot_bytes;
+        NodeRow<R> *nodes = (NodeRow<R> *)(base + L.nodes);
+        int *pool = (int *)(base + L.pool), *next = (int *)(base + L.next);
+        int *head = (int *)(base + L.head), *tail = (int *)(base + L.tail), *count = (int *)(base + L.count);
+        const int n_exp = s_nexp[slot];
+        if (s_active[slot] && n_exp != -2) {
+            const long long q = s_q[slot];
+            int status = s_status[slot];
+            int it = s_it[slot];
+            if (!status && n_exp >= 0) {
+                SerialStream<R> rng;
+                rng.z = s_z[slot]; rng.ctr = s_ctr[slot];
+                const int parent = s_parent[slot];
+                // ---- steer (:237-295) with check_collision (:530-549) and the per-waypoint cost folded in
+                const NodeRow<R> pr = nodes[parent];
+                const uint32_t ctr0 = rng.ctr - 1;                 // position of the n_expand draw
+                R x = pr.x, y = pr.y, th = pr.th, t = pr.t, len = pr.len;
+                R sin0 = 0, cos0 = 0;
+                if (VERIFY) A::sincos(th, &sin0, &cos0);
+                int nwp = 1;
+                bool bad = false, moved = false, degenerate = false;
+                R acc_s2 = 0; uint32_t acc_cnt = 0; unsigned long long acc_mask = 0;
+                R self_s2 = pr.self_s2; int self_hab = pr.self_hab;
+                bool last_is_wp = false;
+                {
+                    const Cls pcl = env.classify(pr.x, pr.y);                            // path[0] = parent object
+                    bad = !point_within_c<R>(env, pcl, pr.x, pr.y) || point_hits_circles_c<R>(env, pcl, pr.x, pr.y);
+                }
+                for (int k = 0; k < n_exp; k++) {
+                    const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());
+                    const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());
+                    if (!(A::fabs(dist) > A::fabs(diff))) continue;
+                    const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());
+                    R dx, dy, movement;
+                    if (VERIFY) {
+                        R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
+                        if (den == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
+                        R radius = A::div(num, den), r2 = A::mul((R)2, radius);
+                        if (r2 == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
+                        th = A::add(th, A::div(num, r2));
+                        R s1v, c1v;
+                        A::sincos(th, &s1v, &c1v);
+                        dx = A::mul(radius, A::sub(s1v, sin0));
+                        dy = A::mul(radius, A::add(-c1v, cos0));
+                        sin0 = s1v; cos0 = c1v;
+                        movement = A::sqrt(A::sq2(dx, dy));
+                        if (vt == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
+                    } else {
+                        if (diff == (R)0 || vt == (R)0) { degenerate = true; break; }
+                        const R phi = -diff;
+                        movement = dist * sinc_small((float)diff * 0.5f);
+                        R sm, cm;
+                        A::sincos(th + (R)0.5 * phi, &sm, &cm);
+                        th += phi;
+                        dx = movement * cm; dy = movement * sm;
+                    }
+                    x = A::add(x, dx); y = A::add(y, dy);
+                    t = A::add(t, A::div(movement, vt));
+                    len = A::add(len, movement);
+                    moved = true;
+                    last_is_wp = movement >= sp.min_dist;                                // :283
+                    if (last_is_wp) {
+                        nwp++;
+                        const Cls cl = env.classify(x, y);
+                        bad = bad || !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+                        Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, cl);
+                        R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+                        if (c.bin >= 0) {
+                            acc_s2 = A::add(acc_s2, ps2);
+                            if (c.hab >= 0) { acc_cnt++; acc_mask |= 1ull << c.hab; }
+                        }
+                        self_s2 = c.bin >= 0 ? ps2 : (R)0; self_hab = c.bin >= 0 ? c.hab : -1;   // provisional leaf state
+                    }
+                }
+                if (!status) {
+                    const bool safe = !(bad || degenerate);
+                    s_nwp[slot] += nwp; s_nprims[slot] += n_exp;
+                    if (P.trace) {
+                        size_t r = (size_t)q * P.I + it;
+                        tr.parent[r] = parent; tr.safe[r] = safe ? 1 : 0; tr.nwp[r] = nwp; tr.upos[r] = s_upos[slot];
+                        R *lf = (R *)tr.leaf + 5 * r;
+                        lf[0] = x; lf[1] = y; lf[2] = th; lf[3] = t; lf[4] = len;
+                    }
+                    if (safe) {
+                        if (moved && !last_is_wp) {     // the leaf state is not one of the waypoints: evaluate it
+                            Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, env.classify(x, y));
+                            self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+                            self_hab = c.bin >= 0 ? c.hab : -1;
+                        }
+                        const int id = s_nnodes[slot]++;                                // :144-145
+                        NodeRow<R> nr;
+                        nr.x = x; nr.y = y; nr.th = th; nr.t = t; nr.len = len; nr.ctr = ctr0; nr.parent = parent; nr.pad_ = 0;
+                        nr.s2 = A::add(A::add(pr.s2, pr.self_s2), acc_s2);
+                        nr.cnt = pr.cnt + (pr.self_hab >= 0 ? 1u : 0u) + acc_cnt;
+                        nr.mask = pr.mask | (pr.self_hab >= 0 ? (1ull << pr.self_hab) : 0ull) | acc_mask;
+                        nr.self_s2 = self_s2; nr.self_hab = self_hab;
+                        nodes[id] = nr;
+                        // ---- time-bin insert                                           :147-151
+                        R fd = floordiv_pos<R>(t, P.bin_interval), fidx = fd + (R)1, curr_bin = A::mul(fidx, P.bin_interval);
+                        int bidx = -1; bool reset = false;
+                        if (curr_bin > P.max_traj) { if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; } }
+                        else { if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else status = AUVRRT_ST_KEY_ERROR; }
+                        if (bidx >= 0) {
+                            const int c_old = count[bidx];
+                            const bool reuse_head = reset && c_old > 0;
+                            const int c = reset ? 0 : c_old;
+                            if (reuse_head) tail[bidx] = head[bidx];
+                            if ((c & 31) == 0 && !reuse_head) {
+                                const int nc = s_nchunks[slot]++;
+                                next[nc] = -1;
+                                if (c == 0) head[bidx] = nc; else next[tail[bidx]] = nc;
+                                tail[bidx] = nc;
+                            }
+                            pool[tail[bidx] * 32 + (c & 31)] = id;
+                            count[bidx] = c + 1;
+                        }
+                        if (!status && t >= P.horizon) {                                // :158-171
+                            const uint32_t cnt = nr.cnt + (self_hab >= 0 ? 1u : 0u);
+                            const unsigned long long mk = nr.mask | (self_hab >= 0 ? (1ull << self_hab) : 0ull);
+                            R c1 = A::mul(P.w2, (R)cnt), c2 = A::add(nr.s2, self_s2), c0 = 0;
+                            if (t > (R)0) { c1 = A::div(c1, t); c2 = A::div(c2, t); }
+                            if (env.H != 0) c0 = A::div(A::mul(P.w1, (R)__popcll(mk)), (R)env.H);
+                            const R total = py_sum3p<R>(c0, c1, c2);
+                            s_ncost[slot]++;
+                            if (total < s_bc0[slot]) {
+                                s_bc0[slot] = total; s_bc1[slot] = c0; s_bc2[slot] = c1; s_bc3[slot] = c2;
+                                s_bestnode[slot] = id; s_bestiter[slot] = it; s_blen[slot] = len; s_bt[slot] = t;
+                            }
+                        }
+                    }
+                    it++;
+                    s_it[slot] = it;
+                    s_z[slot] = rng.z; s_ctr[slot] = rng.ctr; s_upos[slot] = rng.ctr;
+                }
+            }
+            // ---- query finished (budget spent, or an error): chain + record, free the slot
+            if (status || it >= P.I || n_exp == -1) {
+                const int best_node = s_bestnode[slot];
+                if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
+                int depth = 0;
+                if (best_node >= 0) for (int n = best_node; nodes[n].parent >= 0; n = nodes[n].parent) depth++;
+                if (chain_out) {
+                    uint32_t *chain = chain_out + (size_t)q * P.chain_cap;
+                    if (depth > P.chain_cap && status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW;
+                    int n = best_node;
+                    for (int k = depth - 1; k >= 0; k--) { if (k < P.chain_cap) chain[k] = nodes[n].ctr; n = nodes[n].parent; }
+                    for (int k = depth; k < P.chain_cap; k++) chain[k] = 0u;
+                }
+                auvrrt_plan_record_t rec;
+                rec.status = status; rec.n_nodes = s_nnodes[slot]; rec.best_node = best_node; rec.best_iter = s_bestiter[slot];
+                rec.depth = depth; rec.n_path = 0; rec.n_cost_evals = s_ncost[slot]; rec.n_waypoints = s_nwp[slot];
+                rec.n_uniforms = (long long)s_ctr[slot]; rec.n_primitives = s_nprims[slot];
+                rec.cost[0] = best_node >= 0 ? (double)s_bc0[slot] : 0.0; rec.cost[1] = (double)s_bc1[slot];
+                rec.cost[2] = (double)s_bc2[slot]; rec.cost[3] = (double)s_bc3[slot];
+                rec.path_length = (double)s_blen[slot]; rec.t_leaf = (double)s_bt[slot];
+                records[q] = rec;
+                s_active[slot] = 0;
+            }
         }
-        head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
-        int n_nodes = 1, n_chunks = 1, status = AUVRRT_ST_OK;
-        uint32_t upos_mark = 0;
-        int best_node = -1, best_iter = -1, n_cost_evals = 0, n_waypoints = 0;
-        long long n_prims = 0;
-        R best_c0 = A::inf(), best_c1 = 0, best_c2 = 0, best_c3 = 0, best_len = 0, best_t = 0;
-        int it = 0;
-        long long guard = 0;
-        const long long guard_max = 64LL * P.I + 1024;
 
-        while (it < P.I && guard++ < guard_max) {
-            int parent;
-            if (P.mode == 0) {                                                          // :122-127
-                int rb, cn;
-                for (;;) {
-                    rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), rng.next());
-                    if (rb > P.nb || rb < 1) { status = AUVRRT_ST_KEY_ERROR; break; }
-                    cn = count[rb];
-                    if (cn > 0) break;
+        // ============ phase A, same thread, same tree: refill the slot, pick the next parent and draw
+        // n_expand while the tree's rows and bins are still in this SM's L1 ============================
+        {
+            if (!s_active[slot] && !queue_empty) {
+                const long long q = (long long)atomicAdd(qcounter, 1ull);
+                if (q >= Q) queue_empty = true;
+                else {
+                    // ---- init                                                           rrt_dubins.py:105-114
+                    for (int b = 0; b < P.nb + 2; b++) count[b] = 0;
+                    NodeRow<R> r0;
+                    r0.x = starts[5 * q]; r0.y = starts[5 * q + 1]; r0.th = starts[5 * q + 2]; r0.t = starts[5 * q + 3];
+                    r0.len = starts[5 * q + 4]; r0.s2 = (R)0; r0.ctr = 0; r0.parent = -1; r0.cnt = 0; r0.mask = 0ull; r0.pad_ = 0;
+                    Contrib c = point_contrib<R>(env, r0.x, r0.y, r0.t, 0xffffffffu, env.H, env.classify(r0.x, r0.y));
+                    r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+                    r0.self_hab = c.bin >= 0 ? c.hab : -1;
+                    nodes[0] = r0;
+                    head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
+                    s_z[slot] = stream_key(seeds[q]); s_ctr[slot] = 0; s_upos[slot] = 0; s_q[slot] = q; s_nprims[slot] = 0;
+                    s_nnodes[slot] = 1; s_nchunks[slot] = 1; s_it[slot] = 0; s_status[slot] = AUVRRT_ST_OK;
+                    s_bestnode[slot] = -1; s_bestiter[slot] = -1; s_ncost[slot] = 0; s_nwp[slot] = 0; s_guard[slot] = 0;
+                    s_bc0[slot] = A::inf(); s_bc1[slot] = 0; s_bc2[slot] = 0; s_bc3[slot] = 0; s_blen[slot] = 0; s_bt[slot] = 0;
+                    s_active[slot] = 1;
                 }
-                if (status) break;
-                int idx = (int)uniform_ab<R>((R)0, (R)cn, rng.next());
-                if (idx >= cn) { status = AUVRRT_ST_KEY_ERROR; break; }
-                int ch = head[rb];
-                for (int hop = idx >> 5; hop > 0; hop--) ch = next[ch];
-                parent = pool[ch * 32 + (idx & 31)];
-            } else {                                                                    // :136-139, :505-513
-                R rx = uniform_ab<R>(env.minx, env.maxx, rng.next());
-                R ry = uniform_ab<R>(env.miny, env.maxy, rng.next());
-                rng.skip(2);                   // theta and size are drawn and never used
-                R bq = A::inf(), bs = A::inf();
-                int bi = 0;
-                for (int i = 0; i < n_nodes; i++) {
-                    R qq = A::sq2(A::sub(rx, nodes[i].x), A::sub(ry, nodes[i].y));
-                    if (qq < bq) {
-                        if (VERIFY) { R s = A::sqrt(qq); if (s < bs) { bs = s; bi = i; } }
-                        else bi = i;
-                        bq = qq;
+            }
+            int key = 63;                         // inactive trees and skipped trips sort last
+            if (s_active[slot]) {
+                SerialStream<R> rng;
+                rng.z = s_z[slot]; rng.ctr = s_ctr[slot];
+                int parent = -1, status = AUVRRT_ST_OK;
+                bool skip = false;
+                if (P.mode == 0) {                                                      // :122-127
+                    int rb = 0, cn = 0;
+                    for (;;) {
+                        rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), rng.next());
+                        if (rb > P.nb || rb < 1) { status = AUVRRT_ST_KEY_ERROR; break; }
+                        cn = count[rb];
+                        if (cn > 0) break;
                     }
-                }
-                parent = bi;
-                if (nodes[parent].t > P.max_traj) continue;
-            }
-            // ---- steer (:237-295) with check_collision (:530-549) and the per-waypoint cost folded in
-            const NodeRow<R> pr = nodes[parent];
-            const uint32_t ctr0 = rng.ctr;
-            const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
-            R x = pr.x, y = pr.y, th = pr.th, t = pr.t, len = pr.len;
-            R sin0 = 0, cos0 = 0;
-            if (VERIFY) A::sincos(th, &sin0, &cos0);
-            int nwp = 1;
-            bool bad = false, moved = false, degenerate = false;
-            R acc_s2 = 0; uint32_t acc_cnt = 0; unsigned long long acc_mask = 0;
-            R self_s2 = pr.self_s2; int self_hab = pr.self_hab;
-            bool last_is_wp = false;
-            {
-                const Cls pcl = env.classify(pr.x, pr.y);                                // path[0] = parent object
-                bad = !point_within_c<R>(env, pcl, pr.x, pr.y) || point_hits_circles_c<R>(env, pcl, pr.x, pr.y);
-            }
-            for (int k = 0; k < n_exp; k++) {
-                const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());
-                const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());
-                if (!(A::fabs(dist) > A::fabs(diff))) continue;
-                const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());
-                R dx, dy, movement;
-                if (VERIFY) {
-                    R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
-                    if (den == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
-                    R radius = A::div(num, den), r2 = A::mul((R)2, radius);
-                    if (r2 == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
-                    th = A::add(th, A::div(num, r2));
-                    R s1v, c1v;
-                    A::sincos(th, &s1v, &c1v);
-                    dx = A::mul(radius, A::sub(s1v, sin0));
-                    dy = A::mul(radius, A::add(-c1v, cos0));
-                    sin0 = s1v; cos0 = c1v;
-                    movement = A::sqrt(A::sq2(dx, dy));
-                    if (vt == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
-                } else {
-                    if (diff == (R)0 || vt == (R)0) { degenerate = true; break; }
-                    const R phi = -diff;
-                    movement = dist * sinc_small((float)diff * 0.5f);
-                    R sm, cm;
-                    A::sincos(th + (R)0.5 * phi, &sm, &cm);
-                    th += phi;
-                    dx = movement * cm; dy = movement * sm;
-                }
-                x = A::add(x, dx); y = A::add(y, dy);
-                t = A::add(t, A::div(movement, vt));
-                len = A::add(len, movement);
-                moved = true;
-                last_is_wp = movement >= sp.min_dist;                                    // :283
-                if (last_is_wp) {
-                    nwp++;
-                    const Cls cl = env.classify(x, y);
-                    bad = bad || !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
-                    Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, cl);
-                    R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
-                    if (c.bin >= 0) {
-                        acc_s2 = A::add(acc_s2, ps2);
-                        if (c.hab >= 0) { acc_cnt++; acc_mask |= 1ull << c.hab; }
+                    if (!status) {
+                        int idx = (int)uniform_ab<R>((R)0, (R)cn, rng.next());
+                        if (idx >= cn) status = AUVRRT_ST_KEY_ERROR;
+                        else {
+                            int ch = head[rb];
+                            for (int hop = idx >> 5; hop > 0; hop--) ch = next[ch];
+                            parent = pool[ch * 32 + (idx & 31)];
+                        }
                     }
-                    self_s2 = c.bin >= 0 ? ps2 : (R)0; self_hab = c.bin >= 0 ? c.hab : -1;   // provisional leaf state
-                }
-            }
-            if (status) break;
-            const bool safe = !(bad || degenerate);
-            n_waypoints += nwp; n_prims += n_exp;
-            if (P.trace) {
-                size_t r = (size_t)q * P.I + it;
-                tr.parent[r] = parent; tr.safe[r] = safe ? 1 : 0; tr.nwp[r] = nwp; tr.upos[r] = upos_mark;
-                R *lf = (R *)tr.leaf + 5 * r;
-                lf[0] = x; lf[1] = y; lf[2] = th; lf[3] = t; lf[4] = len;
-            }
-            if (safe) {
-                if (moved && !last_is_wp) {     // the leaf state is not one of the waypoints: evaluate it
-                    Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, env.classify(x, y));
-                    self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
-                    self_hab = c.bin >= 0 ? c.hab : -1;
-                }
-                const int id = n_nodes++;                                               // :144-145
-                NodeRow<R> nr;
-                nr.x = x; nr.y = y; nr.th = th; nr.t = t; nr.len = len; nr.ctr = ctr0; nr.parent = parent; nr.pad_ = 0;
-                nr.s2 = A::add(A::add(pr.s2, pr.self_s2), acc_s2);
-                nr.cnt = pr.cnt + (pr.self_hab >= 0 ? 1u : 0u) + acc_cnt;
-                nr.mask = pr.mask | (pr.self_hab >= 0 ? (1ull << pr.self_hab) : 0ull) | acc_mask;
-                nr.self_s2 = self_s2; nr.self_hab = self_hab;
-                nodes[id] = nr;
-                // ---- time-bin insert                                                   :147-151
-                R fd = floordiv_pos<R>(t, P.bin_interval), fidx = fd + (R)1, curr_bin = A::mul(fidx, P.bin_interval);
-                int bidx = -1; bool reset = false;
-                if (curr_bin > P.max_traj) { if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; } }
-                else { if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else { status = AUVRRT_ST_KEY_ERROR; break; } }
-                if (bidx >= 0) {
-                    const int c_old = count[bidx];
-                    const bool reuse_head = reset && c_old > 0;
-                    const int c = reset ? 0 : c_old;
-                    if (reuse_head) tail[bidx] = head[bidx];
-                    if ((c & 31) == 0 && !reuse_head) {
-                        const int nc = n_chunks++;
-                        next[nc] = -1;
-                        if (c == 0) head[bidx] = nc; else next[tail[bidx]] = nc;
-                        tail[bidx] = nc;
+                } else {                                                                // :136-139, :505-513
+                    R rx = uniform_ab<R>(env.minx, env.maxx, rng.next());
+                    R ry = uniform_ab<R>(env.miny, env.maxy, rng.next());
+                    rng.skip(2);                   // theta and size are drawn and never used
+                    R bq = A::inf(), bs = A::inf();
+                    int bi = 0;
+                    const int n_nodes = s_nnodes[slot];
+                    for (int i = 0; i < n_nodes; i++) {
+                        R qq = A::sq2(A::sub(rx, nodes[i].x), A::sub(ry, nodes[i].y));
+                        if (qq < bq) {
+                            if (VERIFY) { R s = A::sqrt(qq); if (s < bs) { bs = s; bi = i; } }
+                            else bi = i;
+                            bq = qq;
+                        }
                     }
-                    pool[tail[bidx] * 32 + (c & 31)] = id;
-                    count[bidx] = c + 1;
+                    parent = bi;
+                    if (nodes[parent].t > P.max_traj) skip = true;                      // `continue`: no steer call
                 }
-                if (t >= P.horizon) {                                                   // :158-171
-                    const uint32_t cnt = nr.cnt + (self_hab >= 0 ? 1u : 0u);
-                    const unsigned long long mk = nr.mask | (self_hab >= 0 ? (1ull << self_hab) : 0ull);
-                    R c1 = A::mul(P.w2, (R)cnt), c2 = A::add(nr.s2, self_s2), c0 = 0;
-                    if (t > (R)0) { c1 = A::div(c1, t); c2 = A::div(c2, t); }
-                    if (env.H != 0) c0 = A::div(A::mul(P.w1, (R)__popcll(mk)), (R)env.H);
-                    const R total = py_sum3p<R>(c0, c1, c2);
-                    n_cost_evals++;
-                    if (total < best_c0) {
-                        best_c0 = total; best_c1 = c0; best_c2 = c1; best_c3 = c2;
-                        best_node = id; best_iter = it; best_len = len; best_t = t;
-                    }
+                int n_exp = 0;
+                if (!status && !skip) {
+                    s_upos[slot] = s_upos[slot];     // (stream position of the previous iteration's end stays)
+                    // the edge's stream position = position of its n_expand draw
+                    n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));     // :259-260
+                    key = n_exp < 62 ? n_exp : 62;
+                }
+                s_z[slot] = rng.z; s_ctr[slot] = rng.ctr; s_parent[slot] = parent; s_nexp[slot] = n_exp;
+                if (status) { s_status[slot] = status; key = 62; s_nexp[slot] = -1; }    // phase B finalises it
+                if (skip) {
+                    s_nexp[slot] = -2;
+                    if (++s_guard[slot] >= guard_max) { key = 62; s_nexp[slot] = -1; }
                 }
             }
-            it++;
-            upos_mark = rng.ctr;
+            // ============================ counting sort of the slots by n_expand ======================
+            if (tid < 64) s_hist[tid] = 0;
+            __syncthreads();
+            const int rank = atomicAdd(&s_hist[key], 1);
+            __syncthreads();
+            if (tid < 32) {                       // exclusive scan of 64 buckets by one warp
+                int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1], v = a0 + a1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (tid >= d) v += o; }
+                s_hist[2 * tid] = v - a0 - a1; s_hist[2 * tid + 1] = v - a1;
+            }
+            __syncthreads();
+            s_order[s_hist[key] + rank] = slot;
         }
-        if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
-        int depth = 0;
-        if (best_node >= 0) for (int n = best_node; nodes[n].parent >= 0; n = nodes[n].parent) depth++;
-        if (chain_out) {
-            uint32_t *chain = chain_out + (size_t)q * P.chain_cap;
-            if (depth > P.chain_cap && status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW;
-            int n = best_node;
-            for (int k = depth - 1; k >= 0; k--) { if (k < P.chain_cap) chain[k] = nodes[n].ctr; n = nodes[n].parent; }
-            for (int k = depth; k < P.chain_cap; k++) chain[k] = 0u;
-        }
-        auvrrt_plan_record_t rec;
-        rec.status = status; rec.n_nodes = n_nodes; rec.best_node = best_node; rec.best_iter = best_iter;
-        rec.depth = depth; rec.n_path = 0; rec.n_cost_evals = n_cost_evals; rec.n_waypoints = n_waypoints;
-        rec.n_uniforms = (long long)rng.ctr; rec.n_primitives = n_prims;
-        rec.cost[0] = best_node >= 0 ? (double)best_c0 : 0.0; rec.cost[1] = (double)best_c1;
-        rec.cost[2] = (double)best_c2; rec.cost[3] = (double)best_c3;
-        rec.path_length = (double)best_len; rec.t_leaf = (double)best_t;
-        records[q] = rec;
+        if (__syncthreads_count(s_active[slot]) == 0) break;      // also publishes s_order
     }
 }
 
@@ -275,7 +349,9 @@ int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seed
     int rc = make_planp<R>(env, p, &P);
     if (rc) return rc;
     EnvBlob<R> b = env_blob<R>(env);
-    int budget = 100 * 1024, sm = 16, mode = 0;
+    // only the hot part of the world model is staged: the per-tree state of 256 trees already takes
+    // ~27 KB of shared memory per CTA and 4 CTAs per SM must fit
+    int budget = 24 * 1024, sm = 16, mode = 0;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
     AUV_CUDA(cudaFuncSetAttribute(k_plan_tpt<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
