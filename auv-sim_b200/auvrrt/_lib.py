@@ -46,7 +46,7 @@ EXPORTS = [
     "auvrrt_steer_dubins", "auvrrt_collide", "auvrrt_collide_points", "auvrrt_cost",
     "auvrrt_cost_point", "auvrrt_edges_dubins_dev", "auvrrt_edges_arc_dev", "auvrrt_edges_dubins",
     "auvrrt_edges_arc", "auvrrt_stream_u", "auvrrt_plan_batch", "auvrrt_plan_workspace_bytes", "auvrrt_plan_workspace_bytes_q",
-    "auvrrt_plan_batch_dev", "auvrrt_materialize", "auvrrt_calibrate_fp32",
+    "auvrrt_plan_batch_dev", "auvrrt_materialize", "auvrrt_calibrate_fp32", "auvrrt_occupancy_dims", "auvrrt_occupancy_grid",
 ]
 
 _lib = None
@@ -101,6 +101,10 @@ def lib():
     L.auvrrt_materialize.argtypes = [vp, _dp, _u64p, _u32p, _i32p, C.c_int64, C.POINTER(PlanParams), C.c_int,
                                      _dp, _i32p]
     L.auvrrt_calibrate_fp32.argtypes = [C.c_int, C.c_int, _dp, _dp]
+    _ip = C.POINTER(C.c_int)
+    L.auvrrt_occupancy_dims.argtypes = [_dp, C.c_double, C.c_double, _dp, _i64p, C.c_int, _ip, _ip, _ip]
+    L.auvrrt_occupancy_grid.argtypes = [_dp, _i64p, C.c_int, _dp, C.c_double, C.c_double, C.c_double, _dp, _i64p,
+                                        C.c_int, C.c_int, _dp, C.c_int64]
     _lib = L
     return L
 

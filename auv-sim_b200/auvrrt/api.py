@@ -264,3 +264,27 @@ def calibrate_fp32(device=0, iters=4096):
     f, ms = C.c_double(0), C.c_double(0)
     check(lib().auvrrt_calibrate_fp32(device, iters, C.byref(f), C.byref(ms)))
     return f.value, ms.value
+
+
+def occupancy_grid(cell_polys, bounds, cell_size, bin_interval, detect_range, tracks, device=0):
+    """SharkOccupancyGrid.convert: list of cell polygons (vertex arrays, cell_list order), boundary bounds,
+    and one [n,3] (x, y, traj_time_stamp) track per shark -> (grid[T, rows, cols], bins[T, 2])"""
+    coff = np.zeros(len(cell_polys) + 1, np.int64)
+    for i, p in enumerate(cell_polys):
+        coff[i + 1] = coff[i] + len(p)
+    cxy = _f64(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in cell_polys]), (-1, 2)) \
+        if len(cell_polys) else np.zeros((0, 2))
+    toff = np.zeros(len(tracks) + 1, np.int64)
+    for i, t in enumerate(tracks):
+        toff[i + 1] = toff[i] + len(t)
+    txy = _f64(np.concatenate([np.asarray(t, dtype=np.float64).reshape(-1, 3) for t in tracks]), (-1, 3))
+    b = _f64(bounds, (4,))
+    T, rows, cols = C.c_int(0), C.c_int(0), C.c_int(0)
+    check(lib().auvrrt_occupancy_dims(_p(b), float(cell_size), float(bin_interval), _p(txy), _p(toff, C.c_int64),
+                                      len(tracks), C.byref(T), C.byref(rows), C.byref(cols)))
+    out = np.zeros((max(T.value, 0), rows.value, cols.value))
+    check(lib().auvrrt_occupancy_grid(_p(cxy), _p(coff, C.c_int64), len(cell_polys), _p(b), float(cell_size),
+                                      float(bin_interval), float(detect_range), _p(txy), _p(toff, C.c_int64),
+                                      len(tracks), device, _p(out), out.size))
+    bins = np.array([[i * bin_interval, (i + 1) * bin_interval] for i in range(T.value)], dtype=np.float64).reshape(-1, 2)
+    return out, bins

@@ -206,6 +206,22 @@ int auvrrt_materialize(const auvrrt_env_t *env, const double *starts, const uint
                        const auvrrt_plan_params_t *params, int precision, double *out_path,
                        int32_t *out_n_path);
 
+/* ---- SharkOccupancyGrid.convert (sharkOccupancyGrid.py:47-71): shark tracks -> AUV-detection grids
+ * SURVEY.md section 8(f) row N2, the producer of the cost function's probs[T][C] input.
+ * cells: C polygons in cell_list order (vertices cell_xy[cell_off[c] .. cell_off[c+1]));
+ * bounds = boundary.bounds; tracks: S sharks in dict order, points (x, y, traj_time_stamp) at
+ * tracks[track_off[s] .. track_off[s+1]).  auvrrt_occupancy_dims gives T (createBinList, :307-320)
+ * and the grid shape; out_grid[T][rows][cols] = resultArr (fp64, bit-identical to the reference).
+ * The value of cell c in bin b (resultCell / createSharkGrid's CSV) is
+ * out_grid[b][int((miny_c - bounds[1]) / cell_size)][int((minx_c - bounds[0]) / cell_size)]. */
+int auvrrt_occupancy_dims(const double bounds[4], double cell_size, double bin_interval,
+                          const double *tracks, const int64_t *track_off, int S, int *T, int *rows,
+                          int *cols);
+int auvrrt_occupancy_grid(const double *cell_xy, const int64_t *cell_off, int C,
+                          const double bounds[4], double cell_size, double bin_interval,
+                          double detect_range, const double *tracks, const int64_t *track_off,
+                          int S, int device, double *out_grid, int64_t out_cap);
+
 /* FP32 FFMA issue-rate calibration kernel for the roofline denominator: runs `iters` dependent
  * FFMA chains on every lane of a full grid and returns achieved FLOP/s (FMA = 2). */
 int auvrrt_calibrate_fp32(int device, int iters, double *out_flops, double *out_ms);

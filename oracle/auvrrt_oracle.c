@@ -655,3 +655,81 @@ void orc_edges_arc_batch(const orc_world_t *w, const double *parents, const uint
     orc_ab_t c = {w, parents, seeds, sp, bits24, safe, nwp_out, leaf_out};
     orc_parallel_for(n, 256, nthreads, orc_ab_body, &c);
 }
+
+/* ---------------------------------------------------------------- SharkOccupancyGrid.convert -- */
+/* path_planning/sharkOccupancyGrid.py:47-71 (convert), :145-172 (constructGrid), :174-204
+ * (constructAUVGrid), :206-243 (constructSharkOccupancyGrid), :245-299 (time bins, convert2DArr),
+ * :307-320 (createBinList).  Cells are polygons (cell_off/cell_xy, in cell_list order); a point
+ * belongs to the FIRST cell with `point.within(cell) or cell.touches(point)` (:232), i.e. closed
+ * containment decided exactly.  tracks: shark s = points trk_off[s]..trk_off[s+1], rows (x, y, t).
+ * out_grid [T][rows][cols] = resultArr; returns T (or -1 if the buffer is too small). */
+void orc_occupancy_dims(const double bounds[4], double cell_size, double bin_interval, const double *trk,
+                        const int64_t *trk_off, int S, int *T, int *rows, int *cols) {
+    double longest = 0;
+    for (int s = 0; s < S; s++)
+        if (trk_off[s + 1] > trk_off[s] && trk[3 * (trk_off[s + 1] - 1) + 2] > longest) longest = trk[3 * (trk_off[s + 1] - 1) + 2];
+    *T = (int)floor(longest / bin_interval);                                           /* :314 */
+    *cols = (int)(ceil(bounds[2] - bounds[0]) / cell_size) + 1;                           /* :160 */
+    *rows = (int)(ceil(bounds[3] - bounds[1]) / cell_size) + 1;
+}
+static int cell_contains_closed(const double *xy, int n, double px, double py) {
+    return orc_point_in_polygon(xy, n, px, py) >= 0;
+}
+int orc_occupancy(const double *cell_xy, const int64_t *cell_off, int C, const double bounds[4], double cell_size,
+                  double bin_interval, double detect_range, const double *trk, const int64_t *trk_off, int S,
+                  double *out_grid, int64_t out_cap) {
+    int T, rows, cols;
+    orc_occupancy_dims(bounds, cell_size, bin_interval, trk, trk_off, S, &T, &rows, &cols);
+    if ((int64_t)T * rows * cols > out_cap) return -1;
+    const int count = (int)ceil(detect_range / cell_size);                             /* :189 */
+    int *crow = (int *)malloc(sizeof(int) * (size_t)(C > 0 ? C : 1)), *ccol = (int *)malloc(sizeof(int) * (size_t)(C > 0 ? C : 1));
+    for (int c = 0; c < C; c++) {                                                      /* cellToIndex :294-299 */
+        double lowx = INFINITY, lowy = INFINITY;
+        for (int64_t k = cell_off[c]; k < cell_off[c + 1]; k++) { lowx = fmin(lowx, cell_xy[2 * k]); lowy = fmin(lowy, cell_xy[2 * k + 1]); }
+        ccol[c] = (int)((lowx - bounds[0]) / cell_size);
+        crow[c] = (int)((lowy - bounds[1]) / cell_size);
+    }
+    double *occ = (double *)malloc(sizeof(double) * (size_t)rows * cols), *auv = (double *)malloc(sizeof(double) * (size_t)rows * cols);
+    for (int b = 0; b < T; b++) {
+        double *grid = out_grid + (size_t)b * rows * cols;
+        for (int i = 0; i < rows * cols; i++) grid[i] = 0.0;
+        for (int s = 0; s < S; s++) {
+            /* constructSharkOccupancyGrid on the points of shark s that fall in bin b (first-match bin, :253-258) */
+            for (int i = 0; i < rows * cols; i++) occ[i] = 0.0;
+            for (int c = 0; c < C; c++) occ[crow[c] * cols + ccol[c]] = 0.01;
+            int64_t npts = 0;
+            for (int64_t k = trk_off[s]; k < trk_off[s + 1]; k++) {
+                double t = trk[3 * k + 2];
+                int tb = -1;
+                for (int bb = 0; bb < T; bb++) if (t >= bb * bin_interval && t <= (bb + 1) * bin_interval) { tb = bb; break; }
+                if (tb != b) continue;
+                npts++;
+                for (int c = 0; c < C; c++)
+                    if (cell_contains_closed(cell_xy + 2 * cell_off[c], (int)(cell_off[c + 1] - cell_off[c]), trk[3 * k], trk[3 * k + 1])) {
+                        occ[crow[c] * cols + ccol[c]] += 1;
+                        break;
+                    }
+            }
+            double nor = (double)npts + C * 0.01;                                       /* :222 */
+            for (int i = 0; i < rows * cols; i++) occ[i] = occ[i] / nor;
+            /* constructAUVGrid */
+            for (int i = 0; i < rows * cols; i++) auv[i] = 0.0;
+            for (int c = 0; c < C; c++) {
+                int row = crow[c], col = ccol[c];
+                for (int i = 0; i < 4 * count; i++) {
+                    int rt = row - 2 * count + i;
+                    for (int j = 0; j < 4 * count; j++) {
+                        int ct = col - 2 * count + j;
+                        if (rt >= 0 && rt < rows && ct >= 0 && ct < cols)
+                            if (sqrt(pow((double)(rt - row), 2.0) + pow((double)(ct - col), 2.0)) <= count)
+                                auv[row * cols + col] += occ[rt * cols + ct];
+                    }
+                }
+            }
+            for (int i = 0; i < rows * cols; i++) grid[i] = grid[i] + auv[i];           /* :166 */
+        }
+        for (int i = 0; i < rows * cols; i++) grid[i] = grid[i] / S;                    /* :170 */
+    }
+    free(crow); free(ccol); free(occ); free(auv);
+    return T;
+}

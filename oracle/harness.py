@@ -228,6 +228,30 @@ def polygon_area(pts):
     return 0.5 * a
 
 
+def lattice_cell_polygons(boundary_pts, cell_size=10.0, min_area=1e-9):
+    """same lattice as lattice_cells(), returning each clipped piece's vertex list (column-major)"""
+    xs = [p[0] for p in boundary_pts]
+    ys = [p[1] for p in boundary_pts]
+    minx, miny, maxx, maxy = min(xs), min(ys), max(xs), max(ys)
+    polys = []
+    nx = int(math.ceil((maxx - minx) / cell_size))
+    ny = int(math.ceil((maxy - miny) / cell_size))
+    for i in range(nx):
+        for j in range(ny):
+            x0, y0 = minx + i * cell_size, miny + j * cell_size
+            piece = clip_polygon_to_rect(boundary_pts, x0, y0, x0 + cell_size, y0 + cell_size)
+            if len(piece) >= 3 and abs(polygon_area(piece)) > min_area:
+                # drop consecutive duplicates the clipper can emit
+                out = []
+                for p in piece:
+                    if not out or (p[0], p[1]) != out[-1]:
+                        out.append((float(p[0]), float(p[1])))
+                if len(out) > 1 and out[0] == out[-1]:
+                    out.pop()
+                polys.append(out)
+    return polys
+
+
 def lattice_cells(boundary_pts, cell_size=10.0, min_area=1e-9):
     """Cell bounds of the 10 m lattice clipped to the boundary polygon, COLUMN-MAJOR order.
 

@@ -296,3 +296,27 @@ def edges_arc_batch(world: OracleWorld, parents, seeds, dist_to_end=2.0, diff_ma
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def occupancy(cell_polys, bounds, cell_size, bin_interval, detect_range, tracks):
+    """SharkOccupancyGrid.convert -> resultArr as an array [T, rows, cols].
+    cell_polys: list of vertex lists; tracks: list (one per shark, dict order) of arrays [n,3] = x, y, t"""
+    coff = np.zeros(len(cell_polys) + 1, np.int64)
+    for i, p in enumerate(cell_polys):
+        coff[i + 1] = coff[i] + len(p)
+    cxy = _f64(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in cell_polys]), (-1, 2))
+    toff = np.zeros(len(tracks) + 1, np.int64)
+    for i, t in enumerate(tracks):
+        toff[i + 1] = toff[i] + len(t)
+    txy = _f64(np.concatenate([np.asarray(t, dtype=np.float64).reshape(-1, 3) for t in tracks]), (-1, 3))
+    b = _f64(bounds, (4,))
+    T, rows, cols = C.c_int(0), C.c_int(0), C.c_int(0)
+    lib().orc_occupancy_dims(_p(b), C.c_double(cell_size), C.c_double(bin_interval), _p(txy),
+                             toff.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(tracks)), C.byref(T), C.byref(rows), C.byref(cols))
+    out = np.zeros((max(T.value, 0), rows.value, cols.value))
+    lib().orc_occupancy.restype = C.c_int
+    r = lib().orc_occupancy(_p(cxy), coff.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(cell_polys)), _p(b),
+                            C.c_double(cell_size), C.c_double(bin_interval), C.c_double(detect_range), _p(txy),
+                            toff.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(tracks)), _p(out), C.c_int64(out.size))
+    assert r == T.value
+    return out

@@ -76,6 +76,12 @@ class Polygon:
     def contains(self, other):
         return other.within(self)
 
+    def touches(self, other):
+        """boundary contact only (used as cell.touches(point) by sharkOccupancyGrid.py:226)"""
+        if hasattr(other, "x") and hasattr(other, "y"):
+            return self._locate(float(other.x), float(other.y)) == 0
+        raise NotImplementedError
+
 
 class Point:
     def __init__(self, x, y=None):
