@@ -156,3 +156,32 @@ def getGridByInterval(interval, gridDict):
     return {tb: g for tb, g in gridDict.items()
             if (tb[0] <= interval[0] <= tb[1]) or (tb[0] >= interval[0] and tb[1] <= interval[1])
             or (tb[0] <= interval[1] <= tb[1])}
+
+
+# ---- raw shark tracks (data/sharkTrackingData.csv of auv-sim) ------------------------------------------
+# No code in the reference reads that file (only a comment, robotSim.py:602); its layout is 32 sharks x 4
+# rows (x, vx, y, vy) x 815 video frames at 30 fps (sharkTrajectory.py:33-37 stamps frame j with
+# t = 0.03 j).  The tracks are in video pixels and cover 24 s, so using them with the Catalina planner
+# needs an explicit map; CATALINA_TRACK_MAP is this build's definition (parity unpinned): the pixel box
+# [370, 1334] x [4, 500] goes onto x in [-330, -80] m, y in [-60, 90] m and time is stretched x20 so the
+# 815 frames span the planner's 500 s horizon.
+CATALINA_TRACK_MAP = {"x0": 370.0, "y0": 4.0, "sx": 250.0 / 964.0, "sy": 150.0 / 496.0, "ox": -330.0, "oy": -60.0,
+                      "frame_dt": 0.03, "time_scale": 20.0}
+
+
+def load_shark_tracking_csv(path):
+    """-> (x[S, N], y[S, N]) raw positions from a sharkTrackingData.csv-style file"""
+    a = np.loadtxt(path, delimiter=",")
+    return a[0::4], a[2::4]
+
+
+def tracks_to_shark_dict(x, y, mapping=CATALINA_TRACK_MAP):
+    """raw (x, y) tracks -> {shark_id: [Motion_plan_state(x, y, traj_time_stamp)]} in the map's frame"""
+    from motion_plan_state import Motion_plan_state
+    m = mapping
+    out = {}
+    for s in range(len(x)):
+        out[s + 1] = [Motion_plan_state(m["ox"] + (float(x[s][j]) - m["x0"]) * m["sx"],
+                                        m["oy"] + (float(y[s][j]) - m["y0"]) * m["sy"],
+                                        traj_time_stamp=j * m["frame_dt"] * m["time_scale"]) for j in range(len(x[s]))]
+    return out

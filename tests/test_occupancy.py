@@ -89,3 +89,33 @@ def test_gpu_dropin_shark_occupancy_grid(golden, catalina_map):
     out = cost.habitat_shark_cost_func(path, 140.0, [], cell, [-3, -3, -4])
     assert out[0] < 0 and out[1][2] == out[0]
     sys.path.remove(PP)
+
+
+@pytest.mark.gpu
+def test_config3_grid_from_shark_tracking_data(golden, golden_dir, catalina_map):
+    """BASELINE config 3, second half: the shark-occupancy cost built from data/sharkTrackingData.csv
+    (frozen as tests/golden/shark_tracks_raw.npz) through the GPU grid builder, then planned with."""
+    sys.path.insert(0, PP)
+    for n in ("sharkOccupancyGrid", "_world", "motion_plan_state", "rrt_dubins", "cost"):
+        sys.modules.pop(n, None)
+    import sharkOccupancyGrid as sog
+    import rrt_dubins
+    from motion_plan_state import Motion_plan_state as M
+    z = np.load(os.path.join(golden_dir, "shark_tracks_raw.npz"))
+    shark = sog.tracks_to_shark_dict(z["x"].astype(np.float64), z["y"].astype(np.float64))
+    assert len(shark) == 32 and len(shark[1]) == 815 and abs(shark[1][-1].traj_time_stamp - 488.4) < 1e-9
+    boundary = [tuple(p) for p in catalina_map["boundary"]]
+    cells = sog.splitCell(boundary, 10)
+    arr, cellgrid = sog.SharkOccupancyGrid(10, boundary, 50, 50, cells).convert(shark)
+    assert list(cellgrid.keys()) == [(50 * i, 50 * (i + 1)) for i in range(9)]
+    polys, bounds, _ = golden
+    tracks = [np.array([[p.x, p.y, p.traj_time_stamp] for p in t]) for t in shark.values()]
+    want = orc.occupancy(polys, bounds, 10.0, 50.0, 50.0, tracks)
+    assert np.array_equal(np.array([arr[k] for k in arr]), want)            # same grids as the oracle, bit for bit
+    obstacles = [M(c[0], c[1], size=c[2]) for c in catalina_map["circles"]]
+    habitats = [M(h[0], h[1], size=h[2]) for h in catalina_map["habitats"]]
+    rrt = rrt_dubins.RRT(boundary, obstacles, cellgrid, cells)
+    res = rrt.exploring(M(-200, 0), habitats, 0.5, 5, 2, 50, traj_time_stamp=True, max_traj_time=450,
+                        weights=[-3, -3, -4], iterations=1024, seed=4, replicas=16)
+    assert res["cost"][1][2] < 0 and res["path"][0][-1].traj_time_stamp >= 420      # the shark term is active
+    sys.path.remove(PP)
