@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_occ_norm(const int *counts, const int *
     occ[i] = __ddiv_rn(v, nor);
 }
 
-__global__ void __launch_bounds__(256) k_occ_auv(const double *occ, const int *sq_off, const int *sq_cells, int T, int S,
+__global__ void __launch_bounds__(256) k_occ_auv(const double *occ, const int *sq_off, int T, int S,
                                                  int rows, int cols, int count, double *auv) {
     const int RC = rows * cols;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(256) k_occ_auv(const double *occ, const int *s
     const double *o = occ + (i - sq);
     double acc = 0.0;
     for (int cc = sq_off[sq]; cc < sq_off[sq + 1]; cc++) {        // one pass per cell mapped to this square (:190)
-        (void)sq_cells;
         for (int a = 0; a < 4 * count; a++) {
             const int rt = row - 2 * count + a;
             for (int b = 0; b < 4 * count; b++) {
@@ -182,7 +181,7 @@ extern "C" int auvrrt_occupancy_grid(const double *cell_xy, const int64_t *cell_
         g_launches++;
     }
     k_occ_norm<<<(unsigned)((tot + 255) / 256), 256>>>((const int *)d_cnt.p, (const int *)d_np.p, (const unsigned char *)d_isc.p, T, S, RC, C, (double *)d_occ.p);
-    k_occ_auv<<<(unsigned)((tot + 255) / 256), 256>>>((const double *)d_occ.p, (const int *)d_sqo.p, (const int *)d_sqc.p, T, S, rows, cols, count, (double *)d_auv.p);
+    k_occ_auv<<<(unsigned)((tot + 255) / 256), 256>>>((const double *)d_occ.p, (const int *)d_sqo.p, T, S, rows, cols, count, (double *)d_auv.p);
     k_occ_avg<<<(unsigned)(((long long)T * RC + 255) / 256), 256>>>((const double *)d_auv.p, T, S, RC, (double *)d_grid.p);
     g_launches += 3;
     AUV_CUDA(cudaGetLastError());

@@ -120,7 +120,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         if (g.gl == 0) {
             NodeRow<R> r0;
             r0.x = sx; r0.y = sy; r0.th = sth; r0.t = st; r0.len = slen;
-            r0.parent = -1; r0.ctr = 0; r0.s2 = (R)0; r0.cnt = 0; r0.mask = 0ull; r0.pad_ = 0;
+            r0.parent = -1; r0.ctr = 0; r0.s2 = (R)0; r0.cnt = 0; r0.mask = 0ull; r0.born = 0;
             Contrib c = point_contrib<R>(env, sx, sy, st, 0xffffffffu, env.H, env.classify(sx, sy));
             r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
             r0.self_hab = c.bin >= 0 ? c.hab : -1;
@@ -168,6 +168,12 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 int ch = BIN_HEAD(ran_bin);
                 for (int hop = idx >> 5; hop > 0; hop--) ch = T.next[ch];
                 parent = T.pool[ch * 32 + (idx & 31)];
+            } else if (P.mode == 2) {
+                // ---- wall-clock pick on the simulated clock (:129-132): every lane walks the same bisection
+                const R ran_time = uniform_ab<R>((R)0, P.ran_time_max, rng.u(ctr));
+                ctr += 1;
+                parent = closest_mps_time<R>(T.row, n_nodes, ran_time, P.plan_dt);
+                if (T.row[parent].t > P.max_traj) continue;                               // :131-132
             } else {
                 // ---- get_random_mps (:333-343) + get_closest_mps (:505-513)
                 R rx = uniform_ab<R>(env.minx, env.maxx, rng.u(ctr));
@@ -222,12 +228,12 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     NodeRow<R> nr;
                     nr.x = o.x; nr.y = o.y; nr.th = o.th; nr.t = o.t; nr.len = o.len; nr.parent = parent; nr.ctr = ctr0;
                     nr.s2 = pre_s2; nr.cnt = pre_cnt; nr.mask = pre_mask; nr.self_s2 = self_s2n; nr.self_hab = self_habn;
-                    nr.pad_ = 0;
+                    nr.born = it;
                     T.row[id] = nr;
                     if (P.mode == 1) { T.nx[id] = o.x; T.ny[id] = o.y; }
                 }
                 // ---- time-bin insert (decision is group-uniform, lane 0 writes)            :147-151
-                {
+                if (P.mode != 2) {                   // `if traj_time_stamp:` -- mode 2 keeps no bins
                     R fd = floordiv_pos<R>(o.t, P.bin_interval);
                     R fidx = fd + (R)1;
                     R curr_bin = A::mul(fidx, P.bin_interval);

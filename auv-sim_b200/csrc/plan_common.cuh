@@ -8,6 +8,7 @@ namespace auv {
 template <typename R> struct PlanP {
     int I, mode, nb, chain_cap, path_cap, trace, cap, nchunks;
     R bin_interval, max_traj, horizon, w1, w2, w3;
+    R ran_time_max, plan_dt;      // mode 2: max_plan_time * freq (:129) and max_plan_time / iterations
     SteerParams<R> sp;
 };
 
@@ -29,7 +30,8 @@ template <typename R> __device__ __forceinline__ R py_sum3p(R c0, R c1, R c2) {
 
 template <typename R> static inline int make_planp(const auvrrt_env *env, const auvrrt_plan_params_t *p, PlanP<R> *out) {
     if (p->iterations < 1) return set_err(AUVRRT_ERR_ARG, "plan: iterations must be >= 1");
-    if (p->mode != 0 && p->mode != 1) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0 or 1");
+    if (p->mode < 0 || p->mode > 2) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0, 1 or 2");
+    if (p->mode == 2 && !(p->max_plan_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: mode 2 needs max_plan_time > 0");
     if (!(p->bin_interval > 0) || !(p->max_traj_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: bin_interval and max_traj_time must be > 0");
     if (env->H > 64) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 64 habitats");
     double nbd = ceil(p->max_traj_time / p->bin_interval);                      // rrt_dubins.py:111
@@ -40,6 +42,8 @@ template <typename R> static inline int make_planp(const auvrrt_env *env, const 
     P.cap = P.I + 1; P.nchunks = P.nb + P.cap / 32 + 4;
     P.bin_interval = (R)p->bin_interval; P.max_traj = (R)p->max_traj_time;
     P.horizon = (R)(p->max_traj_time - 30);                                     // :158
+    P.ran_time_max = (R)(p->max_plan_time * p->freq);
+    P.plan_dt = (R)(p->max_plan_time / (double)p->iterations);
     P.w1 = (R)p->weights[0]; P.w2 = (R)p->weights[1]; P.w3 = (R)p->weights[2];
     double sp[5] = {p->dist_to_end, p->diff_max, p->freq, p->min_dist, p->v};
     P.sp = make_steer_params<R>(sp);
@@ -57,10 +61,27 @@ template <typename R> struct alignas(16) NodeRow {
     int parent;
     uint32_t cnt;
     int self_hab;
-    int pad_;
+    int born;          // steer call that created the node: plan_time_stamp = born * plan_dt (mode 2)
     unsigned long long mask;
 };
 
+
+
+// RRT.get_closest_mps_time (rrt_dubins.py:515-528): the reference's list-slicing pseudo-bisection on
+// plan_time_stamp, restated on the index range [lo, lo + len).  plan_time_stamp of a node is
+// (steer call that created it) * plan_dt on the simulated clock (0 for the root).
+template <typename R>
+__device__ __forceinline__ int closest_mps_time(const NodeRow<R> *rows, int n_nodes, R ran_time, R plan_dt) {
+    typedef typename Policy<R>::A A;
+    int lo = 0, len = n_nodes;
+    while (len > 3) {
+        const int half = len >> 1;
+        const R ls = A::mul((R)rows[lo + half - 1].born, plan_dt), rs = A::mul((R)rows[lo + half + 1].born, plan_dt);
+        const R left_diff = A::fabs(A::sub(ls, ran_time)), right_diff = A::fabs(A::sub(rs, ran_time));
+        if (left_diff >= right_diff) { lo += half; len -= half; } else len = half;
+    }
+    return lo;
+}
 
 // thread-per-tree planner (plan_tpt.cu)
 template <typename R>

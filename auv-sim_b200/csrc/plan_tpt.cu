@@ -174,7 +174,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                         }
                         const int id = s_nnodes[slot]++;                                // :144-145
                         NodeRow<R> nr;
-                        nr.x = x; nr.y = y; nr.th = th; nr.t = t; nr.len = len; nr.ctr = ctr0; nr.parent = parent; nr.pad_ = 0;
+                        nr.x = x; nr.y = y; nr.th = th; nr.t = t; nr.len = len; nr.ctr = ctr0; nr.parent = parent; nr.born = it;
                         nr.s2 = A::add(A::add(pr.s2, pr.self_s2), acc_s2);
                         nr.cnt = pr.cnt + (pr.self_hab >= 0 ? 1u : 0u) + acc_cnt;
                         nr.mask = pr.mask | (pr.self_hab >= 0 ? (1ull << pr.self_hab) : 0ull) | acc_mask;
@@ -183,7 +183,8 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                         // ---- time-bin insert                                           :147-151
                         R fd = floordiv_pos<R>(t, P.bin_interval), fidx = fd + (R)1, curr_bin = A::mul(fidx, P.bin_interval);
                         int bidx = -1; bool reset = false;
-                        if (curr_bin > P.max_traj) { if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; } }
+                        if (P.mode == 2) { }                     // `if traj_time_stamp:` -- mode 2 keeps no bins
+                        else if (curr_bin > P.max_traj) { if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; } }
                         else { if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else status = AUVRRT_ST_KEY_ERROR; }
                         if (bidx >= 0) {
                             const int c_old = count[bidx];
@@ -254,7 +255,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     for (int b = 0; b < P.nb + 2; b++) count[b] = 0;
                     NodeRow<R> r0;
                     r0.x = starts[5 * q]; r0.y = starts[5 * q + 1]; r0.th = starts[5 * q + 2]; r0.t = starts[5 * q + 3];
-                    r0.len = starts[5 * q + 4]; r0.s2 = (R)0; r0.ctr = 0; r0.parent = -1; r0.cnt = 0; r0.mask = 0ull; r0.pad_ = 0;
+                    r0.len = starts[5 * q + 4]; r0.s2 = (R)0; r0.ctr = 0; r0.parent = -1; r0.cnt = 0; r0.mask = 0ull; r0.born = 0;
                     Contrib c = point_contrib<R>(env, r0.x, r0.y, r0.t, 0xffffffffu, env.H, env.classify(r0.x, r0.y));
                     r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
                     r0.self_hab = c.bin >= 0 ? c.hab : -1;
@@ -290,6 +291,10 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                             parent = pool[ch * 32 + (idx & 31)];
                         }
                     }
+                } else if (P.mode == 2) {                                               // :129-132, :515-528
+                    const R ran_time = uniform_ab<R>((R)0, P.ran_time_max, rng.next());
+                    parent = closest_mps_time<R>(nodes, s_nnodes[slot], ran_time, P.plan_dt);
+                    if (nodes[parent].t > P.max_traj) skip = true;
                 } else {                                                                // :136-139, :505-513
                     R rx = uniform_ab<R>(env.minx, env.maxx, rng.next());
                     R ry = uniform_ab<R>(env.miny, env.maxy, rng.next());
@@ -310,7 +315,6 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 }
                 int n_exp = 0;
                 if (!status && !skip) {
-                    s_upos[slot] = s_upos[slot];     // (stream position of the previous iteration's end stays)
                     // the edge's stream position = position of its n_expand draw
                     n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));     // :259-260
                     key = n_exp < 62 ? n_exp : 62;

@@ -81,17 +81,16 @@ class RRT:
                   iterations=None, seed=None, replicas=1):
         """reference :92-176.  Returns {"path length": float, "path": [list[MPS], {(t0,t1): list[MPS]}],
         "cost": [sum, [c0, c1, c2]]}."""
-        if plan_time and not traj_time_stamp:
-            raise NotImplementedError(
-                "plan_time=True with traj_time_stamp=False picks parents by wall-clock plan_time_stamp "
-                "(get_closest_mps_time, :515-528); it is not replayable and not implemented")
-        mode = 0 if plan_time else 1
+        # plan_time & traj_time_stamp: time-bin pick (:122-127); plan_time only: pick by wall-clock
+        # plan_time_stamp (get_closest_mps_time, :129-132) replayed on a simulated clock that spends
+        # max_plan_time evenly over the steer calls; neither: nearest node to a random state (:136-139)
+        mode = (0 if traj_time_stamp else 2) if plan_time else 1
         iters = int(iterations) if iterations is not None else max(1, int(math.ceil(max_plan_time * REFERENCE_STEER_CALLS_PER_SECOND)))
         seed = random.getrandbits(63) if seed is None else int(seed)
         env = self._env(self.obstacle_list, habitats)
         pp = api.plan_params(iters, mode=mode, bin_interval=bin_interval, v=v, max_traj_time=max_traj_time,
                              dist_to_end=self.dist_to_end, diff_max=self.diff_max, freq=self.freq, min_dist=0.5,
-                             weights=weights, chain_cap=255, path_cap=0)
+                             weights=weights, chain_cap=255, path_cap=0, max_plan_time=max_plan_time)
         start = [initial.x, initial.y, initial.theta, initial.traj_time_stamp, initial.length]
         R = max(1, int(replicas))
         starts = np.tile(np.array(start, dtype=np.float64), (R, 1))

@@ -17,6 +17,8 @@
  *     their own host<->device copies on an internal stream.  Functions ending in `_dev` take DEVICE
  *     pointers whose floating type is float (AUVRRT_F32) or double (AUVRRT_F64) plus a cudaStream_t
  *     passed as void*; they enqueue work and return without synchronising.
+ *   - An auvrrt_env_t owns reusable device / pinned scratch for the host-buffer planner entry, so one
+ *     handle must not be used by two threads at once; separate handles are independent.
  *   - There is NO CPU fallback: without a CUDA device every compute entry fails with
  *     AUVRRT_ERR_CUDA.
  */
@@ -144,7 +146,10 @@ double auvrrt_stream_u(uint64_t seed, int64_t k, int bits24);
 typedef struct {
     int32_t iterations;      /* budget: steer calls per query (replaces the wall-clock budget) */
     int32_t mode;            /* 0: traj_time_stamp & plan_time (time-bin pick, :122-127)
-                                1: plan_time False (get_random_mps + get_closest_mps, :136-139) */
+                                1: plan_time False (get_random_mps + get_closest_mps, :136-139)
+                                2: plan_time & not traj_time_stamp (get_closest_mps_time, :129-132,
+                                   :515-528) on a simulated clock: steer call i happens at
+                                   plan time i * max_plan_time / iterations */
     double bin_interval, v, max_traj_time;
     double dist_to_end, diff_max, freq, min_dist;   /* RRT.__init__ defaults 2, 0.5, 30; 0.5 (:141) */
     double weights[3];
@@ -153,6 +158,7 @@ typedef struct {
     int32_t trace;           /* != 0: fill the per-iteration trace arrays (parity tests) */
     int32_t group;           /* lanes cooperating on one tree: 32 (default when 0), 16 or 8; 1 = one thread
                                 per tree, the throughput planner for >= 10^5 queries (no in-kernel paths) */
+    double max_plan_time;    /* the reference's wall-clock budget in seconds; only mode 2 reads it */
 } auvrrt_plan_params_t;
 
 /* one fixed-size record per query: the unit the multi-GPU gather moves */

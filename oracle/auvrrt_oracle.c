@@ -336,10 +336,13 @@ double orc_cost_point(double x, double y, const orc_world_t *w, const uint8_t *v
 typedef struct {
     int iterations;          /* budget: number of steer calls */
     int mode;                /* 0: traj_time_stamp and plan_time (time-bin pick, :122-127)
-                                1: plan_time False (get_random_mps + get_closest_mps, :136-139) */
+                                1: plan_time False (get_random_mps + get_closest_mps, :136-139)
+                                2: plan_time and not traj_time_stamp (get_closest_mps_time, :129-132) with
+                                   time.time() - t_start == (steer calls completed) * max_plan_time / iterations */
     double bin_interval, v, max_traj_time;
     double dist_to_end, diff_max, freq, min_dist;   /* RRT.__init__ defaults 2, .5, 30; 0.5 (:141) */
     double weights[3];
+    double max_plan_time;
 } orc_plan_params_t;
 
 typedef struct {
@@ -353,7 +356,7 @@ typedef struct {
 } orc_trace_t;
 
 typedef struct { double x, y, th, v, t, len; } wp_t;
-typedef struct { wp_t s; int parent; int npath; int path_off; } node_t;
+typedef struct { wp_t s; int parent; int npath; int path_off; double plan_stamp; } node_t;
 typedef struct { int *v; int n, cap; } ilist_t;
 
 static void il_push(ilist_t *l, int x) {
@@ -392,7 +395,7 @@ int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng
     double *pts_buf = (double *)malloc(sizeof(double) * 2 * (size_t)(maxp + 2));
     uint8_t *bin_mask = (uint8_t *)malloc((size_t)(w->T > 0 ? w->T : 1));
     int n_nodes = 0, n_wps = 0, status = ORC_OK;
-    nodes[n_nodes++] = (node_t){{start[0], start[1], start[2], 0.0, start[3], start[4]}, -1, 0, 0};
+    nodes[n_nodes++] = (node_t){{start[0], start[1], start[2], 0.0, start[3], start[4]}, -1, 0, 0, 0.0};
 
     int time_expand = (int)ceil(p->max_traj_time / p->bin_interval);               /* :111 */
     ilist_t *bins = (ilist_t *)calloc((size_t)time_expand + 2, sizeof(ilist_t));
@@ -424,6 +427,17 @@ int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng
             int ran_index = (int)uniform(rng, 0.0, (double)bins[ran_bin].n);       /* :126 */
             if (ran_index >= bins[ran_bin].n) { status = ORC_KEY_ERROR; break; }
             parent = bins[ran_bin].v[ran_index];
+        } else if (p->mode == 2) {
+            double ran_time = uniform(rng, 0.0, p->max_plan_time * p->freq);       /* :129 */
+            int lo = 0, len = n_nodes;                                             /* get_closest_mps_time :515-528 */
+            while (len > 3) {
+                double left_diff = fabs(nodes[lo + len / 2 - 1].plan_stamp - ran_time);
+                double right_diff = fabs(nodes[lo + len / 2 + 1].plan_stamp - ran_time);
+                int index = len / 2;
+                if (left_diff >= right_diff) { lo += index; len -= index; } else len = index;
+            }
+            parent = lo;
+            if (nodes[parent].s.t > p->max_traj_time) continue;                    /* :131-132 */
         } else {
             double rx = uniform(rng, minx, maxx);                                  /* :336-339 */
             double ry = uniform(rng, miny, maxy);
@@ -457,13 +471,15 @@ int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng
         out->n_waypoints_total += nwp + 1;
         if (safe) {
             int id = n_nodes++;
-            nodes[id] = (node_t){{leaf[0], leaf[1], leaf[2], 0.0, leaf[3], leaf[4]}, parent, nwp, n_wps};
+            nodes[id] = (node_t){{leaf[0], leaf[1], leaf[2], 0.0, leaf[3], leaf[4]}, parent, nwp, n_wps,
+                                 (double)it * (p->max_plan_time / (double)I)};   /* time.time() - t_start at steer entry (:252) */
             n_wps += nwp;
-            /* time-bin insert (:147-151) */
-            double fd = py_floordiv(leaf[3], p->bin_interval);
+            /* time-bin insert (:147-151), only `if traj_time_stamp` */
+            double fd = p->mode == 2 ? 0.0 : py_floordiv(leaf[3], p->bin_interval);
             double curr_bin = (fd + 1.0) * p->bin_interval;
             double fidx = fd + 1.0;
-            if (curr_bin > p->max_traj_time) {
+            if (p->mode == 2) {
+            } else if (curr_bin > p->max_traj_time) {
                 if (fidx >= 1.0 && fidx <= (double)time_expand) {      /* resets a live key */
                     int bi = (int)fidx;
                     if (bi * p->bin_interval == curr_bin) { bins[bi].n = 0; il_push(&bins[bi], id); }

@@ -172,14 +172,17 @@ class RecordingRandom:
 
 
 class BudgetClock:
-    """`time` stand-in: time() is 0.0 until `budget` steer calls have completed, then +inf."""
+    """`time` stand-in: time() is `done * dt` (0.0 when dt == 0) until `budget` steer calls have
+    completed, then +inf.  dt > 0 simulates a planner that spends max_plan_time evenly over its steer
+    calls: the clock the wall-clock parent pick (get_closest_mps_time) is replayed on."""
 
-    def __init__(self, budget):
+    def __init__(self, budget, dt=0.0):
         self.budget = budget
         self.done = 0
+        self.dt = dt
 
     def time(self):
-        return 0.0 if self.done < self.budget else float("inf")
+        return self.done * self.dt if self.done < self.budget else float("inf")
 
     def sleep(self, _):
         pass
@@ -351,7 +354,7 @@ def traced_exploring(ref, rrt, initial, habitats, *, iterations, rng, bin_interv
           best_iter: iteration whose node became the final optimum.
     """
     mod = ref.rrt_dubins
-    clock = BudgetClock(iterations)
+    clock = BudgetClock(iterations, (max_plan_time / iterations) if (plan_time and not traj_time_stamp) else 0.0)
     saved = (mod.random, mod.time, mod.habitat_shark_cost_func)
     tr = {"parent": [], "safe": [], "nwp": [], "leaf": [], "upos": []}
     cost_evals = []

@@ -192,14 +192,16 @@ def main():
         specs.append(("A", s, (float(x), float(y)), 1024))
     for s in range(32, 40):
         specs.append(("B", s, (-200.0, 0.0), 1024 if s < 36 else 384))
+    for s in range(48, 52):
+        specs.append(("C", s, (-200.0, 0.0), 768))      # wall-clock parent pick on the simulated clock (N4)
     meta = []
     for mode, seed, start, iters in specs:
         rrt = ref.RRT(poly, obstacles, shark, cells)
         res, tr = H.traced_exploring(
             ref, rrt, MPS(start[0], start[1]), habitats, iterations=iters,
             rng=H.StreamPlayer(seed=seed), bin_interval=5, v=2, shark_interval=50,
-            traj_time_stamp=True, max_plan_time=10.0, max_traj_time=500.0,
-            plan_time=(mode == "A"), weights=(-3, -3, -4))
+            traj_time_stamp=(mode != "C"), max_plan_time=10.0, max_traj_time=500.0,
+            plan_time=(mode != "B"), weights=(-3, -3, -4))
         tag = "%s%d" % (mode, seed)
         ex[tag + "_parent"] = tr["parent"].astype(np.int16)
         ex[tag + "_safe"] = tr["safe"]

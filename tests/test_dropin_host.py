@@ -93,8 +93,6 @@ def test_path_bookkeeping(mods):
     assert r.get_distance_angle(M(0, 0), M(3, 4)) == (5.0, math.atan2(4, 3))
     with pytest.raises(AttributeError):
         r.planning()
-    with pytest.raises(NotImplementedError):
-        r.exploring(M(0, 0), [], 0.5, 5, 2, 50)            # plan_time & not traj_time_stamp: wall-clock mode
 
 
 def test_no_gpu_fails_loudly(mods):

@@ -345,13 +345,13 @@ def _free_starts(oworld, n, seed, box=(-260, -140, -20, 60)):
 def test_exploring_f64_traces_match_reference(api, env, exploring_golden, group):
     """group 32: one warp per tree (plan.cu); group 1: one thread per tree (plan_tpt.cu)"""
     z, meta = exploring_golden
-    for mode in ("A", "B"):
+    for mode in ("A", "B", "C"):
         for iters in sorted({m["iterations"] for m in meta if m["mode"] == mode}):
             ms = [m for m in meta if m["mode"] == mode and m["iterations"] == iters]
             starts = np.array([[m["start"][0], m["start"][1], 0.0, 0.0, 0.0] for m in ms])
             seeds = [m["seed"] for m in ms]
-            pp = api.plan_params(iters, mode=0 if mode == "A" else 1, trace=True, path_cap=1024 if group == 32 else 0,
-                                 chain_cap=96, group=group)
+            pp = api.plan_params(iters, mode={"A": 0, "B": 1, "C": 2}[mode], trace=True, path_cap=1024 if group == 32 else 0,
+                                 chain_cap=96, group=group, max_plan_time=10.0)
             r = api.plan_batch(env, starts, seeds, pp, "f64")
             if group == 1:      # the thread-per-tree planner ships chains; paths come from auvrrt_materialize
                 pp.path_cap = 1024

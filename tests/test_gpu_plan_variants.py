@@ -56,6 +56,7 @@ def test_parameter_sets_on_catalina(api, catalina_map, shark_grid):
         dict(weights=(0.1, -0.7, 1.3)),
         dict(min_dist=0.0), dict(min_dist=1.5),
         dict(mode=1), dict(mode=1, freq=40.0, max_traj_time=120.0),
+        dict(mode=2, max_plan_time=5.0), dict(mode=2, max_plan_time=0.7, freq=12.0, max_traj_time=90.0),
     ]
     for kw in sets:
         _compare(api, env, ow, starts, seeds, kw, groups=(32, 16, 8, 1))

@@ -110,7 +110,7 @@ def test_exploring_traces_bit_exact(exploring_golden, world):
     z, meta = exploring_golden
     for m in meta:
         tag = m["tag"]
-        pp = orc.plan_params(m["iterations"], mode=0 if m["mode"] == "A" else 1)
+        pp = orc.plan_params(m["iterations"], mode={"A": 0, "B": 1, "C": 2}[m["mode"]], max_plan_time=10.0)
         r = orc.exploring(world, [m["start"][0], m["start"][1], 0.0, 0.0, 0.0], pp, seed=m["seed"])
         assert r["status"] == (orc.OK if m["found"] else orc.NO_PATH)
         assert np.array_equal(r["parent"], z[tag + "_parent"])
