@@ -161,6 +161,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     ctr += G;
                 }
                 if (kerr) { status = AUVRRT_ST_KEY_ERROR; break; }
+                g.sync();        // every lane has read the bin counts before lane 0 may update them below
                 R u = rng.u(ctr);
                 ctr += 1;
                 int idx = (int)uniform_ab<R>((R)0, (R)bincnt, u);
@@ -245,7 +246,9 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                         if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else status = AUVRRT_ST_KEY_ERROR;
                     }
                     if (bidx >= 0) {
-                        const int c_old = BIN_COUNT(bidx);
+                        // lane 0 owns the bin metadata: it reads, broadcasts, and writes (no lane may observe
+                        // its update early: n_chunks below must stay identical on every lane)
+                        const int c_old = g.bcast(g.gl == 0 ? BIN_COUNT(bidx) : 0, 0);
                         const bool reuse_head = reset && c_old > 0;
                         const int c = reset ? 0 : c_old;
                         const bool alloc = ((c & 31) == 0) && !reuse_head;

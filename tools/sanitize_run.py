@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""small workload over every kernel for compute-sanitizer (memcheck / racecheck / synccheck)"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "auv-sim_b200"))
+from auvrrt import api  # noqa
+
+world = json.load(open(os.path.join(ROOT, "tests", "golden", "catalina_map.json")))
+g = np.load(os.path.join(ROOT, "tests", "golden", "shark_grid.npz"))
+env = api.Env.from_map(world, g["bins"], g["probs"])
+Q = 48
+starts = np.tile([-200.0, 0.0, 0.0, 0.0, 0.0], (Q, 1)); seeds = np.arange(Q)
+for prec in ("f32", "f64"):
+    for G in (32, 16, 8, 1):
+        for mode in (0, 1, 2):
+            pp = api.plan_params(96, mode=mode, group=G, trace=True, path_cap=512 if G != 1 else 0, freq=40.0 if mode == 0 else 30.0)
+            r = api.plan_batch(env, starts, seeds, pp, prec)
+            assert (r["records"]["status"] <= 1).all()
+    rs = np.random.RandomState(0)
+    parents = np.stack([rs.uniform(-300, -100, 200), rs.uniform(-60, 100, 200), rs.uniform(-6, 6, 200), rs.uniform(0, 400, 200), rs.uniform(0, 500, 200)], 1)
+    api.edges_arc(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], prec)
+    q0 = np.stack([rs.uniform(-400, 50, 300), rs.uniform(-100, 120, 300), rs.uniform(-3, 3, 300)], 1)
+    q1 = q0 + rs.uniform(-20, 20, (300, 3))
+    api.edges_dubins(env, q0, q1, 1.0, 20, prec)
+    os.environ["AUVRRT_EDGES_BRUTE"] = "1"
+    api.edges_dubins(env, q0, q1, 1.0, 20, prec)
+    os.environ["AUVRRT_EDGES_BRUTE"] = "0"
+    api.steer_dubins(q0, q1, 1.0, 9, prec)
+    api.nn(rs.uniform(-400, 50, (5001, 2)), rs.uniform(-400, 50, (7, 2)), prec)
+    api.collide(env, [parents[:5, :2], parents[:0, :2], parents[:70, :2]], prec)
+    api.collide_points(env, parents[:50, :2], prec)
+    api.cost(env, [np.concatenate([parents[:40, :2], parents[:40, 3:4]], 1)], [100.0], [-3, -3, -4], precision=prec)
+    api.cost_point(env, parents[:9, :2], [0] * 10, 1, [-3, -3, -4], prec)
+z = np.load(os.path.join(ROOT, "tests", "golden", "occupancy.npz"))
+polys = [z["cell_xy"][z["cell_off"][i]:z["cell_off"][i + 1]] for i in range(len(z["cell_off"]) - 1)]
+toff, trk = z["c1_toff"], z["c1_trk"]
+api.occupancy_grid(polys, z["bounds"], 10.0, 20.0, 25.0, [trk[toff[i]:toff[i + 1]] for i in range(len(toff) - 1)])
+print("sanitize workload done, launches:", api.launch_count())
