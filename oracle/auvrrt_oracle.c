@@ -749,3 +749,300 @@ int orc_occupancy(const double *cell_xy, const int64_t *cell_off, int C, const d
     free(crow); free(ccol); free(occ); free(auv);
     return T;
 }
+
+/* ================================================================ gym_rrt Planner_RRT ====== */
+/* gym_rrt/envs/rrt_dubins.py: the goal-directed planner RRTEnv.step drives (one node per step).
+ * PINNED against tests/golden/gym_plan.npz (the unmodified class run on the sample sequence, with
+ * random.choice(seq) = seq[int(random() * len(seq))]). */
+typedef struct {
+    double x0, y0, x1, y1;          /* boundary_point[0], boundary_point[1] */
+    int K; const double *circles;   /* [K][3] obstacle x, y, size in list order */
+    double goal_x, goal_y;
+    double exp_rate, dist_to_end, diff_max, freq, cell_side;
+    int subsections;
+} orc_gym_world_t;
+
+/* math.hypot(x, y) as CPython 3.12 evaluates it (Modules/mathmodule.c vector_norm): power-of-two
+ * scaling, double-length accumulation of the squares, one differential correction step. */
+double orc_py_hypot(double a, double b) {
+    double v[2] = {fabs(a), fabs(b)};
+    double max = v[0] > v[1] ? v[0] : v[1];
+    if (isinf(v[0]) || isinf(v[1])) return INFINITY;
+    if (isnan(v[0]) || isnan(v[1])) return NAN;
+    if (max == 0.0) return max;
+    int max_e; frexp(max, &max_e);
+    if (max_e < -1023) return orc_py_hypot(ldexp(a, 1074), ldexp(b, 1074)) * 0x1.0p-1074; /* subnormal inputs; never on this path */
+    double scale = ldexp(1.0, -max_e), csum = 1.0, frac1 = 0.0, frac2 = 0.0;
+    for (int i = 0; i < 2; i++) {
+        double x = v[i] * scale;
+        double hi = x * x, lo = fma(x, x, -hi);
+        double s = csum + hi, e = (csum - s) + hi;       /* dl_fast_sum: |csum| >= |hi| */
+        csum = s; frac1 += lo; frac2 += e;
+    }
+    double h = sqrt(csum - 1.0 + (frac1 + frac2));
+    double hi = -h * h, lo = fma(-h, h, -hi);
+    double s = csum + hi, e = (csum - s) + hi;
+    csum = s; frac1 += lo; frac2 += e;
+    double x = csum - 1.0 + (frac1 + frac2);
+    h += x / (2.0 * h);
+    return h / scale;
+}
+
+/* Planner_RRT.angle_wrap (:420-428): recursion unrolled, same additions */
+static double gym_angle_wrap(double a) {
+    while (!(-M_PI <= a && a <= M_PI)) {
+        if (a > M_PI) a += (-2.0 * M_PI);
+        else if (a < -M_PI) a += (2.0 * M_PI);
+        else return a; /* NaN */
+    }
+    return a;
+}
+
+/* discretize_env (:77-93): rows = int(height) // int(cell_side), cols likewise */
+void orc_gym_grid_shape(const orc_gym_world_t *w, int *rows, int *cols) {
+    long cs = (long)w->cell_side;
+    long hh = (long)(w->y1 - w->y0), ww = (long)(w->x1 - w->x0);
+    /* Python // floors; operands are non-negative here */
+    *rows = cs > 0 ? (int)(hh / cs) : 0;
+    *cols = cs > 0 ? (int)(ww / cs) : 0;
+}
+
+/* add_node_to_grid (:108-154): flat sub-cell id (row * cols + col) * subsections + sub, or -1 when
+ * the node falls past the last row / column (the early returns), or -2 for an IndexError. */
+static int gym_subcell(const orc_gym_world_t *w, int rows, int cols, double x, double y, double theta) {
+    long row = (long)(y / w->cell_side), col = (long)(x / w->cell_side);             /* :115-116 */
+    if (row >= rows) return -1;                                                     /* :118 */
+    if (col >= cols) return -1;                                                     /* :122 */
+    if (row < 0) { row += rows; if (row < 0) return -2; }                           /* list[-k] */
+    if (col < 0) { col += cols; if (col < 0) return -2; }
+    double delta = (2.0 * M_PI) / (double)w->subsections;                           /* grid_cell_rrt.py:52 */
+    double raw = theta / delta;                                                     /* :127 */
+    long sub = (long)floor(raw);                                                    /* :130 */
+    if (sub < 0) sub = (long)(w->subsections + sub);                                /* :134-135 */
+    if (sub == w->subsections) sub -= 1;                                            /* :137-152 (after the input() prompt) */
+    if (sub < 0) { sub += w->subsections; if (sub < 0) return -2; }
+    if (sub >= w->subsections) return -2;
+    return (int)((row * cols + col) * w->subsections + sub);
+}
+
+/* check_within_boundary (:458-471) */
+static int gym_within(const orc_gym_world_t *w, double x, double y) {
+    return (x >= w->x0) && (x <= w->x1) && (y >= w->y0) && (y <= w->y1);
+}
+
+/* check_collision_free (:430-449) on pts[n][>=2] with row stride `ld`: dList never reset */
+static int gym_collision_free(const orc_gym_world_t *w, const double *pts, int n, int ld) {
+    double running = INFINITY;
+    for (int k = 0; k < w->K; k++) {
+        double ox = w->circles[3 * k], oy = w->circles[3 * k + 1];
+        if (n == 0) return -1;   /* min([]) ValueError */
+        for (int i = 0; i < n; i++) {
+            double dx = pts[ld * i] - ox, dy = pts[ld * i + 1] - oy;                /* get_distance_angle(obstacle, point) */
+            double d = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+            if (d < running) running = d;
+        }
+        if (running <= w->circles[3 * k + 2]) return 0;
+    }
+    for (int i = 0; i < n; i++)
+        if (!gym_within(w, pts[ld * i], pts[ld * i + 1])) return 0;
+    return 1;
+}
+
+/* connect_to_goal_curve_alt (:375-418).  Returns 1 and the arc description, 0 for `return None`,
+ * ORC_ZERO_DIV+100 for a ZeroDivisionError.  arc = {x_C, y_C, radius, ang_vel, theta_0, length},
+ * point i = (x_C + r sin(w i + th0), y_C - r cos(w i + th0), w i + th0), i = 0..n_expand. */
+static int gym_goal_arc(const orc_gym_world_t *w, double x, double y, double th, double arc[6], int *n_expand) {
+    double theta0 = th;
+    double gdx = w->goal_x - x, gdy = w->goal_y - y;
+    double theta = atan2(gdy, gdx);                                                 /* get_distance_angle :485 */
+    double diff = gym_angle_wrap(theta - theta0);
+    if (fabs(diff) > M_PI / 2.0) return 0;                                          /* :382 */
+    double r_G = orc_py_hypot(gdx, gdy);                                            /* :386 */
+    double phi_G = atan2(gdy, gdx);
+    double phi, radius;
+    if (phi_G - th != 0.0) phi = 2.0 * gym_angle_wrap(phi_G - th); else return 0;   /* :391-395 */
+    double sn = sin(phi_G - th);
+    if (sn != 0.0) radius = r_G / (2.0 * sn); else return 0;                        /* :397-400 */
+    double length = radius * phi;
+    if (phi > M_PI) { phi -= 2.0 * M_PI; length = -radius * phi; }
+    else if (phi < -M_PI) { phi += 2.0 * M_PI; length = -radius * phi; }
+    double le = length / w->exp_rate;
+    if (le == 0.0) return 100 + ORC_ZERO_DIV;
+    double ang_vel = phi / le;                                                      /* :411 */
+    arc[0] = x - radius * sin(th);                                                  /* :414 */
+    arc[1] = y + radius * cos(th);
+    arc[2] = radius; arc[3] = ang_vel; arc[4] = theta0; arc[5] = length;
+    *n_expand = (int)floor(le);                                                     /* :417 */
+    return 1;
+}
+static void gym_arc_point(const double arc[6], int i, double p[3]) {
+    double a = arc[3] * (double)i + arc[4];
+    p[0] = arc[0] + arc[2] * sin(a);
+    p[1] = arc[1] - arc[2] * cos(a);
+    p[2] = a;
+}
+
+#define GYM_TRACE_W 11
+/* Planner_RRT.planning (:157-196) when actions == NULL, else the RRTEnv.step loop
+ * (gym_rrt/envs/rrt_env.py:206-224) over flat sub-cell ids (empty cells are skipped).
+ * nodes [max_step+1][4] = x, y, theta, traj_time_stamp; node_cell [max_step+1] flat sub-cell or -1;
+ * occupied [max_step+1] flat ids in first-occupancy order; counts NULL or [rows*cols*subsections];
+ * trace NULL or [max_step][11] = parent, nwp, accepted, done, n_nodes, n_occupied, n_uniforms (of generate_one_node),
+ * candidate x, y, theta, t; path [path_cap][3] goal -> start (generate_final_course :318-328).
+ * rec[0..5] = steps, found, n_nodes, n_occupied, n_path, last node; arc_len = final_node.length. */
+int orc_gym_plan(const orc_gym_world_t *w, const double start[3], orc_stream_t *rng, int max_step,
+                 const int32_t *actions, int32_t rec[6], double *nodes, int32_t *parents, int32_t *node_cell,
+                 int32_t *occupied, int32_t *counts, double *trace, double *path, int path_cap, double *arc_len) {
+    int rows, cols; orc_gym_grid_shape(w, &rows, &cols);
+    int maxp = (int)ceil(w->freq) + 2;
+    int cap = max_step + 1, status = ORC_OK;
+    double *wps = (double *)malloc(sizeof(double) * 3 * (size_t)cap * maxp);
+    int *nwp = (int *)calloc(cap, sizeof(int));
+    int *cell_count = (int *)calloc(cap, sizeof(int));   /* per occupied entry */
+    double *pts = (double *)malloc(sizeof(double) * 3 * (maxp + 1));
+    int n = 1, n_occ = 0, steps = 0, found = 0, n_path = 0, goal_checked = -1;
+    if (counts) memset(counts, 0, sizeof(int32_t) * (size_t)rows * cols * w->subsections);
+    nodes[0] = start[0]; nodes[1] = start[1]; nodes[2] = start[2]; nodes[3] = 0.0; parents[0] = -1;
+    *arc_len = 0.0;
+    {   /* __init__ :57 add_node_to_grid(start) */
+        int c = gym_subcell(w, rows, cols, start[0], start[1], start[2]);
+        node_cell[0] = c;
+        if (c == -2) { status = ORC_KEY_ERROR; goto done; }
+        if (c >= 0) { occupied[0] = c; cell_count[0] = 1; n_occ = 1; if (counts) counts[c] = 1; }
+    }
+    for (int it = 0; it < max_step; it++) {
+        int cell, oi = -1;
+        if (!actions) {
+            if (n_occ == 0) { status = ORC_KEY_ERROR; break; }                     /* random.choice([]) IndexError */
+            oi = (int)(next_u(rng) * (double)n_occ);                               /* :176 */
+            cell = occupied[oi];
+        } else {
+            cell = actions[it];
+            for (int j = 0; j < n_occ; j++) if (occupied[j] == cell) { oi = j; break; }
+            if (oi < 0) continue;                                                  /* node_array == [] (:209-215) */
+        }
+        /* generate_one_node :198-238 */
+        int64_t pos0 = rng->pos;
+        int k = (int)(next_u(rng) * (double)cell_count[oi]);                       /* :217 random.choice(node_array) */
+        int pn = -1;
+        for (int j = 0, seen = 0; j < n; j++) if (node_cell[j] == cell) { if (seen == k) { pn = j; break; } seen++; }
+        /* steer :241-283 */
+        double x = nodes[4 * pn], y = nodes[4 * pn + 1], th = nodes[4 * pn + 2], t = nodes[4 * pn + 3];
+        int m = 0;
+        pts[0] = x; pts[1] = y; pts[2] = th;                                       /* path[0] = mps */
+        double n_expand = floor(uniform(rng, 0.0, w->freq) / 1.0);                 /* :251-252 */
+        for (int i = 0; i < (int)n_expand; i++) {
+            double dist = uniform(rng, 0.0, w->dist_to_end);
+            double diff = uniform(rng, -w->diff_max, w->diff_max);
+            if (fabs(dist) > fabs(diff)) {                                         /* :258 */
+                double s1 = dist + diff, s2 = dist - diff, den = -s1 + s2;
+                if (den == 0.0) { status = ORC_ZERO_DIV; break; }
+                double radius = (s1 + s2) / den;
+                if (2.0 * radius == 0.0) { status = ORC_ZERO_DIV; break; }
+                double phi = (s1 + s2) / (2.0 * radius);
+                double ori = th;
+                th = gym_angle_wrap(th + phi);                                     /* :265 */
+                double dx = radius * (sin(th) - sin(ori));
+                double dy = radius * (-cos(th) + cos(ori));
+                x += dx; y += dy;
+                t += sqrt(pow(dx, 2.0) + pow(dy, 2.0)) / 1.0;                      /* velocity = 1 (:241, :274) */
+                m++;
+                pts[3 * m] = x; pts[3 * m + 1] = y; pts[3 * m + 2] = th;
+            }
+        }
+        if (status != ORC_OK) break;
+        if (rng->exhausted) { status = ORC_STREAM_END; break; }
+        int accepted = 0, is_done = 0;
+        int cf = gym_collision_free(w, pts, m + 1, 3);                             /* :222 */
+        if (cf == 1) {
+            nodes[4 * n] = x; nodes[4 * n + 1] = y; nodes[4 * n + 2] = th; nodes[4 * n + 3] = t;
+            parents[n] = pn; nwp[n] = m;
+            memcpy(wps + 3 * (size_t)n * maxp, pts + 3, sizeof(double) * 3 * m);
+            int c = gym_subcell(w, rows, cols, x, y, th);                          /* :226 */
+            node_cell[n] = c;
+            if (c == -2) { status = ORC_KEY_ERROR; break; }
+            if (c >= 0) {
+                int oj = -1;
+                for (int j = 0; j < n_occ; j++) if (occupied[j] == c) { oj = j; break; }
+                if (oj < 0) { oj = n_occ++; occupied[oj] = c; cell_count[oj] = 0; } /* :153-154 */
+                cell_count[oj]++;
+                if (counts) counts[c]++;
+            }
+            n++; accepted = 1;
+        }
+        steps++;
+        /* connect_to_goal_curve_alt(self.mps_list[-1]) (:229): a pure function of the last node, so
+         * it is re-evaluated only when the last node changed */
+        int last = n - 1;
+        if (goal_checked != last) {
+            goal_checked = last;
+            double arc[6]; int ne = 0;
+            int g = gym_goal_arc(w, nodes[4 * last], nodes[4 * last + 1], nodes[4 * last + 2], arc, &ne);
+            if (g >= 100) { status = g - 100; break; }
+            if (g == 1) {
+                /* check_collision_free(final_node) (:232): obstacle-major running minimum over the arc points */
+                int ok = 1; double running = INFINITY, p[3];
+                if (ne + 1 <= 0 && w->K > 0) { status = ORC_KEY_ERROR; break; }
+                for (int kk = 0; kk < w->K && ok; kk++) {
+                    for (int i = 0; i <= ne; i++) {
+                        gym_arc_point(arc, i, p);
+                        double dx = p[0] - w->circles[3 * kk], dy = p[1] - w->circles[3 * kk + 1];
+                        double d = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+                        if (d < running) running = d;
+                    }
+                    if (running <= w->circles[3 * kk + 2]) ok = 0;
+                }
+                for (int i = 0; i <= ne && ok; i++) { gym_arc_point(arc, i, p); if (!gym_within(w, p[0], p[1])) ok = 0; }
+                if (ok) {
+                    is_done = 1; found = 1; *arc_len = arc[5];
+                    /* generate_final_course (:318-328): [final] + reversed(final.path) + reversed(node.path) ... */
+                    double p2[3];
+                    if (ne >= 0) gym_arc_point(arc, ne, p2); else { p2[0] = nodes[4 * last]; p2[1] = nodes[4 * last + 1]; p2[2] = nodes[4 * last + 2]; }
+                    #define GYM_PUSH(a, b, c) do { if (n_path < path_cap) { path[3 * n_path] = (a); path[3 * n_path + 1] = (b); path[3 * n_path + 2] = (c); } n_path++; } while (0)
+                    GYM_PUSH(p2[0], p2[1], p2[2]);
+                    for (int i = ne; i >= 0; i--) { gym_arc_point(arc, i, p2); GYM_PUSH(p2[0], p2[1], p2[2]); }
+                    for (int j = last; parents[j] >= 0; j = parents[j]) {
+                        const double *wj = wps + 3 * (size_t)j * maxp;
+                        for (int i = nwp[j] - 1; i >= 0; i--) GYM_PUSH(wj[3 * i], wj[3 * i + 1], wj[3 * i + 2]);
+                        int pj = parents[j];
+                        GYM_PUSH(nodes[4 * pj], nodes[4 * pj + 1], nodes[4 * pj + 2]);
+                    }
+                    #undef GYM_PUSH
+                }
+            }
+        }
+        if (trace) {
+            double *tr = trace + GYM_TRACE_W * (size_t)(steps - 1);
+            tr[0] = pn; tr[1] = m; tr[2] = accepted; tr[3] = is_done; tr[4] = n; tr[5] = n_occ;
+            tr[6] = (double)(rng->pos - pos0); tr[7] = x; tr[8] = y; tr[9] = th; tr[10] = t;
+        }
+        if (is_done) break;
+    }
+done:
+    rec[0] = steps; rec[1] = found; rec[2] = n; rec[3] = n_occ; rec[4] = n_path; rec[5] = n - 1;
+    if (status == ORC_OK && n_path > path_cap) status = 5; /* overflow */
+    free(wps); free(nwp); free(cell_count); free(pts);
+    return status;
+}
+
+/* batch of independent episodes (own start / goal / seed each), pthread-parallel: the CPU baseline */
+typedef struct { const orc_gym_world_t *w; const double *starts, *goals; const uint64_t *seeds; int max_step;
+                 int32_t *recs; int32_t *status; } orc_gym_batch_t;
+static void orc_gym_body(int64_t q, void *vc) {
+    orc_gym_batch_t *c = (orc_gym_batch_t *)vc;
+    orc_gym_world_t w = *c->w; w.goal_x = c->goals[2 * q]; w.goal_y = c->goals[2 * q + 1];
+    int cap = c->max_step + 1;
+    double *nodes = (double *)malloc(sizeof(double) * 4 * cap);
+    int32_t *ibuf = (int32_t *)malloc(sizeof(int32_t) * 3 * cap);
+    double arc_len;
+    orc_stream_t s = {NULL, 0, orc_stream_key(c->seeds[q]), 0, 0, 0};
+    c->status[q] = orc_gym_plan(&w, c->starts + 3 * q, &s, c->max_step, NULL, c->recs + 6 * q, nodes, ibuf, ibuf + cap,
+                                ibuf + 2 * cap, NULL, NULL, NULL, 0, &arc_len);
+    if (c->status[q] == 5) c->status[q] = ORC_OK;   /* path not requested */
+    free(nodes); free(ibuf);
+}
+void orc_gym_plan_batch(const orc_gym_world_t *w, const double *starts, const double *goals, const uint64_t *seeds,
+                        int Q, int max_step, int nthreads, int32_t *recs, int32_t *status) {
+    orc_gym_batch_t c = {w, starts, goals, seeds, max_step, recs, status};
+    orc_parallel_for(Q, 4, nthreads, orc_gym_body, &c);
+}

@@ -153,6 +153,10 @@ class StreamPlayer:
     def uniform(self, a, b):
         return a + (b - a) * self.random()
 
+    def choice(self, seq):
+        """random.choice on the pre-generated sequence: element int(u * len)."""
+        return seq[int(self.random() * len(seq))]
+
 
 class RecordingRandom:
     """Wraps Python's own Mersenne Twister and records every u it hands out."""
@@ -169,6 +173,9 @@ class RecordingRandom:
 
     def uniform(self, a, b):
         return a + (b - a) * self.random()
+
+    def choice(self, seq):
+        return seq[int(self.random() * len(seq))]
 
 
 class BudgetClock:
@@ -418,3 +425,139 @@ def path_to_array(path):
     """list[Motion_plan_state] -> [n, 6] (x, y, theta, v, traj_time_stamp, length)."""
     return np.array([[p.x, p.y, p.theta, p.v, p.traj_time_stamp, p.length] for p in path],
                     dtype=np.float64).reshape(-1, 6)
+
+
+# ---------------------------------------------------------------------------------------------
+# gym_rrt.envs.rrt_dubins.Planner_RRT (the goal-directed planner the RL environment drives).
+# ---------------------------------------------------------------------------------------------
+_gym_cache = None
+
+
+def load_gym_reference():
+    """Import the unmodified gym_rrt/envs/{rrt_dubins,motion_plan_state_rrt,grid_cell_rrt}.py.
+
+    The package __init__ files pull in `gym` (absent here), so empty package stubs whose __path__
+    points at the reference directories stand in for them; the three modules themselves are the
+    reference's own files, executed unmodified."""
+    global _gym_cache
+    if _gym_cache is not None:
+        return _gym_cache
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    import importlib
+    names = ["gym_rrt", "gym_rrt.envs", "gym_rrt.envs.rrt_dubins", "gym_rrt.envs.motion_plan_state_rrt",
+             "gym_rrt.envs.grid_cell_rrt", "matplotlib", "matplotlib.pyplot", "matplotlib.path",
+             "matplotlib.patches"]
+    saved_mods = {n: sys.modules.pop(n) for n in names if n in sys.modules}
+    saved_path = list(sys.path)
+    sys.path[:0] = [SHIMS]
+    try:
+        pkg = types.ModuleType("gym_rrt")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "gym_rrt")]
+        sub = types.ModuleType("gym_rrt.envs")
+        sub.__path__ = [os.path.join(REFERENCE_ROOT, "gym_rrt", "envs")]
+        sys.modules["gym_rrt"], sys.modules["gym_rrt.envs"] = pkg, sub
+        mod = importlib.import_module("gym_rrt.envs.rrt_dubins")
+        mps = importlib.import_module("gym_rrt.envs.motion_plan_state_rrt")
+        ns = types.SimpleNamespace(rrt_dubins=mod, Planner_RRT=mod.Planner_RRT, MPS=mps.Motion_plan_state)
+    finally:
+        sys.path[:] = saved_path
+        for n in names:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved_mods)
+    _gym_cache = ns
+    return ns
+
+
+GYM_MAIN_OBSTACLES = [(12.0, 38.0, 4.0), (17.0, 34.0, 5.0), (20.0, 29.0, 4.0), (25.0, 25.0, 3.0),
+                      (29.0, 20.0, 4.0), (34.0, 17.0, 3.0), (37.0, 8.0, 5.0)]   # gym_rrt/envs/rrt_dubins.py:509-517
+
+
+def traced_gym_planning(gref, start, goal, boundary, obstacles, *, rng, max_step=200, exp_rate=1,
+                        dist_to_end=2, diff_max=0.5, freq=50, cell_side_length=2, subsections_in_cell=8,
+                        actions=None):
+    """Run the unmodified Planner_RRT on the sequence `rng`; record what each step decided.
+
+    start = (x, y, theta), goal = (x, y), boundary = (x0, y0, x1, y1), obstacles = [(x, y, size)].
+    actions=None drives Planner_RRT.planning (cells drawn with random.choice); otherwise `actions`
+    is a list of (row, col, subsection), or a callable(planner) -> (row, col, subsection) asked
+    max_step times, fed to generate_one_node the way RRTEnv.step does
+    (gym_rrt/envs/rrt_env.py:213-224), an empty cell being skipped by the caller.
+    Returns a dict of arrays (one row per step) plus the final path (goal -> start order)."""
+    M = gref.MPS
+    mod = gref.rrt_dubins
+    s = M(x=start[0], y=start[1], theta=start[2])
+    g = M(x=goal[0], y=goal[1])
+    b = [M(x=boundary[0], y=boundary[1]), M(x=boundary[2], y=boundary[3])]
+    obs = [M(x=o[0], y=o[1], size=o[2]) for o in obstacles]
+    saved_random = mod.random
+    mod.random = rng
+    try:
+        pl = gref.Planner_RRT(s, g, b, obs, [], exp_rate=exp_rate, dist_to_end=dist_to_end, diff_max=diff_max,
+                              freq=freq, cell_side_length=cell_side_length,
+                              subsections_in_cell=subsections_in_cell)
+        index_of = {id(s): 0}
+        rows = []
+        cur = {}
+        orig_steer, orig_gen = pl.steer, pl.generate_one_node
+
+        def steer(mps, *a, **k):
+            cur["parent"] = index_of[id(mps)]
+            out = orig_steer(mps, *a, **k)
+            cur["nwp"] = len(out.path) - 1
+            cur["cand"] = (out.x, out.y, out.theta, out.traj_time_stamp)
+            return out
+
+        def gen(cell, *a, **k):
+            cur.clear()
+            n_before = len(pl.mps_list)
+            pos0 = rng.pos
+            done, path = orig_gen(cell, *a, **k)
+            accepted = len(pl.mps_list) > n_before
+            if accepted:
+                index_of[id(pl.mps_list[-1])] = len(pl.mps_list) - 1
+            rows.append((cur["parent"], cur["nwp"], int(accepted), int(done), len(pl.mps_list),
+                         len(pl.occupied_grid_cells_array), rng.pos - pos0) + cur["cand"])
+            return done, path
+
+        pl.steer, pl.generate_one_node = steer, gen
+        if actions is None:
+            path, step, _ = pl.planning(max_step=max_step)
+            done = bool(rows and rows[-1][3])
+        else:
+            path, step, done = None, 0, False
+            fed = []
+            it = (actions(pl) for _ in range(max_step)) if callable(actions) else iter(actions)
+            for (r, c, k) in it:
+                fed.append((r, c, k))
+                cell = pl.env_grid[r][c].subsection_cells[k]
+                if cell.node_array == []:
+                    continue
+                done, path = pl.generate_one_node(cell)
+                step += 1
+                if done:
+                    break
+    finally:
+        mod.random = saved_random
+    rows = np.array(rows, dtype=np.float64).reshape(-1, 11)
+    out = {
+        "parent": rows[:, 0].astype(np.int32), "nwp": rows[:, 1].astype(np.int32),
+        "accepted": rows[:, 2].astype(np.uint8), "done": rows[:, 3].astype(np.uint8),
+        "n_nodes": rows[:, 4].astype(np.int32), "n_occupied": rows[:, 5].astype(np.int32),
+        "n_uniforms": rows[:, 6].astype(np.int32), "cand": rows[:, 7:11].copy(),
+        "steps": step, "found": bool(done),
+        "occupied": np.array(pl.occupied_grid_cells_array, dtype=np.int32).reshape(-1, 3),
+        "nodes": np.array([[m.x, m.y, m.theta, m.traj_time_stamp] for m in pl.mps_list]),
+        "counts": np.array([[len(sc.node_array) for sc in cell.subsection_cells]
+                            for row in pl.env_grid for cell in row], dtype=np.int32),
+        "grid_shape": np.array([len(pl.env_grid), len(pl.env_grid[0])], dtype=np.int32),
+    }
+    if actions is not None:
+        out["actions"] = np.array(fed, dtype=np.int32).reshape(-1, 3)
+    if done:
+        out["path"] = np.array([[m.x, m.y, m.theta] for m in path])
+        out["goal_arc_length"] = float(path[0].length)
+    else:
+        out["path"] = np.zeros((0, 3))
+        out["goal_arc_length"] = 0.0
+    return out

@@ -320,3 +320,93 @@ def occupancy(cell_polys, bounds, cell_size, bin_interval, detect_range, tracks)
                             toff.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(tracks)), _p(out), C.c_int64(out.size))
     assert r == T.value
     return out
+
+
+# ------------------------------------------------------------------ gym_rrt Planner_RRT ------
+class GymWorld(C.Structure):
+    _fields_ = [("x0", C.c_double), ("y0", C.c_double), ("x1", C.c_double), ("y1", C.c_double),
+                ("K", C.c_int), ("circles", _dp), ("goal_x", C.c_double), ("goal_y", C.c_double),
+                ("exp_rate", C.c_double), ("dist_to_end", C.c_double), ("diff_max", C.c_double),
+                ("freq", C.c_double), ("cell_side", C.c_double), ("subsections", C.c_int)]
+
+
+_ip = C.POINTER(C.c_int32)
+
+
+def gym_world(boundary, obstacles, goal=(0.0, 0.0), exp_rate=1.0, dist_to_end=2.0, diff_max=0.5, freq=50.0,
+              cell_side_length=2.0, subsections_in_cell=8):
+    circles = _f64(obstacles, (-1, 3)) if len(obstacles) else np.zeros((0, 3))
+    w = GymWorld(float(boundary[0]), float(boundary[1]), float(boundary[2]), float(boundary[3]),
+                 len(circles), _p(circles), float(goal[0]), float(goal[1]), float(exp_rate), float(dist_to_end),
+                 float(diff_max), float(freq), float(cell_side_length), int(subsections_in_cell))
+    w._keep = circles
+    return w
+
+
+def gym_grid_shape(w: GymWorld):
+    r, c = C.c_int(), C.c_int()
+    lib().orc_gym_grid_shape(C.byref(w), C.byref(r), C.byref(c))
+    return r.value, c.value
+
+
+def py_hypot(a, b):
+    f = lib().orc_py_hypot
+    f.restype = C.c_double
+    f.argtypes = [C.c_double, C.c_double]
+    return f(a, b)
+
+
+def gym_plan(w: GymWorld, start, max_step=200, seed=None, u=None, actions=None, path_cap=4096, want_counts=True):
+    """Planner_RRT.planning (actions None) or the RRTEnv.step loop over flat sub-cell ids."""
+    L = lib()
+    L.orc_gym_plan.restype = C.c_int
+    start = _f64(start, (3,))
+    cap = max_step + 1
+    rows, cols = gym_grid_shape(w)
+    rec = np.zeros(6, np.int32)
+    nodes = np.zeros((cap, 4))
+    parents = np.zeros(cap, np.int32)
+    node_cell = np.zeros(cap, np.int32)
+    occupied = np.zeros(cap, np.int32)
+    counts = np.zeros(rows * cols * w.subsections, np.int32) if want_counts else None
+    trace = np.zeros((max_step, 11))
+    path = np.zeros((path_cap, 3))
+    arc_len = C.c_double()
+    if u is not None:
+        u = _f64(u, (-1,))
+        rng = Stream(_p(u), len(u), 0, 0, 0, 0)
+    else:
+        rng = Stream(None, 0, L.orc_stream_key(int(seed)), 0, 0, 0)
+    if actions is not None:
+        actions = np.ascontiguousarray(np.asarray(actions, dtype=np.int32))
+        assert len(actions) == max_step
+    st = L.orc_gym_plan(C.byref(w), _p(start), C.byref(rng), C.c_int(max_step),
+                        actions.ctypes.data_as(_ip) if actions is not None else None,
+                        rec.ctypes.data_as(_ip), _p(nodes), parents.ctypes.data_as(_ip), node_cell.ctypes.data_as(_ip),
+                        occupied.ctypes.data_as(_ip), counts.ctypes.data_as(_ip) if want_counts else None,
+                        _p(trace), _p(path), C.c_int(path_cap), C.byref(arc_len))
+    steps, found, n, n_occ, n_path, last = [int(v) for v in rec]
+    tr = trace[:steps]
+    return {
+        "status": st, "steps": steps, "found": bool(found), "n_nodes": n, "last": last,
+        "nodes": nodes[:n].copy(), "parents": parents[:n].copy(), "node_cell": node_cell[:n].copy(),
+        "occupied": occupied[:n_occ].copy(), "counts": counts, "path": path[:min(n_path, path_cap)].copy(),
+        "n_path": n_path, "goal_arc_length": arc_len.value, "n_uniforms_total": int(rng.pos),
+        "parent": tr[:, 0].astype(np.int32), "nwp": tr[:, 1].astype(np.int32), "accepted": tr[:, 2].astype(np.uint8),
+        "done": tr[:, 3].astype(np.uint8), "n_nodes_step": tr[:, 4].astype(np.int32),
+        "n_occupied_step": tr[:, 5].astype(np.int32), "n_uniforms": tr[:, 6].astype(np.int32), "cand": tr[:, 7:11].copy(),
+        "grid_shape": (rows, cols),
+    }
+
+
+def gym_plan_batch(w: GymWorld, starts, goals, seeds, max_step=200, nthreads=0):
+    starts = _f64(starts, (-1, 3))
+    goals = _f64(goals, (-1, 2))
+    seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+    Q = len(seeds)
+    recs = np.zeros((Q, 6), np.int32)
+    status = np.zeros(Q, np.int32)
+    lib().orc_gym_plan_batch(C.byref(w), _p(starts), _p(goals), seeds.ctypes.data_as(C.POINTER(C.c_uint64)),
+                             C.c_int(Q), C.c_int(max_step), C.c_int(nthreads), recs.ctypes.data_as(_ip),
+                             status.ctypes.data_as(_ip))
+    return recs, status

@@ -44,3 +44,40 @@ def exploring_golden():
     z = np.load(os.path.join(GOLDEN, "exploring.npz"))
     meta = json.loads(str(z["meta"]))
     return z, meta
+
+
+class GymEpisode:
+    """One golden episode of gym_rrt Planner_RRT (tests/golden/gym_plan.npz, oracle/make_golden_gym.py)."""
+
+    def __init__(self, z, name):
+        s = z[name + "/setup"]
+        self.name = name
+        self.start, self.goal, self.boundary = s[0:3].copy(), s[3:5].copy(), s[5:9].copy()
+        self.freq, self.cell_side, self.subsections = float(s[9]), float(s[10]), int(s[11])
+        self.max_step, self.seed, self.steps, self.found = int(s[12]), int(s[13]), int(s[14]), bool(s[15])
+        self.goal_arc_length = float(s[16])
+        self.obstacles = z[name + "/obstacles"]
+        self.rows, self.cols = [int(v) for v in z[name + "/grid_shape"]]
+        self.counts_nz = z[name + "/counts_nz"]
+        self.actions = z[name + "/actions"] if (name + "/actions") in z.files else None
+        for k in ("parent", "nwp", "accepted", "done", "n_nodes", "n_occupied", "n_uniforms", "cand", "occupied",
+                  "nodes", "path"):
+            setattr(self, k, z[name + "/" + k])
+
+    def flat(self, rck):
+        rck = np.asarray(rck).reshape(-1, 3)
+        rck = np.column_stack([rck[:, 0] % self.rows, rck[:, 1] % self.cols, rck[:, 2]])   # list[-k] indexing
+        return ((rck[:, 0] * self.cols + rck[:, 1]) * self.subsections + rck[:, 2]).astype(np.int32)
+
+    def flat_actions(self):
+        """actions padded to max_step with -1 (an id no cell has: skipped like an empty cell)"""
+        a = np.full(self.max_step, -1, np.int32)
+        f = self.flat(self.actions)
+        a[:len(f)] = f
+        return a
+
+
+@pytest.fixture(scope="session")
+def gym_golden():
+    z = np.load(os.path.join(GOLDEN, "gym_plan.npz"))
+    return [GymEpisode(z, str(n)) for n in z["names"]]
