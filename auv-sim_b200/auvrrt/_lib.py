@@ -36,6 +36,20 @@ class PlanRecord(C.Structure):
                 ("t_leaf", C.c_double)]
 
 
+class GymParams(C.Structure):
+    _fields_ = [("x0", C.c_double), ("y0", C.c_double), ("x1", C.c_double), ("y1", C.c_double),
+                ("exp_rate", C.c_double), ("dist_to_end", C.c_double), ("diff_max", C.c_double),
+                ("freq", C.c_double), ("cell_side", C.c_double), ("subsections", C.c_int32),
+                ("node_cap", C.c_int32), ("track_counts", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GymRecord(C.Structure):
+    _fields_ = [("status", C.c_int32), ("done", C.c_int32), ("steps", C.c_int32), ("n_nodes", C.c_int32),
+                ("n_occupied", C.c_int32), ("last_parent", C.c_int32), ("last_accepted", C.c_int32),
+                ("last_nwp", C.c_int32), ("last_uniforms", C.c_int32), ("n_path", C.c_int32),
+                ("n_uniforms", C.c_int64), ("cand", C.c_double * 4), ("arc_length", C.c_double)]
+
+
 class PlanTrace(C.Structure):
     _fields_ = [("parent", _i32p), ("safe", _u8p), ("nwp", _i32p), ("leaf", _dp), ("upos", _i64p)]
 
@@ -47,6 +61,8 @@ EXPORTS = [
     "auvrrt_cost_point", "auvrrt_edges_dubins_dev", "auvrrt_edges_arc_dev", "auvrrt_edges_dubins",
     "auvrrt_edges_arc", "auvrrt_stream_u", "auvrrt_plan_batch", "auvrrt_plan_workspace_bytes", "auvrrt_plan_workspace_bytes_q",
     "auvrrt_plan_batch_dev", "auvrrt_materialize", "auvrrt_calibrate_fp32", "auvrrt_occupancy_dims", "auvrrt_occupancy_grid",
+    "auvrrt_gym_create", "auvrrt_gym_destroy", "auvrrt_gym_grid_shape", "auvrrt_gym_reset", "auvrrt_gym_step",
+    "auvrrt_gym_step_dev", "auvrrt_gym_tree", "auvrrt_gym_counts", "auvrrt_gym_counts_dev", "auvrrt_gym_path",
 ]
 
 _lib = None
@@ -105,6 +121,19 @@ def lib():
     L.auvrrt_occupancy_dims.argtypes = [_dp, C.c_double, C.c_double, _dp, _i64p, C.c_int, _ip, _ip, _ip]
     L.auvrrt_occupancy_grid.argtypes = [_dp, _i64p, C.c_int, _dp, C.c_double, C.c_double, C.c_double, _dp, _i64p,
                                         C.c_int, C.c_int, _dp, C.c_int64]
+    _u16p = C.POINTER(C.c_uint16)
+    L.auvrrt_gym_create.argtypes = [_dp, C.c_int, C.POINTER(GymParams), C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.auvrrt_gym_destroy.argtypes = [vp]
+    L.auvrrt_gym_destroy.restype = None
+    L.auvrrt_gym_grid_shape.argtypes = [vp, _ip, _ip]
+    L.auvrrt_gym_reset.argtypes = [vp, _dp, _dp, _u64p]
+    L.auvrrt_gym_step.argtypes = [vp, _i32p, C.c_int, C.c_int, vp]
+    L.auvrrt_gym_step_dev.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.auvrrt_gym_tree.argtypes = [vp, C.c_int64, C.c_int32, _dp, _i32p, _i32p, _i32p, _i32p, _i32p]
+    L.auvrrt_gym_counts.argtypes = [vp, C.c_int64, C.c_int64, _u16p]
+    L.auvrrt_gym_counts_dev.restype = vp
+    L.auvrrt_gym_counts_dev.argtypes = [vp]
+    L.auvrrt_gym_path.argtypes = [vp, C.c_int64, C.c_int32, _dp, _i32p]
     _lib = L
     return L
 

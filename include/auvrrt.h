@@ -228,6 +228,73 @@ int auvrrt_occupancy_grid(const double *cell_xy, const int64_t *cell_off, int C,
                           double detect_range, const double *tracks, const int64_t *track_off,
                           int S, int device, double *out_grid, int64_t out_cap);
 
+/* ---- gym_rrt Planner_RRT: the goal-directed tree RRTEnv.step grows one node at a time ---------
+ * (gym_rrt/envs/rrt_dubins.py:30-503, driven by gym_rrt/envs/rrt_env.py:182-247).  SURVEY.md 8(f) N1.
+ * One handle holds Q independent episodes ("vectorised environments") resident in HBM: the tree
+ * (mps_list), the (row, col, subsection) node lists of env_grid with occupied_grid_cells_array in
+ * first-occupancy order, and optionally the dense node count of every sub-cell (the observation
+ * RRTEnv.convert_rrt_grid_to_1D_num_of_nodes_only builds, rrt_env.py:265-277).
+ * Sub-cells are addressed by the flat id (row * cols + col) * subsections + subsection, the index
+ * RRTEnv.step receives as chosen_grid_cell_idx (rrt_env.py:206-222).
+ * random.choice(seq) is seq[int(u * len(seq))] on the episode's sample sequence. */
+typedef struct auvrrt_gym auvrrt_gym_t;
+
+typedef struct {
+    double x0, y0, x1, y1;        /* boundary_point[0], boundary_point[1] (rrt_dubins.py:47) */
+    double exp_rate, dist_to_end, diff_max, freq;   /* :34 */
+    double cell_side;             /* cell_side_length */
+    int32_t subsections;          /* subsections_in_cell */
+    int32_t node_cap;             /* nodes one episode may hold, start included (steps + 1 is enough) */
+    int32_t track_counts;         /* 1: keep the dense per-sub-cell node counts */
+    int32_t reserved;
+} auvrrt_gym_params_t;
+
+typedef struct {
+    int32_t status;               /* AUVRRT_ST_*; an episode with status != 0 no longer steps */
+    int32_t done;                 /* generate_one_node returned True: a collision-free goal arc exists */
+    int32_t steps;                /* generate_one_node calls so far */
+    int32_t n_nodes;              /* len(mps_list) */
+    int32_t n_occupied;           /* len(occupied_grid_cells_array) */
+    int32_t last_parent;          /* mps_list index steered from in the last step, -1: empty cell, nothing done */
+    int32_t last_accepted;        /* the last step appended its node (valid_new_node) */
+    int32_t last_nwp;             /* arc primitives the last steer kept (len(new_node.path) - 1) */
+    int32_t last_uniforms;        /* uniforms generate_one_node consumed in the last step */
+    int32_t n_path;               /* len(path) of generate_final_course when done, else 0 */
+    int64_t n_uniforms;           /* sample-sequence position */
+    double cand[4];               /* the last steered node: x, y, theta, traj_time_stamp */
+    double arc_length;            /* final_node.length (rrt_dubins.py:409) when done */
+} auvrrt_gym_record_t;            /* 88 bytes */
+
+int auvrrt_gym_create(const double *circles, int K, const auvrrt_gym_params_t *params, int64_t Q,
+                      int precision, int device, auvrrt_gym_t **out);
+void auvrrt_gym_destroy(auvrrt_gym_t *g);
+/* discretize_env (rrt_dubins.py:77-93): rows = int(height) // int(cell_side), cols likewise */
+int auvrrt_gym_grid_shape(const auvrrt_gym_t *g, int *rows, int *cols);
+/* Planner_RRT.__init__ for every episode: starts [Q][3] = x, y, theta; goals [Q][2]; seeds [Q] */
+int auvrrt_gym_reset(auvrrt_gym_t *g, const double *starts, const double *goals, const uint64_t *seeds);
+/* n_steps generate_one_node calls per episode, stopping early at done.  actions == NULL: the cell
+ * is drawn with random.choice(occupied_grid_cells_array) (Planner_RRT.planning, :157-196);
+ * else actions[Q] flat sub-cell ids (n_steps must be 1): RRTEnv.step; an empty cell does nothing.
+ * full_candidates != 0 keeps steering after a collision so that cand[] is the reference's new_node
+ * even for rejected steps (parity tests); 0 stops at the first colliding waypoint.
+ * out_records [Q] may be NULL. */
+int auvrrt_gym_step(auvrrt_gym_t *g, const int32_t *actions, int n_steps, int full_candidates,
+                    auvrrt_gym_record_t *out_records);
+/* same on device buffers (d_actions int32[Q] or NULL, d_records [Q] or NULL), asynchronous on `stream` */
+int auvrrt_gym_step_dev(auvrrt_gym_t *g, const int32_t *d_actions, int n_steps, int full_candidates,
+                        auvrrt_gym_record_t *d_records, void *stream);
+/* episode q's tree: nodes [n][4] = x, y, theta, traj_time_stamp; parents [n]; cells [n] flat
+ * sub-cell id or -1; occupied [n_occupied] in first-occupancy order.  Any pointer may be NULL. */
+int auvrrt_gym_tree(const auvrrt_gym_t *g, int64_t q, int32_t cap, double *nodes, int32_t *parents,
+                    int32_t *cells, int32_t *occupied, int32_t *n_nodes, int32_t *n_occupied);
+/* dense node counts of episodes [q0, q0 + nq): out [nq][rows * cols * subsections] uint16;
+ * needs track_counts.  auvrrt_gym_counts_dev returns the resident device array [Q][...]. */
+int auvrrt_gym_counts(const auvrrt_gym_t *g, int64_t q0, int64_t nq, uint16_t *out);
+const uint16_t *auvrrt_gym_counts_dev(const auvrrt_gym_t *g);
+/* generate_final_course (rrt_dubins.py:318-328) of a done episode: path [n][3] = x, y, theta from
+ * the goal arc's end back to the start (the reference does not reverse it). */
+int auvrrt_gym_path(const auvrrt_gym_t *g, int64_t q, int32_t cap, double *path, int32_t *n_path);
+
 /* FP32 FFMA issue-rate calibration kernel for the roofline denominator: runs `iters` dependent
  * FFMA chains on every lane of a full grid and returns achieved FLOP/s (FMA = 2). */
 int auvrrt_calibrate_fp32(int device, int iters, double *out_flops, double *out_ms);
