@@ -408,6 +408,49 @@ def extras(env, dev, args, api, adev):
                                    "equivalent_all_pairs_tflops": ne * flop_edge / mean_c / 1e12,
                                    "note": "same results as the all-pairs kernel; the grid skips circles that cannot touch a waypoint's cell"}
     del q0, q1, safe, word, length
+
+    # vectorised gym_rrt Planner_RRT (RRTEnv's planner, freq = 10), one thread per episode
+    try:
+        from auvrrt import gym as agym
+        from oracle import orc
+        OBST = [(12.0, 38.0, 4.0), (17.0, 34.0, 5.0), (20.0, 29.0, 4.0), (25.0, 25.0, 3.0), (29.0, 20.0, 4.0),
+                (34.0, 17.0, 3.0), (37.0, 8.0, 5.0)]                      # gym_rrt/envs/rrt_dubins.py:509-517
+        Qg, max_step = 262144, 200
+        rg = np.random.default_rng(5)
+        gs = np.column_stack([rg.uniform(5, 15, Qg), rg.uniform(5, 15, Qg), rg.uniform(-np.pi, np.pi, Qg)])
+        gg = np.column_stack([rg.uniform(35, 45, Qg), rg.uniform(35, 45, Qg)])
+        gseed = np.arange(Qg, dtype=np.uint64)
+        gb = agym.GymBatch((0, 0, 50, 50), OBST, Qg, freq=10.0, node_cap=max_step + 1, precision=agym.F32, device=dev.index)
+        d_recs = torch.zeros(Qg * 88, dtype=torch.uint8, device=dev)
+
+        def gym_run():
+            gb.reset(gs, gg, gseed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib_check(agym.lib().auvrrt_gym_step_dev(gb.handle, None, max_step, 0, d_recs.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream))
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3
+        from auvrrt._lib import check as _lib_check
+        gym_run()
+        ts = [gym_run() for _ in range(3)]
+        recs = np.frombuffer(d_recs.cpu().numpy().tobytes(), dtype=agym.GYM_RECORD_DTYPE)
+        steps = float(recs["steps"].sum())
+        nthreads = orc.num_threads()
+        qs = min(Qg, 512 * nthreads)
+        w = orc.gym_world((0, 0, 50, 50), OBST, freq=10.0)
+        t0 = time.perf_counter()
+        crec, _ = orc.gym_plan_batch(w, gs[:qs], gg[:qs], gseed[:qs], max_step=max_step)
+        ct = time.perf_counter() - t0
+        out["gym_planner"] = {"episodes": Qg, "max_step": max_step, "steps_per_s": steps / float(np.mean(ts)),
+                              "episodes_per_s": Qg / float(np.mean(ts)), "seconds": float(np.mean(ts)),
+                              "found_fraction": float(recs["done"].mean()), "kernel": "k_gym_run<float>",
+                              "cpu_port_steps_per_s": float(crec[:, 0].sum()) / ct, "cpu_cores": nthreads,
+                              "cpu_found_fraction": float(crec[:, 1].mean()),
+                              "note": "Planner_RRT.planning(max_step=200) per episode, main()'s obstacle course"}
+        gb.close()
+    except Exception as ex:
+        out["gym_planner"] = {"error": repr(ex)}
     return out
 
 
