@@ -1046,3 +1046,210 @@ void orc_gym_plan_batch(const orc_gym_world_t *w, const double *starts, const do
     orc_gym_batch_t c = {w, starts, goals, seeds, max_step, recs, status};
     orc_parallel_for(Q, 4, nthreads, orc_gym_body, &c);
 }
+
+/* ================================================================ lattice A* (fixed length, SOG) == */
+/* path_planning/astar_fixLenSOG.py: class astar, method astar (:551-657) with its helpers
+ * (:178-264, :380-414, :436-547).  Deterministic (no random draws); IEEE add / mul / sqrt only, so the
+ * restatement is expected to agree with the reference BIT FOR BIT.
+ * PINNED against tests/golden/astar.npz (the unmodified module run by oracle/harness.py).
+ * Inputs the reference derives through unpinned third parties are taken as inputs here: the boundary
+ * centroid (shapely/GEOS, :191) and the cell bounds after Python's round(v, 2) (:494-495). */
+typedef struct {
+    int K; const double *circles;     /* [K][3] obstacle_list order */
+    int E; const double *boundary;    /* [E][2] boundary_list corners */
+    double centroid[2];
+    int H; const double *habitats;    /* [H][3] habitat_list */
+    int T; const double *bins;        /* [T][2] shark-grid time bins, dict order */
+    int C; const double *cells_r;     /* [C][4] cell bounds rounded to 2 decimals, dict order */
+    const double *probs;              /* [T][C] */
+    const double *topn;               /* [T][C+1] prefix sums over probabilities sorted descending (orc_astar_topn) */
+} orc_astar_world_t;
+
+static int cmp_desc(const void *a, const void *b) {
+    double x = *(const double *)a, y = *(const double *)b;
+    return x < y ? 1 : (x > y ? -1 : 0);
+}
+/* get_top_n_prob (:520-536) for every n: sort descending, add one by one starting from int 0 */
+void orc_astar_topn(const double *probs, int T, int C, double *topn) {
+    double *tmp = (double *)malloc(sizeof(double) * (C > 0 ? C : 1));
+    for (int t = 0; t < T; t++) {
+        memcpy(tmp, probs + (size_t)t * C, sizeof(double) * C);
+        qsort(tmp, C, sizeof(double), cmp_desc);
+        double total = 0.0;
+        topn[(size_t)t * (C + 1)] = 0.0;
+        for (int i = 0; i < C; i++) { total += tmp[i]; topn[(size_t)t * (C + 1) + i + 1] = total; }
+    }
+    free(tmp);
+}
+
+/* same_side / point_in_triangle / within_bounds (:178-203); np.cross of 2-vectors = a0*b1 - a1*b0 */
+static int astar_same_side(const double p1[2], const double p2[2], const double a[2], const double b[2]) {
+    double ux = b[0] - a[0], uy = b[1] - a[1];
+    double cp1 = ux * (p1[1] - a[1]) - uy * (p1[0] - a[0]);
+    double cp2 = ux * (p2[1] - a[1]) - uy * (p2[0] - a[0]);
+    return cp1 * cp2 >= 0.0;
+}
+static int astar_in_triangle(const double p[2], const double a[2], const double b[2], const double c[2]) {
+    return astar_same_side(p, a, b, c) && astar_same_side(p, b, a, c) && astar_same_side(p, c, a, b);
+}
+int orc_astar_within_bounds(const orc_astar_world_t *w, double x, double y) {
+    double p[2] = {x, y};
+    for (int i = 0; i < w->E; i++) {
+        const double *a = w->boundary + 2 * i, *b = w->boundary + 2 * ((i + 1) % w->E);
+        if (astar_in_triangle(p, a, b, w->centroid)) return 1;
+    }
+    return 0;
+}
+/* collision_free (:205-221): per obstacle, no running minimum */
+int orc_astar_collision_free(const orc_astar_world_t *w, double x, double y) {
+    for (int k = 0; k < w->K; k++) {
+        double dx = x - w->circles[3 * k], dy = y - w->circles[3 * k + 1];
+        if (sqrt(pow(dx, 2.0) + pow(dy, 2.0)) <= w->circles[3 * k + 2]) return 0;
+    }
+    return 1;
+}
+/* get_cell_prob's key search (:486-505): first cell, in dict order, whose rounded box passes the abs test */
+int orc_astar_find_cell(const orc_astar_world_t *w, double x, double y) {
+    for (int c = 0; c < w->C; c++) {
+        const double *b = w->cells_r + 4 * c;
+        double dx = fabs(b[0] - b[2]), dy = fabs(b[1] - b[3]);
+        if (fabs(x - b[0]) <= dx && fabs(x - b[2]) <= dx && fabs(y - b[1]) <= dy && fabs(y - b[3]) <= dy) return c;
+    }
+    return -1;
+}
+static double astar_euclid(double ax, double ay, double bx, double by) {             /* module-level :18-29 */
+    double dx = fabs(ax - bx), dy = fabs(ay - by);
+    return sqrt(dx * dx + dy * dy);
+}
+/* Walkable (:223-246); -1 when the loop could not terminate */
+static int astar_walkable(const orc_astar_world_t *w, double cx, double cy, double px, double py) {
+    double sx = cx, sy = cy;
+    double stepx = (double)(long)(fabs(px - cx) / 5.0), stepy = (double)(long)(fabs(py - cy) / 5.0);
+    long guard = 0;
+    while (sx <= px && sy <= py) {
+        double ix = sx, iy = sy;
+        sx += stepx; sy += stepy;
+        if (!orc_astar_collision_free(w, ix, iy)) return 0;
+        if (++guard > 10000000L) return -1;
+    }
+    return 1;
+}
+
+#define ASTAR_PATH_W 6
+/* rec = {n_expanded, n_nodes, n_path, n_smooth}; path rows start -> goal: x, y, pathLen, time_stamp, cost, f;
+ * keep[i] = 1 when smoothPath (:416-452) keeps trajectory point i; expand_order NULL or [node_cap] node ids in
+ * the order they left the open list; node_xy NULL or [node_cap][2].  Status: ORC_OK, ORC_NO_PATH (open list ran
+ * empty: returns None), ORC_KEY_ERROR (AttributeError :489 no time bin / TypeError :602 no cell / IndexError
+ * :532, :419, :652), 5 = node_cap / path_cap too small. */
+int orc_astar(const orc_astar_world_t *w, const double start[2], double velocity, double limit, const double weights[4],
+              int node_cap, int path_cap, int32_t rec[4], double *cost_out, double *path, uint8_t *keep,
+              int32_t *expand_order, double *node_xy) {
+    static const double DX[8] = {0, 0, -10, 10, -10, -10, 10, 10}, DY[8] = {-10, 10, 0, 0, -10, 10, -10, 10};   /* :255 */
+    const double w2 = weights[1], w3 = weights[2], w4 = weights[3];
+    double *nx = (double *)malloc(sizeof(double) * 5 * (size_t)node_cap), *ny = nx + node_cap, *nlen = ny + node_cap,
+           *nf = nlen + node_cap, *ncost = nf + node_cap;
+    int32_t *nts = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)node_cap), *npar = nts + node_cap;
+    uint8_t *alive = (uint8_t *)calloc(node_cap, 1);
+    uint8_t *visited = (uint8_t *)calloc(600 * 600, 1);                              /* :121 */
+    int n = 0, n_exp = 0, status = ORC_NO_PATH, goal = -1;
+    rec[0] = rec[1] = rec[2] = rec[3] = 0; *cost_out = 0.0;
+    nx[0] = start[0]; ny[0] = start[1]; nlen[0] = 0.0; nf[0] = 0.0; ncost[0] = 0.0; nts[0] = 0; npar[0] = -1; alive[0] = 1; n = 1;
+    for (;;) {
+        int cur = -1;
+        for (int i = 0; i < n; i++)                                                  /* :577-583 first strict minimum */
+            if (alive[i] && (cur < 0 || nf[i] < nf[cur])) cur = i;
+        if (cur < 0) break;                                                          /* while len(open_list) > 0 */
+        alive[cur] = 0;
+        if (expand_order) expand_order[n_exp] = cur;
+        n_exp++;
+        if (fabs(nlen[cur] - limit) <= 10.0) { goal = cur; status = ORC_OK; break; }  /* :588 */
+        for (int d = 0; d < 8; d++) {
+            double px = nx[cur] + DX[d], py = ny[cur] + DY[d];                       /* :261 */
+            if (!orc_astar_within_bounds(w, px, py)) continue;
+            if (!orc_astar_collision_free(w, px, py)) continue;
+            double plen = nlen[cur] + astar_euclid(nx[cur], ny[cur], px, py);        /* :636 */
+            double dist_left = fabs(limit - plen);
+            long ts = (long)(plen / velocity);                                       /* :638 int() */
+            int tb = -1;
+            for (int t = 0; t < w->T; t++)                                           /* findCurrSOG :454-468 */
+                if ((double)ts <= w->bins[2 * t + 1] && (double)ts >= w->bins[2 * t]) { tb = t; break; }
+            if (tb < 0) { status = ORC_KEY_ERROR; goto done; }
+            int cell = orc_astar_find_cell(w, px, py);
+            if (cell < 0) { status = ORC_KEY_ERROR; goto done; }
+            double g = ncost[cur] - w4 * w->probs[(size_t)tb * w->C + cell];          /* :641 */
+            long nn = (long)dist_left;
+            if (nn > w->C) { status = ORC_KEY_ERROR; goto done; }                     /* probabilities[index] IndexError */
+            double h = -w2 * dist_left - w3 * (double)w->H - w4 * w->topn[(size_t)tb * (w->C + 1) + nn];   /* :644 */
+            double f = g + h;
+            long xi = (long)(px + 500.0), yi = (long)(py + 200.0);                   /* get_indices :405-414 */
+            if (xi < 0) xi += 600;
+            if (yi < 0) yi += 600;
+            if (xi < 0 || xi >= 600 || yi < 0 || yi >= 600) { status = ORC_KEY_ERROR; goto done; }
+            if (!visited[xi * 600 + yi]) {                                           /* :654-656 */
+                if (n >= node_cap) { status = 5; goto done; }
+                nx[n] = px; ny[n] = py; nlen[n] = plen; nf[n] = f; ncost[n] = g; nts[n] = (int32_t)ts; npar[n] = cur; alive[n] = 1;
+                n++;
+                visited[xi * 600 + yi] = 1;
+            }
+        }
+    }
+done:
+    rec[0] = n_exp; rec[1] = n;
+    if (node_xy) for (int i = 0; i < n; i++) { node_xy[2 * i] = nx[i]; node_xy[2 * i + 1] = ny[i]; }
+    if (status == ORC_OK) {
+        int np_ = 0;
+        for (int j = goal; j >= 0; j = npar[j]) np_++;
+        rec[2] = np_;
+        *cost_out = ncost[goal];                                                     /* cost[0] */
+        if (np_ > path_cap) status = 5;
+        else if (np_ < 2) status = ORC_KEY_ERROR;                                     /* smoothPath: trajectory[1] IndexError */
+        else {
+            int i = np_ - 1;
+            for (int j = goal; j >= 0; j = npar[j], i--) {
+                double *r = path + ASTAR_PATH_W * i;
+                r[0] = nx[j]; r[1] = ny[j]; r[2] = nlen[j]; r[3] = (double)nts[j]; r[4] = ncost[j]; r[5] = nf[j];
+                keep[i] = 1;
+            }
+            /* smoothPath (:416-452) */
+            int index = 0, check = 0, curp;
+            index += 1; curp = index;
+            while (index < np_ - 1) {
+                int wk = astar_walkable(w, path[ASTAR_PATH_W * check], path[ASTAR_PATH_W * check + 1],
+                                        path[ASTAR_PATH_W * curp], path[ASTAR_PATH_W * curp + 1]);
+                if (wk < 0) { status = ORC_KEY_ERROR; break; }
+                if (wk) {
+                    int inside = 0;
+                    for (int hh = 0; hh < w->H && !inside; hh++)
+                        if (astar_euclid(w->habitats[3 * hh], w->habitats[3 * hh + 1], path[ASTAR_PATH_W * curp],
+                                         path[ASTAR_PATH_W * curp + 1]) <= w->habitats[3 * hh + 2]) inside = 1;
+                    if (!inside) keep[curp] = 0;
+                    index += 1; curp = index;
+                } else {
+                    check = curp; index += 1; curp = index;
+                }
+            }
+            int ns = 0;
+            for (int k = 0; k < np_; k++) ns += keep[k];
+            rec[3] = ns;
+        }
+    }
+    free(nx); free(nts); free(alive); free(visited);
+    return status;
+}
+
+/* batch of independent queries {start x, y, path_len_limit, w1..w4, velocity}[8], pthread-parallel */
+typedef struct { const orc_astar_world_t *w; const double *queries; int node_cap, path_cap; int32_t *recs; double *cost;
+                 int32_t *status; } orc_astar_batch_t;
+static void orc_astar_body(int64_t q, void *vc) {
+    orc_astar_batch_t *c = (orc_astar_batch_t *)vc;
+    const double *Q = c->queries + 8 * q;
+    double *path = (double *)malloc(sizeof(double) * ASTAR_PATH_W * (size_t)c->path_cap);
+    uint8_t *keep = (uint8_t *)malloc(c->path_cap);
+    c->status[q] = orc_astar(c->w, Q, Q[7], Q[2], Q + 3, c->node_cap, c->path_cap, c->recs + 4 * q, c->cost + q, path, keep, NULL, NULL);
+    free(path); free(keep);
+}
+void orc_astar_batch(const orc_astar_world_t *w, const double *queries, int Q, int node_cap, int path_cap, int nthreads,
+                     int32_t *recs, double *cost, int32_t *status) {
+    orc_astar_batch_t c = {w, queries, node_cap, path_cap, recs, cost, status};
+    orc_parallel_for(Q, 1, nthreads, orc_astar_body, &c);
+}

@@ -561,3 +561,98 @@ def traced_gym_planning(gref, start, goal, boundary, obstacles, *, rng, max_step
         out["path"] = np.zeros((0, 3))
         out["goal_arc_length"] = 0.0
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# path_planning/astar_fixLenSOG.py: the fixed-length lattice A* with the shark-occupancy cost.
+# ---------------------------------------------------------------------------------------------
+_astar_cache = None
+
+
+def load_astar_reference():
+    """Import the unmodified path_planning/astar_fixLenSOG.py the way the reference's own driver does
+    (astarAnalysis.py:10-14: repository root on sys.path, so `catalina`, `motion_plan_state`,
+    `sharkOccupancyGrid` and `cost` resolve to the root-level modules).  `splitCell` -- shapely.ops.split,
+    whose cell order is unpinned -- is only used to label a CSV shark grid when none is passed in, so the
+    harness always passes the grid and stubs splitCell out."""
+    global _astar_cache
+    if _astar_cache is not None:
+        return _astar_cache
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    import importlib
+    names = ["path_planning", "path_planning.astar_fixLenSOG", "catalina", "motion_plan_state", "sharkOccupancyGrid",
+             "cost", "shapely", "shapely.geometry", "shapely.wkt", "shapely.ops", "geopy", "geopy.distance",
+             "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.patches", "matplotlib.collections",
+             "matplotlib.path", "descartes"]
+    saved_mods = {n: sys.modules.pop(n) for n in names if n in sys.modules}
+    saved_path = list(sys.path)
+    sys.path[:0] = [SHIMS, REFERENCE_ROOT]
+    try:
+        mod = importlib.import_module("path_planning.astar_fixLenSOG")
+        mod.splitCell = lambda poly, size: []
+        mps = importlib.import_module("motion_plan_state")
+        shp = importlib.import_module("shapely.geometry")
+        ns = types.SimpleNamespace(mod=mod, astar=mod.astar, Node=mod.Node, MPS=mps.Motion_plan_state, Polygon=shp.Polygon)
+    finally:
+        sys.path[:] = saved_path
+        for n in names:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved_mods)
+    _astar_cache = ns
+    return ns
+
+
+def round_cells(cells):
+    """cell bounds as get_cell_prob compares them: every coordinate through Python's round(v, 2)
+    (astar_fixLenSOG.py:494-495)"""
+    return np.array([[round(float(v), 2) for v in c] for c in cells], dtype=np.float64).reshape(-1, 4)
+
+
+def traced_astar(aref, start, circles, boundary, habitats, bins, cells, probs, *, velocity=1, path_len_limit=300,
+                 weights=(0, 10, 10, 100)):
+    """Run the unmodified astar.astar (prints swallowed); -> dict with the expansion order, the node path,
+    the cost list and which trajectory points smoothPath kept, or {"raised": ExceptionName}."""
+    import contextlib
+    import io
+    M = aref.MPS
+    grid = {}
+    for t, (b0, b1) in enumerate(bins):
+        key = (int(b0), int(b1)) if float(b0).is_integer() and float(b1).is_integer() else (float(b0), float(b1))
+        grid[key] = {tuple(float(v) for v in c): float(probs[t][i]) for i, c in enumerate(cells)}
+    obst = [M(c[0], c[1], size=c[2]) for c in circles]
+    bnd = [M(p[0], p[1]) for p in boundary]
+    hab = [M(h[0], h[1], size=h[2]) for h in habitats]
+    expanded = []
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = aref.astar((start[0], start[1]), obst, bnd, hab, grid, {}, velocity)
+        orig = a.curr_neighbors
+
+        def curr_neighbors(node, bl):
+            expanded.append((node.position[0], node.position[1], float(node.pathLen), float(node.f), float(node.cost),
+                             float(node.time_stamp)))
+            return orig(node, bl)
+        a.curr_neighbors = curr_neighbors
+        try:
+            r = a.astar(path_len_limit, list(weights), {})
+        except Exception as ex:       # AttributeError (no time bin), TypeError (no cell), IndexError (top-n)
+            out["raised"] = type(ex).__name__
+            r = None
+    out["expanded"] = np.array(expanded, dtype=np.float64).reshape(-1, 6)
+    out["n_visited"] = int(a.visited_nodes.sum())
+    c = aref.Polygon([(p[0], p[1]) for p in boundary]).centroid.coords[0]
+    out["centroid"] = np.array(c, dtype=np.float64)
+    if r is not None:
+        nodes = r["node"]
+        out["nodes"] = np.array([[n.position[0], n.position[1], float(n.pathLen), float(n.time_stamp), float(n.cost),
+                                  float(n.f)] for n in nodes], dtype=np.float64)
+        out["cost"] = float(r["cost"])
+        out["cost_list"] = np.array(r["cost list"], dtype=np.float64)
+        kept = {(p.x, p.y) for p in r["path"]}
+        out["smooth_keep"] = np.array([(n.position[0], n.position[1]) in kept for n in nodes], dtype=np.uint8)
+        assert out["smooth_keep"].sum() == len(r["path"]) == r["path length"]
+        out["smooth_path"] = np.array([[p.x, p.y, p.traj_time_stamp] for p in r["path"]], dtype=np.float64)
+    elif "raised" not in out:
+        out["exhausted"] = True      # open list ran empty: astar() returns None
+    return out

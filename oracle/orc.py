@@ -410,3 +410,60 @@ def gym_plan_batch(w: GymWorld, starts, goals, seeds, max_step=200, nthreads=0):
                              C.c_int(Q), C.c_int(max_step), C.c_int(nthreads), recs.ctypes.data_as(_ip),
                              status.ctypes.data_as(_ip))
     return recs, status
+
+
+# ------------------------------------------------------------------ lattice A* (astar_fixLenSOG) ---
+class AstarWorld(C.Structure):
+    _fields_ = [("K", C.c_int), ("circles", _dp), ("E", C.c_int), ("boundary", _dp), ("centroid", C.c_double * 2),
+                ("H", C.c_int), ("habitats", _dp), ("T", C.c_int), ("bins", _dp), ("C", C.c_int), ("cells_r", _dp),
+                ("probs", _dp), ("topn", _dp)]
+
+
+def astar_world(circles, boundary, centroid, habitats, bins, cells_rounded, probs):
+    """cells_rounded: cell bounds after Python's round(v, 2) (oracle/harness.py round_cells)."""
+    L = lib()
+    keep = dict(circles=_f64(circles, (-1, 3)) if len(circles) else np.zeros((0, 3)),
+                boundary=_f64(boundary, (-1, 2)),
+                habitats=_f64(habitats, (-1, 3)) if len(habitats) else np.zeros((0, 3)),
+                bins=_f64(bins, (-1, 2)) if len(bins) else np.zeros((0, 2)),
+                cells=_f64(cells_rounded, (-1, 4)) if len(cells_rounded) else np.zeros((0, 4)))
+    T, Cc = len(keep["bins"]), len(keep["cells"])
+    keep["probs"] = _f64(probs, (T, Cc)) if T and Cc else np.zeros((T, Cc))
+    keep["topn"] = np.zeros((T, Cc + 1))
+    L.orc_astar_topn(_p(keep["probs"]), C.c_int(T), C.c_int(Cc), _p(keep["topn"]))
+    w = AstarWorld(len(keep["circles"]), _p(keep["circles"]), len(keep["boundary"]), _p(keep["boundary"]),
+                   (C.c_double * 2)(float(centroid[0]), float(centroid[1])), len(keep["habitats"]), _p(keep["habitats"]),
+                   T, _p(keep["bins"]), Cc, _p(keep["cells"]), _p(keep["probs"]), _p(keep["topn"]))
+    w._keep = keep
+    return w
+
+
+def astar(w: AstarWorld, start, velocity=1.0, path_len_limit=300.0, weights=(0, 10, 10, 100), node_cap=4096, path_cap=512):
+    L = lib()
+    L.orc_astar.restype = C.c_int
+    rec = np.zeros(4, np.int32)
+    cost = C.c_double()
+    path = np.zeros((path_cap, 6))
+    keep = np.zeros(path_cap, np.uint8)
+    order = np.zeros(node_cap, np.int32)
+    xy = np.zeros((node_cap, 2))
+    st = L.orc_astar(C.byref(w), _p(_f64(start, (2,))), C.c_double(velocity), C.c_double(path_len_limit),
+                     _p(_f64(weights, (4,))), C.c_int(node_cap), C.c_int(path_cap), rec.ctypes.data_as(_ip),
+                     C.byref(cost), _p(path), keep.ctypes.data_as(C.POINTER(C.c_uint8)), order.ctypes.data_as(_ip), _p(xy))
+    n_exp, n, n_path, n_smooth = [int(v) for v in rec]
+    ok = st == 0
+    return {"status": st, "n_expanded": n_exp, "n_nodes": n, "n_path": n_path, "n_smooth": n_smooth, "cost": cost.value,
+            "path": path[:n_path].copy() if ok else np.zeros((0, 6)), "keep": keep[:n_path].copy() if ok else np.zeros(0, np.uint8),
+            "expand_order": order[:n_exp].copy(), "node_xy": xy[:n].copy()}
+
+
+def astar_batch(w: AstarWorld, queries, node_cap=4096, path_cap=512, nthreads=0):
+    """queries [Q][8] = start x, y, path_len_limit, w1, w2, w3, w4, velocity"""
+    queries = _f64(queries, (-1, 8))
+    Q = len(queries)
+    recs = np.zeros((Q, 4), np.int32)
+    cost = np.zeros(Q)
+    status = np.zeros(Q, np.int32)
+    lib().orc_astar_batch(C.byref(w), _p(queries), C.c_int(Q), C.c_int(node_cap), C.c_int(path_cap), C.c_int(nthreads),
+                          recs.ctypes.data_as(_ip), _p(cost), status.ctypes.data_as(_ip))
+    return recs, cost, status

@@ -73,6 +73,23 @@ class Polygon:
                     inside = not inside
         return 1 if inside else -1
 
+    @property
+    def centroid(self):
+        """GEOS Centroid for an area: signed-area-weighted mean of the fan triangles (base = first
+        vertex) of the closed ring.  Ulp-level agreement with a particular GEOS build is not claimed
+        (parity unpinned); callers treat the centroid as an input (astar_fixLenSOG.py:191)."""
+        ring = self.exterior.coords
+        bx, by = ring[0]
+        area2_sum = 0.0
+        cx3 = cy3 = 0.0
+        for i in range(len(ring) - 1):
+            (x1, y1), (x2, y2) = ring[i], ring[i + 1]
+            a2 = (x1 - bx) * (y2 - by) - (x2 - bx) * (y1 - by)
+            cx3 += a2 * (bx + x1 + x2)
+            cy3 += a2 * (by + y1 + y2)
+            area2_sum += a2
+        return Point(cx3 / 3.0 / area2_sum, cy3 / 3.0 / area2_sum)
+
     def contains(self, other):
         return other.within(self)
 
@@ -89,6 +106,10 @@ class Point:
             x, y = x
         self.x = float(x)
         self.y = float(y)
+
+    @property
+    def coords(self):
+        return [(self.x, self.y)]
 
     def within(self, poly):
         return poly._locate(self.x, self.y) > 0

@@ -81,3 +81,33 @@ class GymEpisode:
 def gym_golden():
     z = np.load(os.path.join(GOLDEN, "gym_plan.npz"))
     return [GymEpisode(z, str(n)) for n in z["names"]]
+
+
+class AstarCase:
+    """One golden query of astar_fixLenSOG.astar (tests/golden/astar.npz, oracle/make_golden_astar.py)."""
+
+    def __init__(self, z, name):
+        s = z[name + "/setup"]
+        self.name = name
+        self.start, self.limit, self.weights = s[0:2].copy(), float(s[2]), s[3:7].copy()
+        self.velocity, self.n_bins = float(s[7]), int(s[8])
+        self.outcome = str(z[name + "/outcome"])
+        self.expanded = z[name + "/expanded"]
+        self.n_visited = int(z[name + "/n_visited"])
+        if self.outcome == "ok":
+            self.nodes, self.cost_list = z[name + "/nodes"], z[name + "/cost_list"]
+            self.smooth_keep, self.smooth_path = z[name + "/smooth_keep"], z[name + "/smooth_path"]
+            self.cost = float(z[name + "/cost"])
+
+    @property
+    def want_status(self):
+        return {"ok": 0, "none": 1}.get(self.outcome, 3)
+
+
+@pytest.fixture(scope="session")
+def astar_golden(catalina_map, shark_grid):
+    z = np.load(os.path.join(GOLDEN, "astar.npz"))
+    bins, probs = shark_grid
+    world = dict(circles=catalina_map["circles"], boundary=catalina_map["boundary"], habitats=catalina_map["habitats"],
+                 centroid=z["centroid"], cells_rounded=z["cells_rounded"], bins=bins, probs=probs)
+    return world, [AstarCase(z, str(n)) for n in z["names"]]
