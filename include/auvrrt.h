@@ -295,6 +295,56 @@ const uint16_t *auvrrt_gym_counts_dev(const auvrrt_gym_t *g);
  * the goal arc's end back to the start (the reference does not reverse it). */
 int auvrrt_gym_path(const auvrrt_gym_t *g, int64_t q, int32_t cap, double *path, int32_t *n_path);
 
+/* ---- fixed-length lattice A* with the shark-occupancy cost -----------------
+ * path_planning/astar_fixLenSOG.py: class astar (:114-141), method astar (:551-657) and its helpers
+ * within_bounds (:178-203), collision_free (:205-221), curr_neighbors (:248-266), findCurrSOG
+ * (:454-468), get_cell_prob (:486-510), get_top_n_prob (:520-536), smoothPath / Walkable (:223-246,
+ * :416-452).  Deterministic; fp64 with separately rounded operations, bit-identical to the
+ * reference.  One warp per query, Q independent queries (start, length limit, weights, velocity)
+ * against one world.  Inputs the reference obtains through third parties are passed in: the
+ * boundary centroid (shapely, :191) and the cell bounds after Python's round(v, 2) (:494-495). */
+typedef struct auvrrt_astar_env auvrrt_astar_env_t;
+
+typedef struct {
+    double start[2];              /* self.start */
+    double path_len_limit;        /* pathLenLimit */
+    double weights[4];            /* w1..w4 (w1 is unused by the reference) */
+    double velocity;              /* AUV_velocity */
+} auvrrt_astar_query_t;           /* 64 bytes */
+
+typedef struct {
+    int32_t status;               /* AUVRRT_ST_OK; NO_PATH: the open list ran empty (astar returns None);
+                                     KEY_ERROR: AttributeError (no time bin holds the time stamp, :489),
+                                     TypeError (no cell holds the point, :602), IndexError (:532, :419,
+                                     :652); OVERFLOW: node_cap / path_cap too small */
+    int32_t n_expanded;           /* nodes taken off the open list */
+    int32_t n_nodes;              /* nodes ever put on the open list (start included) */
+    int32_t n_path;               /* len(result["node"]) */
+    int32_t n_smooth;             /* result["path length"] = len(smoothPath(...)) */
+    int32_t reserved;
+    double cost;                  /* result["cost"] = cost of the last node */
+    double path_len;              /* its pathLen */
+} auvrrt_astar_record_t;          /* 40 bytes */
+
+int auvrrt_astar_env_create(const double *circles, int K, const double *boundary, int E,
+                            const double centroid[2], const double *habitats, int H,
+                            const double *bins, int T, const double *cells_rounded, int C,
+                            const double *probs, int device, auvrrt_astar_env_t **out);
+void auvrrt_astar_env_destroy(auvrrt_astar_env_t *env);
+/* paths [Q][path_cap][6] rows start -> goal = x, y, pathLen, time_stamp, cost, f (result["node"]);
+ * keep [Q][path_cap] = 1 where smoothPath keeps the trajectory point (result["path"]);
+ * expand_order NULL or [Q][node_cap] node ids in the order they left the open list;
+ * node_xy NULL or [Q][node_cap][2].  paths / keep may be NULL (records only). */
+int auvrrt_astar_batch(auvrrt_astar_env_t *env, const auvrrt_astar_query_t *queries, int64_t Q,
+                       int32_t node_cap, int32_t path_cap, auvrrt_astar_record_t *records,
+                       double *paths, uint8_t *keep, int32_t *expand_order, double *node_xy);
+/* device buffers; workspace of auvrrt_astar_workspace_bytes(Q, node_cap) bytes; asynchronous on `stream` */
+int64_t auvrrt_astar_workspace_bytes(int64_t Q, int32_t node_cap);
+int auvrrt_astar_batch_dev(auvrrt_astar_env_t *env, const auvrrt_astar_query_t *d_queries, int64_t Q,
+                           int32_t node_cap, int32_t path_cap, void *d_workspace,
+                           int64_t workspace_bytes, auvrrt_astar_record_t *d_records, double *d_paths,
+                           uint8_t *d_keep, int32_t *d_expand_order, double *d_node_xy, void *stream);
+
 /* FP32 FFMA issue-rate calibration kernel for the roofline denominator: runs `iters` dependent
  * FFMA chains on every lane of a full grid and returns achieved FLOP/s (FMA = 2). */
 int auvrrt_calibrate_fp32(int device, int iters, double *out_flops, double *out_ms);
