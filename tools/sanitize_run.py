@@ -40,4 +40,30 @@ z = np.load(os.path.join(ROOT, "tests", "golden", "occupancy.npz"))
 polys = [z["cell_xy"][z["cell_off"][i]:z["cell_off"][i + 1]] for i in range(len(z["cell_off"]) - 1)]
 toff, trk = z["c1_toff"], z["c1_trk"]
 api.occupancy_grid(polys, z["bounds"], 10.0, 20.0, 25.0, [trk[toff[i]:toff[i + 1]] for i in range(len(toff) - 1)])
+# gym planner (both builds; stepping, one-launch planning, agent actions, counts, path)
+from auvrrt import gym  # noqa: E402
+from auvrrt import astar  # noqa: E402
+OBST = [(12.0, 38.0, 4.0), (17.0, 34.0, 5.0), (20.0, 29.0, 4.0), (25.0, 25.0, 3.0), (29.0, 20.0, 4.0)]
+for prec in (gym.F32, gym.F64):
+    Qg = 70
+    rs = np.random.default_rng(1)
+    b = gym.GymBatch((0, 0, 50, 50), OBST, Qg, freq=10.0, node_cap=61, track_counts=True, precision=prec)
+    b.reset(np.column_stack([rs.uniform(5, 15, Qg), rs.uniform(5, 15, Qg), rs.uniform(-3, 3, Qg)]),
+            np.column_stack([rs.uniform(35, 45, Qg), rs.uniform(35, 45, Qg)]), np.arange(Qg))
+    for it in range(5):
+        cnt = b.counts()
+        b.step(np.argmax(cnt > 0, axis=1).astype(np.int32), full_candidates=bool(it & 1))
+    r = b.plan(55)
+    for q in np.flatnonzero(r["done"])[:3]:
+        b.path(int(q)); b.tree(int(q))
+    b.close()
+# lattice A*
+ga = np.load(os.path.join(ROOT, "tests", "golden", "astar.npz"))
+aenv = astar.AstarEnv(world["circles"], world["boundary"], world["habitats"], g["bins"], ga["cells_rounded"], g["probs"],
+                      centroid=ga["centroid"], cells_are_rounded=True)
+qa = astar.make_queries([[-212.34, 55.12], [-150.0, 30.0], [-600.0, 300.0], [-300.5, 80.25], [-60.0, -20.0]], 90.0)
+ra = astar.astar_batch(aenv, qa, trace=True)
+assert (ra["records"]["status"][[0, 1, 3, 4]] == 0).all()
+astar.astar_batch(aenv, qa, node_cap=40, want_paths=False)
+aenv.close()
 print("sanitize workload done, launches:", api.launch_count())
