@@ -7,7 +7,7 @@
 // expansion the warp does
 //   1. argmin of f over the alive nodes: lanes stride over the node array (coalesced fp64 loads),
 //      then a 5-step shuffle reduction on (f, index);
-//   2. the 8 neighbours on lanes 0..7: triangle-fan bounds test around the boundary centroid,
+//   2. the 8 neighbours, four lanes each: triangle-fan bounds test around the boundary centroid,
 //      per-obstacle circle test, path length, time stamp -> time bin, cell lookup through a bucket
 //      grid whose candidates are tested with the reference's own predicate in dict order, g, top-n
 //      heuristic from per-bin prefix sums of the sorted probabilities, visited bitmap;
@@ -64,26 +64,30 @@ __device__ __forceinline__ bool astar_same_side(double p1x, double p1y, double p
     const double cp2 = AD::sub(AD::mul(ux, AD::sub(p2y, ay)), AD::mul(uy, AD::sub(p2x, ax)));
     return AD::mul(cp1, cp2) >= 0.0;
 }
-// within_bounds (:188-203): inside any triangle (corner i, corner i+1, centroid)
-__device__ __forceinline__ bool astar_within_bounds(const AstarDev &e, double px, double py) {
-    for (int i = 0; i < e.E; i++) {
+// within_bounds (:188-203): inside any triangle (corner i, corner i+1, centroid); triangles i = part, part + parts, ...
+__device__ __forceinline__ bool astar_within_bounds(const AstarDev &e, double px, double py, int part = 0, int parts = 1) {
+    bool in = false;
+    for (int i = part; i < e.E; i += parts) {
         const int j = i + 1 == e.E ? 0 : i + 1;
         const double ax = e.boundary[2 * i], ay = e.boundary[2 * i + 1], bx = e.boundary[2 * j], by = e.boundary[2 * j + 1];
-        if (astar_same_side(px, py, ax, ay, bx, by, e.cx, e.cy) && astar_same_side(px, py, bx, by, ax, ay, e.cx, e.cy) &&
-            astar_same_side(px, py, e.cx, e.cy, ax, ay, bx, by))
-            return true;
+        in |= astar_same_side(px, py, ax, ay, bx, by, e.cx, e.cy) && astar_same_side(px, py, bx, by, ax, ay, e.cx, e.cy) &&
+              astar_same_side(px, py, e.cx, e.cy, ax, ay, bx, by);
     }
-    return false;
+    return in;
 }
-// collision_free (:205-221)
-__device__ __forceinline__ bool astar_collision_free(const AstarDev &e, double px, double py) {
+// collision_free (:205-221).  The reference tests sqrt(dx^2 + dy^2) <= size; sqrt is monotone and correctly
+// rounded, so that is exactly  dx^2 + dy^2 <= thr  with thr = the largest double whose rounded root is <= size
+// (computed on the host, sqrt_le_threshold): no fp64 square root in the loop.  circles rows are x, y, thr.
+// `part`/`parts`: the circles k = part, part + parts, ... (lanes of one neighbour split the list).
+__device__ __forceinline__ bool astar_hits(const AstarDev &e, double px, double py, int part, int parts) {
     bool hit = false;
-    for (int k = 0; k < e.K; k++) {
+    for (int k = part; k < e.K; k += parts) {
         const double dx = AD::sub(px, e.circles[3 * k]), dy = AD::sub(py, e.circles[3 * k + 1]);
-        hit |= AD::sqrt(AD::sq2(dx, dy)) <= e.circles[3 * k + 2];
+        hit |= AD::sq2(dx, dy) <= e.circles[3 * k + 2];
     }
-    return !hit;
+    return hit;
 }
+__device__ __forceinline__ bool astar_collision_free(const AstarDev &e, double px, double py) { return !astar_hits(e, px, py, 0, 1); }
 // get_cell_prob's key search (:486-505): the reference's predicate on the bucket's candidates, dict order
 __device__ __forceinline__ int astar_find_cell(const AstarDev &e, double px, double py) {
     const double fx = floor(AD::mul(AD::sub(px, e.gx0), e.inv_bs)), fy = floor(AD::mul(AD::sub(py, e.gy0), e.inv_bs));
@@ -163,11 +167,17 @@ __global__ void __launch_bounds__(32 * ASTAR_WARPS) k_astar(AstarDev e, const au
         // 2. the 8 neighbours (:255: (0,-10) (0,10) (-10,0) (10,0) (-10,-10) (-10,10) (10,-10) (10,10))
         int err = 0; bool add = false;
         double px = 0, py = 0, plen = 0, g = 0, f = 0; int ts = 0; unsigned vword = 0, vbit = 0;
-        if (lane < 8) {
-            const double ddx = lane < 2 ? 0.0 : ((lane == 2 || lane == 4 || lane == 5) ? -10.0 : 10.0);
-            const double ddy = (lane == 0 || lane == 4 || lane == 6) ? -10.0 : ((lane == 2 || lane == 3) ? 0.0 : 10.0);
+        {
+            // four lanes per neighbour: they split the boundary triangles and the obstacle list, OR their verdicts,
+            // then lane 0 of the four carries the neighbour through the cost terms
+            const int d = lane >> 2, part = lane & 3;
+            const double ddx = d < 2 ? 0.0 : ((d == 2 || d == 4 || d == 5) ? -10.0 : 10.0);
+            const double ddy = (d == 0 || d == 4 || d == 6) ? -10.0 : ((d == 2 || d == 3) ? 0.0 : 10.0);
             px = AD::add(cx, ddx); py = AD::add(cy, ddy);
-            if (astar_within_bounds(e, px, py) && astar_collision_free(e, px, py)) {
+            unsigned in = astar_within_bounds(e, px, py, part, 4) ? 1u : 0u, hit = astar_hits(e, px, py, part, 4) ? 1u : 0u;
+            in |= __shfl_xor_sync(0xffffffffu, in, 1); hit |= __shfl_xor_sync(0xffffffffu, hit, 1);
+            in |= __shfl_xor_sync(0xffffffffu, in, 2); hit |= __shfl_xor_sync(0xffffffffu, hit, 2);
+            if (part == 0 && in && !hit) {
                 plen = AD::add(clen, astar_euclid(cx, cy, px, py));                                 // :636
                 const double dist_left = fabs(AD::sub(limit, plen));
                 const long long tsl = (long long)AD::div(plen, vel);                                // int()
@@ -271,6 +281,21 @@ static AstarDev astar_dev(const auvrrt_astar_env *e) {
 
 using namespace auv;
 
+// the largest double t with sqrt(t), correctly rounded, <= r; -1 when no non-negative t qualifies
+static double sqrt_le_threshold(double r) {
+    if (!(r >= 0.0)) return -1.0;
+    if (std::isinf(r)) return r;
+    double t = r * r;
+    if (std::isinf(t)) t = 1.7976931348623157e308;
+    while (sqrt(t) > r) t = nextafter(t, -INFINITY);
+    for (;;) {
+        const double u = nextafter(t, INFINITY);
+        if (std::isinf(u) || sqrt(u) > r) break;
+        t = u;
+    }
+    return t;
+}
+
 extern "C" int auvrrt_astar_env_create(const double *circles, int K, const double *boundary, int E, const double centroid[2],
                                        const double *habitats, int H, const double *bins, int T, const double *cells_rounded,
                                        int C, const double *probs, int device, auvrrt_astar_env_t **out) {
@@ -329,6 +354,13 @@ extern "C" int auvrrt_astar_env_create(const double *circles, int K, const doubl
         if (pass == 0) { for (size_t i = 0; i < nb; i++) boff[i + 1] += boff[i]; bcells.assign((size_t)boff[nb] + 1, 0); }
     }
     e->n_boff = nb + 1;
+    // circles as x, y, thr with  sqrt_rn(s) <= size  <=>  s <= thr  (see astar_hits)
+    std::vector<double> circ_thr((size_t)3 * (K > 0 ? K : 1), 0.0);
+    for (int k = 0; k < K; k++) {
+        circ_thr[3 * k] = circles[3 * k]; circ_thr[3 * k + 1] = circles[3 * k + 1];
+        circ_thr[3 * k + 2] = sqrt_le_threshold(circles[3 * k + 2]);
+    }
+    circles = circ_thr.data();
     // flatten
     std::vector<double> f64;
     auto push = [&](const double *p, size_t n) { size_t o = f64.size(); if (n) f64.insert(f64.end(), p, p + n); else f64.push_back(0.0); return o; };
