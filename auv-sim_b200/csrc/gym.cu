@@ -39,7 +39,7 @@ namespace auv {
 
 template <typename R> struct GymP {
     R x0, y0, x1, y1, exp_rate, d2e, dmax, neg_dmax, freq, cell_side, delta_theta;
-    int ns, rows, cols, K, cap, ncells;
+    int ns, rows, cols, K, cap, ncells, hsize, hshift;
     long long Q;
 };
 
@@ -55,6 +55,8 @@ template <typename R> struct GymS {
     unsigned *npos;
     // per occupied entry [cap][Q]
     int *occ_cell, *occ_count, *occ_tail;
+    // occupied-cell hash [hsize][Q]
+    int *hkey, *hval;
     uint16_t *counts;                       // [Q][ncells] or nullptr
 };
 
@@ -241,11 +243,26 @@ __global__ void __launch_bounds__(128) k_gym_reset(GymP<R> P, GymS<R> S, const d
     int n_occ = 0;
     if (c >= 0) {
         GS(occ_cell, 0) = c; GS(occ_count, 0) = 1; GS(occ_tail, 0) = 0; n_occ = 1;
+        const unsigned h = ((unsigned)c * 2654435761u) >> P.hshift;
+        GS(hkey, h) = c + 1; GS(hval, h) = 0;
         if (S.counts) S.counts[(size_t)q * P.ncells + c] = 1;
     }
     S.n_nodes[q] = 1; S.n_occ[q] = n_occ; S.steps[q] = 0; S.done[q] = 0; S.goal_checked[q] = -1; S.arc_ne[q] = -1; S.npath[q] = 0;
     S.spos[q] = 0u;
     S.status[q] = c == -2 ? AUVRRT_ST_KEY_ERROR : AUVRRT_ST_OK;
+}
+
+// occupied-cell lookup: open-addressing table [HS][Q] (key = sub-cell id + 1, 0 = empty; value = index into the
+// occupied list).  Replaces a linear scan of occupied_grid_cells_array, which streamed ~n_occ/2 rows per step.
+template <typename R>
+__device__ __forceinline__ int gym_occ_find(const GymP<R> &P, const GymS<R> &S, long long q, int c, unsigned &slot) {
+    unsigned h = ((unsigned)c * 2654435761u) >> P.hshift;
+    for (;;) {
+        const int k = GS(hkey, h);
+        if (k == 0) { slot = h; return -1; }
+        if (k == c + 1) { slot = h; return GS(hval, h); }
+        h = (h + 1) & (unsigned)(P.hsize - 1);
+    }
 }
 
 template <typename R>
@@ -256,8 +273,10 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
     R *circ = reinterpret_cast<R *>(gym_smem);
     for (int i = threadIdx.x; i < 3 * P.K; i += blockDim.x) circ[i] = circ_g[i];
     __syncthreads();
-    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (q >= P.Q) return;
+    const long long q_raw = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool mine = q_raw < P.Q;
+    const long long q = mine ? q_raw : P.Q - 1;          // out-of-range lanes stay in the warp for the collectives
+    const int lane = threadIdx.x & 31;
     Stream<R> st;
     st.key = S.key[q]; st.ext = nullptr; st.n_ext = 0;
     int n = S.n_nodes[q], n_occ = S.n_occ[q], steps = S.steps[q], done = S.done[q], status = S.status[q];
@@ -266,82 +285,123 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
     const R gx = S.gx[q], gy = S.gy[q];
     int last_parent = -1, last_acc = 0, last_nwp = 0, last_used = 0, n_path = done ? S.npath[q] : 0;
     R cx = 0, cy = 0, cth = 0, ct = 0, arc_len = done ? S.arc[(size_t)5 * P.Q + q] : (R)0;
-    for (int it = 0; it < n_steps && !done && status == AUVRRT_ST_OK; it++) {
-        int oi = -1, cellid;
-        last_parent = -1; last_acc = 0; last_nwp = 0; last_used = 0;
-        if (!actions) {
-            if (n_occ == 0) { status = AUVRRT_ST_KEY_ERROR; break; }                     // random.choice([])
-            oi = (int)A::mul(st.u(pos++), (R)n_occ);                                    // :176
-            if (!Policy<R>::VERIFY) oi = min(oi, n_occ - 1);
-            cellid = GS(occ_cell, oi);
-        } else {
-            cellid = actions[q];
-            for (int j = 0; j < n_occ; j++) if (GS(occ_cell, j) == cellid) { oi = j; break; }
-            if (oi < 0) break;                                                          // node_array == [] (:209-215)
-        }
-        const unsigned pos0 = pos;
-        const int cnt = GS(occ_count, oi);
-        int k = (int)A::mul(st.u(pos++), (R)cnt);                                       // :217
-        if (!Policy<R>::VERIFY) k = min(k, cnt - 1);
-        int pn = GS(occ_tail, oi);
-        for (int h = cnt - 1 - k; h > 0; h--) pn = GS(prev, pn);
-        R x = GS(nx, pn), y = GS(ny, pn), th = GS(nth, pn), t = GS(nt, pn);
-        bool free = gym_point_free<R>(P, circ, x, y);                                   // path[0] = the node steered from
-        unsigned used = 0;
-        const unsigned steer_pos = pos;
-        const int m = gym_steer<R>(P, circ, st, pos, x, y, th, t, free, full != 0, status, used, nullptr, 0);
-        pos += used;
-        if (status != AUVRRT_ST_OK) break;
-        last_parent = pn; last_nwp = m; last_used = (int)(pos - pos0);
-        cx = x; cy = y; cth = th; ct = t;
-        if (free) {                                                                     // :222-227
-            if (n >= P.cap) { status = AUVRRT_ST_OVERFLOW; break; }
-            GS(nx, n) = x; GS(ny, n) = y; GS(nth, n) = th; GS(nt, n) = t;
-            GS(parent, n) = pn; GS(nwp, n) = m; GS(npos, n) = steer_pos;
-            const int c = gym_subcell<R>(P, x, y, th);
-            GS(cell, n) = c;
-            if (c == -2) { status = AUVRRT_ST_KEY_ERROR; break; }
-            if (c >= 0) {
-                int oj = -1;
-                for (int j = 0; j < n_occ; j++) if (GS(occ_cell, j) == c) { oj = j; break; }
-                if (oj < 0) { oj = n_occ++; GS(occ_cell, oj) = c; GS(occ_count, oj) = 0; GS(occ_tail, oj) = -1; }   // :153-154
-                GS(prev, n) = GS(occ_tail, oj);
-                GS(occ_tail, oj) = n;
-                GS(occ_count, oj) = GS(occ_count, oj) + 1;
-                if (S.counts) { uint16_t *cp = S.counts + (size_t)q * P.ncells + c; *cp = (uint16_t)(*cp + 1); }
+    for (int it = 0; it < n_steps; it++) {
+        bool live = mine && !done && status == AUVRRT_ST_OK;
+        if (!__any_sync(0xffffffffu, live)) break;
+        bool want_arc = false;
+        R arc[6] = {0, 0, 0, 0, 0, 0}; int ne = -1;
+        if (live) {
+            int oi = -1, cellid = 0;
+            unsigned hslot;
+            last_parent = -1; last_acc = 0; last_nwp = 0; last_used = 0;
+            if (!actions) {
+                if (n_occ == 0) { status = AUVRRT_ST_KEY_ERROR; live = false; }              // random.choice([])
+                else {
+                    oi = (int)A::mul(st.u(pos++), (R)n_occ);                                // :176
+                    if (!Policy<R>::VERIFY) oi = min(oi, n_occ - 1);
+                    cellid = GS(occ_cell, oi);
+                }
             } else {
-                GS(prev, n) = -1;
+                cellid = actions[q];
+                oi = cellid >= 0 ? gym_occ_find<R>(P, S, q, cellid, hslot) : -1;
+                if (oi < 0) live = false;                                                   // node_array == [] (:209-215)
             }
-            n++; last_acc = 1;
+            if (live) {
+                const unsigned pos0 = pos;
+                const int cnt = GS(occ_count, oi);
+                int k = (int)A::mul(st.u(pos++), (R)cnt);                                   // :217
+                if (!Policy<R>::VERIFY) k = min(k, cnt - 1);
+                int pn = GS(occ_tail, oi);
+                for (int h = cnt - 1 - k; h > 0; h--) pn = GS(prev, pn);
+                R x = GS(nx, pn), y = GS(ny, pn), th = GS(nth, pn), t = GS(nt, pn);
+                bool free = gym_point_free<R>(P, circ, x, y);                               // path[0] = the node steered from
+                unsigned used = 0;
+                const unsigned steer_pos = pos;
+                const int m = gym_steer<R>(P, circ, st, pos, x, y, th, t, free, full != 0, status, used, nullptr, 0);
+                pos += used;
+                if (status != AUVRRT_ST_OK) live = false;
+                else {
+                    last_parent = pn; last_nwp = m; last_used = (int)(pos - pos0);
+                    cx = x; cy = y; cth = th; ct = t;
+                    if (free) {                                                             // :222-227
+                        const int c = gym_subcell<R>(P, x, y, th);
+                        if (n >= P.cap) { status = AUVRRT_ST_OVERFLOW; live = false; }
+                        else if (c == -2) { status = AUVRRT_ST_KEY_ERROR; live = false; }
+                        else {
+                            GS(nx, n) = x; GS(ny, n) = y; GS(nth, n) = th; GS(nt, n) = t;
+                            GS(parent, n) = pn; GS(nwp, n) = m; GS(npos, n) = steer_pos;
+                            GS(cell, n) = c;
+                            if (c >= 0) {
+                                int oj = gym_occ_find<R>(P, S, q, c, hslot);
+                                if (oj < 0) {                                               // :153-154
+                                    oj = n_occ++;
+                                    GS(occ_cell, oj) = c; GS(occ_count, oj) = 0; GS(occ_tail, oj) = -1;
+                                    GS(hkey, hslot) = c + 1; GS(hval, hslot) = oj;
+                                }
+                                GS(prev, n) = GS(occ_tail, oj);
+                                GS(occ_tail, oj) = n;
+                                GS(occ_count, oj) = GS(occ_count, oj) + 1;
+                                if (S.counts) { uint16_t *cp = S.counts + (size_t)q * P.ncells + c; *cp = (uint16_t)(*cp + 1); }
+                            } else {
+                                GS(prev, n) = -1;
+                            }
+                            n++; last_acc = 1;
+                        }
+                    }
+                    if (live) {
+                        steps++;
+                        // connect_to_goal_curve_alt(self.mps_list[-1]) (:229) depends on the last node only
+                        const int last = n - 1;
+                        if (goal_checked != last) {
+                            goal_checked = last;
+                            const int g = gym_goal_arc<R>(P, gx, gy, GS(nx, last), GS(ny, last), GS(nth, last), arc, ne);
+                            if (g >= 100) status = g - 100;
+                            else if (g == 1) {
+                                if (ne < 0 && P.K > 0) status = AUVRRT_ST_KEY_ERROR;          // min([]) ValueError
+                                else want_arc = true;
+                            }
+                        }
+                    }
+                }
+            }
         }
-        steps++;
-        // connect_to_goal_curve_alt(self.mps_list[-1]) (:229) depends on the last node only
-        const int last = n - 1;
-        if (goal_checked != last) {
-            goal_checked = last;
-            R arc[6]; int ne = 0;
-            const int g = gym_goal_arc<R>(P, gx, gy, GS(nx, last), GS(ny, last), GS(nth, last), arc, ne);
-            if (g >= 100) { status = g - 100; break; }
-            if (g == 1) {
-                if (ne < 0 && P.K > 0) { status = AUVRRT_ST_KEY_ERROR; break; }           // min([]) ValueError
-                bool ok = true;
-                for (int i = 0; i <= ne && ok; i++) {
-                    R px, py, pa;
-                    gym_arc_point<R>(arc, i, px, py, pa);
-                    ok = gym_point_free<R>(P, circ, px, py);
-                }
-                if (ok) {
-                    done = 1; arc_len = arc[5];
+        // check_collision_free(final_node) (:232), warp-cooperative: the arcs of this warp's episodes are tested one
+        // after the other with the 32 lanes taking 32 consecutive arc points each round (a point is a pure function
+        // of its index), stopping at the first round that holds a colliding point.
+        unsigned pending = __ballot_sync(0xffffffffu, want_arc);
+        bool arc_ok = false;
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            R a6[6];
 #pragma unroll
-                    for (int j = 0; j < 6; j++) S.arc[(size_t)j * P.Q + q] = arc[j];
-                    S.arc_ne[q] = ne;
-                    n_path = 1 + (ne + 1);
-                    for (int j = last; GS(parent, j) >= 0; j = GS(parent, j)) n_path += GS(nwp, j) + 1;
-                    S.npath[q] = n_path;
+            for (int j = 0; j < 6; j++) a6[j] = __shfl_sync(0xffffffffu, arc[j], src);
+            const int ne_s = __shfl_sync(0xffffffffu, ne, src);
+            bool ok = true;
+            for (int base = 0; base <= ne_s; base += 32) {
+                const int i = base + lane;
+                bool okp = true;
+                if (i <= ne_s) {
+                    R px, py, pa;
+                    gym_arc_point<R>(a6, i, px, py, pa);
+                    okp = gym_point_free<R>(P, circ, px, py);
                 }
+                if (!__all_sync(0xffffffffu, okp)) { ok = false; break; }
             }
+            if (lane == src) arc_ok = ok;
+        }
+        if (want_arc && arc_ok) {
+            const int last = n - 1;
+            done = 1; arc_len = arc[5];
+#pragma unroll
+            for (int j = 0; j < 6; j++) S.arc[(size_t)j * P.Q + q] = arc[j];
+            S.arc_ne[q] = ne;
+            n_path = 1 + (ne + 1);
+            for (int j = last; GS(parent, j) >= 0; j = GS(parent, j)) n_path += GS(nwp, j) + 1;
+            S.npath[q] = n_path;
         }
     }
+    if (!mine) return;
     S.n_nodes[q] = n; S.n_occ[q] = n_occ; S.steps[q] = steps; S.done[q] = done; S.status[q] = status;
     S.goal_checked[q] = goal_checked; S.spos[q] = pos;
     if (recs) {
@@ -389,6 +449,12 @@ __global__ void k_gym_path(GymP<R> P, GymS<R> S, const R *circ, long long q, int
     }
 }
 
+static int gym_hash_size(int cap) {
+    int h = 16;
+    while (h < 2 * cap) h <<= 1;
+    return h;
+}
+
 template <typename R> static GymP<R> make_gymp(const auvrrt_gym *g) {
     GymP<R> P;
     const auvrrt_gym_params_t &p = g->p;
@@ -398,6 +464,9 @@ template <typename R> static GymP<R> make_gymp(const auvrrt_gym *g) {
     P.delta_theta = (R)((2.0 * M_PI) / (double)p.subsections);                          // grid_cell_rrt.py:52
     P.ns = p.subsections; P.rows = g->rows; P.cols = g->cols; P.K = g->K; P.cap = p.node_cap; P.ncells = g->ncells;
     P.Q = g->Q;
+    P.hsize = gym_hash_size(p.node_cap);
+    P.hshift = 32;
+    for (int h = P.hsize; h > 1; h >>= 1) P.hshift--;
     return P;
 }
 
@@ -414,6 +483,8 @@ template <typename R> static size_t gym_carve(GymS<R> *S, unsigned char *base, i
     S->parent = (int *)take(4 * nq); S->cell = (int *)take(4 * nq); S->prev = (int *)take(4 * nq); S->nwp = (int *)take(4 * nq);
     S->npos = (unsigned *)take(4 * nq);
     S->occ_cell = (int *)take(4 * nq); S->occ_count = (int *)take(4 * nq); S->occ_tail = (int *)take(4 * nq);
+    const size_t hq = (size_t)gym_hash_size(cap) * q;
+    S->hkey = (int *)take(4 * hq); S->hval = (int *)take(4 * hq);
     S->counts = counts ? (uint16_t *)take(2 * q * (size_t)ncells) : nullptr;
     return off;
 }
@@ -441,6 +512,7 @@ template <typename R>
 static int gym_reset_t(auvrrt_gym *g, const double *d_starts, const double *d_goals, const uint64_t *d_seeds, cudaStream_t s) {
     const GymS<R> &S = *(const GymS<R> *)g->S;
     if (S.counts) AUV_CUDA(cudaMemsetAsync(S.counts, 0, 2 * (size_t)g->Q * g->ncells, s));
+    AUV_CUDA(cudaMemsetAsync(S.hkey, 0, 4 * (size_t)gym_hash_size(g->p.node_cap) * (size_t)g->Q, s));
     k_gym_reset<R><<<(unsigned)((g->Q + 127) / 128), 128, 0, s>>>(make_gymp<R>(g), S, d_starts, d_goals, d_seeds);
     g_launches++;
     AUV_CUDA(cudaGetLastError());
