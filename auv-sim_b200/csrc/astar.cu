@@ -205,21 +205,25 @@ __global__ void __launch_bounds__(32 * ASTAR_WARPS) k_astar(AstarDev e, const au
                 }
             }
         }
+        // the reference handles the neighbours in order and raises at the first one that fails: the ones before it
+        // have already been put on the open list
         const unsigned errm = __ballot_sync(0xffffffffu, err != 0);
-        if (errm) { status = AUVRRT_ST_KEY_ERROR; break; }
+        const unsigned before = errm ? ((1u << (__ffs(errm) - 1)) - 1u) : 0xffffffffu;
         // 3. ordered append
-        const unsigned addm = __ballot_sync(0xffffffffu, add);
+        const unsigned addm = __ballot_sync(0xffffffffu, add) & before;
         const int n_add = __popc(addm);
         if (n + n_add > cap) { status = AUVRRT_ST_OVERFLOW; break; }
-        if (add) {
+        if (add && ((addm >> lane) & 1u)) {
             const int slot = n + __popc(addm & ((1u << lane) - 1u));
             nx[slot] = px; ny[slot] = py; nlen[slot] = plen; nf[slot] = f; ncost[slot] = g; nts[slot] = ts; npar[slot] = cur;
             atomicOr(&alive[slot >> 5], 1u << (slot & 31));
             atomicOr(&visited[vword], vbit);
         }
+        if (errm) { n += n_add; status = AUVRRT_ST_KEY_ERROR; break; }
         n += n_add;
         __syncwarp();
     }
+    __syncwarp();
     // result (:590-617) on lane 0
     if (lane == 0) {
         auvrrt_astar_record_t r;

@@ -103,3 +103,51 @@ def test_caps_and_errors(astar, astar_golden):
     with pytest.raises(AuvrrtError):
         astar.AstarEnv(world["circles"], world["boundary"][:2], world["habitats"], world["bins"], world["cells_rounded"],
                        world["probs"], centroid=(0.0, 0.0), cells_are_rounded=True)
+
+
+def test_random_worlds_vs_oracle(astar):
+    """synthetic worlds: convex boundaries with 3..7 corners, random obstacles, lattice cells of other sizes with
+    unrounded bounds, other time-bin widths -- still bit for bit"""
+    rs = np.random.default_rng(33)
+    n_ok = 0
+    for trial in range(6):
+        E = int(rs.integers(3, 8))
+        ang = np.sort(rs.uniform(0, 2 * np.pi, E))
+        R = rs.uniform(120, 200)
+        boundary = np.column_stack([R * np.cos(ang), R * np.sin(ang)]) * rs.uniform(0.8, 1.0, (E, 1)) + rs.uniform(-50, 50, 2)
+        K = int(rs.integers(0, 15))
+        circles = np.column_stack([rs.uniform(-R, R, K), rs.uniform(-R, R, K), rs.uniform(2, 15, K)]) + np.array([boundary[:, 0].mean(), boundary[:, 1].mean(), 0]) if K else np.zeros((0, 3))
+        H = int(rs.integers(0, 6))
+        habitats = np.column_stack([rs.uniform(-R, R, H), rs.uniform(-R, R, H), rs.uniform(5, 30, H)]) if H else np.zeros((0, 3))
+        cs = float(rs.choice([10.0, 7.5, 20.0]))
+        x0, y0, x1, y1 = boundary[:, 0].min(), boundary[:, 1].min(), boundary[:, 0].max(), boundary[:, 1].max()
+        xs, ys = np.arange(x0, x1, cs), np.arange(y0, y1, cs)
+        cells = np.array([[x, y, min(x + cs, x1), min(y + cs, y1)] for x in xs for y in ys]) + rs.uniform(0, 1e-4, (len(xs) * len(ys), 4)) * 0
+        cells_r = astar.round_cells(cells)
+        T = int(rs.integers(3, 9)); bw = float(rs.choice([40.0, 50.0, 75.0]))
+        bins = np.array([[t * bw, (t + 1) * bw] for t in range(T)])
+        probs = rs.random((T, len(cells))) * (rs.random((T, len(cells))) < 0.3)
+        cen = astar.polygon_centroid(boundary)
+        env = astar.AstarEnv(circles, boundary, habitats, bins, cells_r, probs, centroid=cen, cells_are_rounded=True)
+        ow = orc.astar_world(circles, boundary, cen, habitats, bins, cells_r, probs)
+        Q = 48
+        q = np.zeros(Q, astar.ASTAR_QUERY_DTYPE)
+        c0 = np.array(cen)
+        q["start"] = np.round(c0 + rs.uniform(-0.5 * R, 0.5 * R, (Q, 2)), 2)
+        q["path_len_limit"] = rs.choice([50.0, 90.0, 130.0, 200.0], Q)
+        q["weights"] = np.column_stack([np.zeros(Q), rs.choice([0.0, 3.0, 10.0], Q), rs.choice([0.0, 10.0], Q), rs.choice([1.0, 50.0, 100.0], Q)])
+        q["velocity"] = rs.choice([0.8, 1.0, 2.0], Q)
+        r = astar.astar_batch(env, q, trace=True)
+        oq = np.column_stack([q["start"], q["path_len_limit"], q["weights"], q["velocity"]])
+        recs, cost, status = orc.astar_batch(ow, oq)
+        g = r["records"]
+        assert np.array_equal(g["status"], status), trial
+        assert np.array_equal(g["n_expanded"], recs[:, 0]) and np.array_equal(g["n_nodes"], recs[:, 1])
+        ok = status == 0
+        n_ok += int(ok.sum())
+        assert np.array_equal(g["cost"][ok], cost[ok]) and np.array_equal(g["n_smooth"][ok], recs[ok, 3])
+        for i in np.flatnonzero(ok)[:4]:
+            o = orc.astar(ow, q["start"][i], q["velocity"][i], q["path_len_limit"][i], q["weights"][i])
+            assert np.array_equal(r["paths"][i][:g["n_path"][i]], o["path"]) and np.array_equal(r["keep"][i][:g["n_path"][i]], o["keep"])
+        env.close()
+    assert n_ok > 60

@@ -201,3 +201,45 @@ def test_errors(gym):
     with pytest.raises(AuvrrtError):
         b.step(np.zeros(2, np.int32), records=True) if False else b._run(np.zeros(2, np.int32), 2, False, True)
     b.close()
+
+
+def test_random_worlds_vs_oracle_f64(gym):
+    """other boundaries (incl. one away from the origin), obstacle sets in non-monotone size order (the
+    running-minimum quirk matters), cell sizes, subsection counts, exp_rate / dist_to_end / diff_max"""
+    rs = np.random.default_rng(21)
+    total = mism = 0
+    for trial in range(10):
+        x0, y0 = [(0.0, 0.0), (0.0, 0.0), (-40.0, -25.0), (10.0, 5.0)][trial % 4]
+        W, Hh = rs.uniform(40, 120), rs.uniform(40, 120)
+        boundary = (x0, y0, x0 + W, y0 + Hh)
+        K = int(rs.integers(0, 12))
+        obstacles = np.column_stack([rs.uniform(x0 + 0.2 * W, x0 + 0.8 * W, K), rs.uniform(y0 + 0.2 * Hh, y0 + 0.8 * Hh, K),
+                                     rs.uniform(1.0, 7.0, K)]) if K else np.zeros((0, 3))
+        kw = dict(exp_rate=float(rs.choice([1.0, 0.5, 2.0])), dist_to_end=float(rs.choice([2.0, 3.5])),
+                  diff_max=float(rs.choice([0.5, 0.9])), freq=float(rs.choice([10.0, 25.0, 50.0])),
+                  cell_side_length=float(rs.choice([2.0, 3.0, 5.0])), subsections_in_cell=int(rs.choice([4, 8, 12])))
+        Q, max_step = 256, 80
+        starts = np.column_stack([rs.uniform(x0 + 2, x0 + 0.15 * W, Q), rs.uniform(y0 + 2, y0 + 0.15 * Hh, Q), rs.uniform(-np.pi, np.pi, Q)])
+        goals = np.column_stack([rs.uniform(x0 + 0.85 * W, x0 + W - 2, Q), rs.uniform(y0 + 0.85 * Hh, y0 + Hh - 2, Q)])
+        seeds = rs.integers(0, 2**40, Q).astype(np.uint64)
+        w = orc.gym_world(boundary, obstacles, **kw)
+        want, st = orc.gym_plan_batch(w, starts, goals, seeds, max_step=max_step)
+        b = gym.GymBatch(boundary, obstacles, Q, node_cap=max_step + 1, precision=gym.F64, **kw)
+        b.reset(starts, goals, seeds)
+        r = b.plan(max_step)
+        assert np.array_equal(r["status"], st), trial
+        ok = st == 0
+        same = (r["steps"] == want[:, 0]) & (r["done"] == want[:, 1]) & (r["n_nodes"] == want[:, 2]) & (r["n_occupied"] == want[:, 3])
+        total += int(ok.sum()); mism += int((~same & ok).sum())
+        # one full tree per world, float for float
+        q = int(np.flatnonzero(ok)[0])
+        w1 = orc.gym_world(boundary, obstacles, goals[q], **kw)
+        o = orc.gym_plan(w1, starts[q], max_step=max_step, seed=int(seeds[q]))
+        if same[q]:
+            t = b.tree(q)
+            assert np.allclose(t["nodes"], o["nodes"], rtol=1e-9, atol=1e-9) and np.array_equal(t["parents"], o["parents"])
+            assert np.array_equal(t["occupied"], o["occupied"]) and np.array_equal(t["cells"], o["node_cell"])
+            if o["found"]:
+                assert np.allclose(b.path(q), o["path"], rtol=1e-9, atol=1e-9)
+        b.close()
+    assert total > 2000 and mism <= 2, (total, mism)
