@@ -141,14 +141,17 @@ __global__ void __launch_bounds__(32 * ASTAR_WARPS) k_astar(AstarDev e, const au
         alive[0] = 1u;
     }
     __syncwarp();
-    int n = 1, n_exp = 0, status = AUVRRT_ST_NO_PATH, goal = -1;
+    int n = 1, n_exp = 0, status = AUVRRT_ST_NO_PATH, goal = -1, lo_word = 0;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     for (;;) {
         // 1. first strict minimum of f among the alive nodes (:577-583)
         double bf = INF; int bi = 0x7fffffff;
-        for (int i0 = 0; i0 < n; i0 += 32) {
+        while (lo_word < ((n - 1) >> 5) && alive[lo_word] == 0u) lo_word++;      // leading blocks of expanded nodes stay dead
+        for (int i0 = lo_word << 5; i0 < n; i0 += 32) {
+            const unsigned aw = alive[i0 >> 5];
+            if (aw == 0u) continue;
             const int i = i0 + lane;
-            const bool a = (alive[i0 >> 5] >> lane) & 1u;
+            const bool a = (aw >> lane) & 1u;
             if (a && i < n) { const double f = nf[i]; if (bi == 0x7fffffff || f < bf) { bf = f; bi = i; } }
         }
 #pragma unroll

@@ -3,9 +3,10 @@
 //
 // Q independent episodes live in HBM, one THREAD per episode: the per-step work of one episode is a
 // serial chain (pick cell -> pick node -> steer <= freq arcs -> test -> goal arc), and a trainer
-// steps thousands of environments at once, so episodes are the parallel axis.  All per-episode
-// arrays are laid out [slot][Q] (slot = node / occupied entry), so the 32 lanes of a warp touch
-// consecutive addresses whenever they walk their own trees in step.
+// steps thousands of environments at once, so episodes are the parallel axis.  A node is one 64-byte row,
+// the rows of an episode are contiguous (lanes are at different slots of their own trees, so a [slot][Q]
+// layout would touch one 32-byte sector per 4-byte field); occupied sub-cells are found through a small
+// open-addressing table per episode; the goal-arc test is done by the whole warp, arc by arc.
 //
 //   k_gym_reset   Planner_RRT.__init__ (:34-74): node 0, its sub-cell, occupied list, counts
 //   k_gym_run     n_steps x generate_one_node (:198-238), cell from random.choice (planning,
@@ -43,20 +44,26 @@ template <typename R> struct GymP {
     long long Q;
 };
 
+// One node = one 64-byte row (two 32-byte sectors), rows of an episode contiguous: appending a node writes
+// whole sectors and steering from a node reads one, whichever slot each lane of the warp is at.
+template <typename R> struct alignas(16) GymNode {
+    R x, y, th, t;                       // mps_list[i]: x, y, theta, traj_time_stamp
+    int parent, cell, prev, nwp;         // parent index; sub-cell (-1 none); previous node of the same sub-cell; kept primitives
+    unsigned npos;                       // sample-sequence position of its steer (replayed by k_gym_path)
+    int pad[(64 - 4 * (int)sizeof(R) - 20) / 4];
+};
+struct GymOcc { int cell, count, tail, pad; };      // occupied_grid_cells_array[i] + len / last node of its node_array
+struct GymHash { int key, val; };                   // open addressing: key = sub-cell id + 1 (0 = empty) -> occupied index
+
 template <typename R> struct GymS {
     // per episode
     R *gx, *gy, *arc;                       // goal; arc [6][Q] = x_C, y_C, radius, ang_vel, theta_0, length
     uint64_t *key;
     int *n_nodes, *n_occ, *steps, *done, *status, *goal_checked, *arc_ne, *npath;
     unsigned *spos;
-    // per node [cap][Q]
-    R *nx, *ny, *nth, *nt;
-    int *parent, *cell, *prev, *nwp;
-    unsigned *npos;
-    // per occupied entry [cap][Q]
-    int *occ_cell, *occ_count, *occ_tail;
-    // occupied-cell hash [hsize][Q]
-    int *hkey, *hval;
+    GymNode<R> *nodes;                      // [Q][cap]
+    GymOcc *occ;                            // [Q][cap]
+    GymHash *hash;                          // [Q][hsize]
     uint16_t *counts;                       // [Q][ncells] or nullptr
 };
 
@@ -226,7 +233,9 @@ template <typename R> __device__ __forceinline__ void gym_arc_point(const R arc[
     py = A::sub(arc[1], A::mul(arc[2], c));
 }
 
-#define GS(arr, slot) S.arr[(size_t)(slot) * (size_t)P.Q + (size_t)q]
+#define ND(i) S.nodes[(size_t)q * (size_t)P.cap + (size_t)(i)]
+#define OC(i) S.occ[(size_t)q * (size_t)P.cap + (size_t)(i)]
+#define HT(h) S.hash[(size_t)q * (size_t)P.hsize + (size_t)(h)]
 
 template <typename R>
 __global__ void __launch_bounds__(128) k_gym_reset(GymP<R> P, GymS<R> S, const double *starts, const double *goals,
@@ -236,15 +245,15 @@ __global__ void __launch_bounds__(128) k_gym_reset(GymP<R> P, GymS<R> S, const d
     const R x = (R)starts[3 * q], y = (R)starts[3 * q + 1], th = (R)starts[3 * q + 2];
     S.gx[q] = (R)goals[2 * q]; S.gy[q] = (R)goals[2 * q + 1];
     S.key[q] = stream_key(seeds[q]);
-    GS(nx, 0) = x; GS(ny, 0) = y; GS(nth, 0) = th; GS(nt, 0) = (R)0;
-    GS(parent, 0) = -1; GS(prev, 0) = -1; GS(nwp, 0) = 0; GS(npos, 0) = 0u;
+    ND(0).x = x; ND(0).y = y; ND(0).th = th; ND(0).t = (R)0;
+    ND(0).parent = -1; ND(0).prev = -1; ND(0).nwp = 0; ND(0).npos = 0u;
     const int c = gym_subcell<R>(P, x, y, th);                                          // :57
-    GS(cell, 0) = c;
+    ND(0).cell = c;
     int n_occ = 0;
     if (c >= 0) {
-        GS(occ_cell, 0) = c; GS(occ_count, 0) = 1; GS(occ_tail, 0) = 0; n_occ = 1;
+        OC(0).cell = c; OC(0).count = 1; OC(0).tail = 0; n_occ = 1;
         const unsigned h = ((unsigned)c * 2654435761u) >> P.hshift;
-        GS(hkey, h) = c + 1; GS(hval, h) = 0;
+        HT(h).key = c + 1; HT(h).val = 0;
         if (S.counts) S.counts[(size_t)q * P.ncells + c] = 1;
     }
     S.n_nodes[q] = 1; S.n_occ[q] = n_occ; S.steps[q] = 0; S.done[q] = 0; S.goal_checked[q] = -1; S.arc_ne[q] = -1; S.npath[q] = 0;
@@ -252,15 +261,15 @@ __global__ void __launch_bounds__(128) k_gym_reset(GymP<R> P, GymS<R> S, const d
     S.status[q] = c == -2 ? AUVRRT_ST_KEY_ERROR : AUVRRT_ST_OK;
 }
 
-// occupied-cell lookup: open-addressing table [HS][Q] (key = sub-cell id + 1, 0 = empty; value = index into the
+// occupied-cell lookup: open-addressing table per episode (key = sub-cell id + 1, 0 = empty; value = index into the
 // occupied list).  Replaces a linear scan of occupied_grid_cells_array, which streamed ~n_occ/2 rows per step.
 template <typename R>
 __device__ __forceinline__ int gym_occ_find(const GymP<R> &P, const GymS<R> &S, long long q, int c, unsigned &slot) {
     unsigned h = ((unsigned)c * 2654435761u) >> P.hshift;
     for (;;) {
-        const int k = GS(hkey, h);
+        const int k = HT(h).key;
         if (k == 0) { slot = h; return -1; }
-        if (k == c + 1) { slot = h; return GS(hval, h); }
+        if (k == c + 1) { slot = h; return HT(h).val; }
         h = (h + 1) & (unsigned)(P.hsize - 1);
     }
 }
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
                 else {
                     oi = (int)A::mul(st.u(pos++), (R)n_occ);                                // :176
                     if (!Policy<R>::VERIFY) oi = min(oi, n_occ - 1);
-                    cellid = GS(occ_cell, oi);
+                    cellid = OC(oi).cell;
                 }
             } else {
                 cellid = actions[q];
@@ -308,12 +317,12 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
             }
             if (live) {
                 const unsigned pos0 = pos;
-                const int cnt = GS(occ_count, oi);
+                const int cnt = OC(oi).count;
                 int k = (int)A::mul(st.u(pos++), (R)cnt);                                   // :217
                 if (!Policy<R>::VERIFY) k = min(k, cnt - 1);
-                int pn = GS(occ_tail, oi);
-                for (int h = cnt - 1 - k; h > 0; h--) pn = GS(prev, pn);
-                R x = GS(nx, pn), y = GS(ny, pn), th = GS(nth, pn), t = GS(nt, pn);
+                int pn = OC(oi).tail;
+                for (int h = cnt - 1 - k; h > 0; h--) pn = ND(pn).prev;
+                R x = ND(pn).x, y = ND(pn).y, th = ND(pn).th, t = ND(pn).t;
                 bool free = gym_point_free<R>(P, circ, x, y);                               // path[0] = the node steered from
                 unsigned used = 0;
                 const unsigned steer_pos = pos;
@@ -328,22 +337,22 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
                         if (n >= P.cap) { status = AUVRRT_ST_OVERFLOW; live = false; }
                         else if (c == -2) { status = AUVRRT_ST_KEY_ERROR; live = false; }
                         else {
-                            GS(nx, n) = x; GS(ny, n) = y; GS(nth, n) = th; GS(nt, n) = t;
-                            GS(parent, n) = pn; GS(nwp, n) = m; GS(npos, n) = steer_pos;
-                            GS(cell, n) = c;
+                            ND(n).x = x; ND(n).y = y; ND(n).th = th; ND(n).t = t;
+                            ND(n).parent = pn; ND(n).nwp = m; ND(n).npos = steer_pos;
+                            ND(n).cell = c;
                             if (c >= 0) {
                                 int oj = gym_occ_find<R>(P, S, q, c, hslot);
                                 if (oj < 0) {                                               // :153-154
                                     oj = n_occ++;
-                                    GS(occ_cell, oj) = c; GS(occ_count, oj) = 0; GS(occ_tail, oj) = -1;
-                                    GS(hkey, hslot) = c + 1; GS(hval, hslot) = oj;
+                                    OC(oj).cell = c; OC(oj).count = 0; OC(oj).tail = -1;
+                                    HT(hslot).key = c + 1; HT(hslot).val = oj;
                                 }
-                                GS(prev, n) = GS(occ_tail, oj);
-                                GS(occ_tail, oj) = n;
-                                GS(occ_count, oj) = GS(occ_count, oj) + 1;
+                                ND(n).prev = OC(oj).tail;
+                                OC(oj).tail = n;
+                                OC(oj).count = OC(oj).count + 1;
                                 if (S.counts) { uint16_t *cp = S.counts + (size_t)q * P.ncells + c; *cp = (uint16_t)(*cp + 1); }
                             } else {
-                                GS(prev, n) = -1;
+                                ND(n).prev = -1;
                             }
                             n++; last_acc = 1;
                         }
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
                         const int last = n - 1;
                         if (goal_checked != last) {
                             goal_checked = last;
-                            const int g = gym_goal_arc<R>(P, gx, gy, GS(nx, last), GS(ny, last), GS(nth, last), arc, ne);
+                            const int g = gym_goal_arc<R>(P, gx, gy, ND(last).x, ND(last).y, ND(last).th, arc, ne);
                             if (g >= 100) status = g - 100;
                             else if (g == 1) {
                                 if (ne < 0 && P.K > 0) status = AUVRRT_ST_KEY_ERROR;          // min([]) ValueError
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *
             for (int j = 0; j < 6; j++) S.arc[(size_t)j * P.Q + q] = arc[j];
             S.arc_ne[q] = ne;
             n_path = 1 + (ne + 1);
-            for (int j = last; GS(parent, j) >= 0; j = GS(parent, j)) n_path += GS(nwp, j) + 1;
+            for (int j = last; ND(j).parent >= 0; j = ND(j).parent) n_path += ND(j).nwp + 1;
             S.npath[q] = n_path;
         }
     }
@@ -426,12 +435,12 @@ __global__ void k_gym_path(GymP<R> P, GymS<R> S, const R *circ, long long q, int
     const int ne = S.arc_ne[q];
     const int last = S.n_nodes[q] - 1;
     long long total = 1 + (ne + 1);
-    for (int j = last; GS(parent, j) >= 0; j = GS(parent, j)) total += GS(nwp, j) + 1;
+    for (int j = last; ND(j).parent >= 0; j = ND(j).parent) total += ND(j).nwp + 1;
     *n_out = (int)total;
     if (total > cap) return;
     long long w = 0;
     R px, py, pa;
-    if (ne >= 0) gym_arc_point<R>(arc, ne, px, py, pa); else { px = GS(nx, last); py = GS(ny, last); pa = GS(nth, last); }
+    if (ne >= 0) gym_arc_point<R>(arc, ne, px, py, pa); else { px = ND(last).x; py = ND(last).y; pa = ND(last).th; }
     path[0] = (double)px; path[1] = (double)py; path[2] = (double)pa; w = 1;
     for (int i = ne; i >= 0; i--) {
         gym_arc_point<R>(arc, i, px, py, pa);
@@ -439,13 +448,13 @@ __global__ void k_gym_path(GymP<R> P, GymS<R> S, const R *circ, long long q, int
     }
     Stream<R> st;
     st.key = S.key[q]; st.ext = nullptr; st.n_ext = 0;
-    for (int j = last; GS(parent, j) >= 0; j = GS(parent, j)) {
-        const int pj = GS(parent, j), m = GS(nwp, j);
-        R x = GS(nx, pj), y = GS(ny, pj), th = GS(nth, pj), t = GS(nt, pj);
+    for (int j = last; ND(j).parent >= 0; j = ND(j).parent) {
+        const int pj = ND(j).parent, m = ND(j).nwp;
+        R x = ND(pj).x, y = ND(pj).y, th = ND(pj).th, t = ND(pj).t;
         bool free = true; int status = 0; unsigned used = 0;
-        gym_steer<R>(P, circ, st, GS(npos, j), x, y, th, t, free, true, status, used, path, w + m - 1);   // waypoint k -> row w + m-1-k
+        gym_steer<R>(P, circ, st, ND(j).npos, x, y, th, t, free, true, status, used, path, w + m - 1);   // waypoint k -> row w + m-1-k
         w += m;
-        path[3 * w] = (double)GS(nx, pj); path[3 * w + 1] = (double)GS(ny, pj); path[3 * w + 2] = (double)GS(nth, pj); w++;
+        path[3 * w] = (double)ND(pj).x; path[3 * w + 1] = (double)ND(pj).y; path[3 * w + 2] = (double)ND(pj).th; w++;
     }
 }
 
@@ -479,12 +488,9 @@ template <typename R> static size_t gym_carve(GymS<R> *S, unsigned char *base, i
     S->n_nodes = (int *)take(4 * q); S->n_occ = (int *)take(4 * q); S->steps = (int *)take(4 * q); S->done = (int *)take(4 * q);
     S->status = (int *)take(4 * q); S->goal_checked = (int *)take(4 * q); S->arc_ne = (int *)take(4 * q); S->npath = (int *)take(4 * q);
     S->spos = (unsigned *)take(4 * q);
-    S->nx = (R *)take(sizeof(R) * nq); S->ny = (R *)take(sizeof(R) * nq); S->nth = (R *)take(sizeof(R) * nq); S->nt = (R *)take(sizeof(R) * nq);
-    S->parent = (int *)take(4 * nq); S->cell = (int *)take(4 * nq); S->prev = (int *)take(4 * nq); S->nwp = (int *)take(4 * nq);
-    S->npos = (unsigned *)take(4 * nq);
-    S->occ_cell = (int *)take(4 * nq); S->occ_count = (int *)take(4 * nq); S->occ_tail = (int *)take(4 * nq);
-    const size_t hq = (size_t)gym_hash_size(cap) * q;
-    S->hkey = (int *)take(4 * hq); S->hval = (int *)take(4 * hq);
+    S->nodes = (GymNode<R> *)take(sizeof(GymNode<R>) * nq);
+    S->occ = (GymOcc *)take(sizeof(GymOcc) * nq);
+    S->hash = (GymHash *)take(sizeof(GymHash) * (size_t)gym_hash_size(cap) * q);
     S->counts = counts ? (uint16_t *)take(2 * q * (size_t)ncells) : nullptr;
     return off;
 }
@@ -512,7 +518,7 @@ template <typename R>
 static int gym_reset_t(auvrrt_gym *g, const double *d_starts, const double *d_goals, const uint64_t *d_seeds, cudaStream_t s) {
     const GymS<R> &S = *(const GymS<R> *)g->S;
     if (S.counts) AUV_CUDA(cudaMemsetAsync(S.counts, 0, 2 * (size_t)g->Q * g->ncells, s));
-    AUV_CUDA(cudaMemsetAsync(S.hkey, 0, 4 * (size_t)gym_hash_size(g->p.node_cap) * (size_t)g->Q, s));
+    AUV_CUDA(cudaMemsetAsync(S.hash, 0, sizeof(GymHash) * (size_t)gym_hash_size(g->p.node_cap) * (size_t)g->Q, s));
     k_gym_reset<R><<<(unsigned)((g->Q + 127) / 128), 128, 0, s>>>(make_gymp<R>(g), S, d_starts, d_goals, d_seeds);
     g_launches++;
     AUV_CUDA(cudaGetLastError());
@@ -538,13 +544,6 @@ static int gym_path_t(const auvrrt_gym *g, int64_t q, int cap, double *d_path, i
     return AUVRRT_OK;
 }
 
-// strided gather of one episode's column out of a [slot][Q] array
-template <typename T> static int gym_col(const T *d, int64_t Q, int64_t q, int n, T *out) {
-    if (n <= 0) return AUVRRT_OK;
-    AUV_CUDA(cudaMemcpy2D(out, sizeof(T), d + q, sizeof(T) * (size_t)Q, sizeof(T), (size_t)n, cudaMemcpyDeviceToHost));
-    return AUVRRT_OK;
-}
-
 template <typename R>
 static int gym_tree_t(const auvrrt_gym *g, int64_t q, int32_t cap, double *nodes, int32_t *parents, int32_t *cells,
                       int32_t *occupied, int32_t *n_nodes, int32_t *n_occupied) {
@@ -555,18 +554,20 @@ static int gym_tree_t(const auvrrt_gym *g, int64_t q, int32_t cap, double *nodes
     if (n_nodes) *n_nodes = n;
     if (n_occupied) *n_occupied = no;
     if (n > cap) return set_err(AUVRRT_ERR_ARG, "gym_tree: cap %d < n_nodes %d", cap, n);
-    int rc;
-    if (nodes) {
-        std::vector<R> col((size_t)n);
-        const R *src[4] = {S.nx, S.ny, S.nth, S.nt};
-        for (int j = 0; j < 4; j++) {
-            if ((rc = gym_col<R>(src[j], g->Q, q, n, col.data()))) return rc;
-            for (int i = 0; i < n; i++) nodes[4 * i + j] = (double)col[i];
+    if (nodes || parents || cells) {
+        std::vector<GymNode<R>> rows((size_t)(n > 0 ? n : 1));
+        AUV_CUDA(cudaMemcpy(rows.data(), S.nodes + (size_t)q * g->p.node_cap, sizeof(GymNode<R>) * (size_t)n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            if (nodes) { nodes[4 * i] = (double)rows[i].x; nodes[4 * i + 1] = (double)rows[i].y; nodes[4 * i + 2] = (double)rows[i].th; nodes[4 * i + 3] = (double)rows[i].t; }
+            if (parents) parents[i] = rows[i].parent;
+            if (cells) cells[i] = rows[i].cell;
         }
     }
-    if (parents && (rc = gym_col<int>(S.parent, g->Q, q, n, parents))) return rc;
-    if (cells && (rc = gym_col<int>(S.cell, g->Q, q, n, cells))) return rc;
-    if (occupied && (rc = gym_col<int>(S.occ_cell, g->Q, q, no, occupied))) return rc;
+    if (occupied) {
+        std::vector<GymOcc> rows((size_t)(no > 0 ? no : 1));
+        AUV_CUDA(cudaMemcpy(rows.data(), S.occ + (size_t)q * g->p.node_cap, sizeof(GymOcc) * (size_t)no, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < no; i++) occupied[i] = rows[i].cell;
+    }
     return AUVRRT_OK;
 }
 
