@@ -82,3 +82,53 @@ def habitat_time_cost_func(path, length, habitats, dist, weights=[1, -1, -1]):
     cost[2] = cost[2] / (0.5 * d)
     cost[1] = weights[1] * sum(visited) / len(habitats)
     return [sum(cost), cost]
+
+
+class Cost:
+    """Drop-in for the root-level cost.py class of auv-sim (/root/reference/cost.py:10-214), the four-weight twin
+    the A* drivers use (`from cost import Cost`, astar_fixLenSOG.py:16, astarAnalysis.py:37-41).  The small
+    methods are the host helpers above; `habitat_shark_cost_func` runs on the GPU (auvrrt_cost, fp64
+    verification build) and reproduces the twin's differences from path_planning/cost.py: the extra
+    w1 * length / peri term, no guard for a time stamp outside every bin (the previous waypoint's bin is
+    reused; UnboundLocalError when there is none yet, :187-191) and the unconditional division by
+    total_traj_time (:203-204)."""
+
+    def __init__(self):
+        self.cost = 0
+
+    def test_cost_func(self, path, length, bonus_area, weights=[1, 0]):
+        return test_cost_func(path, length, bonus_area, weights)
+
+    def habitat_num_cost_func(self, path, length, habitats, weights=[1, 1]):
+        return habitat_num_cost_func(path, length, habitats, weights)
+
+    def cost_of_edge(self, new_node, habitat_open_list, habitat_closed_list, weights):
+        return cost_of_edge(new_node, habitat_open_list, habitat_closed_list, weights)
+
+    def habitat_time_cost_func(self, path, length, habitats, dist, weights=[1, -1, -1]):
+        return habitat_time_cost_func(path, length, habitats, dist, weights)
+
+    def habitat_shark_cost_func(self, path, length, peri, total_traj_time, habitats, shark_dict, weight):
+        """-> [sum(cost), [w1 * length / peri, w2 * visited / len(habitats), w3-term / T, w4-term / T]]"""
+        w1, w2, w3, w4 = weight[0], weight[1], weight[2], weight[3]
+        cost = [0 for _ in range(len(weight))]
+        cost[0] = w1 * length / peri
+        bins = list(shark_dict)
+        pts, last = [], None
+        for mps in path:
+            t = mps.traj_time_stamp
+            if any(t >= b[0] and t <= b[1] for b in bins):
+                last = t
+            elif last is None:
+                raise UnboundLocalError("cannot access local variable 'temp_time' where it is not associated with a value")
+            pts.append([mps.x, mps.y, last])          # a stamp outside every bin reuses the previous waypoint's bin
+        if total_traj_time == 0:
+            raise ZeroDivisionError("float division by zero" if isinstance(total_traj_time, float) else "division by zero")
+        env = _env_for(habitats, shark_dict)
+        pts = np.array(pts, dtype=np.float64).reshape(-1, 3)
+        out = api.cost(env, [pts], [float(total_traj_time)], [float(w2), float(w3), float(w4)], precision="f64")[0]
+        c1, c2, c3 = float(out[1]), float(out[2]), float(out[3])
+        if total_traj_time < 0:                       # the kernel only normalises for T > 0 (path_planning/cost.py:193)
+            c2, c3 = c2 / total_traj_time, c3 / total_traj_time
+        cost[1], cost[2], cost[3] = c1, c2, c3
+        return [sum(cost), cost]

@@ -55,6 +55,35 @@ def main():
                 data[name + "/" + k] = t[k]
             data[name + "/cost"] = np.array(t["cost"])
         print("%-16s %-22s expanded %4d visited %4d  %.1fs" % (name, outcome, len(t["expanded"]), t["n_visited"], time.time() - t0))
+    # the four-weight Cost twin (root cost.py:151-214) the A* drivers score paths with (astarAnalysis.py:37-41)
+    rc = aref.mod            # astar_fixLenSOG did `from cost import Cost`: the root-level class
+    M = aref.MPS
+    grid = {}
+    for t, (b0, b1) in enumerate(z["bins"]):
+        grid[(int(b0), int(b1))] = {tuple(float(v) for v in c): float(z["probs"][t][i]) for i, c in enumerate(cells)}
+    habs = [M(h[0], h[1], size=h[2]) for h in w["habitats"]]
+    twin = []
+    for name, start, limit, weights, vel, nb in CASES:
+        if (name + "/nodes") not in data:
+            continue
+        nodes = data[name + "/nodes"]
+        for k, (stamps, T, wts) in enumerate([(nodes[:, 3], float(nodes[-1, 3]) or 1.0, (1.0, -3.0, -3.0, -4.0)),
+                                              (nodes[:, 3] * 2.5, 321.5, (0.5, 10.0, 10.0, 100.0)),     # stamps past the last bin
+                                              (nodes[:, 3], -7.0, (2.0, 1.0, 0.25, 3.0)),
+                                              (nodes[:, 3] * 2.5 - 40.0, 100.0, (1.0, 1.0, 1.0, 1.0))]):  # first stamp in no bin
+            path = [M(r[0], r[1], traj_time_stamp=float(ts)) for r, ts in zip(nodes, stamps)]
+            try:
+                res = rc.Cost().habitat_shark_cost_func(path, float(nodes[-1, 2]), 1234.5, T, habs, grid, list(wts))
+                row = [res[0]] + list(res[1]) + [0.0]
+            except UnboundLocalError:
+                row = [0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+            twin.append((name, k, T, wts, row))
+    data["twin/case"] = np.array([t[0] for t in twin])
+    data["twin/variant"] = np.array([t[1] for t in twin])
+    data["twin/T"] = np.array([t[2] for t in twin])
+    data["twin/weights"] = np.array([t[3] for t in twin])
+    data["twin/result"] = np.array([t[4] for t in twin])
+    print("Cost twin rows:", len(twin), "raised:", int(sum(t[4][5] for t in twin)))
     out = os.path.join(ROOT, "tests", "golden", "astar.npz")
     np.savez_compressed(out, **data)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -90,3 +90,34 @@ def test_dropin_matches_golden(mods, astar_golden, catalina_map):
     many = s.astar_many([c.start for c in ok], [c.limit for c in ok], [c.weights for c in ok])
     for r, c in zip(many, ok):
         assert r["cost"] == c.cost and r["path length"] == len(c.smooth_path)
+
+
+@pytest.mark.gpu
+def test_cost_twin_matches_reference(mods, astar_golden, catalina_map):
+    """root-level cost.py Cost.habitat_shark_cost_func (the A* drivers' scorer) through the drop-in, bit for bit"""
+    A, M = mods
+    import cost as dropin_cost
+    world, cases = astar_golden
+    z = np.load(os.path.join(ROOT, "tests", "golden", "astar.npz"))
+    by_name = {c.name: c for c in cases}
+    grid = {}
+    for t, (b0, b1) in enumerate(world["bins"]):
+        grid[(int(b0), int(b1))] = {tuple(float(v) for v in c): float(world["probs"][t][i]) for i, c in enumerate(catalina_map["cells"])}
+    habs = [M(h[0], h[1], size=h[2]) for h in world["habitats"]]
+    n_ok = n_raise = 0
+    for name, k, T, wts, want in zip(z["twin/case"], z["twin/variant"], z["twin/T"], z["twin/weights"], z["twin/result"]):
+        nodes = by_name[str(name)].nodes
+        stamps = [nodes[:, 3], nodes[:, 3] * 2.5, nodes[:, 3], nodes[:, 3] * 2.5 - 40.0][int(k)]
+        path = [M(r[0], r[1], traj_time_stamp=float(ts)) for r, ts in zip(nodes, stamps)]
+        args = (path, float(nodes[-1, 2]), 1234.5, float(T), habs, grid, [float(v) for v in wts])
+        if want[5]:
+            with pytest.raises(UnboundLocalError):
+                dropin_cost.Cost().habitat_shark_cost_func(*args)
+            n_raise += 1
+        else:
+            got = dropin_cost.Cost().habitat_shark_cost_func(*args)
+            assert got[0] == want[0] and list(got[1]) == list(want[1:5]), (name, k)
+            n_ok += 1
+    assert n_ok >= 20 and n_raise >= 4
+    with pytest.raises(ZeroDivisionError):
+        dropin_cost.Cost().habitat_shark_cost_func(path[:0], 1.0, 2.0, 0.0, habs, grid, [1, 1, 1, 1])
