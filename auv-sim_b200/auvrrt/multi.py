@@ -25,9 +25,10 @@ def _comm_device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
-def gather_records(local: np.ndarray, n_queries: int) -> np.ndarray:
-    """all-gather the per-query plan records of every rank, in global query order.
-    `local` is this rank's structured array (RECORD_DTYPE) for its shard_range()."""
+def gather_records(local: np.ndarray, n_queries: int, dtype=None) -> np.ndarray:
+    """all-gather the per-query records of every rank, in global query order.
+    `local` is this rank's structured array (RECORD_DTYPE unless `dtype` says otherwise) for its shard_range()."""
+    RECORD_DTYPE = np.dtype(dtype) if dtype is not None else globals()["RECORD_DTYPE"]
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = _comm_device()
     sizes = [shard_range(n_queries, r, world) for r in range(world)]
@@ -93,4 +94,54 @@ def plan_sharded(env, starts, seeds, params, precision="f32", plan_fn=None):
     local = plan_fn(env, starts[lo:hi], seeds[lo:hi], params, precision)["records"] if hi > lo else np.zeros(0, RECORD_DTYPE)
     allrec = gather_records(local, Q)
     best = global_best(local, lo)
+    return allrec, best
+
+
+def gym_plan_sharded(boundary, obstacles, starts, goals, seeds, max_step=200, run_fn=None, **batch_kw):
+    """Planner_RRT.planning for every episode, episodes sharded contiguously over the ranks; returns the
+    records of ALL episodes in global order (one all-gather of 88-byte records, no data-path collective).
+    `run_fn(boundary, obstacles, starts, goals, seeds, max_step, **batch_kw) -> records` defaults to the CUDA
+    planner (auvrrt.gym.GymBatch); tests inject a stand-in to exercise the host logic on gloo."""
+    from .gym import GYM_RECORD_DTYPE
+    if run_fn is None:
+        def run_fn(boundary, obstacles, starts, goals, seeds, max_step, **kw):
+            from .gym import GymBatch
+            kw.setdefault("node_cap", max_step + 1)
+            b = GymBatch(boundary, obstacles, len(seeds), **kw)
+            try:
+                b.reset(starts, goals, seeds)
+                return b.plan(max_step)
+            finally:
+                b.close()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    starts = np.asarray(starts, dtype=np.float64).reshape(-1, 3)
+    goals = np.asarray(goals, dtype=np.float64).reshape(-1, 2)
+    seeds = np.asarray(seeds, dtype=np.uint64)
+    Q = len(seeds)
+    lo, hi = shard_range(Q, rank, world)
+    local = run_fn(boundary, obstacles, starts[lo:hi], goals[lo:hi], seeds[lo:hi], max_step, **batch_kw) if hi > lo \
+        else np.zeros(0, GYM_RECORD_DTYPE)
+    return gather_records(local, Q, GYM_RECORD_DTYPE)
+
+
+def astar_sharded(env, queries, run_fn=None, **batch_kw):
+    """lattice-A* queries sharded contiguously over the ranks -> (records of ALL queries in global order, index of
+    the minimum-cost successful query, -1 if none; ties to the lowest index).  `env` is this rank's AstarEnv."""
+    from .astar import ASTAR_QUERY_DTYPE, ASTAR_RECORD_DTYPE
+    if run_fn is None:
+        def run_fn(env, q, **kw):
+            from .astar import astar_batch
+            kw.setdefault("want_paths", False)
+            return astar_batch(env, q, **kw)["records"]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    queries = np.ascontiguousarray(queries, dtype=ASTAR_QUERY_DTYPE)
+    Q = len(queries)
+    lo, hi = shard_range(Q, rank, world)
+    local = run_fn(env, queries[lo:hi], **batch_kw) if hi > lo else np.zeros(0, ASTAR_RECORD_DTYPE)
+    allrec = gather_records(local, Q, ASTAR_RECORD_DTYPE)
+    ok = allrec["status"] == 0
+    best = -1
+    if ok.any():
+        keys = _orderable(np.where(ok, allrec["cost"], np.inf))
+        best = int(np.lexsort((np.arange(Q), keys))[0])
     return allrec, best
