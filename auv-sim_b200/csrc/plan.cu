@@ -32,10 +32,15 @@ namespace auv {
                            cudaGetErrorString(e_));                                         \
     } while (0)
 
-static const int PLAN_THREADS = 256;
+#ifndef AUV_PLAN_THREADS
+#define AUV_PLAN_THREADS 128  // 4 warps per CTA: config 2's 4096 trees (one warp each) spread as 6-7 CTAs = 24-28 warps per SM;
+                              // with 256-thread CTAs 68 SMs held 32 warps and 80 held 24, and the kernel waited for the
+                              // fuller ones (measured 15.5 ms -> 14.7 ms)
+#endif
+static const int PLAN_THREADS = AUV_PLAN_THREADS;
 #ifndef AUV_PLAN_MINB
-#define AUV_PLAN_MINB 4      // resident CTAs per SM the fp32 register allocation targets: 4 x 8 warps hold all
-                             // 4096 trees of config 2 in ONE wave (measured 20.5 ms vs 22.4 ms at 2)
+#define AUV_PLAN_MINB 8      // resident CTAs per SM the fp32 register allocation targets (64 registers): 8 x 4 warps hold
+                             // all 4096 trees of config 2 in ONE wave (measured 20.5 ms vs 22.4 ms at half that)
 #endif
 
 struct WsLayout {
@@ -72,7 +77,7 @@ template <typename R> struct Tree {
 // parent pick reads count[bin] once per draw, so this takes a global round trip off every draw.
 #define AUV_BINS_SMEM 128
 template <typename R, int G, bool BS>
-__global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : 2)
+__global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : AUV_PLAN_MINB / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
