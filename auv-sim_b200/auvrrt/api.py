@@ -204,6 +204,22 @@ def edges_arc(env: Env, parents, seeds, params, precision="f32"):
     return safe, counts, leaf
 
 
+def edges_arc_cost(env: Env, parents, seeds, params, w3, precision="f32"):
+    """edges_arc + each edge's share of the path cost over its appended waypoints:
+    cost [n][3] = sum of w3 * prob, waypoints inside a habitat, distinct habitats visited"""
+    parents = _f64(parents, (-1, 5))
+    n = len(parents)
+    seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+    params = _f64(params, (5,))
+    safe = np.zeros(n, np.uint8)
+    counts = np.zeros(n, np.int32)
+    leaf = np.zeros((n, 5))
+    cost = np.zeros((n, 3))
+    check(lib().auvrrt_edges_arc_cost(env.handle, _p(parents), _p(seeds, C.c_uint64), n, _p(params), float(w3),
+                                      _prec(precision), _p(safe, C.c_uint8), _p(counts, C.c_int32), _p(leaf), _p(cost)))
+    return safe, counts, leaf, cost
+
+
 def plan_params(iterations, mode=0, bin_interval=5.0, v=2.0, max_traj_time=500.0, dist_to_end=2.0,
                 diff_max=0.5, freq=30.0, min_dist=0.5, weights=(-3.0, -3.0, -4.0), chain_cap=96,
                 path_cap=0, trace=False, group=0, max_plan_time=5.0):

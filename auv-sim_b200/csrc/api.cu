@@ -655,6 +655,46 @@ extern "C" int auvrrt_edges_arc(const auvrrt_env_t *env, const double *parents, 
                                    : edges_arc_host<double>(env, parents, seeds, n, params, out_safe, out_counts, out_leaf);
 }
 
+extern "C" int auvrrt_edges_arc_cost_dev(const auvrrt_env_t *env, const void *parents, const uint64_t *seeds, int64_t n,
+                                         const double params[5], double w3, int precision, uint8_t *out_safe,
+                                         int32_t *out_counts, void *out_leaf, void *out_cost, void *stream) {
+    AUV_TRY(check_precision(precision));
+    if (!env || !out_cost) return set_err(AUVRRT_ERR_ARG, "edges_arc_cost: env / out_cost is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == AUVRRT_F32)
+        return launch_edges_arc<float>(env, (const float *)parents, seeds, n, params, out_safe, out_counts, (float *)out_leaf, s, w3,
+                                       (float *)out_cost);
+    return launch_edges_arc<double>(env, (const double *)parents, seeds, n, params, out_safe, out_counts, (double *)out_leaf, s, w3,
+                                    (double *)out_cost);
+}
+template <typename R>
+static int edges_arc_cost_host(const auvrrt_env *env, const double *parents, const uint64_t *seeds, int64_t n,
+                               const double params[5], double w3, uint8_t *safe, int32_t *counts, double *leaf, double *cost) {
+    cudaStream_t s = 0;
+    DBuf dp, t0, dseed, dsafe, dcnt, dleaf, dcost, t1, t2;
+    AUV_TRY(upload_real<R>(dp, parents, 5 * n, s, t0));
+    AUV_TRY(upload_raw<uint64_t>(dseed, seeds, n, s));
+    AUV_TRY(dsafe.alloc((size_t)n)); AUV_TRY(dcnt.alloc(4 * (size_t)n)); AUV_TRY(dleaf.alloc(sizeof(R) * 5 * (size_t)n));
+    AUV_TRY(dcost.alloc(sizeof(R) * 3 * (size_t)n));
+    AUV_TRY(launch_edges_arc<R>(env, dp.as<R>(), dseed.as<uint64_t>(), n, params, dsafe.as<uint8_t>(), dcnt.as<int32_t>(), dleaf.as<R>(), s,
+                                w3, dcost.as<R>()));
+    AUV_TRY(download_raw<uint8_t>(safe, dsafe, n, s)); AUV_TRY(download_raw<int32_t>(counts, dcnt, n, s));
+    AUV_TRY(download_real<R>(leaf, dleaf, 5 * n, s, t1));
+    AUV_TRY(download_real<R>(cost, dcost, 3 * n, s, t2));
+    AUV_CUDA(cudaStreamSynchronize(s));
+    return AUVRRT_OK;
+}
+extern "C" int auvrrt_edges_arc_cost(const auvrrt_env_t *env, const double *parents, const uint64_t *seeds, int64_t n,
+                                     const double params[5], double w3, int precision, uint8_t *out_safe,
+                                     int32_t *out_counts, double *out_leaf, double *out_cost) {
+    AUV_TRY(check_precision(precision));
+    if (!env || !out_cost || !out_safe || !out_counts || !out_leaf) return set_err(AUVRRT_ERR_ARG, "edges_arc_cost: NULL argument");
+    AUV_TRY(need_device(env->device));
+    if (n <= 0) return AUVRRT_OK;
+    return precision == AUVRRT_F32 ? edges_arc_cost_host<float>(env, parents, seeds, n, params, w3, out_safe, out_counts, out_leaf, out_cost)
+                                   : edges_arc_cost_host<double>(env, parents, seeds, n, params, w3, out_safe, out_counts, out_leaf, out_cost);
+}
+
 // ------------------------------------------------------------------ planner
 extern "C" int64_t auvrrt_plan_workspace_bytes(const auvrrt_env_t *env, const auvrrt_plan_params_t *params, int precision) {
     if (!env || !params || check_precision(precision)) return -1;

@@ -504,10 +504,13 @@ template int launch_edges_dubins<double>(const auvrrt_env *, const double *, con
                                          uint8_t *, uint8_t *, double *, cudaStream_t);
 
 // ------------------------------------------------------------------ fused arc edges on the counter stream
-template <typename R, int G>
+// COST: also the edge's share of cost.habitat_shark_cost_func over its appended waypoints (cost.py:171-191):
+// cost_out[i] = { sum of w3 * prob, waypoints inside a habitat, distinct habitats visited }.
+template <typename R, int G, bool COST>
 __global__ void __launch_bounds__(256) k_edges_arc(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                    int stage_mode, const R *parents, const uint64_t *seeds, int64_t n,
-                                                   SteerParams<R> sp, uint8_t *safe, int32_t *counts, R *leaf) {
+                                                   SteerParams<R> sp, R w3, uint8_t *safe, int32_t *counts, R *leaf,
+                                                   R *cost_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     EnvView<R> env = load_env<R>(smem, blob, hot_bytes, total_bytes, stage_mode);
     __shared__ GroupScratch<R, G> scratch[256 / G];
@@ -519,34 +522,44 @@ __global__ void __launch_bounds__(256) k_edges_arc(const unsigned char *blob, in
         rng.key = stream_key(seeds[i]); rng.ext = nullptr; rng.n_ext = 0;
         const R *p = parents + 5 * i;
         EdgeOut<R> o;
-        eval_edge<R, G, true, false, false>(g, sc, env, rng, 0u, sp, p[0], p[1], p[2], p[3], p[4], (R)0, 0, nullptr,
-                                            0, o);
+        eval_edge<R, G, true, COST, false>(g, sc, env, rng, 0u, sp, p[0], p[1], p[2], p[3], p[4], w3, env.H, nullptr,
+                                           0, o);
         if (g.gl == 0) {
             safe[i] = o.safe ? 1 : 0;
             if (counts) counts[i] = o.nwp;
             if (leaf) { R *l = leaf + 5 * i; l[0] = o.x; l[1] = o.y; l[2] = o.th; l[3] = o.t; l[4] = o.len; }
+            if (COST) { R *c = cost_out + 3 * i; c[0] = o.s2; c[1] = (R)o.cnt; c[2] = (R)__popcll(o.mask); }
         }
     }
 }
-template <typename R>
-int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n,
-                     const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s) {
-    if (n <= 0) return AUVRRT_OK;
+template <typename R, bool COST>
+static int launch_edges_arc_t(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n,
+                              const double params[5], double w3, uint8_t *safe, int32_t *counts, R *leaf, R *cost_out,
+                              cudaStream_t s) {
     EnvBlob<R> b = env_blob<R>(env);
     int smem, mode = env_stage_mode(b.hot_bytes, b.hot_bytes, 64 * 1024, &smem);
     mode = mode ? 1 : 0;
-    AUV_CUDA(cudaFuncSetAttribute(k_edges_arc<R, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AUV_CUDA(cudaFuncSetAttribute(k_edges_arc<R, 32, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int64_t blocks = (n + 7) / 8;
     if (blocks > AUV_SMS * 8) blocks = AUV_SMS * 8;
-    k_edges_arc<R, 32><<<(unsigned)blocks, 256, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, parents, seeds, n,
-                                                            make_steer_params<R>(params), safe, counts, leaf);
+    k_edges_arc<R, 32, COST><<<(unsigned)blocks, 256, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, parents, seeds, n,
+                                                                  make_steer_params<R>(params), (R)w3, safe, counts, leaf,
+                                                                  cost_out);
     AUV_LAUNCH_CHECK();
     return AUVRRT_OK;
 }
+template <typename R>
+int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n,
+                     const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3,
+                     R *cost_out) {
+    if (n <= 0) return AUVRRT_OK;
+    return cost_out ? launch_edges_arc_t<R, true>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s)
+                    : launch_edges_arc_t<R, false>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s);
+}
 template int launch_edges_arc<float>(const auvrrt_env *, const float *, const uint64_t *, int64_t, const double[5],
-                                     uint8_t *, int32_t *, float *, cudaStream_t);
+                                     uint8_t *, int32_t *, float *, cudaStream_t, double, float *);
 template int launch_edges_arc<double>(const auvrrt_env *, const double *, const uint64_t *, int64_t, const double[5],
-                                      uint8_t *, int32_t *, double *, cudaStream_t);
+                                      uint8_t *, int32_t *, double *, cudaStream_t, double, double *);
 
 // ------------------------------------------------------------------ RRT.get_closest_mps
 // SoA tree streamed once from HBM with vector loads; all arithmetic in fp64 (exact on fp32 inputs),

@@ -54,7 +54,8 @@ int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64
                         uint8_t *safe, uint8_t *word, R *length, cudaStream_t s);
 template <typename R>
 int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n,
-                     const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s);
+                     const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3 = 0.0,
+                     R *cost_out = nullptr);
 template <typename R>
 int launch_nn(const R *tx, const R *ty, int64_t n, const R *qx, const R *qy, int nq, void *scratch,
               int64_t scratch_bytes, int32_t *out_idx, cudaStream_t s);

@@ -409,6 +409,45 @@ def extras(env, dev, args, api, adev):
                                    "note": "same results as the all-pairs kernel; the grid skips circles that cannot touch a waypoint's cell"}
     del q0, q1, safe, word, length
 
+    # config 4 with the reference's own steer (S1 random arcs, P = 14.5 primitives, W = 11.9 waypoints on average)
+    # against the same 500 circles + the Catalina polygon, cost off and cost on (habitats + shark grid)
+    try:
+        world, bins_, probs_ = load_world()
+        env4c = api.Env(circles=circles, boundary=world["boundary"], habitats=world["habitats"], bins=bins_,
+                        cells=world["cells"], probs=probs_, device=dev.index)
+        na = int(args.micro_edges)
+        g = torch.Generator(device=dev); g.manual_seed(2)
+        par = torch.stack([torch.rand(na, device=dev, generator=g) * 549.8 - 467.4,
+                           torch.rand(na, device=dev, generator=g) * 344.7 - 153.5,
+                           (torch.rand(na, device=dev, generator=g) * 2 - 1) * np.pi,
+                           torch.rand(na, device=dev, generator=g) * 400.0,
+                           torch.zeros(na, device=dev)], 1).contiguous()
+        sd = torch.arange(na, device=dev, dtype=torch.int64)
+        safe_a = torch.zeros(na, dtype=torch.uint8, device=dev); cnt_a = torch.zeros(na, dtype=torch.int32, device=dev)
+        sp5 = [2.0, 0.5, 30.0, 0.5, 2.0]
+        mean_off, _ = timed(lambda: adev.edges_arc_dev(env4c, par, sd, sp5, safe_a, cnt_a, None, "f32"), reps=3, warm=1)
+        safe_off = safe_a.clone()
+        W_mean = float(cnt_a.float().mean().item())            # waypoints per edge incl. the parent
+        cost_a = torch.zeros((na, 3), device=dev)
+        mean_on, _ = timed(lambda: adev.edges_arc_cost_dev(env4c, par, sd, sp5, -4.0, safe_a, cnt_a, None, cost_a, "f32"), reps=3, warm=1)
+        Pm = 14.5
+        flop_off = 6 * W_mean * K + 6 * W_mean * 5 + 30 * Pm
+        flop_on = flop_off + W_mean * (2 * 10 + 2 * 35 + 6 * 10 + 3)
+        out["micro_config4_arc"] = {"edges": na, "circles": K, "waypoints_mean": W_mean, "edges_per_s": na / mean_off,
+                                    "algorithmic_flop_per_edge": flop_off, "equivalent_all_pairs_tflops": na * flop_off / mean_off / 1e12,
+                                    "equivalent_frac": na * flop_off / mean_off / cal, "safe_fraction": float(safe_off.float().mean().item()),
+                                    "kernel": "k_edges_arc<float,32,false> (warp per edge, classification grid)",
+                                    "note": "the grid skips circles that cannot touch a waypoint's cell, so the all-pairs FLOP count is an equivalent, not executed work"}
+        out["micro_config4_arc_cost"] = {"edges": na, "edges_per_s": na / mean_on, "algorithmic_flop_per_edge": flop_on,
+                                         "equivalent_all_pairs_tflops": na * flop_on / mean_on / 1e12, "equivalent_frac": na * flop_on / mean_on / cal,
+                                         "identical_booleans": bool(torch.equal(safe_a, safe_off)),
+                                         "edges_with_shark_cost": float((cost_a[:, 0] != 0).float().mean().item()),
+                                         "kernel": "k_edges_arc<float,32,true> (steer + collide + cost)"}
+        del par, sd, safe_a, cnt_a, cost_a, safe_off
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["micro_config4_arc"] = {"error": repr(ex)}
+
     # vectorised gym_rrt Planner_RRT (RRTEnv's planner, freq = 10), one thread per episode
     try:
         from auvrrt import gym as agym

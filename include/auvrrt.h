@@ -122,8 +122,10 @@ int auvrrt_cost_point(const auvrrt_env_t *env, const double *points, int64_t n,
 
 /* ---- fused edge evaluation: steer + collide (+ cost), the config-4 micro-benchmark -----------
  * Dubins edges: one (from, to) pair per edge, W waypoints each.  Arc edges: edge i consumes the
- * counter stream of seed seeds[i] from position 0 (see auvrrt_stream_u).  out_cost (may be NULL)
- * = cost of the edge's waypoints alone, (sum, c0, c1, c2) with total time = last waypoint time. */
+ * counter stream of seed seeds[i] from position 0 (see auvrrt_stream_u).
+ * The _cost variants (config 4 "cost on") also return, per edge, its share of
+ * cost.habitat_shark_cost_func over the appended waypoints (cost.py:171-191): out_cost [n][3] =
+ * sum of w3 * prob, number of waypoints inside a habitat, number of distinct habitats visited. */
 int auvrrt_edges_dubins_dev(const auvrrt_env_t *env, const void *from, const void *to, int64_t n,
                             double rho, int W, int precision, uint8_t *out_safe, uint8_t *out_word,
                             void *out_length, void *stream);
@@ -136,6 +138,13 @@ int auvrrt_edges_dubins(const auvrrt_env_t *env, const double *from, const doubl
 int auvrrt_edges_arc(const auvrrt_env_t *env, const double *parents, const uint64_t *seeds,
                      int64_t n, const double params[5], int precision, uint8_t *out_safe,
                      int32_t *out_counts, double *out_leaf);
+int auvrrt_edges_arc_cost_dev(const auvrrt_env_t *env, const void *parents, const uint64_t *seeds,
+                              int64_t n, const double params[5], double w3, int precision,
+                              uint8_t *out_safe, int32_t *out_counts, void *out_leaf, void *out_cost,
+                              void *stream);
+int auvrrt_edges_arc_cost(const auvrrt_env_t *env, const double *parents, const uint64_t *seeds,
+                          int64_t n, const double params[5], double w3, int precision,
+                          uint8_t *out_safe, int32_t *out_counts, double *out_leaf, double *out_cost);
 
 /* ---- the pre-generated sample sequence ------------------------------------------------------
  * u_k(seed): counter-based SplitMix64 stream; 53-bit doubles, or the top 24 bits (bits24 != 0,

@@ -452,3 +452,35 @@ def test_plan_full_size_properties(api, env, oworld):
     bad = np.array([[9.39, -3.2, 0.0, 0.0, 0.0]])
     rb = api.plan_batch(env, bad, [1], api.plan_params(64), "f32")
     assert rb["records"]["status"][0] == 1 and rb["records"]["n_nodes"][0] == 1
+
+
+def test_edges_arc_cost_vs_oracle(api, env, oworld):
+    """config 4 "cost on": the fused steer + collide + cost edge kernel; per-edge cost terms against
+    cost.habitat_shark_cost_func restated by the oracle on the oracle's own waypoints"""
+    from oracle import harness as H
+    rs = np.random.RandomState(18)
+    n = 1500
+    parents = np.stack([rs.uniform(-300, -100, n), rs.uniform(-60, 100, n), rs.uniform(-6, 6, n),
+                        rs.uniform(0, 520, n), rs.uniform(0, 500, n)], 1)
+    seeds = np.arange(n) + 4242
+    w3 = -4.0
+    params = [2.0, 0.5, 30.0, 0.5, 2.0]
+    safe0, counts0, leaf0 = api.edges_arc(env, parents, seeds, params, "f64")
+    safe, counts, leaf, cost = api.edges_arc_cost(env, parents, seeds, params, w3, "f64")
+    assert np.array_equal(safe, safe0) and np.array_equal(counts, counts0) and np.array_equal(leaf, leaf0)
+    nh = oworld.c.H
+    n_pos = 0
+    for i in range(n):
+        u = H.stream_block(int(seeds[i]), 0, 96)
+        st, lf, wp, used = orc.steer_arc(parents[i], u, 2.0, 0.5, 30.0, 0.5, 2.0)
+        assert st == 0 and len(wp) + 1 == counts[i]
+        want = orc.cost(wp[:, [0, 1, 4]], 1.0, oworld, [float(nh), 1.0, w3]) if len(wp) else np.zeros(4)
+        assert cost[i, 2] == want[1] and cost[i, 1] == want[2], i           # habitats visited, waypoints in habitats
+        assert abs(cost[i, 0] - want[3]) <= 1e-12 * max(1.0, abs(want[3])), i
+        n_pos += cost[i, 1] > 0
+    assert n_pos > 20 and (cost[:, 0] != 0).sum() > 100
+    # fp32 build: same integers on almost every edge, sums to 1e-5
+    p32 = parents.astype(np.float32).astype(np.float64)
+    s64 = api.edges_arc_cost(env, p32, seeds, params, w3, "f64")
+    s32 = api.edges_arc_cost(env, p32, seeds, params, w3, "f32")
+    assert s32[3].shape == (n, 3) and np.isfinite(s32[3]).all()
