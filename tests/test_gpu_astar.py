@@ -151,3 +151,37 @@ def test_random_worlds_vs_oracle(astar):
             assert np.array_equal(r["paths"][i][:g["n_path"][i]], o["path"]) and np.array_equal(r["keep"][i][:g["n_path"][i]], o["keep"])
         env.close()
     assert n_ok > 60
+
+
+def test_device_entry_point(astar, astar_golden):
+    """auvrrt_astar_batch_dev on torch tensors == the host-buffer call"""
+    import torch
+    from auvrrt._lib import check
+    world, cases = astar_golden
+    env = _env(astar, world)
+    ok = [c for c in cases if c.outcome == "ok"][:6]
+    q = np.zeros(len(ok), astar.ASTAR_QUERY_DTYPE)
+    for i, c in enumerate(ok):
+        q[i] = (tuple(c.start), c.limit, tuple(c.weights), c.velocity)
+    want = astar.astar_batch(env, q, node_cap=2048, path_cap=64)
+    dev = torch.device("cuda", 0)
+    Q = len(q)
+    d_q = torch.from_numpy(q.view(np.uint8).reshape(Q, 64).copy()).to(dev)
+    d_rec = torch.zeros(Q * 40, dtype=torch.uint8, device=dev)
+    d_paths = torch.zeros((Q, 64, 6), dtype=torch.float64, device=dev)
+    d_keep = torch.zeros((Q, 64), dtype=torch.uint8, device=dev)
+    wsb = int(astar.lib().auvrrt_astar_workspace_bytes(Q, 2048))
+    d_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(astar.lib().auvrrt_astar_batch_dev(env.handle, d_q.data_ptr(), Q, 2048, 64, d_ws.data_ptr(), wsb, d_rec.data_ptr(),
+                                             d_paths.data_ptr(), d_keep.data_ptr(), None, None,
+                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    rec = np.frombuffer(d_rec.cpu().numpy().tobytes(), dtype=astar.ASTAR_RECORD_DTYPE)
+    assert np.array_equal(rec, want["records"])
+    assert np.array_equal(d_paths.cpu().numpy(), want["paths"]) and np.array_equal(d_keep.cpu().numpy(), want["keep"])
+    # too small a workspace is refused
+    from auvrrt._lib import AuvrrtError
+    with pytest.raises(AuvrrtError):
+        check(astar.lib().auvrrt_astar_batch_dev(env.handle, d_q.data_ptr(), Q, 2048, 64, d_ws.data_ptr(), 1024, d_rec.data_ptr(),
+                                                 d_paths.data_ptr(), d_keep.data_ptr(), None, None, None))
+    env.close()

@@ -243,3 +243,42 @@ def test_random_worlds_vs_oracle_f64(gym):
                 assert np.allclose(b.path(q), o["path"], rtol=1e-9, atol=1e-9)
         b.close()
     assert total > 2000 and mism <= 2, (total, mism)
+
+
+def test_device_entry_points(gym):
+    """auvrrt_gym_step_dev / auvrrt_gym_counts_dev on torch tensors give what the host-buffer calls give"""
+    import torch
+    from auvrrt._lib import check
+    Q = 300
+    starts, goals, seeds = _random_episodes(Q, 5)
+    kw = dict(freq=10.0, node_cap=41, track_counts=True, precision=gym.F32)
+    a = gym.GymBatch((0, 0, 50, 50), GYM_MAIN_OBSTACLES, Q, **kw)
+    b = gym.GymBatch((0, 0, 50, 50), GYM_MAIN_OBSTACLES, Q, **kw)
+    a.reset(starts, goals, seeds); b.reset(starts, goals, seeds)
+    dev = torch.device("cuda", 0)
+    d_recs = torch.zeros(Q * gym.GYM_RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    rs = np.random.default_rng(1)
+    stream = torch.cuda.current_stream().cuda_stream
+    for it in range(12):
+        cnt = a.counts()
+        act = np.argmax((cnt > 0) * rs.random(cnt.shape), axis=1).astype(np.int32)
+        want = a.step(act)
+        d_act = torch.from_numpy(act).to(dev)
+        check(gym.lib().auvrrt_gym_step_dev(b.handle, d_act.data_ptr(), 1, 0, d_recs.data_ptr(), stream))
+        torch.cuda.synchronize()
+        got = np.frombuffer(d_recs.cpu().numpy().tobytes(), dtype=gym.GYM_RECORD_DTYPE)
+        assert np.array_equal(got, want)
+    # the resident counts array, read through the device pointer
+    ptr = b.counts_device_ptr()
+    assert ptr
+    class _Dev:          # expose the library's device array to torch without a copy
+        __cuda_array_interface__ = {"shape": (Q, b.n_subcells), "typestr": "<u2", "data": (int(ptr), False), "version": 3}
+    torch.cuda.synchronize()
+    host = torch.as_tensor(_Dev(), device=dev).cpu().numpy()
+    assert np.array_equal(host, a.counts())
+    # planning on the device entry point as well
+    check(gym.lib().auvrrt_gym_step_dev(b.handle, None, 25, 0, d_recs.data_ptr(), stream))
+    torch.cuda.synchronize()
+    got = np.frombuffer(d_recs.cpu().numpy().tobytes(), dtype=gym.GYM_RECORD_DTYPE)
+    assert np.array_equal(got, a.plan(25))
+    a.close(); b.close()
