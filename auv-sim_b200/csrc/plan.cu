@@ -39,8 +39,9 @@ namespace auv {
 #endif
 static const int PLAN_THREADS = AUV_PLAN_THREADS;
 #ifndef AUV_PLAN_MINB
-#define AUV_PLAN_MINB 8      // resident CTAs per SM the fp32 register allocation targets (64 registers): 8 x 4 warps hold
-                             // all 4096 trees of config 2 in ONE wave (measured 20.5 ms vs 22.4 ms at half that)
+#define AUV_PLAN_MINB 7      // resident CTAs per SM the fp32 register allocation targets: 7 x 4 warps = 28 warps is what one
+                             // wave of config 2 needs (4096 trees / 148 SMs = 27.7) and leaves 72 registers per thread
+                             // (measured 14.6 ms at 8 CTAs / 64 registers, 13.7 ms at 7 / 72, 20.7 ms at 6 / 80: two waves)
 #endif
 
 struct WsLayout {
@@ -77,7 +78,7 @@ template <typename R> struct Tree {
 // parent pick reads count[bin] once per draw, so this takes a global round trip off every draw.
 #define AUV_BINS_SMEM 128
 template <typename R, int G, bool BS>
-__global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : AUV_PLAN_MINB / 2)
+__global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : (AUV_PLAN_MINB + 1) / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
