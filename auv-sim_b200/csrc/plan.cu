@@ -77,6 +77,7 @@ template <typename R> struct Tree {
 // memory as u16 (needs <= 126 time bins and <= 65535 nodes / chunks): the rejection loop of the
 // parent pick reads count[bin] once per draw, so this takes a global round trip off every draw.
 #define AUV_BINS_SMEM 128
+template <typename R> struct BestPlan { R c0, c1, c2, len, t; int node, iter; };
 template <typename R, int G, bool BS>
 __global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : (AUV_PLAN_MINB + 1) / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
@@ -86,6 +87,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     const bool VERIFY = Policy<R>::VERIFY;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ GroupScratch<R, G> scratch[PLAN_THREADS / G];
+    __shared__ BestPlan<R> best_s[PLAN_THREADS / G];
     __shared__ unsigned short binmeta[BS ? PLAN_THREADS / G : 1][3][BS ? AUV_BINS_SMEM : 1];
     EnvView<R> env;
     {
@@ -139,12 +141,15 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
         int n_nodes = 1, n_chunks = 1;
         uint32_t ctr = 0, upos_mark = 0;
         int status = AUVRRT_ST_OK;
-        int best_node = -1, best_iter = -1, n_cost_evals = 0;
-        long long n_waypoints = 0, n_prims = 0;
-        R best_c[4] = {A::inf(), 0, 0, 0}, best_len = 0, best_t = 0;
+        int n_cost_evals = 0;
+        unsigned n_waypoints = 0, n_prims = 0;
+        // the best plan so far: only its total is compared every iteration; the rest lives in shared memory
+        // (written by lane 0 on the rare improvement), which frees registers for the edge evaluation
+        R best_total = A::inf();
+        if (g.gl == 0) { BestPlan<R> b0; b0.c0 = b0.c1 = b0.c2 = b0.len = b0.t = (R)0; b0.node = -1; b0.iter = -1; best_s[threadIdx.x / G] = b0; }
         int it = 0;
-        long long guard = 0;
-        const long long guard_max = 64LL * P.I + 1024;
+        int guard = 0;
+        const int guard_max = (int)min(64LL * P.I + 1024, 2147483647LL);
 
         while (it < P.I && guard++ < guard_max) {
             int parent;
@@ -290,10 +295,12 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     }
                     total = g.bcast(total, 0);
                     n_cost_evals++;
-                    if (total < best_c[0]) {                                               // :169 strict <
-                        best_c[0] = total; best_c[1] = g.bcast(c0, 0); best_c[2] = g.bcast(c1, 0);
-                        best_c[3] = g.bcast(c2, 0);
-                        best_node = id; best_iter = it; best_len = o.len; best_t = o.t;
+                    if (total < best_total) {                                              // :169 strict <
+                        best_total = total;
+                        if (g.gl == 0) {
+                            BestPlan<R> b; b.c0 = c0; b.c1 = c1; b.c2 = c2; b.len = o.len; b.t = o.t; b.node = id; b.iter = it;
+                            best_s[threadIdx.x / G] = b;
+                        }
                     }
                 }
                 g.sync();
@@ -301,6 +308,10 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             it++;
             upos_mark = ctr;
         }
+        g.sync();
+        const BestPlan<R> best = best_s[threadIdx.x / G];
+        const int best_node = best.node, best_iter = best.iter;
+        const R best_c[4] = {best_total, best.c0, best.c1, best.c2}, best_len = best.len, best_t = best.t;
         if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
         // ---- optimal path: chain of stream positions, optional waypoints             :174-176, :321-331
         int depth = 0, n_path = 0;
@@ -349,7 +360,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             auvrrt_plan_record_t rec;
             rec.status = status; rec.n_nodes = n_nodes; rec.best_node = best_node; rec.best_iter = best_iter;
             rec.depth = depth; rec.n_path = n_path; rec.n_cost_evals = n_cost_evals;
-            rec.n_waypoints = (int32_t)n_waypoints; rec.n_uniforms = (long long)ctr; rec.n_primitives = n_prims;
+            rec.n_waypoints = (int32_t)n_waypoints; rec.n_uniforms = (long long)ctr; rec.n_primitives = (long long)n_prims;
             rec.cost[0] = best_node >= 0 ? (double)best_c[0] : 0.0; rec.cost[1] = (double)best_c[1];
             rec.cost[2] = (double)best_c[2]; rec.cost[3] = (double)best_c[3];
             rec.path_length = (double)best_len; rec.t_leaf = (double)best_t;
