@@ -120,7 +120,10 @@ __device__ int astar_walkable(const AstarDev &e, double cx, double cy, double px
     return 1;
 }
 
-__global__ void __launch_bounds__(32 * ASTAR_WARPS) k_astar(AstarDev e, const auvrrt_astar_query_t *queries, long long Q, int cap,
+#ifndef AUV_ASTAR_MINB
+#define AUV_ASTAR_MINB 8      // 64 registers, 32 warps per SM: the serial expansion loop is latency-bound (measured +26 % over 6 CTAs / 80 registers)
+#endif
+__global__ void __launch_bounds__(32 * ASTAR_WARPS, AUV_ASTAR_MINB) k_astar(AstarDev e, const auvrrt_astar_query_t *queries, long long Q, int cap,
                                                             int path_cap, unsigned char *ws, auvrrt_astar_record_t *recs, double *paths,
                                                             uint8_t *keep, int *expand_order, double *node_xy) {
     __shared__ unsigned s_alive[ASTAR_WARPS][128];            // cap <= 4096 nodes

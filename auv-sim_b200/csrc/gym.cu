@@ -274,8 +274,11 @@ __device__ __forceinline__ int gym_occ_find(const GymP<R> &P, const GymS<R> &S, 
     }
 }
 
+#ifndef AUV_GYM_MINB
+#define AUV_GYM_MINB 8
+#endif
 template <typename R>
-__global__ void __launch_bounds__(128) k_gym_run(GymP<R> P, GymS<R> S, const R *circ_g, const int32_t *actions, int n_steps,
+__global__ void __launch_bounds__(128, sizeof(R) == 4 ? AUV_GYM_MINB : 4) k_gym_run(GymP<R> P, GymS<R> S, const R *circ_g, const int32_t *actions, int n_steps,
                                                  int full, auvrrt_gym_record_t *recs) {
     typedef typename Policy<R>::A A;
     extern __shared__ __align__(16) unsigned char gym_smem[];
