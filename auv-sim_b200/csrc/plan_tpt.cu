@@ -15,9 +15,12 @@
 
 namespace auv {
 
-static const int TPT_THREADS = 256;
+#ifndef AUV_TPT_THREADS
+#define AUV_TPT_THREADS 128   // finer work units than 256 (measured +1..4 % at 1.3e5 - 2.6e5 queries)
+#endif
+static const int TPT_THREADS = AUV_TPT_THREADS;
 #ifndef AUV_TPT_MINB
-#define AUV_TPT_MINB 4
+#define AUV_TPT_MINB 8
 #endif
 
 // serial view of the counter stream: u_ctr, u_ctr+1, ... with the counter product kept incrementally

@@ -1,5 +1,5 @@
-for lib in libauvrrt.so libauvrrt_a8g10.so libauvrrt_a10g12.so; do
-  echo "== $lib"
-  AUVRRT_LIB=$PWD/auv-sim_b200/auvrrt/$lib python tools/gym_bench.py 2>&1 | grep "f32 Q=262144\|f32 Q=65536"
-  AUVRRT_LIB=$PWD/auv-sim_b200/auvrrt/$lib python tools/astar_bench.py 2>&1 | grep "Q=4736\|Q=1:"
+for lib in libauvrrt.so libauvrrt_t128_7.so libauvrrt_t128_8.so; do
+  for q in 262144 131072; do
+  AUVRRT_LIB=$PWD/auv-sim_b200/auvrrt/$lib python bench.py --no-extras --steps 3 --warmup 2 --queries $q --group 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$lib', $q, d['ms_per_step'], d['value'])"
+  done
 done
