@@ -344,8 +344,14 @@ template int launch_cost_point<double>(const auvrrt_env *, const double *, int64
 // ------------------------------------------------------------------ fused Dubins edges (config 4)
 // One thread per edge: six-word solve, W waypoints kept in registers, then every waypoint against
 // every (inflated) circle read as a shared-memory broadcast, then the polygon test.
+#ifndef AUV_ED_THREADS
+#define AUV_ED_THREADS 256
+#endif
+#ifndef AUV_ED_MINB
+#define AUV_ED_MINB 1
+#endif
 template <typename R, int WT>
-__global__ void __launch_bounds__(256) k_edges_dubins(const unsigned char *blob, int hot_bytes, int total_bytes,
+__global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                       int stage_mode, const R *from, const R *to, int64_t n, R rho,
                                                       int W, uint8_t *safe, uint8_t *word, R *length) {
     typedef typename Policy<R>::A A;
@@ -484,12 +490,12 @@ int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64
     if (W < 2 || W > 32) return set_err(AUVRRT_ERR_UNSUPPORTED, "edges_dubins (all-pairs): W must be in [2, 32], got %d", W);
     int smem, mode = env_stage_mode(b.hot_bytes, b.hot_bytes, 64 * 1024, &smem);
     mode = mode ? 1 : 0;
-    int64_t blocks = (n + 255) / 256;
-    if (blocks > AUV_SMS * 16) blocks = AUV_SMS * 16;
+    int64_t blocks = (n + AUV_ED_THREADS - 1) / AUV_ED_THREADS;
+    if (blocks > AUV_SMS * 16 * (256 / AUV_ED_THREADS)) blocks = AUV_SMS * 16 * (256 / AUV_ED_THREADS);
 #define AUV_ED(WT)                                                                                                 \
     {                                                                                                              \
         AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins<R, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-        k_edges_dubins<R, WT><<<(unsigned)blocks, 256, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, from,  \
+        k_edges_dubins<R, WT><<<(unsigned)blocks, AUV_ED_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, from,  \
                                                                    to, n, (R)rho, W, safe, word, length);          \
     }
     if (W <= 8) AUV_ED(8) else if (W <= 12) AUV_ED(12) else if (W <= 16) AUV_ED(16) else if (W <= 20) AUV_ED(20)
