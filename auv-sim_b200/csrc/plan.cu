@@ -78,13 +78,16 @@ template <typename R> struct Tree {
 // parent pick reads count[bin] once per draw, so this takes a global round trip off every draw.
 #define AUV_BINS_SMEM 128
 template <typename R> struct BestPlan { R c0, c1, c2, len, t; int node, iter; };
-template <typename R, int G, bool BS>
+// MODE >= 0 compiles the kernel for that parent-pick mode alone (the other modes' code -- about 1000 instructions that
+// the compiler otherwise places inside the hot loop -- disappears); MODE < 0 reads P.mode at run time.
+template <typename R, int G, bool BS, int MODE>
 __global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : (AUV_PLAN_MINB + 1) / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
     typedef typename Policy<R>::A A;
     const bool VERIFY = Policy<R>::VERIFY;
+    const int pick_mode = MODE >= 0 ? MODE : P.mode;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ GroupScratch<R, G> scratch[PLAN_THREADS / G];
     __shared__ BestPlan<R> best_s[PLAN_THREADS / G];
@@ -133,7 +136,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
             r0.self_hab = c.bin >= 0 ? c.hab : -1;
             T.row[0] = r0;
-            if (P.mode == 1) { T.nx[0] = sx; T.ny[0] = sy; }
+            if (pick_mode == 1) { T.nx[0] = sx; T.ny[0] = sy; }
         }
         g.sync();
         if (g.gl == 0) { SET_BIN_HEAD(1, 0); SET_BIN_TAIL(1, 0); SET_BIN_COUNT(1, 1); T.pool[0] = 0; T.next[0] = -1; }
@@ -153,7 +156,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
 
         while (it < P.I && guard++ < guard_max) {
             int parent;
-            if (P.mode == 0) {
+            if (pick_mode == 0) {
                 // ---- pick a random non-empty time bin, then a random node in it           :122-127
                 int ran_bin = 0, bincnt = 0;
                 bool kerr = false;
@@ -180,7 +183,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 int ch = BIN_HEAD(ran_bin);
                 for (int hop = idx >> 5; hop > 0; hop--) ch = T.next[ch];
                 parent = T.pool[ch * 32 + (idx & 31)];
-            } else if (P.mode == 2) {
+            } else if (pick_mode == 2) {
                 // ---- wall-clock pick on the simulated clock (:129-132): every lane walks the same bisection
                 const R ran_time = uniform_ab<R>((R)0, P.ran_time_max, rng.u(ctr));
                 ctr += 1;
@@ -242,10 +245,10 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     nr.s2 = pre_s2; nr.cnt = pre_cnt; nr.mask = pre_mask; nr.self_s2 = self_s2n; nr.self_hab = self_habn;
                     nr.born = it;
                     T.row[id] = nr;
-                    if (P.mode == 1) { T.nx[id] = o.x; T.ny[id] = o.y; }
+                    if (pick_mode == 1) { T.nx[id] = o.x; T.ny[id] = o.y; }
                 }
                 // ---- time-bin insert (decision is group-uniform, lane 0 writes)            :147-151
-                if (P.mode != 2) {                   // `if traj_time_stamp:` -- mode 2 keeps no bins
+                if (pick_mode != 2) {                   // `if traj_time_stamp:` -- mode 2 keeps no bins
                     R fd = floordiv_pos<R>(o.t, P.bin_interval);
                     R fidx = fd + (R)1;
                     R curr_bin = A::mul(fidx, P.bin_interval);
@@ -415,7 +418,7 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <typename R, int G, bool BS> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
+template <typename R, int G, bool BS, int MODE> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
     EnvBlob<R> b = env_blob<R>(env);
     // only the small hot part of the world model is staged in shared memory when it is tight: with 4
     // CTAs per SM the probability table (39 KB for Catalina) is better served by the larger L1
@@ -424,9 +427,9 @@ template <typename R, int G, bool BS> static int plan_geometry(const auvrrt_env 
     int sm = 16, mode = 0;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
-    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS>, PLAN_THREADS, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE>, PLAN_THREADS, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan: kernel does not fit on an SM (smem %d)", sm);
     int nsm = 0, dev = 0;
     AUV_CUDA(cudaGetDevice(&dev));
@@ -435,7 +438,7 @@ template <typename R, int G, bool BS> static int plan_geometry(const auvrrt_env 
     return AUVRRT_OK;
 }
 
-template <typename R, int G, bool BS>
+template <typename R, int G, bool BS, int MODE>
 static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
                          const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
                          auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
@@ -444,7 +447,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     int rc = make_planp<R>(env, p, &P);
     if (rc) return rc;
     int grid, smem, mode;
-    rc = plan_geometry<R, G, BS>(env, &grid, &smem, &mode);
+    rc = plan_geometry<R, G, BS, MODE>(env, &grid, &smem, &mode);
     if (rc) return rc;
     WsLayout L = make_layout<R>(P.cap, P.nb, P.nchunks);
     const int gpc = PLAN_THREADS / G;
@@ -459,7 +462,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     auvrrt_plan_trace_t tr;
     if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
     EnvBlob<R> b = env_blob<R>(env);
-    k_plan<R, G, BS><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+    k_plan<R, G, BS, MODE><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
                                                   (unsigned char *)workspace + 256, (unsigned long long *)workspace,
                                                   records, chain, path, tr);
     AUV_LAUNCH_CHECK2();
@@ -473,8 +476,14 @@ static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t 
                          cudaStream_t s, int64_t *need_bytes) {
     const double nb = ceil(p->max_traj_time / p->bin_interval);
     const bool bs = nb + 2 <= AUV_BINS_SMEM && p->iterations < 65000 && !getenv("AUVRRT_PLAN_BINS_GLOBAL");
-    if (bs) return launch_plan_gb<R, G, true>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes);
-    return launch_plan_gb<R, G, false>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes);
+    // the fast build's default mode (time-bin pick) gets its own compilation of the kernel
+#define AUV_PLAN_ARGS env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes
+    if constexpr (sizeof(R) == 4) {
+        if (p->mode == 0 && !getenv("AUVRRT_PLAN_GENERIC"))
+            return bs ? launch_plan_gb<R, G, true, 0>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, 0>(AUV_PLAN_ARGS);
+    }
+    return bs ? launch_plan_gb<R, G, true, -1>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, -1>(AUV_PLAN_ARGS);
+#undef AUV_PLAN_ARGS
 }
 
 template <typename R>

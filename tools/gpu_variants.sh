@@ -1,3 +1,3 @@
-for lib in libauvrrt.so libauvrrt_k128_5.so libauvrrt_k128_6.so; do
-  AUVRRT_LIB=$PWD/auv-sim_b200/auvrrt/$lib python bench.py --steps 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); m=d['extras']['micro_config4']; print('$lib', m['edges_per_s'], m['frac'], m['safe_fraction'])"
+for gen in "" 1; do
+  env ${gen:+AUVRRT_PLAN_GENERIC=1} python bench.py --no-extras --steps 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('generic=$gen', d['ms_per_step'], d['value'], d['e2e']['value'])"
 done
