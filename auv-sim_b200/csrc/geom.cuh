@@ -86,13 +86,23 @@ template <typename R> __device__ __forceinline__ bool point_within(const EnvView
     return inside && !boundary;
 }
 
+// the full test out of line, for the fast build's rare "cell needs the whole ring" case: called with scalars and
+// pointers only, so the world-model view stays in registers at the call site
+template <typename R>
+__device__ __noinline__ bool point_within_outlined(const R *vx, const R *vy, int E, int convex, R px, R py) {
+    EnvView<R> e;
+    e.px = vx; e.py = vy; e.E = E; e.convex = convex;
+    return point_within<R>(e, px, py);
+}
+
 // same, short-circuited by the classification grid: definitive code, else (fast build, convex ring)
 // only the candidate edges of the cell, else the full test
 template <typename R> __device__ __forceinline__ bool point_within_c(const EnvView<R> &env, const Cls &cl, R px, R py) {
     const unsigned pc = cl.code & 3u;
     if (pc == 1u) return true;
     if (pc == 2u) return false;
-    if (Policy<R>::VERIFY || (cl.code & AUV_GRID_POLY_FULL)) return point_within<R>(env, px, py);
+    if (Policy<R>::VERIFY) return point_within<R>(env, px, py);
+    if (cl.code & AUV_GRID_POLY_FULL) return point_within_outlined<R>(env.px, env.py, env.E, env.convex, px, py);
     const unsigned w2 = env.word2(cl);
     bool in = true;
 #pragma unroll
