@@ -238,10 +238,12 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
                 g.sync();
                 const int nw = __popc(wpm);
                 bool h = false;
+#pragma unroll 1                       // rare path: keep it small, it sits inside the hot loop
                 for (int k = g.gl; k < env.K; k += G) {
                     R ccx = env.cx[k], ccy = env.cy[k];
                     R q = A::inf();
                     if (base == 0) q = A::sq2(A::sub(sc.wx[G], ccx), A::sub(sc.wy[G], ccy));
+#pragma unroll 1
                     for (int j = 0; j < nw; j++) {
                         R qq = A::sq2(A::sub(sc.wx[j], ccx), A::sub(sc.wy[j], ccy));
                         q = qq < q ? qq : q;
@@ -295,6 +297,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
     if (DO_COLLIDE && n_exp == 0 && env.K > 0 && !parent_clear && parent_many) {
         // the path is [parent] alone: test it against the circles
         bool h = false;
+#pragma unroll 1
         for (int k = g.gl; k < env.K; k += G) {
             R q = A::sq2(A::sub(px, env.cx[k]), A::sub(py, env.cy[k]));
             if (VERIFY) h = h || (A::sqrt(q) <= env.creff[k]);

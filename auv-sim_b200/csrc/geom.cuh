@@ -130,11 +130,24 @@ template <typename R> __device__ __forceinline__ bool point_hits_circles(const E
     return hit;
 }
 
+// the all-circles loop out of line for the fast build's rare "more than 3 candidate circles" cells
+template <typename R>
+__device__ __noinline__ bool point_hits_circles_outlined(const R *cx, const R *cy, const R *creff2, int K, R x, R y) {
+    typedef typename Policy<R>::A A;
+    bool hit = false;
+#pragma unroll 1
+    for (int k = 0; k < K; k++) hit = hit || (A::sq2(A::sub(x, cx[k]), A::sub(y, cy[k])) <= creff2[k]);
+    return hit;
+}
+
 // same through the classification grid: clear cell, else the cell's <= 3 candidate circles, else all
 template <typename R> __device__ __forceinline__ bool point_hits_circles_c(const EnvView<R> &env, const Cls &cl, R x, R y) {
     typedef typename Policy<R>::A A;
     if (cl.code & 4u) return false;
-    if (cl.code & AUV_GRID_CIRC_MANY) return point_hits_circles<R>(env, x, y);
+    if (cl.code & AUV_GRID_CIRC_MANY) {
+        if (Policy<R>::VERIFY) return point_hits_circles<R>(env, x, y);
+        return point_hits_circles_outlined<R>(env.cx, env.cy, env.creff2, env.K, x, y);
+    }
     const unsigned w1 = env.word1(cl);
     bool hit = false;
 #pragma unroll
