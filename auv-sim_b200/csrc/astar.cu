@@ -437,7 +437,10 @@ extern "C" int auvrrt_astar_batch(auvrrt_astar_env_t *env, const auvrrt_astar_qu
     if (expand_order) AUV_CUDA(cudaMalloc(&de.p, 4 * q * (size_t)node_cap));
     if (node_xy) AUV_CUDA(cudaMalloc(&dn.p, 16 * q * (size_t)node_cap));
     AUV_CUDA(cudaMemcpyAsync(dq.p, queries, sizeof(auvrrt_astar_query_t) * q, cudaMemcpyHostToDevice, env->stream));
-    if (paths) AUV_CUDA(cudaMemsetAsync(dk.p, 0, q * (size_t)path_cap, env->stream));
+    if (paths) {     // rows past a query's path read as zeros
+        AUV_CUDA(cudaMemsetAsync(dk.p, 0, q * (size_t)path_cap, env->stream));
+        AUV_CUDA(cudaMemsetAsync(dp.p, 0, 48 * q * (size_t)path_cap, env->stream));
+    }
     int rc = auvrrt_astar_batch_dev(env, (const auvrrt_astar_query_t *)dq.p, Q, node_cap, path_cap, env->d_ws, (int64_t)env->ws_bytes,
                                     (auvrrt_astar_record_t *)dr.p, (double *)dp.p, (uint8_t *)dk.p, (int32_t *)de.p, (double *)dn.p, env->stream);
     if (rc != AUVRRT_OK) { cudaStreamSynchronize(env->stream); return rc; }

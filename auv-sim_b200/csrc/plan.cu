@@ -181,6 +181,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 int idx = (int)uniform_ab<R>((R)0, (R)bincnt, u);
                 if (idx >= bincnt) { status = AUVRRT_ST_KEY_ERROR; break; }
                 int ch = BIN_HEAD(ran_bin);
+#pragma unroll 1
                 for (int hop = idx >> 5; hop > 0; hop--) ch = T.next[ch];
                 parent = T.pool[ch * 32 + (idx & 31)];
             } else if (pick_mode == 2) {
