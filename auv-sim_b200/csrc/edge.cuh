@@ -233,7 +233,8 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             // all circles, waypoints broadcast through shared memory
             const bool circles_needed = g.ballot(is_wp && !(cl.code & 4u) && (cl.code & AUV_GRID_CIRC_MANY)) != 0u ||
                                         (base == 0 && !parent_clear && parent_many);
-            if (env.K > 0 && circles_needed) {
+            // (an edge that already left the polygon is unsafe whatever the circles say)
+            if (env.K > 0 && circles_needed && !outside) {
                 if (is_wp) { int slot = __popc(wpm & ((1u << g.gl) - 1u)); sc.wx[slot] = x; sc.wy[slot] = y; }
                 g.sync();
                 const int nw = __popc(wpm);

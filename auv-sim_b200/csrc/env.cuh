@@ -116,11 +116,15 @@ template <typename R> struct EnvView {
         bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w);
         grid = (const unsigned *)(blob_global + h->off_grid);
     }
-    // classification of the cell containing (x, y); all-ambiguous outside the grid
+    // classification of the cell containing (x, y); off the grid: outside the polygon, everything else ambiguous
     __device__ __forceinline__ Cls classify(R x, R y) const {
         Cls c;
         R fx = (x - gx0) * ginv, fy = (y - gy0) * ginv;
-        if (!(fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny)) { c.code = AUV_GRID_ALL_AMBIG; c.idx = -1; return c; }
+        if (!(fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny)) {
+            // the grid covers the polygon's bounding box plus one cell all round: a point off the grid is outside the
+            // polygon (code 2) whatever else is undecided about it
+            c.code = AUV_GRID_ALL_AMBIG | (gnx > 0 ? 2u : 0u); c.idx = -1; return c;
+        }
         c.idx = (int)fy * gnx + (int)fx;
         c.code = __ldg(grid + 3 * c.idx);
         return c;

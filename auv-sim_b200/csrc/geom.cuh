@@ -97,12 +97,15 @@ __device__ __noinline__ bool point_within_outlined(const R *vx, const R *vy, int
 
 // same, short-circuited by the classification grid: definitive code, else (fast build, convex ring)
 // only the candidate edges of the cell, else the full test
-template <typename R> __device__ __forceinline__ bool point_within_c(const EnvView<R> &env, const Cls &cl, R px, R py) {
+// OUTLINE: call the rare full tests out of line (planner kernels, where they would otherwise sit in the hot loop);
+// the thread-per-edge micro-benchmark kernels on dense synthetic worlds keep them inline.
+template <typename R, bool OUTLINE = true> __device__ __forceinline__ bool point_within_c(const EnvView<R> &env, const Cls &cl, R px, R py) {
     const unsigned pc = cl.code & 3u;
     if (pc == 1u) return true;
     if (pc == 2u) return false;
     if (Policy<R>::VERIFY) return point_within<R>(env, px, py);
-    if (cl.code & AUV_GRID_POLY_FULL) return point_within_outlined<R>(env.px, env.py, env.E, env.convex, px, py);
+    if (cl.code & AUV_GRID_POLY_FULL)
+        return OUTLINE ? point_within_outlined<R>(env.px, env.py, env.E, env.convex, px, py) : point_within<R>(env, px, py);
     const unsigned w2 = env.word2(cl);
     bool in = true;
 #pragma unroll
@@ -141,11 +144,11 @@ __device__ __noinline__ bool point_hits_circles_outlined(const R *cx, const R *c
 }
 
 // same through the classification grid: clear cell, else the cell's <= 3 candidate circles, else all
-template <typename R> __device__ __forceinline__ bool point_hits_circles_c(const EnvView<R> &env, const Cls &cl, R x, R y) {
+template <typename R, bool OUTLINE = true> __device__ __forceinline__ bool point_hits_circles_c(const EnvView<R> &env, const Cls &cl, R x, R y) {
     typedef typename Policy<R>::A A;
     if (cl.code & 4u) return false;
     if (cl.code & AUV_GRID_CIRC_MANY) {
-        if (Policy<R>::VERIFY) return point_hits_circles<R>(env, x, y);
+        if (Policy<R>::VERIFY || !OUTLINE) return point_hits_circles<R>(env, x, y);
         return point_hits_circles_outlined<R>(env.cx, env.cy, env.creff2, env.K, x, y);
     }
     const unsigned w1 = env.word1(cl);

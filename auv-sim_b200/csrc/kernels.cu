@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(co
 // is tested only against the <= 3 circles that can touch its grid cell (all circles if the cell has
 // more).  Exact by construction (env.cuh); ~70x fewer instructions than the all-pairs loop at K=500.
 template <typename R>
-__global__ void __launch_bounds__(256) k_edges_dubins_culled(const unsigned char *blob, int hot_bytes, int total_bytes,
+__global__ void __launch_bounds__(256, 4) k_edges_dubins_culled(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                              int stage_mode, const R *from, const R *to, int64_t n,
                                                              R rho, int W, uint8_t *safe, uint8_t *word, R *length) {
     typedef typename Policy<R>::A A;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) k_edges_dubins_culled(const unsigned char
                 R x, y, th;
                 if (k < W - 1) smp.at(A::mul((R)k, step), x, y, th); else { x = b[0]; y = b[1]; }
                 const Cls cl = env.classify(x, y);
-                bad = bad || point_hits_circles_c<R>(env, cl, x, y) || !point_within_c<R>(env, cl, x, y);
+                bad = bad || !point_within_c<R, false>(env, cl, x, y) || point_hits_circles_c<R, false>(env, cl, x, y);   // polygon first: one grid code decides most points
             }
             ok = !bad;
         }
@@ -512,8 +512,11 @@ template int launch_edges_dubins<double>(const auvrrt_env *, const double *, con
 // ------------------------------------------------------------------ fused arc edges on the counter stream
 // COST: also the edge's share of cost.habitat_shark_cost_func over its appended waypoints (cost.py:171-191):
 // cost_out[i] = { sum of w3 * prob, waypoints inside a habitat, distinct habitats visited }.
+#ifndef AUV_EA_MINB
+#define AUV_EA_MINB 4      // 64 registers, 32 warps per SM (measured: 1.33e9 edges/s vs 1.0e9 at the default 89 registers)
+#endif
 template <typename R, int G, bool COST>
-__global__ void __launch_bounds__(256) k_edges_arc(const unsigned char *blob, int hot_bytes, int total_bytes,
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? AUV_EA_MINB : 1) k_edges_arc(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                    int stage_mode, const R *parents, const uint64_t *seeds, int64_t n,
                                                    SteerParams<R> sp, R w3, uint8_t *safe, int32_t *counts, R *leaf,
                                                    R *cost_out) {
