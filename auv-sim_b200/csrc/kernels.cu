@@ -607,7 +607,10 @@ __global__ void __launch_bounds__(256) k_nn_partial(const R *__restrict__ tx, co
         // array in flight per thread: the scan is HBM-bound, so memory-level parallelism is what counts
         const int64_t n4 = n / 4;
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        const int NN_UNROLL = 4;
+#ifndef AUV_NN_UNROLL
+#define AUV_NN_UNROLL 3      // loads in flight per thread and array; measured on 2^27 nodes: 2 -> 5.72, 3 -> 5.85, 4 -> 5.42, 5 -> 5.37 TB/s
+#endif
+        const int NN_UNROLL = AUV_NN_UNROLL;
         for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < n4; v0 += stride * NN_UNROLL) {
             R xs[NN_UNROLL][4], ys[NN_UNROLL][4];
 #pragma unroll
@@ -703,7 +706,10 @@ __global__ void __launch_bounds__(256) k_nn_final(const double *part_s, const lo
         out_idx[q] = (int32_t)bi;
     }
 }
-static const int NN_BLOCKS = AUV_SMS * 8;
+#ifndef AUV_NN_BPS
+#define AUV_NN_BPS 8
+#endif
+static const int NN_BLOCKS = AUV_SMS * AUV_NN_BPS;
 int64_t nn_scratch_bytes(int nq) { return (int64_t)nq * NN_BLOCKS * 16 + 256; }
 template <typename R>
 int launch_nn(const R *tx, const R *ty, int64_t n, const R *qx, const R *qy, int nq, void *scratch,
