@@ -350,6 +350,7 @@ template int launch_cost_point<double>(const auvrrt_env *, const double *, int64
 #ifndef AUV_ED_MINB
 #define AUV_ED_MINB 1
 #endif
+#define AUV_ED_TILE 512      // circles kept as float4 triples in shared memory (8 KB); more circles read the SoA arrays
 template <typename R, int WT>
 __global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                       int stage_mode, const R *from, const R *to, int64_t n, R rho,
@@ -358,6 +359,13 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(co
     const bool VERIFY = Policy<R>::VERIFY;
     extern __shared__ __align__(16) unsigned char smem[];
     EnvView<R> env = load_env<R>(smem, blob, hot_bytes, total_bytes, stage_mode);
+    __shared__ float4 circ4[AUV_ED_TILE];
+    const bool use_tile = !VERIFY && env.K <= AUV_ED_TILE;
+    if (use_tile) {
+        for (int j = threadIdx.x; j < env.K; j += blockDim.x)
+            circ4[j] = make_float4((float)env.cx[j], (float)env.cy[j], (float)env.creff2[j], 0.f);
+        __syncthreads();
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         const R *a = from + 3 * i, *b = to + 3 * i;
@@ -401,28 +409,35 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(co
                     wx[k] -= ox; wy[k] -= oy;
                     pp[k] = fmaf(wy[k], wy[k], wx[k] * wx[k]);
                     ppmax = fmaxf(ppmax, pp[k]);
+                    wx[k] *= (R)-2; wy[k] *= (R)-2;            // exact scaling: -2 p.c = c.(-2p)
                 }
-                for (int c = 0; c < env.K; c++) {
-                    const R cxr = env.cx[c] - ox, cyr = env.cy[c] - oy;
-                    const R cc = fmaf(cyr, cyr, cxr * cxr), m2x = (R)-2 * cxr, m2y = (R)-2 * cyr;
-                    R qa = A::inf(), qb = A::inf(), qc = A::inf(), qd4 = A::inf();    // 4 independent min chains
+                const R g0 = (R)4e-6 * ppmax;
+                {
+                    for (int c = 0; c < env.K; c++) {
+                        // circles as (x, y, r_eff^2) in shared memory: one 16-byte load each (staged once per block below)
+                        const float4 ci = use_tile ? circ4[c]
+                                                   : make_float4((float)env.cx[c], (float)env.cy[c], (float)env.creff2[c], 0.f);
+                        const R cxr = ci.x - ox, cyr = ci.y - oy;
+                        const R cc = fmaf(cyr, cyr, cxr * cxr);
+                        R qa = A::inf(), qb = A::inf(), qc = A::inf(), qd4 = A::inf();    // 4 independent min chains
 #pragma unroll
-                    for (int k = 0; k < WT; k += 4) {
-                        qa = fminf(qa, fmaf(m2y, wy[k], fmaf(m2x, wx[k], pp[k])));
-                        if (k + 1 < WT) qb = fminf(qb, fmaf(m2y, wy[k + 1], fmaf(m2x, wx[k + 1], pp[k + 1])));
-                        if (k + 2 < WT) qc = fminf(qc, fmaf(m2y, wy[k + 2], fmaf(m2x, wx[k + 2], pp[k + 2])));
-                        if (k + 3 < WT) qd4 = fminf(qd4, fmaf(m2y, wy[k + 3], fmaf(m2x, wx[k + 3], pp[k + 3])));
-                    }
-                    const R q = fminf(fminf(qa, qb), fminf(qc, qd4));
-                    const R d2 = q + cc, r2 = env.creff2[c];
-                    const R guard = (R)4e-6 * (cc + ppmax);
-                    if (d2 <= r2 + guard) {
-                        if (d2 < r2 - guard) hit = true;
-                        else {                                   // too close to call: direct formula
-                            R qd = A::inf();
+                        for (int k = 0; k < WT; k += 4) {
+                            qa = fminf(qa, fmaf(cyr, wy[k], fmaf(cxr, wx[k], pp[k])));
+                            if (k + 1 < WT) qb = fminf(qb, fmaf(cyr, wy[k + 1], fmaf(cxr, wx[k + 1], pp[k + 1])));
+                            if (k + 2 < WT) qc = fminf(qc, fmaf(cyr, wy[k + 2], fmaf(cxr, wx[k + 2], pp[k + 2])));
+                            if (k + 3 < WT) qd4 = fminf(qd4, fmaf(cyr, wy[k + 3], fmaf(cxr, wx[k + 3], pp[k + 3])));
+                        }
+                        const R q = fminf(fminf(qa, qb), fminf(qc, qd4));
+                        const R t = (q + cc) - ci.z;                 // d^2 - r_eff^2
+                        const R guard = fmaf((R)4e-6, cc, g0);
+                        if (t <= guard) {
+                            if (t < -guard) hit = true;
+                            else {                                   // too close to call: direct formula
+                                R qd = A::inf();
 #pragma unroll
-                            for (int k = 0; k < WT; k++) qd = fminf(qd, A::sq2(wx[k] - cxr, wy[k] - cyr));
-                            hit = hit || (qd <= r2);
+                                for (int k = 0; k < WT; k++) qd = fminf(qd, A::sq2((R)-0.5 * wx[k] - cxr, (R)-0.5 * wy[k] - cyr));
+                                hit = hit || (qd <= ci.z);
+                            }
                         }
                     }
                 }
