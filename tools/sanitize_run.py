@@ -24,6 +24,7 @@ for prec in ("f32", "f64"):
     rs = np.random.RandomState(0)
     parents = np.stack([rs.uniform(-300, -100, 200), rs.uniform(-60, 100, 200), rs.uniform(-6, 6, 200), rs.uniform(0, 400, 200), rs.uniform(0, 500, 200)], 1)
     api.edges_arc(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], prec)
+    api.edges_arc_cost(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, prec)
     q0 = np.stack([rs.uniform(-400, 50, 300), rs.uniform(-100, 120, 300), rs.uniform(-3, 3, 300)], 1)
     q1 = q0 + rs.uniform(-20, 20, (300, 3))
     api.edges_dubins(env, q0, q1, 1.0, 20, prec)
