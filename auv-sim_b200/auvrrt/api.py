@@ -43,8 +43,8 @@ def launch_count():
     return int(lib().auvrrt_launch_count())
 
 
-def stream_u(seed, k, bits24=False):
-    return lib().auvrrt_stream_u(int(seed), int(k), int(bits24))
+def stream_u(seed, k, f32u=False):
+    return lib().auvrrt_stream_u(int(seed), int(k), int(f32u))
 
 
 class Env:

@@ -16,9 +16,9 @@ extern "C" int auvrrt_device_count(void) {
     return n;
 }
 extern "C" int64_t auvrrt_launch_count(void) { return g_launches; }
-extern "C" double auvrrt_stream_u(uint64_t seed, int64_t k, int bits24) {
-    uint64_t z = stream_bits(stream_key(seed), (uint64_t)k);
-    return bits24 ? (double)(z >> 40) * 0x1.0p-24 : (double)(z >> 11) * 0x1.0p-53;
+extern "C" double auvrrt_stream_u(uint64_t seed, int64_t k, int f32) {
+    uint64_t z = stream_bits(stream_key(seed), (uint32_t)k);
+    return f32 ? (double)(z >> 41) * 0x1.0p-23 : (double)(z >> 11) * 0x1.0p-53;
 }
 
 // ------------------------------------------------------------------ env blob builder (host)

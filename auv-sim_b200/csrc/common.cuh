@@ -63,10 +63,17 @@ template <> struct Policy<float> { static const bool VERIFY = false; typedef Ar<
 template <> struct Policy<double> { static const bool VERIFY = true; typedef Ar<double, true> A; };
 
 // ------------------------------------------------------------------ the uniform stream
-// u_k(seed) = top bits of SplitMix64's finaliser applied to key(seed) + (k+1) * golden.  Pure
-// function of (seed, k): any lane can evaluate any position (what makes the warp-parallel steer
-// possible) and the host can pre-generate the identical sequence for the reference
-// (auvrrt_stream_u, oracle/harness.py stream_block).
+// The pre-generated sample sequence.  Position k of the stream of `seed` is the 64-bit word
+//   hi(k) = M32a(c * 0x9E3779B9 + key_lo),  lo(k) = M32b(c * 0x85EBCA77 + key_hi),  c = k + 1 (mod 2^32)
+// where M32a / M32b are two 2-round xorshift-multiply mixers on 32-bit words (the constants of the
+// hash-prospector "lowbias32" functions, without their last xorshift, which only touches low bits) and
+// key = stream_key(seed) (SplitMix64 finaliser, once per query).  32-bit multiplies only: a draw costs
+// ~10 instructions in the fp32 build (round 1 hashed with SplitMix64: two 64-bit multiplies per draw, 13 %
+// of the planner's instructions).  Pure function of (seed, k): any lane can evaluate any position (what
+// makes the warp-parallel steer possible) and the host can pre-generate the identical sequence for the
+// reference (auvrrt_stream_u, oracle/harness.py stream_block).
+//   fp64 build:  u = (hi:lo >> 11) * 2^-53     (53 bits)
+//   fp32 build:  u = (hi >> 9) * 2^-23         (the top 23 bits of the same word; exact in fp32, in [0, 1))
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
@@ -75,16 +82,49 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 __host__ __device__ __forceinline__ uint64_t stream_key(uint64_t seed) {
     return mix64((seed + 1) * 0x9E3779B97F4A7C15ULL);
 }
-__host__ __device__ __forceinline__ uint64_t stream_bits(uint64_t key, uint64_t k) {
-    return mix64(key + (k + 1) * 0x9E3779B97F4A7C15ULL);
+#define AUV_WEYL_HI 0x9E3779B9u
+#define AUV_WEYL_LO 0x85EBCA77u
+// w = c * AUV_WEYL_HI + key_lo  ->  hi word
+__host__ __device__ __forceinline__ uint32_t mix32a(uint32_t w) {
+    w ^= w >> 16; w *= 0x21F0AAADu; w ^= w >> 15; w *= 0x735A2D97u;
+    return w;
 }
-template <typename R> __device__ __forceinline__ R bits_to_u(uint64_t z);
-template <> __device__ __forceinline__ double bits_to_u<double>(uint64_t z) {
-    return (double)(z >> 11) * 0x1.0p-53;
+// w = c * AUV_WEYL_LO + key_hi  ->  lo word
+__host__ __device__ __forceinline__ uint32_t mix32b(uint32_t w) {
+    w ^= w >> 15; w *= 0xD168AAADu; w ^= w >> 15; w *= 0xAF723597u;
+    return w;
 }
-template <> __device__ __forceinline__ float bits_to_u<float>(uint64_t z) {
-    return (float)(uint32_t)(z >> 40) * 0x1.0p-24f;   // 24 bits: exact in fp32, in [0, 1)
+__host__ __device__ __forceinline__ uint32_t stream_hi(uint64_t key, uint32_t k) {
+    return mix32a((k + 1u) * AUV_WEYL_HI + (uint32_t)key);
 }
+__host__ __device__ __forceinline__ uint32_t stream_lo(uint64_t key, uint32_t k) {
+    return mix32b((k + 1u) * AUV_WEYL_LO + (uint32_t)(key >> 32));
+}
+__host__ __device__ __forceinline__ uint64_t stream_bits(uint64_t key, uint32_t k) {
+    return ((uint64_t)stream_hi(key, k) << 32) | (uint64_t)stream_lo(key, k);
+}
+
+// A DRAW is what the kernels carry for one stream position: u in [0, 1) in the fp64 build, 1 + u in
+// [1, 2) in the fp32 build (the 23 bits dropped into a float's mantissa: no integer-to-float
+// conversion).  uniform_ab() and unit() are the only consumers.
+template <typename R> struct Draw;
+template <> struct Draw<double> {
+    static __device__ __forceinline__ double at(uint64_t key, uint32_t k) {
+        return (double)(stream_bits(key, k) >> 11) * 0x1.0p-53;
+    }
+    static __device__ __forceinline__ double from_words(uint32_t hi, uint32_t lo) {
+        return (double)((((uint64_t)hi << 32) | (uint64_t)lo) >> 11) * 0x1.0p-53;
+    }
+    static __device__ __forceinline__ double from_unit(double u) { return u; }
+};
+template <> struct Draw<float> {
+    static __device__ __forceinline__ float from_hi(uint32_t hi) { return __uint_as_float((hi >> 9) | 0x3f800000u); }
+    static __device__ __forceinline__ float at(uint64_t key, uint32_t k) { return from_hi(stream_hi(key, k)); }
+    static __device__ __forceinline__ float from_unit(double u) { return (float)u + 1.0f; }
+};
+// the draw as a plain u in [0, 1)
+__device__ __forceinline__ double unit(double d) { return d; }
+__device__ __forceinline__ float unit(float d) { return d - 1.0f; }
 
 // Where a stream comes from: the counter hash, or an explicit pre-generated array (replaying a
 // recorded CPython Mersenne-Twister sequence through the same kernels).
@@ -94,19 +134,46 @@ template <typename R> struct Stream {
     int64_t n_ext;
     // Positions past the end of an explicit stream read as 0.5: lanes prefetch a window of positions
     // speculatively, so only a CONSUMED position past the end is an error (see consumed_ok()).
-    __device__ __forceinline__ R u(uint32_t k) const {
-        if (ext) return ((int64_t)k < n_ext) ? (R)ext[k] : (R)0.5;
-        return bits_to_u<R>(stream_bits(key, k));
+    __device__ __forceinline__ R u(uint32_t k) const {      // a draw (see Draw<R>)
+        if (ext) return Draw<R>::from_unit(((int64_t)k < n_ext) ? ext[k] : 0.5);
+        return Draw<R>::at(key, k);
     }
     __device__ __forceinline__ bool consumed_ok(uint32_t ctr_end) const {
         return !ext || (int64_t)ctr_end <= n_ext;
     }
 };
 
-// random.uniform(a, b) = a + (b - a) * random()      (CPython Lib/random.py)
-template <typename R> __device__ __forceinline__ R uniform_ab(R a, R b, R u) {
-    typedef typename Policy<R>::A A;
-    return A::add(a, A::mul(A::sub(b, a), u));
+// serial view of the counter stream: u_ctr, u_ctr+1, ... with the two Weyl products kept incrementally
+template <typename R> struct SerialStream {
+    uint32_t wa, wb;   // c * AUV_WEYL_HI + key_lo, c * AUV_WEYL_LO + key_hi for c = ctr (the next draw adds one step first)
+    uint32_t ctr;
+    __device__ __forceinline__ void init(uint64_t key) { wa = (uint32_t)key; wb = (uint32_t)(key >> 32); ctr = 0; }
+    __device__ __forceinline__ void seek(uint64_t key, uint32_t pos) {
+        wa = pos * AUV_WEYL_HI + (uint32_t)key; wb = pos * AUV_WEYL_LO + (uint32_t)(key >> 32); ctr = pos;
+    }
+    __device__ __forceinline__ R next();
+    __device__ __forceinline__ void skip(uint32_t n) { wa += n * AUV_WEYL_HI; wb += n * AUV_WEYL_LO; ctr += n; }
+};
+template <> __device__ __forceinline__ float SerialStream<float>::next() {
+    wa += AUV_WEYL_HI; ctr++;
+    return Draw<float>::from_hi(mix32a(wa));
+}
+template <> __device__ __forceinline__ double SerialStream<double>::next() {
+    wa += AUV_WEYL_HI; wb += AUV_WEYL_LO; ctr++;
+    return Draw<double>::from_words(mix32a(wa), mix32b(wb));
+}
+
+// random.uniform(a, b) = a + (b - a) * random()      (CPython Lib/random.py) on a draw d.
+// fp64: the reference's two rounded operations.  fp32: ONE fma on the mantissa form,
+// (a - (b - a)) + (b - a) * (1 + u); b - a and a - (b - a) are loop invariants.  Whenever a - (b - a) is
+// exact in fp32 (the steer's (0, 2), (-0.5, 0.5), (0, 30), (0, 2v)) this is a + (b - a) * u rounded once.
+template <typename R> __device__ __forceinline__ R uniform_ab(R a, R b, R d);
+template <> __device__ __forceinline__ double uniform_ab<double>(double a, double b, double d) {
+    return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), d));
+}
+template <> __device__ __forceinline__ float uniform_ab<float>(float a, float b, float d) {
+    const float w = b - a;
+    return fmaf(w, d, a - w);
 }
 
 // Python float floor division  t // w  for w > 0 (Objects/floatobject.c float_floor_div): the

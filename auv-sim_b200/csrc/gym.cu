@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128, sizeof(R) == 4 ? AUV_GYM_MINB : 4) k_gym_
             if (!actions) {
                 if (n_occ == 0) { status = AUVRRT_ST_KEY_ERROR; live = false; }              // random.choice([])
                 else {
-                    oi = (int)A::mul(st.u(pos++), (R)n_occ);                                // :176
+                    oi = (int)A::mul(unit(st.u(pos++)), (R)n_occ);                                // :176
                     if (!Policy<R>::VERIFY) oi = min(oi, n_occ - 1);
                     cellid = OC(oi).cell;
                 }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128, sizeof(R) == 4 ? AUV_GYM_MINB : 4) k_gym_
             if (live) {
                 const unsigned pos0 = pos;
                 const int cnt = OC(oi).count;
-                int k = (int)A::mul(st.u(pos++), (R)cnt);                                   // :217
+                int k = (int)A::mul(unit(st.u(pos++)), (R)cnt);                                   // :217
                 if (!Policy<R>::VERIFY) k = min(k, cnt - 1);
                 int pn = OC(oi).tail;
                 for (int h = cnt - 1 - k; h > 0; h--) pn = ND(pn).prev;

@@ -23,15 +23,6 @@ static const int TPT_THREADS = AUV_TPT_THREADS;
 #define AUV_TPT_MINB 8
 #endif
 
-// serial view of the counter stream: u_ctr, u_ctr+1, ... with the counter product kept incrementally
-template <typename R> struct SerialStream {
-    uint64_t z;        // key + (ctr) * golden: the next draw hashes z + golden
-    uint32_t ctr;
-    __device__ __forceinline__ void init(uint64_t key) { z = key; ctr = 0; }
-    __device__ __forceinline__ R next() { z += 0x9E3779B97F4A7C15ULL; ctr++; return bits_to_u<R>(mix64(z)); }
-    __device__ __forceinline__ void skip(uint32_t n) { z += (uint64_t)n * 0x9E3779B97F4A7C15ULL; ctr += n; }
-};
-
 struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count; };
 
 template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchunks) {
@@ -97,7 +88,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
             int it = s_it[slot];
             if (!status && n_exp >= 0) {
                 SerialStream<R> rng;
-                rng.z = s_z[slot]; rng.ctr = s_ctr[slot];
+                rng.wa = (uint32_t)s_z[slot]; rng.wb = (uint32_t)(s_z[slot] >> 32); rng.ctr = s_ctr[slot];
                 const int parent = s_parent[slot];
                 // ---- steer (:237-295) with check_collision (:530-549) and the per-waypoint cost folded in
                 const NodeRow<R> pr = nodes[parent];
@@ -219,7 +210,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     }
                     it++;
                     s_it[slot] = it;
-                    s_z[slot] = rng.z; s_ctr[slot] = rng.ctr; s_upos[slot] = rng.ctr;
+                    s_z[slot] = (unsigned long long)rng.wa | ((unsigned long long)rng.wb << 32); s_ctr[slot] = rng.ctr; s_upos[slot] = rng.ctr;
                 }
             }
             // ---- query finished (budget spent, or an error): chain + record, free the slot
@@ -274,7 +265,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
             int key = 63;                         // inactive trees and skipped trips sort last
             if (s_active[slot]) {
                 SerialStream<R> rng;
-                rng.z = s_z[slot]; rng.ctr = s_ctr[slot];
+                rng.wa = (uint32_t)s_z[slot]; rng.wb = (uint32_t)(s_z[slot] >> 32); rng.ctr = s_ctr[slot];
                 int parent = -1, status = AUVRRT_ST_OK;
                 bool skip = false;
                 if (P.mode == 0) {                                                      // :122-127
@@ -322,7 +313,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));     // :259-260
                     key = n_exp < 62 ? n_exp : 62;
                 }
-                s_z[slot] = rng.z; s_ctr[slot] = rng.ctr; s_parent[slot] = parent; s_nexp[slot] = n_exp;
+                s_z[slot] = (unsigned long long)rng.wa | ((unsigned long long)rng.wb << 32); s_ctr[slot] = rng.ctr; s_parent[slot] = parent; s_nexp[slot] = n_exp;
                 if (status) { s_status[slot] = status; key = 62; s_nexp[slot] = -1; }    // phase B finalises it
                 if (skip) {
                     s_nexp[slot] = -2;

@@ -147,9 +147,12 @@ int auvrrt_edges_arc_cost(const auvrrt_env_t *env, const double *parents, const 
                           uint8_t *out_safe, int32_t *out_counts, double *out_leaf, double *out_cost);
 
 /* ---- the pre-generated sample sequence ------------------------------------------------------
- * u_k(seed): counter-based SplitMix64 stream; 53-bit doubles, or the top 24 bits (bits24 != 0,
- * what the AUVRRT_F32 build consumes).  Host-side evaluation for callers that replay it. */
-double auvrrt_stream_u(uint64_t seed, int64_t k, int bits24);
+ * u_k(seed): counter hash built from 32-bit multiplies: position k is the word
+ * hi:lo, hi = M32a((k+1) * 0x9E3779B9 + key_lo), lo = M32b((k+1) * 0x85EBCA77 + key_hi),
+ * key = SplitMix64 finaliser of (seed+1) * golden; u = (word >> 11) * 2^-53, or (f32u != 0, what the
+ * AUVRRT_F32 build consumes) its top 23 bits, (word >> 41) * 2^-23.  Host-side evaluation for
+ * callers that replay it (e.g. to feed the unmodified reference). */
+double auvrrt_stream_u(uint64_t seed, int64_t k, int f32u);
 
 /* ---- RRT.exploring (rrt_dubins.py:92-176): batched independent planning queries --------------*/
 typedef struct {

@@ -42,7 +42,7 @@ typedef struct {
 /* ---------------------------------------------------------------- uniform stream ----------- */
 typedef struct {
     const double *ext; int64_t n_ext;   /* explicit pre-generated stream, or NULL */
-    uint64_t key; int bits24;           /* else: counter-based SplitMix64 stream */
+    uint64_t key; int f32u;           /* else: the counter-hash stream; f32u != 0: the fp32 build's 23-bit u */
     int64_t pos; int exhausted;
 } orc_stream_t;
 
@@ -51,10 +51,23 @@ static uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
+/* The pre-generated sample sequence (restated from DESIGN.md section 3, independently of the product's
+ * csrc/common.cuh; tests check that harness, oracle and product agree): position k of seed's stream is
+ * the 64-bit word hi:lo with  hi = M32a(c * 0x9E3779B9 + key_lo), lo = M32b(c * 0x85EBCA77 + key_hi),
+ * c = k + 1 mod 2^32, key = SplitMix64 finaliser of (seed + 1) * golden.  u = (word >> 11) * 2^-53, or
+ * (f32 != 0, what the fp32 build consumes) the top 23 bits, (word >> 41) * 2^-23. */
 uint64_t orc_stream_key(uint64_t seed) { return mix64((seed + 1) * 0x9E3779B97F4A7C15ULL); }
-double orc_stream_u(uint64_t seed, int64_t k, int bits24) {
-    uint64_t z = mix64(orc_stream_key(seed) + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ULL);
-    return bits24 ? (double)(z >> 40) * 0x1.0p-24 : (double)(z >> 11) * 0x1.0p-53;
+static uint64_t stream_word(uint64_t key, int64_t k) {
+    uint32_t c = (uint32_t)(k + 1);
+    uint32_t a = c * 0x9E3779B9u + (uint32_t)key;
+    a ^= a >> 16; a *= 0x21F0AAADu; a ^= a >> 15; a *= 0x735A2D97u;
+    uint32_t b = c * 0x85EBCA77u + (uint32_t)(key >> 32);
+    b ^= b >> 15; b *= 0xD168AAADu; b ^= b >> 15; b *= 0xAF723597u;
+    return ((uint64_t)a << 32) | (uint64_t)b;
+}
+double orc_stream_u(uint64_t seed, int64_t k, int f32) {
+    uint64_t z = stream_word(orc_stream_key(seed), k);
+    return f32 ? (double)(z >> 41) * 0x1.0p-23 : (double)(z >> 11) * 0x1.0p-53;
 }
 static double next_u(orc_stream_t *s) {
     int64_t k = s->pos++;
@@ -62,8 +75,8 @@ static double next_u(orc_stream_t *s) {
         if (k >= s->n_ext) { s->exhausted = 1; return 0.5; }
         return s->ext[k];
     }
-    uint64_t z = mix64(s->key + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ULL);
-    return s->bits24 ? (double)(z >> 40) * 0x1.0p-24 : (double)(z >> 11) * 0x1.0p-53;
+    uint64_t z = stream_word(s->key, k);
+    return s->f32u ? (double)(z >> 41) * 0x1.0p-23 : (double)(z >> 11) * 0x1.0p-53;
 }
 /* random.uniform(a, b): CPython Lib/random.py */
 static double uniform(orc_stream_t *s, double a, double b) { return a + (b - a) * next_u(s); }
@@ -531,11 +544,11 @@ int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng
  * starts [Q][5]; seeds [Q]; out_result [Q][5]; out_counts [Q][3] = nodes, cost evals, waypoints */
 typedef struct {
     const orc_world_t *w; const double *starts; const uint64_t *seeds; const orc_plan_params_t *p;
-    int bits24; double *out_result; int64_t *out_counts; int32_t *out_status;
+    int f32u; double *out_result; int64_t *out_counts; int32_t *out_status;
 } orc_eb_t;
 static void orc_eb_body(int64_t q, void *vc) {
     orc_eb_t *c = (orc_eb_t *)vc;
-    orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[q]), c->bits24, 0, 0};
+    orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[q]), c->f32u, 0, 0};
     orc_trace_t tr; memset(&tr, 0, sizeof(tr));
     int st = orc_exploring(c->w, c->starts + 5 * (size_t)q, &rng, c->p, &tr);
     if (c->out_status) c->out_status[q] = st;
@@ -543,9 +556,9 @@ static void orc_eb_body(int64_t q, void *vc) {
     if (c->out_counts) { c->out_counts[3 * q] = tr.n_nodes; c->out_counts[3 * q + 1] = tr.n_cost_evals; c->out_counts[3 * q + 2] = tr.n_waypoints_total; }
 }
 int orc_exploring_batch(const orc_world_t *w, const double *starts, const uint64_t *seeds, int Q,
-                        const orc_plan_params_t *p, int bits24, double *out_result,
+                        const orc_plan_params_t *p, int f32u, double *out_result,
                         int64_t *out_counts, int32_t *out_status, int nthreads) {
-    orc_eb_t c = {w, starts, seeds, p, bits24, out_result, out_counts, out_status};
+    orc_eb_t c = {w, starts, seeds, p, f32u, out_result, out_counts, out_status};
     orc_parallel_for(Q, 1, nthreads, orc_eb_body, &c);
     return 0;
 }
@@ -648,11 +661,11 @@ void orc_edges_dubins_batch(const orc_world_t *w, const double *q0, const double
 /* arc-steer edges on the counter stream: edge i uses stream seed seeds[i] from position 0 */
 typedef struct {
     const orc_world_t *w; const double *parents; const uint64_t *seeds; const orc_steer_params_t *sp;
-    int bits24; uint8_t *safe; int32_t *nwp_out; double *leaf_out;
+    int f32u; uint8_t *safe; int32_t *nwp_out; double *leaf_out;
 } orc_ab_t;
 static void orc_ab_body(int64_t i, void *vc) {
     orc_ab_t *c = (orc_ab_t *)vc;
-    orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[i]), c->bits24, 0, 0};
+    orc_stream_t rng = {NULL, 0, orc_stream_key(c->seeds[i]), c->f32u, 0, 0};
     const int maxp = (int)ceil(c->sp->freq) + 2;
     double leaf[5]; int nwp;
     double *wp = (double *)malloc(sizeof(double) * 8 * (size_t)maxp), *pts = wp + 6 * (size_t)maxp;
@@ -666,9 +679,9 @@ static void orc_ab_body(int64_t i, void *vc) {
     free(wp);
 }
 void orc_edges_arc_batch(const orc_world_t *w, const double *parents, const uint64_t *seeds,
-                         int64_t n, const orc_steer_params_t *sp, int bits24, uint8_t *safe,
+                         int64_t n, const orc_steer_params_t *sp, int f32u, uint8_t *safe,
                          int32_t *nwp_out, double *leaf_out, int nthreads) {
-    orc_ab_t c = {w, parents, seeds, sp, bits24, safe, nwp_out, leaf_out};
+    orc_ab_t c = {w, parents, seeds, sp, f32u, safe, nwp_out, leaf_out};
     orc_parallel_for(n, 256, nthreads, orc_ab_body, &c);
 }
 

@@ -83,12 +83,15 @@ def load_reference():
 
 
 # ---------------------------------------------------------------------------------------------
-# The pre-generated sample sequence: counter-based SplitMix64 stream.
-# u_k(seed) is a pure function of (seed, k), so the GPU can evaluate any position without state
-# and numpy can pre-generate the same doubles for the reference.  (Restated independently of the
-# product's csrc/rng.cuh; tests check both agree.)
+# The pre-generated sample sequence: a counter hash with 32-bit multiplies.
+# Position k of seed's stream is the 64-bit word hi:lo,
+#   hi = M32a(c * 0x9E3779B9 + key_lo),  lo = M32b(c * 0x85EBCA77 + key_hi),  c = k + 1 mod 2^32,
+# key = SplitMix64 finaliser of (seed + 1) * golden.  u_k(seed) is a pure function of (seed, k), so
+# the GPU can evaluate any position without state and numpy can pre-generate the same doubles for
+# the reference.  (Restated independently of the product's csrc/common.cuh; tests check both agree.)
 # ---------------------------------------------------------------------------------------------
 _M64 = (1 << 64) - 1
+_M32 = (1 << 32) - 1
 _GOLDEN = 0x9E3779B97F4A7C15
 
 
@@ -103,39 +106,46 @@ def stream_key(seed: int) -> int:
 
 
 def stream_bits(seed: int, k: int) -> int:
-    return _mix64((stream_key(seed) + (k + 1) * _GOLDEN) & _M64)
+    key = stream_key(seed)
+    c = (k + 1) & _M32
+    a = (c * 0x9E3779B9 + (key & _M32)) & _M32
+    a ^= a >> 16; a = (a * 0x21F0AAAD) & _M32; a ^= a >> 15; a = (a * 0x735A2D97) & _M32
+    b = (c * 0x85EBCA77 + (key >> 32)) & _M32
+    b ^= b >> 15; b = (b * 0xD168AAAD) & _M32; b ^= b >> 15; b = (b * 0xAF723597) & _M32
+    return (a << 32) | b
 
 
 def stream_u53(seed: int, k: int) -> float:
     return (stream_bits(seed, k) >> 11) * (2.0 ** -53)
 
 
-def stream_u24(seed: int, k: int) -> float:
-    """The fp32 build's uniform: top 24 bits, exactly representable in fp32, in [0, 1)."""
-    return (stream_bits(seed, k) >> 40) * (2.0 ** -24)
+def stream_u23(seed: int, k: int) -> float:
+    """The fp32 build's uniform: the top 23 bits, exactly representable in fp32, in [0, 1)."""
+    return (stream_bits(seed, k) >> 41) * (2.0 ** -23)
 
 
-def stream_block(seed: int, start: int, n: int, bits24: bool = False) -> np.ndarray:
-    """Vectorised u_k for k in [start, start+n) as float64."""
+def stream_block(seed: int, start: int, n: int, f32u: bool = False) -> np.ndarray:
+    """Vectorised u_k for k in [start, start+n) as float64 (f32u: the fp32 build's 23-bit u)."""
+    key = stream_key(seed)
     with np.errstate(over="ignore"):
-        key = np.uint64(stream_key(seed))
-        k = np.arange(start + 1, start + n + 1, dtype=np.uint64)
-        z = key + k * np.uint64(_GOLDEN)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    if bits24:
-        return (z >> np.uint64(40)).astype(np.float64) * (2.0 ** -24)
+        c = np.arange(start + 1, start + n + 1, dtype=np.uint64).astype(np.uint32)
+        a = c * np.uint32(0x9E3779B9) + np.uint32(key & _M32)
+        a ^= a >> np.uint32(16); a *= np.uint32(0x21F0AAAD); a ^= a >> np.uint32(15); a *= np.uint32(0x735A2D97)
+        b = c * np.uint32(0x85EBCA77) + np.uint32(key >> 32)
+        b ^= b >> np.uint32(15); b *= np.uint32(0xD168AAAD); b ^= b >> np.uint32(15); b *= np.uint32(0xAF723597)
+    z = (a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64)
+    if f32u:
+        return (z >> np.uint64(41)).astype(np.float64) * (2.0 ** -23)
     return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
 
 
 class StreamPlayer:
     """Stands in for the `random` module inside the reference: plays u_0, u_1, ..."""
 
-    def __init__(self, seed=None, values=None, bits24=False):
+    def __init__(self, seed=None, values=None, f32u=False):
         self.seed = seed
         self.values = None if values is None else np.asarray(values, dtype=np.float64)
-        self.bits24 = bits24
+        self.f32u = f32u
         self.pos = 0
         self._block = None
         self._block_start = 0
@@ -147,7 +157,7 @@ class StreamPlayer:
             return float(self.values[k])
         if self._block is None or not (self._block_start <= k < self._block_start + len(self._block)):
             self._block_start = k
-            self._block = stream_block(self.seed, k, 4096, self.bits24)
+            self._block = stream_block(self.seed, k, 4096, self.f32u)
         return float(self._block[k - self._block_start])
 
     def uniform(self, a, b):

@@ -35,7 +35,7 @@ class World(C.Structure):
 
 
 class Stream(C.Structure):
-    _fields_ = [("ext", _dp), ("n_ext", C.c_int64), ("key", C.c_uint64), ("bits24", C.c_int),
+    _fields_ = [("ext", _dp), ("n_ext", C.c_int64), ("key", C.c_uint64), ("f32u", C.c_int),
                 ("pos", C.c_int64), ("exhausted", C.c_int)]
 
 
@@ -124,8 +124,8 @@ class OracleWorld:
                    world["cells"] if with_cells else (), probs)
 
 
-def stream_u(seed, k, bits24=False):
-    return lib().orc_stream_u(int(seed), int(k), int(bits24))
+def stream_u(seed, k, f32u=False):
+    return lib().orc_stream_u(int(seed), int(k), int(f32u))
 
 
 def nn(tree_xy, q):
@@ -188,7 +188,7 @@ def plan_params(iterations, mode=0, bin_interval=5.0, v=2.0, max_traj_time=500.0
                       diff_max, freq, min_dist, (C.c_double * 3)(*[float(x) for x in weights]), float(max_plan_time))
 
 
-def exploring(world: OracleWorld, start, params: PlanParams, seed=None, u=None, bits24=False,
+def exploring(world: OracleWorld, start, params: PlanParams, seed=None, u=None, f32u=False,
               path_cap=4096):
     """-> dict(status, parent, safe, nwp, leaf, upos, cost_evals, result, path, ...)"""
     I = params.iterations
@@ -213,7 +213,7 @@ def exploring(world: OracleWorld, start, params: PlanParams, seed=None, u=None, 
         u = _f64(u, (-1,))
         rng = Stream(_p(u), len(u), 0, 0, 0, 0)
     else:
-        rng = Stream(None, 0, lib().orc_stream_key(int(seed)), int(bits24), 0, 0)
+        rng = Stream(None, 0, lib().orc_stream_key(int(seed)), int(f32u), 0, 0)
     st = lib().orc_exploring(C.byref(world.c), _p(start), C.byref(rng), C.byref(params), C.byref(tr))
     return {
         "status": st, "parent": parent, "safe": safe, "nwp": nwp, "leaf": leaf, "upos": upos,
@@ -224,7 +224,7 @@ def exploring(world: OracleWorld, start, params: PlanParams, seed=None, u=None, 
     }
 
 
-def exploring_batch(world: OracleWorld, starts, seeds, params: PlanParams, bits24=False, nthreads=0):
+def exploring_batch(world: OracleWorld, starts, seeds, params: PlanParams, f32u=False, nthreads=0):
     starts = _f64(starts, (-1, 5))
     seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
     Q = len(seeds)
@@ -232,7 +232,7 @@ def exploring_batch(world: OracleWorld, starts, seeds, params: PlanParams, bits2
     counts = np.zeros((Q, 3), np.int64)
     status = np.zeros(Q, np.int32)
     lib().orc_exploring_batch(C.byref(world.c), _p(starts), seeds.ctypes.data_as(C.POINTER(C.c_uint64)),
-                              C.c_int(Q), C.byref(params), C.c_int(int(bits24)), _p(res),
+                              C.c_int(Q), C.byref(params), C.c_int(int(f32u)), _p(res),
                               counts.ctypes.data_as(C.POINTER(C.c_int64)),
                               status.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nthreads))
     return res, counts, status
@@ -279,7 +279,7 @@ def edges_dubins_batch(world: OracleWorld, q0, q1, rho, W, nthreads=0):
 
 
 def edges_arc_batch(world: OracleWorld, parents, seeds, dist_to_end=2.0, diff_max=0.5, freq=30.0,
-                    min_dist=0.5, velocity=2.0, bits24=False, nthreads=0):
+                    min_dist=0.5, velocity=2.0, f32u=False, nthreads=0):
     parents = _f64(parents, (-1, 5))
     seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
     n = len(seeds)
@@ -288,7 +288,7 @@ def edges_arc_batch(world: OracleWorld, parents, seeds, dist_to_end=2.0, diff_ma
     nwp = np.zeros(n, np.int32)
     leaf = np.zeros((n, 5))
     lib().orc_edges_arc_batch(C.byref(world.c), _p(parents), seeds.ctypes.data_as(C.POINTER(C.c_uint64)),
-                              C.c_int64(n), C.byref(sp), C.c_int(int(bits24)),
+                              C.c_int64(n), C.byref(sp), C.c_int(int(f32u)),
                               safe.ctypes.data_as(C.POINTER(C.c_uint8)),
                               nwp.ctypes.data_as(C.POINTER(C.c_int32)), _p(leaf), C.c_int(nthreads))
     return safe, nwp, leaf

@@ -319,7 +319,7 @@ def test_edges_arc_vs_oracle(api, env, oworld):
     assert np.array_equal(safe, want_safe) and np.array_equal(counts, want_nwp)
     assert close(leaf, want_leaf, TOL64)
     p32 = parents.astype(np.float32).astype(np.float64)
-    want_safe, want_nwp, want_leaf = orc.edges_arc_batch(oworld, p32, seeds, velocity=2.0, bits24=True)
+    want_safe, want_nwp, want_leaf = orc.edges_arc_batch(oworld, p32, seeds, velocity=2.0, f32u=True)
     safe, counts, leaf = api.edges_arc(env, p32, seeds, [2.0, 0.5, 30.0, 0.5, 2.0], "f32")
     assert np.mean(safe != want_safe) < 0.002 and np.mean(counts != want_nwp) < 0.002
     ok = counts == want_nwp

@@ -19,11 +19,11 @@ def test_stream_matches_harness():
     from oracle import harness as H
     for seed in (0, 1, 12345, 2**40 + 7):
         blk = H.stream_block(seed, 5, 64)
-        blk24 = H.stream_block(seed, 5, 64, bits24=True)
+        blk23 = H.stream_block(seed, 5, 64, f32u=True)
         for j in range(64):
             assert orc.stream_u(seed, 5 + j) == blk[j] == H.stream_u53(seed, 5 + j)
-            assert orc.stream_u(seed, 5 + j, True) == blk24[j] == H.stream_u24(seed, 5 + j)
-            assert np.float32(blk24[j]) == blk24[j] and 0.0 <= blk24[j] < 1.0
+            assert orc.stream_u(seed, 5 + j, True) == blk23[j] == H.stream_u23(seed, 5 + j)
+            assert np.float32(blk23[j]) == blk23[j] and 0.0 <= blk23[j] < 1.0
 
 
 def test_steer_arc_bit_exact(golden_dir):
