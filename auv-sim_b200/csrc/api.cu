@@ -111,6 +111,20 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         h.gs = gs; h.gx0 = h.bbox[0] - gs; h.gy0 = h.bbox[1] - gs;
         h.gnx = (int)ceil(wx / gs) + 2; h.gny = (int)ceil(wy / gs) + 2;
     }
+    // --- fine x table for the shark-cell lookup (env.cuh XCell): ~0.25 m buckets from two buckets left of the
+    // first breakpoint to two buckets right of the last one
+    h.nxc = 0; h.xc0 = 0.0; h.xcw = 1.0;
+    if (NB >= 2 && (double)brk[NB - 1] > (double)brk[0]) {
+        const double span = (double)brk[NB - 1] - (double)brk[0];
+        int nb_ = (int)ceil(span / 0.25);
+        if (nb_ > 4092) nb_ = 4092;
+        if (nb_ < 1) nb_ = 1;
+        h.xcw = span / nb_ * (1.0 + 1e-12);
+        h.xc0 = (double)brk[0] - 2.0 * h.xcw;
+        h.nxc = nb_ + 4;
+    }
+    h.off_xcell = take(sizeof(XCell<R>) * (size_t)h.nxc);
+    h.ext_bytes = (int)o;
     h.off_grid = take(12 * (size_t)h.gnx * h.gny);
     // --- uniform time bins?
     h.bins_uniform = 0; h.bin_s0 = 0.0; h.bin_w = 1.0;
@@ -263,10 +277,32 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
                     }
                 }
                 code |= cc << 16;
-                grid[3 * ((size_t)iy * h.gnx + ix)] = code;
-                grid[3 * ((size_t)iy * h.gnx + ix) + 1] = w1;
-                grid[3 * ((size_t)iy * h.gnx + ix) + 2] = w2;
+                const size_t ncell = (size_t)h.gnx * h.gny, ci = (size_t)iy * h.gnx + ix;      // three planes
+                grid[ci] = code; grid[ncell + ci] = w1; grid[2 * ncell + ci] = w2;
             }
+    }
+    // --- fine x table: a bucket is decided when no breakpoint lies within `margin` of it (the rounding of the
+    // device's bucket index is orders of magnitude below the margin)
+    {
+        const double margin = sizeof(R) == 4 ? 2e-3 : 1e-6;
+        XCell<R> *xc = (XCell<R> *)(blob.data() + h.off_xcell);
+        for (int b = 0; b < h.nxc; b++) {
+            const double xa = h.xc0 + b * h.xcw - margin, xb_ = h.xc0 + (b + 1) * h.xcw + margin;
+            XCell<R> e; e.c1 = (R)0; e.v = -2;
+            if (xb_ < (double)brk[0] || xa > (double)brk[NB - 1]) e.v = -1;
+            else {
+                const int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)xa) - brk.begin()) - 1;   // last brk <= xa
+                bool has_break = false;
+                for (int i = std::max(lo_i, 0); i < NB && (double)brk[i] <= xb_; i++)
+                    if ((double)brk[i] >= xa) { has_break = true; break; }
+                if (!has_break && lo_i >= 0 && lo_i + 1 < NB) {
+                    const int p = 2 * lo_i + 1, k0 = piece[p], k1 = piece[p + 1];
+                    if (k0 >= k1) e.v = -1;
+                    else if (cand_cell[k0] < (1 << 30)) { e.c1 = cand_c1[k0]; e.v = cand_cell[k0] | (k1 - k0 > 1 ? (1 << 30) : 0); }
+                }
+            }
+            xc[b] = e;
+        }
     }
     memcpy(blob.data(), &h, sizeof(h));
     *hout = h;

@@ -40,14 +40,22 @@ template <> struct Ar<float, false> {
     static __device__ __forceinline__ R add(R a, R b) { return a + b; }
     static __device__ __forceinline__ R sub(R a, R b) { return a - b; }
     static __device__ __forceinline__ R mul(R a, R b) { return a * b; }
-    static __device__ __forceinline__ R div(R a, R b) { return __fdividef(a, b); }
+    // a * rcp.approx.ftz(b): <= 2 ulp; no denormal-divisor fix-up code (divisors here are lengths / velocities
+    // bounded away from the denormal range)
+    static __device__ __forceinline__ R div(R a, R b) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+        return a * r;
+    }
     static __device__ __forceinline__ R sqrt(R a) { return sqrtf(a); }
     static __device__ __forceinline__ R sq2(R dx, R dy) { return fmaf(dy, dy, dx * dx); }
     // fast build: two-term Cody-Waite reduction to [-pi, pi] (exact product for |a| < 2^10 * 2pi),
     // then the MUFU sine / cosine (abs. error ~4e-7 on the reduced range): headings here are a few
     // radians, so the error per arc primitive is < 1e-6 m, far inside the 1e-5 relative bar
     static __device__ __forceinline__ void sincos(R a, R *s, R *c) {
-        const float k = rintf(a * 0.15915494309189535f);
+        // nearest integer of a / 2pi through the 1.5 * 2^23 magic constant (|a / 2pi| < 2^22): two full-rate
+        // instructions instead of FRND on the conversion pipe
+        const float k = __fadd_rn(__fmaf_rn(a, 0.15915494309189535f, 12582912.f), -12582912.f);
         float r = fmaf(k, -6.28318548202514648f, a);         // 2pi rounded to fp32 ...
         r = fmaf(k, 1.74845553146951715e-7f, r);             // ... plus its rounding error
         *s = __sinf(r); *c = __cosf(r);

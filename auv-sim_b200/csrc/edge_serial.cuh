@@ -1,0 +1,195 @@
+// edge_serial.cuh -- one candidate edge evaluated by ONE thread, primitive by primitive, exactly as the
+// reference's serial loop runs it:
+//   RRT.steer, the random-arc rollout            (/root/reference/path_planning/rrt_dubins.py:252-295)
+//   RRT.check_collision on the path so far       (rrt_dubins.py:530-549)
+//   the per-waypoint part of cost.habitat_shark_cost_func   (/root/reference/path_planning/cost.py:171-191)
+// Used by the thread-per-edge kernel (edges_tpe.cu: independent edges, the north star's "batched
+// steer+collide+cost kernel ... one candidate edge per thread") and by the thread-per-tree planner
+// (plan_tpt.cu).  edge.cuh is the warp-cooperative evaluation of the same edge.
+//
+// ALLPAIRS = false: every waypoint is classified by the grid of env.cuh (one load decides most tests).
+// ALLPAIRS = true : every waypoint against every circle, polygon edge and habitat -- the all-pairs
+//                   work SURVEY.md 8(d) counts (6 W K + 6 W E + ... FLOP per edge), for the roofline.
+#pragma once
+#include "edge.cuh"
+
+namespace auv {
+
+// circles for the all-pairs test of the fast build, relative to an origin o (the polygon's bounding-box
+// centre): |p - c|^2 - r^2 = |p'|^2 + (-2 c').p' + (|c'|^2 - r^2) with p' = p - o, c' = c - o, so a pair
+// costs 2 FFMA + 1 FMNMX (half that with the packed FFMA2 / FMNMX3 forms over two circles).  The
+// expansion cancels: a minimum within `guard` of the decision is re-evaluated with the direct formula.
+struct CircPair {           // two circles a, b
+    float2 m2x, m2y;        // -2 c'_x, -2 c'_y
+    float2 k;               // |c'|^2 - r_eff^2
+};
+struct CircTable {
+    const CircPair *pair;   // ceil(K / 2) entries in shared memory; a missing second circle repeats the first
+    int npair;
+    float ox, oy;           // origin
+    float ccmax;            // max |c'|^2: scale of the rounding error of the expansion
+};
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+// fill a CircTable from the staged world model (all threads of the CTA; caller syncs)
+__device__ __forceinline__ void circ_table_fill(CircPair *dst, const EnvView<float> &env, float ox, float oy) {
+    const int np = (env.K + 1) >> 1;
+    for (int j = threadIdx.x; j < np; j += blockDim.x) {
+        const int a = 2 * j, b = (2 * j + 1 < env.K) ? 2 * j + 1 : 2 * j;
+        const float ax = env.cx[a] - ox, ay = env.cy[a] - oy, bx = env.cx[b] - ox, by = env.cy[b] - oy;
+        CircPair p;
+        p.m2x = make_float2(-2.f * ax, -2.f * bx);
+        p.m2y = make_float2(-2.f * ay, -2.f * by);
+        p.k = make_float2(fmaf(ay, ay, ax * ax) - env.creff2[a], fmaf(by, by, bx * bx) - env.creff2[b]);
+        dst[j] = p;
+    }
+}
+__device__ __forceinline__ float circ_table_ccmax(const EnvView<float> &env, float ox, float oy) {
+    float m = 0.f;
+    for (int k = 0; k < env.K; k++) {
+        const float ax = env.cx[k] - ox, ay = env.cy[k] - oy;
+        m = fmaxf(m, fmaf(ay, ay, ax * ax));
+    }
+    return m;
+}
+
+// does (x, y) hit any (inflated) circle: every circle, no culling
+template <typename R>
+__device__ __forceinline__ bool point_hits_circles_all(const EnvView<R> &env, const CircTable &ct, R x, R y) {
+    return point_hits_circles<R>(env, x, y);
+}
+template <>
+__device__ __forceinline__ bool point_hits_circles_all<float>(const EnvView<float> &env, const CircTable &ct, float x, float y) {
+    if (ct.pair == nullptr) return point_hits_circles<float>(env, x, y);
+    const float xr = x - ct.ox, yr = y - ct.oy;
+    const float pp = fmaf(yr, yr, xr * xr);
+    const float2 x2 = make_float2(xr, xr), y2 = make_float2(yr, yr);
+    float q0 = Ar<float, false>::inf(), q1 = q0;
+    int j = 0;
+#pragma unroll 4
+    for (; j + 1 < ct.npair; j += 2) {
+        const CircPair a = ct.pair[j], b = ct.pair[j + 1];
+        const float2 qa = ffma2(a.m2y, y2, ffma2(a.m2x, x2, a.k));
+        const float2 qb = ffma2(b.m2y, y2, ffma2(b.m2x, x2, b.k));
+        q0 = fminf(q0, fminf(qa.x, qa.y));
+        q1 = fminf(q1, fminf(qb.x, qb.y));
+    }
+    if (j < ct.npair) {
+        const CircPair a = ct.pair[j];
+        const float2 qa = ffma2(a.m2y, y2, ffma2(a.m2x, x2, a.k));
+        q0 = fminf(q0, fminf(qa.x, qa.y));
+    }
+    const float t = fminf(q0, q1) + pp;                // min_k (d_k^2 - r_k^2)
+    const float guard = 4e-6f * (pp + ct.ccmax);
+    if (t > guard) return false;
+    if (t < -guard) return true;
+    return point_hits_circles<float>(env, x, y);       // too close to call: the direct formula
+}
+
+// unsafe point?  (outside the polygon, on its boundary, or inside an inflated circle)
+template <typename R, bool ALLPAIRS>
+__device__ __forceinline__ bool point_unsafe(const EnvView<R> &env, const CircTable &ct, const Cls &cl, R x, R y) {
+    if (ALLPAIRS) return !point_within<R>(env, x, y) || point_hits_circles_all<R>(env, ct, x, y);
+    return !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+}
+
+// what one thread carries along an edge
+template <typename R> struct ArcEdge {
+    R x, y, th, t, len;
+    R sin0, cos0;              // fp64 build: sin / cos of the heading the next primitive starts from
+    int nwp;                   // len(new.path): appended waypoints + 1 (path[0] = parent)
+    bool bad, moved, degenerate, last_is_wp;
+    R s2; uint32_t cnt; unsigned long long mask;     // cost sums over the APPENDED waypoints
+    R self_s2; int self_hab;                         // contribution of the provisional leaf state
+    int status;
+};
+
+// path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
+template <typename R, bool ALLPAIRS>
+__device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const CircTable &ct, ArcEdge<R> &e, R px, R py, R pth,
+                                               R pt, R plen, R parent_self_s2, int parent_self_hab) {
+    typedef typename Policy<R>::A A;
+    e.x = px; e.y = py; e.th = pth; e.t = pt; e.len = plen;
+    e.sin0 = 0; e.cos0 = 0;
+    if (Policy<R>::VERIFY) A::sincos(pth, &e.sin0, &e.cos0);
+    e.nwp = 1; e.moved = false; e.degenerate = false; e.last_is_wp = false;
+    e.s2 = 0; e.cnt = 0; e.mask = 0ull; e.self_s2 = parent_self_s2; e.self_hab = parent_self_hab; e.status = 0;
+    Cls pcl; pcl.code = 0; pcl.idx = -1;
+    if (!ALLPAIRS) pcl = env.classify(px, py);
+    e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
+}
+
+// one arc primitive (rrt_dubins.py:264-284).  Returns false when the edge must stop (ZeroDivisionError in
+// the fp64 build; a degenerate 2^-23 draw in the fp32 build, which rejects the sample).
+template <typename R, bool COST, bool SELF, bool ALLPAIRS>
+__device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircTable &ct, const SteerParams<R> &sp, R w3,
+                                              SerialStream<R> &rng, ArcEdge<R> &e) {
+    typedef typename Policy<R>::A A;
+    const bool VERIFY = Policy<R>::VERIFY;
+    const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());                          // :264
+    const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());                  // :265
+    if (!(A::fabs(dist) > A::fabs(diff))) return true;                               // :266
+    const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());                        // :279
+    R movement;
+    if (VERIFY) {
+        R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
+        if (den == (R)0) { e.status = AUVRRT_ST_ZERO_DIV; return false; }
+        R radius = A::div(num, den), r2 = A::mul((R)2, radius);                      // :270
+        if (r2 == (R)0) { e.status = AUVRRT_ST_ZERO_DIV; return false; }
+        e.th = A::add(e.th, A::div(num, r2));                                        // :271, :274
+        R s1v, c1v;
+        A::sincos(e.th, &s1v, &c1v);
+        const R dx = A::mul(radius, A::sub(s1v, e.sin0));                            // :275
+        const R dy = A::mul(radius, A::add(-c1v, e.cos0));                           // :276
+        e.sin0 = s1v; e.cos0 = c1v;
+        movement = A::sqrt(A::sq2(dx, dy));                                          // :280
+        if (vt == (R)0) { e.status = AUVRRT_ST_ZERO_DIV; return false; }
+        e.x = A::add(e.x, dx); e.y = A::add(e.y, dy);
+        e.t = A::add(e.t, A::div(movement, vt));                                     // :281
+        e.len = A::add(e.len, movement);
+    } else {
+        // stable restatement of the arc (edge.cuh): turn angle -diff, chord = dist * sinc(diff / 2), heading
+        // at mid-arc; no radius * (sin - sin) cancellation, no sqrt
+        if (diff == (R)0 || vt == (R)0) { e.degenerate = true; return false; }
+        const R half = (R)0.5 * diff;
+        movement = dist * sinc_small((float)half);
+        R sm, cm;
+        A::sincos(e.th - half, &sm, &cm);
+        e.th -= diff;
+        e.x = A::fma(movement, cm, e.x); e.y = A::fma(movement, sm, e.y);
+        e.t = A::fma(movement, A::div((R)1, vt), e.t);
+        e.len += movement;
+    }
+    e.moved = true;
+    e.last_is_wp = movement >= sp.min_dist;                                          // :283
+    if (e.last_is_wp) {
+        e.nwp++;
+        Cls cl; cl.code = AUV_GRID_ALL_AMBIG; cl.idx = -1;
+        if (ALLPAIRS) e.bad = e.bad || point_unsafe<R, true>(env, ct, cl, e.x, e.y);
+        else {
+            cl = env.classify(e.x, e.y);
+            // the common cell: strictly inside the polygon (code 1) and clear of every circle (bit 2)
+            if (__builtin_expect((cl.code & 7u) != 5u, 0)) e.bad = e.bad || point_unsafe<R, false>(env, ct, cl, e.x, e.y);
+        }
+        if (COST) {
+            const Contrib c = point_contrib<R>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl);
+            const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+            if (c.bin >= 0) {
+                e.s2 = A::add(e.s2, ps2);
+                if (c.hab >= 0) { e.cnt++; e.mask |= 1ull << c.hab; }
+            }
+            if (SELF) { e.self_s2 = c.bin >= 0 ? ps2 : (R)0; e.self_hab = c.bin >= 0 ? c.hab : -1; }
+        }
+    }
+    return true;
+}
+
+}  // namespace auv

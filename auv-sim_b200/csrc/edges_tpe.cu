@@ -1,0 +1,172 @@
+// edges_tpe.cu -- the batched steer + collide + cost kernel, ONE CANDIDATE EDGE PER THREAD (sm_100a).
+//
+//   RRT.steer (random-arc rollout)   /root/reference/path_planning/rrt_dubins.py:252-295
+//   RRT.check_collision              rrt_dubins.py:530-549
+//   habitat_shark_cost_func, the per-waypoint loop   /root/reference/path_planning/cost.py:171-191
+//
+// Edge i = (parents[i], seeds[i]): the edge consumes the sample sequence of its seed from position 0
+// (n_expand, then 2-3 uniforms per arc primitive).  A thread runs the reference's
+// serial loop for its edge (edge_serial.cuh); the world model's hot part (circles, polygon, habitats,
+// bins, cell index) and, when it fits, the probability table are staged in shared memory by one TMA
+// bulk copy per CTA.
+//
+// Divergence control.  n_expand is uniform in [0, freq): 32 arbitrary edges in a warp would leave half
+// the lanes idle in the primitive loop.  Each CTA therefore takes a batch of 256 x AUV_TPE_EPT consecutive
+// edges, (1) draws n_expand for all of them with coalesced loads, (2) counting-sorts the batch by
+// n_expand in shared memory, (3) lets its warps pull groups of 32 edges of (nearly) equal n_expand off a
+// shared counter, longest first.  Inputs and outputs stay in the caller's order.
+#include <stdlib.h>
+#include "launch.h"
+#include "edge_serial.cuh"
+
+namespace auv {
+
+#ifndef AUV_TPE_THREADS
+#define AUV_TPE_THREADS 256
+#endif
+#ifndef AUV_TPE_EPT
+#define AUV_TPE_EPT 8             // edges per thread per batch: batch = 2048 edges
+#endif
+#ifndef AUV_TPE_MINB
+#define AUV_TPE_MINB 3
+#endif
+#define AUV_TPE_BUCKETS 64
+#define AUV_TPE_MAXPAIRS 256      // all-pairs circle table in shared memory: up to 512 circles (6 KB)
+
+template <typename R, bool COST, bool ALLPAIRS>
+__global__ void __launch_bounds__(AUV_TPE_THREADS, sizeof(R) == 4 ? AUV_TPE_MINB : 1)
+k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *__restrict__ parents,
+                const uint64_t *__restrict__ seeds, long long n, SteerParams<R> sp, R w3, uint8_t *__restrict__ safe,
+                int32_t *__restrict__ counts, R *__restrict__ leaf, R *__restrict__ cost_out) {
+    typedef typename Policy<R>::A A;
+    const int T = AUV_TPE_THREADS, BATCH = AUV_TPE_THREADS * AUV_TPE_EPT;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned short s_order[BATCH];
+    __shared__ int s_hist[AUV_TPE_BUCKETS];
+    __shared__ int s_next;
+    __shared__ CircPair s_pairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_TPE_MAXPAIRS : 1];
+    EnvView<R> env;
+    if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
+    else {
+        uint64_t *bar = (uint64_t *)smem;
+        stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
+        env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
+        env.bind_grid(blob, smem + 16);
+    }
+    CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
+    if constexpr (ALLPAIRS && sizeof(R) == 4) {
+        if (env.K > 0 && env.K <= 2 * AUV_TPE_MAXPAIRS) {
+            ct.ox = 0.5f * (float)(env.minx + env.maxx); ct.oy = 0.5f * (float)(env.miny + env.maxy);
+            circ_table_fill(s_pairs, env, ct.ox, ct.oy);
+            ct.ccmax = circ_table_ccmax(env, ct.ox, ct.oy);
+            ct.pair = s_pairs; ct.npair = (env.K + 1) >> 1;
+        }
+    }
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long n_batches = (n + BATCH - 1) / BATCH;
+    for (long long b = blockIdx.x; b < n_batches; b += gridDim.x) {
+        const long long base = b * BATCH;
+        const int cnt = (int)((n - base) < (long long)BATCH ? (n - base) : (long long)BATCH);
+        // ---- (1) n_expand of every edge of the batch: floor(uniform(0, freq)) on stream position 0   :259-260
+        if (tid < AUV_TPE_BUCKETS) s_hist[tid] = 0;
+        if (tid == 0) s_next = 0;
+        __syncthreads();
+        unsigned char key[AUV_TPE_EPT];
+        unsigned short rank[AUV_TPE_EPT];
+#pragma unroll
+        for (int e = 0; e < AUV_TPE_EPT; e++) {
+            const int j = e * T + tid;
+            key[e] = 255;
+            if (j < cnt) {
+                const uint64_t k64 = stream_key(seeds[base + j]);
+                const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, Draw<R>::at(k64, 0u)));
+                key[e] = (unsigned char)(n_exp < 0 ? 0 : (n_exp < AUV_TPE_BUCKETS - 1 ? n_exp : AUV_TPE_BUCKETS - 1));
+                rank[e] = (unsigned short)atomicAdd(&s_hist[key[e]], 1);
+            }
+        }
+        __syncthreads();
+        // ---- (2) counting sort: exclusive scan of the 64 buckets by one warp, then scatter
+        if (tid < 32) {
+            const int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1];
+            int v = a0 + a1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if (tid >= d) v += o; }
+            s_hist[2 * tid] = v - a0 - a1; s_hist[2 * tid + 1] = v - a1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < AUV_TPE_EPT; e++)
+            if (key[e] != 255) s_order[s_hist[key[e]] + rank[e]] = (unsigned short)(e * T + tid);
+        __syncthreads();
+        // ---- (3) warps pull groups of 32 edges of (nearly) equal n_expand, longest first
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&s_next, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            const int pos = cnt - 1 - (g * 32 + lane);
+            if (cnt - 1 - g * 32 < 0) break;
+            if (pos >= 0) {
+                const long long i = base + (long long)s_order[pos];
+                const R *p = parents + 5 * i;
+                const R px = p[0], py = p[1], pth = p[2], pt = p[3], plen = p[4];
+                SerialStream<R> rng;
+                rng.init(stream_key(seeds[i]));
+                const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
+                ArcEdge<R> ed;
+                arc_edge_begin<R, ALLPAIRS>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1);
+                for (int k = 0; k < n_exp; k++)
+                    if (!arc_edge_step<R, COST, false, ALLPAIRS>(env, ct, sp, w3, rng, ed)) break;
+                safe[i] = (ed.status == 0 && !(ed.bad || ed.degenerate)) ? 1 : 0;
+                if (counts) counts[i] = ed.nwp;
+                if (leaf) { R *l = leaf + 5 * i; l[0] = ed.x; l[1] = ed.y; l[2] = ed.th; l[3] = ed.t; l[4] = ed.len; }
+                if (COST) { R *c = cost_out + 3 * i; c[0] = ed.s2; c[1] = (R)ed.cnt; c[2] = (R)__popcll(ed.mask); }
+            }
+        }
+        __syncthreads();        // s_order / s_hist / s_next are rewritten by the next batch
+    }
+}
+
+template <typename R, bool COST, bool ALLPAIRS>
+static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n, const double params[5],
+                        double w3, uint8_t *safe, int32_t *counts, R *leaf, R *cost_out, cudaStream_t s) {
+    EnvBlob<R> b = env_blob<R>(env);
+    // fp32: hot part + probability table in shared memory when they fit next to 3 resident CTAs' worth
+    int budget = sizeof(R) == 4 ? 56 * 1024 : 100 * 1024;
+    if (const char *ev = getenv("AUVRRT_TPE_STAGE_KB")) budget = atoi(ev) * 1024;
+    int sm = 16, mode = 0;
+    if (COST && b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
+    else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
+    auto kern = k_edges_arc_tpe<R, COST, ALLPAIRS>;
+    AUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    int per_sm = 0, nsm = 0, dev = 0;
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AUV_TPE_THREADS, sm));
+    if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "edges_arc (thread per edge): kernel does not fit on an SM (smem %d)", sm);
+    AUV_CUDA(cudaGetDevice(&dev));
+    AUV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t batch = (int64_t)AUV_TPE_THREADS * AUV_TPE_EPT;
+    int64_t blocks = (n + batch - 1) / batch;
+    if (blocks > (int64_t)nsm * per_sm) blocks = (int64_t)nsm * per_sm;
+    kern<<<(unsigned)blocks, AUV_TPE_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, parents, seeds, (long long)n,
+                                                        make_steer_params<R>(params), (R)w3, safe, counts, leaf, cost_out);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(AUVRRT_ERR_CUDA, "edges_arc (thread per edge) launch: %s", cudaGetErrorString(e));
+    return AUVRRT_OK;
+}
+
+template <typename R>
+int launch_edges_arc_tpe(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n, const double params[5],
+                         uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3, R *cost_out, bool allpairs) {
+    if (n <= 0) return AUVRRT_OK;
+    if (cost_out)
+        return allpairs ? launch_tpe_t<R, true, true>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s)
+                        : launch_tpe_t<R, true, false>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s);
+    return allpairs ? launch_tpe_t<R, false, true>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s)
+                    : launch_tpe_t<R, false, false>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s);
+}
+template int launch_edges_arc_tpe<float>(const auvrrt_env *, const float *, const uint64_t *, int64_t, const double[5], uint8_t *,
+                                         int32_t *, float *, cudaStream_t, double, float *, bool);
+template int launch_edges_arc_tpe<double>(const auvrrt_env *, const double *, const uint64_t *, int64_t, const double[5],
+                                          uint8_t *, int32_t *, double *, cudaStream_t, double, double *, bool);
+
+}  // namespace auv

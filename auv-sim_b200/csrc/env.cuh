@@ -36,20 +36,23 @@ struct EnvHeader {
     int off_probs;
     int off_xb;        // x-bucket table for the shark-cell pieces (u16 per bucket), staged
     int nxb;           // number of x buckets (0: none)
-    int off_grid;      // classification grid (3 x u32 per cell), not staged: read through L1/L2
+    int off_grid;      // classification grid (3 planes of u32, one word per cell each), not staged: read through L1/L2
     int gnx, gny;      // grid dimensions (0: no grid)
     int bins_uniform;  // 1: bins are [s0 + i w, s0 + (i+1) w], contiguous and in order
-    int pad_[1];
+    int off_xcell;     // fine x table for the shark-cell lookup (XCell<R> per bucket), bytes [total_bytes, ext_bytes)
+    int nxc;           // buckets in it (0: none)
+    int ext_bytes;     // a kernel with shared memory to spare stages [0, ext_bytes)
     double bbox[4];    // minx, miny, maxx, maxy of the polygon (Polygon.bounds, rrt_dubins.py:334)
     double gx0, gy0, gs;   // grid origin and cell size
     double bin_s0, bin_w;
     double xb0, xbw;       // x-bucket origin and width
-    double pad2_;
+    double xc0, xcw;       // fine x table origin and bucket width
 };
 static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignment of the arrays");
 
 // Classification grid (built once on the host, see api.cu): three u32 words per cell of a uniform
-// grid over the polygon's bounding box, so that most waypoints are classified by ONE load instead
+// grid over the polygon's bounding box (stored as three planes: word 0 of every cell, then word 1, then word 2, so
+// the one word most waypoints need is dense in L1), so that most waypoints are classified by ONE load instead
 // of the loops over circles / polygon edges / habitats / shark cells, and the rest by a short
 // per-cell candidate list.  A code is only definitive when every point of the cell (plus a rounding
 // margin) gets the same answer from the exact test; candidate lists hold every object that can
@@ -75,11 +78,20 @@ static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignmen
 
 struct Cls { unsigned code; int idx; };   // word 0 and the cell index (-1 outside the grid)
 
+// Fine x table for the shark-cell lookup (cost.py:181-184, see the cell index above).  Bucket b covers
+// [xc0 + b w, xc0 + (b+1) w]; when no breakpoint lies within a margin of it, every x of the bucket is in the
+// same open piece and the entry holds that piece's FIRST candidate:
+//   v >= 0 : cell id (bits 0-29) of the first candidate, c1 its lower y bound; bit 30: more candidates follow
+//   v == -1: the piece has no candidate (no cell contains this x)
+//   v == -2: a breakpoint is near: walk the breakpoints (find_cell)
+template <typename R> struct alignas(8) XCell { R c1; int v; };
+
 template <typename R> struct EnvView {
     int K, E, H, T, C, NB, NP, convex;
-    int gnx, gny, bins_uniform, nxb;
-    R gx0, gy0, ginv, bin_s0, bin_w, bin_winv, xb0, xbinv;
+    int gnx, gny, ncell, bins_uniform, nxb, nxc;
+    R gx0, gy0, ginv, gxo, gyo, bin_s0, bin_w, bin_winv, xb0, xbinv, xcinv, xco;
     const unsigned *grid;
+    const XCell<R> *xcell;
     const unsigned short *xb;
     R minx, miny, maxx, maxy;
     const R *cx, *cy, *cr, *creff, *creff2;
@@ -113,24 +125,44 @@ template <typename R> struct EnvView {
         gnx = h->gnx; gny = h->gny; bins_uniform = h->bins_uniform; nxb = h->nxb;
         xb0 = (R)h->xb0; xbinv = (R)(1.0 / h->xbw); xb = (const unsigned short *)(hot + h->off_xb);
         gx0 = (R)h->gx0; gy0 = (R)h->gy0; ginv = (R)(1.0 / h->gs);
+        gxo = (R)(-h->gx0 / h->gs); gyo = (R)(-h->gy0 / h->gs);
         bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w);
         grid = (const unsigned *)(blob_global + h->off_grid);
+        ncell = gnx * gny;
+        nxc = h->nxc; xcinv = (R)(1.0 / h->xcw); xco = (R)(-h->xc0 / h->xcw);
+        xcell = (const XCell<R> *)(blob_global + h->off_xcell);
+    }
+    // the fine x table staged in shared memory too (the kernel copied [0, ext_bytes))
+    __device__ __forceinline__ void bind_xcell_staged(const unsigned char *hot) {
+        const EnvHeader *h = (const EnvHeader *)hot;
+        xcell = (const XCell<R> *)(hot + h->off_xcell);
     }
     // classification of the cell containing (x, y); off the grid: outside the polygon, everything else ambiguous
     __device__ __forceinline__ Cls classify(R x, R y) const {
         Cls c;
-        R fx = (x - gx0) * ginv, fy = (y - gy0) * ginv;
-        if (!(fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny)) {
+        int ix, iy;
+        if (sizeof(R) == 4) {
+            // floor via round-toward-minus-infinity onto 2^23: two full-rate instructions per coordinate instead of
+            // F2I on the conversion pipe; anything out of range (negative, huge, NaN) fails the unsigned compares
+            const float fx = fmaf((float)x, (float)ginv, (float)gxo), fy = fmaf((float)y, (float)ginv, (float)gyo);
+            ix = __float_as_int(__fadd_rd(fx, 8388608.f)) - 0x4B000000;
+            iy = __float_as_int(__fadd_rd(fy, 8388608.f)) - 0x4B000000;
+        } else {
+            const R fx = (x - gx0) * ginv, fy = (y - gy0) * ginv;
+            const bool in = fx >= (R)0 && fy >= (R)0 && fx < (R)gnx && fy < (R)gny;
+            ix = in ? (int)fx : -1; iy = in ? (int)fy : -1;
+        }
+        if (!((unsigned)ix < (unsigned)gnx && (unsigned)iy < (unsigned)gny)) {
             // the grid covers the polygon's bounding box plus one cell all round: a point off the grid is outside the
             // polygon (code 2) whatever else is undecided about it
             c.code = AUV_GRID_ALL_AMBIG | (gnx > 0 ? 2u : 0u); c.idx = -1; return c;
         }
-        c.idx = (int)fy * gnx + (int)fx;
-        c.code = __ldg(grid + 3 * c.idx);
+        c.idx = iy * gnx + ix;
+        c.code = __ldg(grid + c.idx);
         return c;
     }
-    __device__ __forceinline__ unsigned word1(const Cls &c) const { return __ldg(grid + 3 * c.idx + 1); }
-    __device__ __forceinline__ unsigned word2(const Cls &c) const { return __ldg(grid + 3 * c.idx + 2); }
+    __device__ __forceinline__ unsigned word1(const Cls &c) const { return __ldg(grid + ncell + c.idx); }
+    __device__ __forceinline__ unsigned word2(const Cls &c) const { return __ldg(grid + 2 * ncell + c.idx); }
 };
 
 // ---- TMA bulk staging -------------------------------------------------------------------------

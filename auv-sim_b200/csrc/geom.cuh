@@ -175,7 +175,20 @@ struct Contrib {
 
 template <typename R>
 __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
-    if (env.NB == 0 || !(x >= env.brk[0]) || !(x <= env.brk[env.NB - 1])) return -1;
+    if (env.NB == 0) return -1;
+    if (env.nxc > 0) {
+        // fine x table: most buckets hold no breakpoint, so the piece and its first candidate are known
+        int b;
+        if (sizeof(R) == 4) b = __float_as_int(__fadd_rd(fmaf((float)x, (float)env.xcinv, (float)env.xco), 8388608.f)) - 0x4B000000;
+        else { const R fb = x * env.xcinv + env.xco; b = fb >= (R)0 ? (fb < (R)env.nxc ? (int)fb : env.nxc - 1) : 0; }
+        b = min(max(b, 0), env.nxc - 1);      // the first and last buckets lie outside every cell
+        const XCell<R> e = env.xcell[b];
+        if (e.v >= 0) {
+            if (y >= e.c1) return e.v & 0x3FFFFFFF;
+            if (!(e.v >> 30)) return -1;
+        } else if (e.v == -1) return -1;
+    }
+    if (!(x >= env.brk[0]) || !(x <= env.brk[env.NB - 1])) return -1;
     int lo;                                   // largest i with brk[i] <= x
     if (env.nxb > 0) {
         // x-bucket table: index of the last breakpoint <= the bucket's left edge (0 if none), then a

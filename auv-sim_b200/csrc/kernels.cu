@@ -577,6 +577,13 @@ int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *se
                      const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3,
                      R *cost_out) {
     if (n <= 0) return AUVRRT_OK;
+    // default: one thread per edge (edges_tpe.cu).  AUVRRT_EDGES_VARIANT=warp selects the warp-per-edge kernel
+    // above (lower latency for a handful of edges); AUVRRT_EDGES_BRUTE=1 the all-pairs variant of the
+    // thread-per-edge kernel (every waypoint against every circle / polygon edge / habitat: the roofline run).
+    const char *variant = getenv("AUVRRT_EDGES_VARIANT"), *brute = getenv("AUVRRT_EDGES_BRUTE");
+    if (!(variant && variant[0] == 'w'))
+        return launch_edges_arc_tpe<R>(env, parents, seeds, n, params, safe, counts, leaf, s, w3, cost_out,
+                                       brute && brute[0] == '1');
     return cost_out ? launch_edges_arc_t<R, true>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s)
                     : launch_edges_arc_t<R, false>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s);
 }

@@ -56,6 +56,10 @@ template <typename R>
 int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n,
                      const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3 = 0.0,
                      R *cost_out = nullptr);
+// ---- edges_tpe.cu: the same edges, one thread per edge (default); allpairs: no classification grid
+template <typename R>
+int launch_edges_arc_tpe(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n, const double params[5],
+                         uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3, R *cost_out, bool allpairs);
 template <typename R>
 int launch_nn(const R *tx, const R *ty, int64_t n, const R *qx, const R *qy, int nq, void *scratch,
               int64_t scratch_bytes, int32_t *out_idx, cudaStream_t s);

@@ -12,6 +12,7 @@
 // Per-tree workspace (private to the thread): AoS node rows (one 64-byte row in fp32: x,y,theta,t |
 // len,s2,self_s2,ctr | parent,cnt,self_hab | mask) and the chunked time bins of plan.cu.
 #include "plan_common.cuh"
+#include "edge_serial.cuh"
 
 namespace auv {
 
@@ -93,64 +94,17 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 // ---- steer (:237-295) with check_collision (:530-549) and the per-waypoint cost folded in
                 const NodeRow<R> pr = nodes[parent];
                 const uint32_t ctr0 = rng.ctr - 1;                 // position of the n_expand draw
-                R x = pr.x, y = pr.y, th = pr.th, t = pr.t, len = pr.len;
-                R sin0 = 0, cos0 = 0;
-                if (VERIFY) A::sincos(th, &sin0, &cos0);
-                int nwp = 1;
-                bool bad = false, moved = false, degenerate = false;
-                R acc_s2 = 0; uint32_t acc_cnt = 0; unsigned long long acc_mask = 0;
-                R self_s2 = pr.self_s2; int self_hab = pr.self_hab;
-                bool last_is_wp = false;
-                {
-                    const Cls pcl = env.classify(pr.x, pr.y);                            // path[0] = parent object
-                    bad = !point_within_c<R>(env, pcl, pr.x, pr.y) || point_hits_circles_c<R>(env, pcl, pr.x, pr.y);
-                }
-                for (int k = 0; k < n_exp; k++) {
-                    const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());
-                    const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());
-                    if (!(A::fabs(dist) > A::fabs(diff))) continue;
-                    const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());
-                    R dx, dy, movement;
-                    if (VERIFY) {
-                        R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
-                        if (den == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
-                        R radius = A::div(num, den), r2 = A::mul((R)2, radius);
-                        if (r2 == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
-                        th = A::add(th, A::div(num, r2));
-                        R s1v, c1v;
-                        A::sincos(th, &s1v, &c1v);
-                        dx = A::mul(radius, A::sub(s1v, sin0));
-                        dy = A::mul(radius, A::add(-c1v, cos0));
-                        sin0 = s1v; cos0 = c1v;
-                        movement = A::sqrt(A::sq2(dx, dy));
-                        if (vt == (R)0) { status = AUVRRT_ST_ZERO_DIV; break; }
-                    } else {
-                        if (diff == (R)0 || vt == (R)0) { degenerate = true; break; }
-                        const R phi = -diff;
-                        movement = dist * sinc_small((float)diff * 0.5f);
-                        R sm, cm;
-                        A::sincos(th + (R)0.5 * phi, &sm, &cm);
-                        th += phi;
-                        dx = movement * cm; dy = movement * sm;
-                    }
-                    x = A::add(x, dx); y = A::add(y, dy);
-                    t = A::add(t, A::div(movement, vt));
-                    len = A::add(len, movement);
-                    moved = true;
-                    last_is_wp = movement >= sp.min_dist;                                // :283
-                    if (last_is_wp) {
-                        nwp++;
-                        const Cls cl = env.classify(x, y);
-                        bad = bad || !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
-                        Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, cl);
-                        R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
-                        if (c.bin >= 0) {
-                            acc_s2 = A::add(acc_s2, ps2);
-                            if (c.hab >= 0) { acc_cnt++; acc_mask |= 1ull << c.hab; }
-                        }
-                        self_s2 = c.bin >= 0 ? ps2 : (R)0; self_hab = c.bin >= 0 ? c.hab : -1;   // provisional leaf state
-                    }
-                }
+                ArcEdge<R> ed;
+                CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
+                arc_edge_begin<R, false>(env, ct, ed, pr.x, pr.y, pr.th, pr.t, pr.len, pr.self_s2, pr.self_hab);
+                for (int k = 0; k < n_exp; k++)
+                    if (!arc_edge_step<R, true, true, false>(env, ct, sp, P.w3, rng, ed)) break;
+                status = ed.status;
+                const R x = ed.x, y = ed.y, th = ed.th, t = ed.t, len = ed.len;
+                const int nwp = ed.nwp;
+                const bool bad = ed.bad, moved = ed.moved, degenerate = ed.degenerate, last_is_wp = ed.last_is_wp;
+                const R acc_s2 = ed.s2; const uint32_t acc_cnt = ed.cnt; const unsigned long long acc_mask = ed.mask;
+                R self_s2 = ed.self_s2; int self_hab = ed.self_hab;
                 if (!status) {
                     const bool safe = !(bad || degenerate);
                     s_nwp[slot] += nwp; s_nprims[slot] += n_exp;

@@ -312,6 +312,104 @@ def main():
         dist.destroy_process_group()
 
 
+def catalina_parents(world, n, dev, seed=3):
+    """n tree-node-like parent states (x, y, theta, traj_time_stamp, length) uniform over the FREE space of the
+    Catalina map: inside the boundary polygon and outside every (inflated) obstacle circle; theta uniform,
+    traj_time_stamp uniform in [0, 400] s (inside the shark grid's time bins), length 0"""
+    import torch
+    poly = torch.tensor(world["boundary"], device=dev, dtype=torch.float32)
+    circ = np.array(world["circles"])
+    reff = np.maximum.accumulate(circ[::-1, 2])[::-1].copy()
+    cx = torch.tensor(circ[:, 0], device=dev, dtype=torch.float32); cy = torch.tensor(circ[:, 1], device=dev, dtype=torch.float32)
+    cr = torch.tensor(reff + 0.01, device=dev, dtype=torch.float32)
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    out = torch.empty((n, 5), device=dev, dtype=torch.float32)
+    have = 0
+    chunk = min(n, 1 << 24)
+    ax, ay = poly[:, 0], poly[:, 1]
+    bx, by = torch.roll(ax, -1), torch.roll(ay, -1)
+    while have < n:
+        x = torch.rand(chunk, device=dev, generator=g) * 549.8 - 467.4
+        y = torch.rand(chunk, device=dev, generator=g) * 344.7 - 153.5
+        cross = (bx - ax)[None] * (y[:, None] - ay[None]) - (by - ay)[None] * (x[:, None] - ax[None])
+        ok = (cross < 0).all(1) | (cross > 0).all(1)
+        ok &= (((x[:, None] - cx[None]) ** 2 + (y[:, None] - cy[None]) ** 2) > (cr * cr)[None]).all(1)
+        x, y = x[ok], y[ok]
+        m = min(n - have, x.numel())
+        out[have:have + m, 0] = x[:m]; out[have:have + m, 1] = y[:m]
+        have += m
+    out[:, 2] = (torch.rand(n, device=dev, generator=g) * 2 - 1) * np.pi
+    out[:, 3] = torch.rand(n, device=dev, generator=g) * 400.0
+    out[:, 4] = 0
+    return out
+
+
+def micro_catalina(env, dev, n_edges, api, adev, cal_flops, timed):
+    """SURVEY 8(d) "Catalina scale": independent arc edges (S1 steer + K1 collide + C1 cost) on the real map,
+    K = 27 circles, E = 5, H = 10 habitats, T x C = 10 x 986 shark grid -- where the north star's 1e10 edges/s lives.
+    One thread per edge (edges_tpe.cu).  Three runs on the same edges: classification grid with cost on (the
+    product path) and off, and the all-pairs variant (every waypoint against every circle / polygon edge / habitat),
+    whose executed work is what SURVEY's FLOP formula counts."""
+    import torch
+    world, bins_, _ = load_world()
+    K, E, H, T = len(world["circles"]), len(world["boundary"]), len(world["habitats"]), len(bins_)
+    par = catalina_parents(world, n_edges, dev)
+    sd = torch.arange(n_edges, device=dev, dtype=torch.int64)
+    safe = torch.zeros(n_edges, dtype=torch.uint8, device=dev); cnt = torch.zeros(n_edges, dtype=torch.int32, device=dev)
+    leaf = torch.zeros((n_edges, 5), device=dev); cost = torch.zeros((n_edges, 3), device=dev)
+    sp5 = [2.0, 0.5, 30.0, 0.5, 2.0]
+    out = {}
+    saved = {k: os.environ.get(k) for k in ("AUVRRT_EDGES_VARIANT", "AUVRRT_EDGES_BRUTE")}
+    try:
+        os.environ["AUVRRT_EDGES_VARIANT"] = "tpe"
+        os.environ["AUVRRT_EDGES_BRUTE"] = "0"
+        t_on, _ = timed(lambda: adev.edges_arc_cost_dev(env, par, sd, sp5, -4.0, safe, cnt, leaf, cost, "f32"), reps=3, warm=1)
+        safe_grid = safe.clone(); cost_grid = cost.clone(); cnt_grid = cnt.clone()
+        W = float(cnt.float().mean().item()); Pm = 14.5
+        acc = float(safe.float().mean().item())
+        t_off, _ = timed(lambda: adev.edges_arc_dev(env, par, sd, sp5, safe, cnt, leaf, "f32"), reps=3, warm=1)
+        same_off = bool(torch.equal(safe, safe_grid))
+        os.environ["AUVRRT_EDGES_BRUTE"] = "1"
+        t_all, _ = timed(lambda: adev.edges_arc_cost_dev(env, par, sd, sp5, -4.0, safe, cnt, leaf, cost, "f32"), reps=3, warm=1)
+        R_rows = 35
+        flop_geo = 6 * W * K + 6 * W * E + 30 * Pm
+        flop_cost = (W - 1) * (2 * T + 2 * R_rows + 6 * H + 3)        # every appended waypoint is costed (the parent is not)
+        flop = flop_geo + flop_cost
+        peak = cal_flops / 1e12
+        out["micro_catalina_arc_cost"] = {
+            "edges": n_edges, "circles": K, "polygon_edges": E, "habitats": H, "time_bins": T, "cells": int(len(world["cells"])),
+            "waypoints_per_edge": W, "primitives_per_edge": Pm, "safe_fraction": acc,
+            "edges_per_s": n_edges / t_on, "seconds": t_on,
+            "kernel": "k_edges_arc_tpe<float,COST,grid> (one thread per edge, classification grid)",
+            "algorithmic_flop_per_edge": flop, "equivalent_all_pairs_tflops": n_edges * flop / t_on / 1e12,
+            "equivalent_frac": n_edges * flop / t_on / cal_flops,
+            "edges_with_shark_cost": float((cost_grid[:, 0] != 0).float().mean().item()),
+            "note": "the grid decides most waypoint tests with one load, so the all-pairs FLOP count is an equivalent here; "
+                    "the executed-work roofline is micro_catalina_arc_cost_allpairs (same edges, same results)"}
+        out["micro_catalina_arc"] = {"edges": n_edges, "edges_per_s": n_edges / t_off, "seconds": t_off, "identical_booleans": same_off,
+                                     "algorithmic_flop_per_edge": flop_geo, "equivalent_frac": n_edges * flop_geo / t_off / cal_flops,
+                                     "kernel": "k_edges_arc_tpe<float,no cost,grid>"}
+        d = (cost - cost_grid).abs()
+        out["micro_catalina_arc_cost_allpairs"] = {
+            "edges": n_edges, "edges_per_s": n_edges / t_all, "seconds": t_all,
+            "kernel": "k_edges_arc_tpe<float,COST,all pairs> (FFMA2 over circle pairs)",
+            "roofline": {"bound": "fp32", "achieved": n_edges * flop / t_all / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": n_edges * flop / t_all / cal_flops, "algorithmic_flop_per_edge": flop,
+                         "peak_source": "FFMA calibration kernel measured live in this run"},
+            "booleans_differ_fraction": float((safe != safe_grid).float().mean().item()),
+            "counts_identical": bool(torch.equal(cnt, cnt_grid)),
+            "cost_terms_max_abs_diff": [float(d[:, j].max().item()) for j in range(3)]}
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    del par, sd, safe, cnt, leaf, cost
+    torch.cuda.empty_cache()
+    return out
+
+
 def extras(env, dev, args, api, adev):
     """secondary measurements: NN scan against the HBM roofline, config-4 micro-benchmark, fp64 build"""
     import torch
@@ -349,6 +447,13 @@ def extras(env, dev, args, api, adev):
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                           "algorithmic_bytes": "8 B per node per pass"}
     del tx, ty
+
+    # Catalina scale: independent steer + collide + cost edges, one thread per edge
+    try:
+        cal_c, _ = api.calibrate_fp32(dev.index, 8192)
+        out.update(micro_catalina(env, dev, int(args.micro_edges), api, adev, cal_c, timed))
+    except Exception as ex:
+        out["micro_catalina_arc_cost"] = {"error": repr(ex)}
 
     # throughput planner (one thread per tree) at config-5 scale: 65536 queries resident on one GPU
     try:

@@ -32,6 +32,29 @@ if what == "edges":
     for _ in range(3):
         adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32")
     torch.cuda.synchronize()
+elif what.startswith("catalina"):
+    # python tools/micro_run.py catalina[-allpairs|-nocost] n : the thread-per-edge arc kernel at Catalina scale
+    import os
+    world, bins_, probs_ = bench.load_world()
+    env = api.Env.from_map(world, bins_, probs_, device=0)
+    par = bench.catalina_parents(world, n, dev)
+    sd = torch.arange(n, device=dev, dtype=torch.int64)
+    safe = torch.zeros(n, dtype=torch.uint8, device=dev); cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+    leaf = torch.zeros((n, 5), device=dev); cost = torch.zeros((n, 3), device=dev)
+    os.environ["AUVRRT_EDGES_BRUTE"] = "1" if "allpairs" in what else "0"
+    reps = int(os.environ.get("MICRO_REPS", "3"))
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if "nocost" in what:
+            adev.edges_arc_dev(env, par, sd, [2.0, 0.5, 30.0, 0.5, 2.0], safe, cnt, leaf, "f32")
+        else:
+            adev.edges_arc_cost_dev(env, par, sd, [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, safe, cnt, leaf, cost, "f32")
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    print(what, "n", n, "edges/s %.4g" % (n / min(ts)), "times", ["%.4f" % t for t in ts], "safe", float(safe.float().mean()),
+          "W", float(cnt.float().mean()), "env", {k: os.environ[k] for k in os.environ if k.startswith("AUVRRT_")})
 else:
     tx = torch.rand(n, device=dev) * 550 - 467; ty = torch.rand(n, device=dev) * 345 - 153
     qx = torch.tensor([-200.0], device=dev); qy = torch.tensor([0.0], device=dev)
