@@ -57,7 +57,13 @@ __device__ __forceinline__ float sinc_small(float h) {
 }
 
 // wp_out rows: (x, y, theta, v, traj_time_stamp, length)
-template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP>
+// FLAT = false: the counter stream with slot addressing: the edge owns 1 + 3 n_expand
+//   positions, primitive k reads ctr + 1 + 3k (dist), + 1 (diff) and, only if abs(dist) > abs(diff), + 2
+//   (velocity_temp): every lane knows its positions, no offsets to resolve.
+// FLAT = true : an explicit recorded stream (e.g. a CPython Mersenne-Twister sequence) consumed back to back,
+//   2 or 3 uniforms per primitive: the per-position step goes to shared memory and log2(G) rounds of pointer
+//   doubling give each lane the offset of its primitive.
+template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP, bool FLAT = false>
 __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &sc, const EnvView<R> &env,
                                           const Stream<R> &rng, uint32_t ctr, const SteerParams<R> &sp,
                                           R px, R py, R pth, R pt, R plen, R w3, int n_hab,
@@ -94,58 +100,70 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
 
     for (int base = 0; base < n_exp; base += G) {
         const int nact = min(G, n_exp - base);          // active primitives in this chunk
-        // ---- 1. window of uniforms, one hash per lane per round
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            int s = g.gl + G * r;
-            sc.us[s] = (s < 3 * nact) ? rng.u(ctr + (uint32_t)s) : (R)0;
-        }
-        g.sync();
-        // ---- 2. stream offset of every primitive: pointer doubling over step(s) in {2, 3}
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            int s = g.gl + G * r;
-            int nx = 3 * G;
-            if (s <= 3 * G - 3) {
-                R dist = uniform_ab<R>((R)0, sp.d2e, sc.us[s]);
-                R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, sc.us[s + 1]);
-                nx = s + 2 + (A::fabs(dist) > A::fabs(diff) ? 1 : 0);
-                if (nx > 3 * G) nx = 3 * G;
-            }
-            sc.jmp[0][s] = (unsigned char)nx;
-        }
-        if (g.gl == 0) {
-#pragma unroll
-            for (int d = 0; d < LOG; d++) sc.jmp[d][3 * G] = (unsigned char)(3 * G);
-        }
-        g.sync();
-#pragma unroll
-        for (int d = 1; d < LOG; d++) {
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                int s = g.gl + G * r;
-                sc.jmp[d][s] = sc.jmp[d - 1][sc.jmp[d - 1][s]];
-            }
-            g.sync();
-        }
-        int o = 0;
-#pragma unroll
-        for (int d = 0; d < LOG; d++)
-            if ((g.gl >> d) & 1) o = sc.jmp[d][o];
         const bool act = g.gl < nact;
-        // ---- 3. this lane's primitive                                          rrt_dubins.py:264-284
         R dist = 0, diff = 0, vt = 1;
         bool valid = false;
-        if (act) {
-            dist = uniform_ab<R>((R)0, sp.d2e, sc.us[o]);
-            diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, sc.us[o + 1]);
-            valid = A::fabs(dist) > A::fabs(diff);
-            if (valid) vt = uniform_ab<R>((R)0, sp.two_vel, sc.us[o + 2]);
-        }
-        // offset just past the chunk's last active primitive
-        int o_end = g.bcast(o + 2 + (valid ? 1 : 0), nact - 1);
-        ctr += (uint32_t)o_end;
+        if (FLAT) {
+            // ---- 1. window of uniforms, one hash per lane per round
+    #pragma unroll
+            for (int r = 0; r < 3; r++) {
+                int s = g.gl + G * r;
+                sc.us[s] = (s < 3 * nact) ? rng.u(ctr + (uint32_t)s) : (R)0;
+            }
+            g.sync();
+            // ---- 2. stream offset of every primitive: pointer doubling over step(s) in {2, 3}
+    #pragma unroll
+            for (int r = 0; r < 3; r++) {
+                int s = g.gl + G * r;
+                int nx = 3 * G;
+                if (s <= 3 * G - 3) {
+                    R dist = uniform_ab<R>((R)0, sp.d2e, sc.us[s]);
+                    R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, sc.us[s + 1]);
+                    nx = s + 2 + (A::fabs(dist) > A::fabs(diff) ? 1 : 0);
+                    if (nx > 3 * G) nx = 3 * G;
+                }
+                sc.jmp[0][s] = (unsigned char)nx;
+            }
+            if (g.gl == 0) {
+    #pragma unroll
+                for (int d = 0; d < LOG; d++) sc.jmp[d][3 * G] = (unsigned char)(3 * G);
+            }
+            g.sync();
+    #pragma unroll
+            for (int d = 1; d < LOG; d++) {
+    #pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    int s = g.gl + G * r;
+                    sc.jmp[d][s] = sc.jmp[d - 1][sc.jmp[d - 1][s]];
+                }
+                g.sync();
+            }
+            int o = 0;
+    #pragma unroll
+            for (int d = 0; d < LOG; d++)
+                if ((g.gl >> d) & 1) o = sc.jmp[d][o];
+                // ---- 3. this lane's primitive                                          rrt_dubins.py:264-284
+            if (act) {
+                dist = uniform_ab<R>((R)0, sp.d2e, sc.us[o]);
+                diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, sc.us[o + 1]);
+                valid = A::fabs(dist) > A::fabs(diff);
+                if (valid) vt = uniform_ab<R>((R)0, sp.two_vel, sc.us[o + 2]);
+            }
+            // offset just past the chunk's last active primitive
+            int o_end = g.bcast(o + 2 + (valid ? 1 : 0), nact - 1);
+            ctr += (uint32_t)o_end;
 
+        } else {
+            // ---- 1-3. slot addressing: this lane's primitive reads its own three positions     rrt_dubins.py:264-279
+            if (act) {
+                const uint32_t p0 = ctr + 3u * (uint32_t)g.gl;
+                dist = uniform_ab<R>((R)0, sp.d2e, rng.u(p0));
+                diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.u(p0 + 1u));
+                valid = A::fabs(dist) > A::fabs(diff);
+                if (valid) vt = uniform_ab<R>((R)0, sp.two_vel, rng.u(p0 + 2u));
+            }
+            ctr += 3u * (uint32_t)nact;
+        }
         R phi = 0, radius = 0, chord = 0;
         if (valid) {
             if (VERIFY) {

@@ -136,7 +136,7 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
     const bool VERIFY = Policy<R>::VERIFY;
     const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());                          // :264
     const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());                  // :265
-    if (!(A::fabs(dist) > A::fabs(diff))) return true;                               // :266
+    if (!(A::fabs(dist) > A::fabs(diff))) { rng.skip(1u); return true; }             // :266; the velocity slot stays unread
     const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());                        // :279
     R movement;
     if (VERIFY) {

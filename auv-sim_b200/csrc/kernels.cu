@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(128) k_steer_arc(const R *parents, int64_t n, 
         rng.key = 0; rng.ext = u + uoff[i]; rng.n_ext = uoff[i + 1] - uoff[i];
         const R *p = parents + 5 * i;
         EdgeOut<R> o;
-        eval_edge<R, G, false, false, true>(g, sc, env, rng, 0u, sp, p[0], p[1], p[2], p[3], p[4], (R)0, 0,
-                                            wp + (size_t)i * wp_cap * 6, wp_cap, o);
+        eval_edge<R, G, false, false, true, true>(g, sc, env, rng, 0u, sp, p[0], p[1], p[2], p[3], p[4], (R)0, 0,
+                                                  wp + (size_t)i * wp_cap * 6, wp_cap, o);   // FLAT: explicit streams
         if (g.gl == 0) {
             R *l = leaf + 5 * i;
             l[0] = o.x; l[1] = o.y; l[2] = o.th; l[3] = o.t; l[4] = o.len;

@@ -161,6 +161,11 @@ int orc_steer_arc(const double parent[5], orc_stream_t *rng, const orc_steer_par
                 double *w = wp + 6 * n++;
                 w[0] = x; w[1] = y; w[2] = th; w[3] = vt; w[4] = t; w[5] = len;
             }
+        } else if (!rng->ext) {
+            /* slot addressing of the counter stream: a primitive owns three positions
+             * (dist, diff, velocity_temp); the reference never draws velocity_temp here, so the slot is left
+             * unread.  An explicit (recorded) stream is flat: nothing to skip. */
+            rng->pos++;
         }
     }
     leaf[0] = x; leaf[1] = y; leaf[2] = th; leaf[3] = t; leaf[4] = len;

@@ -140,28 +140,77 @@ def stream_block(seed: int, start: int, n: int, f32u: bool = False) -> np.ndarra
 
 
 class StreamPlayer:
-    """Stands in for the `random` module inside the reference: plays u_0, u_1, ..."""
+    """Stands in for the `random` module inside the reference: plays u_0, u_1, ...
 
-    def __init__(self, seed=None, values=None, f32u=False):
+    Slot addressing of RRT.steer.  In the stream of a planning query a steer call
+    owns 1 + 3 * n_expand consecutive positions: its n_expand draw, then THREE slots per arc primitive
+    (dist, diff, velocity_temp).  The reference only draws velocity_temp when abs(dist) > abs(diff)
+    (/root/reference/path_planning/rrt_dubins.py:266,279); otherwise the primitive's third slot is left
+    unread and the reference's next draw is served from the next primitive's first slot.  The harness
+    brackets every steer call with begin_steer() / end_steer() so that the player can do that skipping;
+    the reference itself is unmodified and sees a plain flat sequence of uniforms (`served` records it).
+    Outside steer calls (parent picks) and without the bracket the player is plain flat.
+    """
+
+    def __init__(self, seed=None, values=None, f32u=False, record=False):
         self.seed = seed
         self.values = None if values is None else np.asarray(values, dtype=np.float64)
         self.f32u = f32u
         self.pos = 0
         self._block = None
         self._block_start = 0
+        self._steer = None          # inside a steer call: [draws served, dist, edge base position, n_expand]
+        self.served = [] if record else None
+
+    def begin_steer(self):
+        self._steer = {"n": 0, "dist": None, "base": self.pos, "n_expand": None}
+
+    def end_steer(self):
+        st, self._steer = self._steer, None
+        if st is not None and st["n_expand"] is not None:
+            self.pos = st["base"] + 1 + 3 * st["n_expand"]      # past the edge's slots, read or not
+
+    def uniform(self, a, b):
+        st = self._steer
+        if st is None:
+            return a + (b - a) * self.random()
+        # inside steer: draw 0 is n_expand; then per primitive slot 0 = dist, slot 1 = diff, slot 2 =
+        # velocity_temp, which the reference asks for only when abs(dist) > abs(diff)
+        if st["n_expand"] is None:
+            v = a + (b - a) * self.random()
+            st["n_expand"] = int(math.floor(v / 1))
+            st["slot"] = 0
+            return v
+        if st["slot"] == 0:
+            v = a + (b - a) * self.random()
+            st["dist"] = v
+            st["slot"] = 1
+            return v
+        if st["slot"] == 1:
+            v = a + (b - a) * self.random()
+            if abs(st["dist"]) > abs(v):
+                st["slot"] = 2
+            else:
+                self.pos += 1       # the unread velocity slot
+                st["slot"] = 0
+            return v
+        v = a + (b - a) * self.random()
+        st["slot"] = 0
+        return v
 
     def random(self) -> float:
         k = self.pos
         self.pos += 1
         if self.values is not None:
-            return float(self.values[k])
-        if self._block is None or not (self._block_start <= k < self._block_start + len(self._block)):
-            self._block_start = k
-            self._block = stream_block(self.seed, k, 4096, self.f32u)
-        return float(self._block[k - self._block_start])
-
-    def uniform(self, a, b):
-        return a + (b - a) * self.random()
+            u = float(self.values[k])
+        else:
+            if self._block is None or not (self._block_start <= k < self._block_start + len(self._block)):
+                self._block_start = k
+                self._block = stream_block(self.seed, k, 4096, self.f32u)
+            u = float(self._block[k - self._block_start])
+        if self.served is not None:
+            self.served.append(u)
+        return u
 
     def choice(self, seq):
         """random.choice on the pre-generated sequence: element int(u * len)."""
@@ -387,7 +436,13 @@ def traced_exploring(ref, rrt, initial, habitats, *, iterations, rng, bin_interv
         for i in range(len(index_of), len(rrt.mps_list)):
             index_of[id(rrt.mps_list[i])] = i
         tr["parent"].append(index_of[id(mps)])
-        new = orig_steer(mps, *a, **k)
+        if hasattr(rng, "begin_steer"):
+            rng.begin_steer()
+        try:
+            new = orig_steer(mps, *a, **k)
+        finally:
+            if hasattr(rng, "end_steer"):
+                rng.end_steer()
         tr["nwp"].append(len(new.path))
         tr["leaf"].append((new.x, new.y, new.theta, new.traj_time_stamp, new.length))
         return new
