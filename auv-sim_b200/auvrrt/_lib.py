@@ -74,7 +74,7 @@ EXPORTS = [
     "auvrrt_gym_create", "auvrrt_gym_destroy", "auvrrt_gym_grid_shape", "auvrrt_gym_reset", "auvrrt_gym_step",
     "auvrrt_gym_step_dev", "auvrrt_gym_tree", "auvrrt_gym_counts", "auvrrt_gym_counts_dev", "auvrrt_gym_path",
     "auvrrt_astar_env_create", "auvrrt_astar_env_destroy", "auvrrt_astar_batch", "auvrrt_astar_workspace_bytes",
-    "auvrrt_astar_batch_dev", "auvrrt_edges_arc_cost_dev", "auvrrt_edges_arc_cost",
+    "auvrrt_astar_batch_dev", "auvrrt_edges_arc_cost_dev", "auvrrt_edges_arc_cost", "auvrrt_env_host_blob",
 ]
 
 _lib = None
@@ -100,6 +100,9 @@ def lib():
                                     _dp, C.c_int, C.POINTER(vp)]
     L.auvrrt_env_destroy.argtypes = [vp]
     L.auvrrt_env_destroy.restype = None
+    L.auvrrt_env_host_blob.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int,
+                                       _dp, C.c_int, vp, C.c_int64]
+    L.auvrrt_env_host_blob.restype = C.c_int64
     L.auvrrt_nn.argtypes = [_dp, _dp, C.c_int64, _dp, _dp, C.c_int, C.c_int, C.c_int, _i32p]
     L.auvrrt_nn_dev.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int, vp, C.c_int64, vp, vp]
     L.auvrrt_nn_scratch_bytes.restype = C.c_int64

@@ -87,6 +87,38 @@ class Env:
             pass
 
 
+# EnvHeader of csrc/env.cuh: 38 ints then 14 doubles
+_HEADER_INTS = ["K", "E", "H", "T", "C", "NB", "NP", "NCAND", "convex", "hot_bytes", "total_bytes",
+                "off_cx", "off_cy", "off_cr", "off_creff", "off_creff2", "off_px", "off_py",
+                "off_hx", "off_hy", "off_hr", "off_hr2", "off_b0", "off_b1",
+                "off_brk", "off_piece", "off_c1", "off_cell", "off_probs", "off_xb", "nxb", "off_pfirst",
+                "off_grid", "gnx", "gny", "bins_uniform", "pad0", "pad1"]
+_HEADER_DOUBLES = ["minx", "miny", "maxx", "maxy", "gx0", "gy0", "gs", "bin_s0", "bin_w", "xb0", "xbw", "pad2", "pad3"]
+
+
+def env_host_blob(circles=(), boundary=(), habitats=(), bins=(), cells=(), probs=None, precision="f32"):
+    """The flattened world model as the kernels read it, built on the host (no device needed): returns
+    (header dict, raw bytes as a uint8 array).  Used by the CPU-only tests of the classification grid and the
+    shark-cell index."""
+    circles, boundary, habitats = _f64(circles, (-1, 3)), _f64(boundary, (-1, 2)), _f64(habitats, (-1, 3))
+    bins, cells = _f64(bins, (-1, 2)), _f64(cells, (-1, 4))
+    T, Cn = len(bins), len(cells)
+    probs = _f64(probs if probs is not None else np.zeros((T, Cn)), (T, Cn))
+    args = (_p(circles), len(circles), _p(boundary), len(boundary), _p(habitats), len(habitats), _p(bins), T, _p(cells), Cn,
+            _p(probs), _prec(precision))
+    n = int(lib().auvrrt_env_host_blob(*args, None, 0))
+    if n < 0:
+        raise ValueError(lib().auvrrt_last_error().decode())
+    raw = np.zeros(n, np.uint8)
+    lib().auvrrt_env_host_blob(*args, raw.ctypes.data_as(C.c_void_p), n)
+    ni = len(_HEADER_INTS)
+    hi = raw[:4 * ni].view(np.int32)
+    hd = raw[4 * ni:4 * ni + 8 * len(_HEADER_DOUBLES)].view(np.float64)
+    h = {k: int(v) for k, v in zip(_HEADER_INTS, hi)}
+    h.update({k: float(v) for k, v in zip(_HEADER_DOUBLES, hd)})
+    return h, raw
+
+
 def nn(tree_xy, queries_xy, precision="f64", device=0):
     """RRT.get_closest_mps for every query: index of the nearest tree node."""
     t = _f64(tree_xy, (-1, 2))

@@ -85,15 +85,23 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     h.off_creff2 = take(sr * K);
     h.off_px = take(sr * E); h.off_py = take(sr * E);
     h.off_hx = take(sr * H); h.off_hy = take(sr * H); h.off_hr = take(sr * H); h.off_hr2 = take(sr * H);
-    h.off_b0 = take(sr * T); h.off_b1 = take(sr * T);
-    h.off_brk = take(sr * NB); h.off_piece = take(4 * (size_t)(NP + 1)); h.off_c1 = take(sr * cand_c1.size());
+    // sentinels in front of / behind three arrays keep the lookups of geom.cuh free of bounds branches:
+    // b1[-1] = b0[0];  brk[-1] = -inf, brk[NB] = +inf;  pfirst[-2] = pfirst[-1] = "no candidate"
+    h.off_b0 = take(sr * T); h.off_b1 = take(sr * (T + 2)) + 2 * (int)sr;
+    h.off_brk = take(sr * (NB + 4)) + 2 * (int)sr;
+    h.off_piece = take(4 * (size_t)(NP + 1)); h.off_c1 = take(sr * cand_c1.size());
     h.off_cell = take(4 * cand_cell.size());
-    // x-bucket table over the breakpoints (find_cell): ~4 buckets per breakpoint, at most 4096
+    h.off_pfirst = take(sizeof(PFirst<R>) * (size_t)(NP + 2)) + 2 * (int)sizeof(PFirst<R>);
+    // x-bucket table over the breakpoints (find_cell): buckets of at most 0.25 m (at most 8192 of them), from one
+    // bucket left of the first breakpoint to one bucket right of the last
     h.nxb = 0; h.xb0 = 0.0; h.xbw = 1.0;
-    if (NB >= 2 && NB < 65535 && (double)brk[NB - 1] > (double)brk[0]) {
-        h.nxb = std::min(4096, std::max(16, 4 * NB));
-        h.xb0 = (double)brk[0];
-        h.xbw = ((double)brk[NB - 1] - (double)brk[0]) / h.nxb * (1.0 + 1e-12);
+    if (NB >= 2 && NB < 32760 && (double)brk[NB - 1] > (double)brk[0]) {
+        const double span = (double)brk[NB - 1] - (double)brk[0];
+        int nin = (int)ceil(span / 0.25);
+        nin = std::min(8190, std::max(16, nin));
+        h.xbw = span / nin * (1.0 + 1e-12);
+        h.xb0 = (double)brk[0] - h.xbw;
+        h.nxb = nin + 2;
     }
     h.off_xb = take(2 * (size_t)h.nxb);
     h.hot_bytes = (int)o;
@@ -111,20 +119,6 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         h.gs = gs; h.gx0 = h.bbox[0] - gs; h.gy0 = h.bbox[1] - gs;
         h.gnx = (int)ceil(wx / gs) + 2; h.gny = (int)ceil(wy / gs) + 2;
     }
-    // --- fine x table for the shark-cell lookup (env.cuh XCell): ~0.25 m buckets from two buckets left of the
-    // first breakpoint to two buckets right of the last one
-    h.nxc = 0; h.xc0 = 0.0; h.xcw = 1.0;
-    if (NB >= 2 && (double)brk[NB - 1] > (double)brk[0]) {
-        const double span = (double)brk[NB - 1] - (double)brk[0];
-        int nb_ = (int)ceil(span / 0.25);
-        if (nb_ > 4092) nb_ = 4092;
-        if (nb_ < 1) nb_ = 1;
-        h.xcw = span / nb_ * (1.0 + 1e-12);
-        h.xc0 = (double)brk[0] - 2.0 * h.xcw;
-        h.nxc = nb_ + 4;
-    }
-    h.off_xcell = take(sizeof(XCell<R>) * (size_t)h.nxc);
-    h.ext_bytes = (int)o;
     h.off_grid = take(12 * (size_t)h.gnx * h.gny);
     // --- uniform time bins?
     h.bins_uniform = 0; h.bin_s0 = 0.0; h.bin_w = 1.0;
@@ -134,7 +128,11 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
             if (!((R)bins[2 * i + 1] > (R)bins[2 * i])) ok = false;
             if (i + 1 < T && (R)bins[2 * i + 1] != (R)bins[2 * i + 2]) ok = false;
         }
-        if (ok) { h.bins_uniform = 1; h.bin_s0 = bins[0]; h.bin_w = (bins[2 * T - 1] - bins[0]) / T; }
+        // ... and equally wide (find_bin guesses the bin arithmetically and corrects by at most one)
+        const double w = (bins[2 * T - 1] - bins[0]) / T;
+        for (int i = 0; i < T && ok; i++)
+            if (fabs(bins[2 * i + 1] - (bins[0] + (i + 1) * w)) > 0.25 * w) ok = false;
+        if (ok) { h.bins_uniform = 1; h.bin_s0 = bins[0]; h.bin_w = w; }
     }
     std::vector<unsigned char> blob(o, 0);
     auto arr = [&](int off) { return (R *)(blob.data() + off); };
@@ -152,13 +150,33 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         arr(h.off_hr2)[i] = r * r;
     }
     for (int i = 0; i < T; i++) { arr(h.off_b0)[i] = (R)bins[2 * i]; arr(h.off_b1)[i] = (R)bins[2 * i + 1]; }
+    arr(h.off_b1)[-1] = T > 0 ? (R)bins[0] : (R)0;
     for (int i = 0; i < NB; i++) arr(h.off_brk)[i] = brk[i];
+    arr(h.off_brk)[NB] = (R)INFINITY;
+    arr(h.off_brk)[-1] = (R)-INFINITY;
     {
+        // entry = 1 + (index of the last breakpoint left of the bucket, -1 if none); bit 15: more than one breakpoint
+        // lies in the bucket grown by the margin -> walk.  The margin (2e-3 m fp32, 1e-6 m fp64) is far above the
+        // rounding error of the device's bucket index, so an x that the device files under bucket b has at most
+        // that one undecided breakpoint to its right.
+        const double margin = sizeof(R) == 4 ? 2e-3 : 1e-6;
         unsigned short *xb = (unsigned short *)(blob.data() + h.off_xb);
         for (int b = 0; b < h.nxb; b++) {
-            double left = h.xb0 + b * h.xbw;
-            int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)left) - brk.begin()) - 1;
-            xb[b] = (unsigned short)std::max(lo_i, 0);      // the device walks +-1 from here: any start is exact
+            const double xa = h.xb0 + b * h.xbw - margin, xe = h.xb0 + (b + 1) * h.xbw + margin;
+            int lo_i = -1, inside = 0;
+            for (int i = 0; i < NB; i++) {
+                if ((double)brk[i] < xa) lo_i = i;
+                else if ((double)brk[i] <= xe) inside++;
+            }
+            xb[b] = (unsigned short)((lo_i + 1) | (inside > 1 ? 0x8000 : 0));
+        }
+        PFirst<R> *pf = (PFirst<R> *)(blob.data() + h.off_pfirst);
+        { PFirst<R> none; none.c1 = (R)0; none.v = -1; pf[-2] = none; pf[-1] = none; }
+        for (int p = 0; p < NP; p++) {
+            PFirst<R> e; e.c1 = (R)0; e.v = -1;
+            const int k0 = piece[p], k1 = piece[p + 1];
+            if (k1 > k0) { e.c1 = cand_c1[k0]; e.v = cand_cell[k0] | (k1 - k0 > 1 ? (1 << 30) : 0); }
+            pf[p] = e;
         }
     }
     memcpy(blob.data() + h.off_piece, piece.data(), 4 * piece.size());
@@ -224,7 +242,10 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
                         }
                     if (outer_const) code |= 2u;
                     else if (efull || ne > 2) code |= AUV_GRID_POLY_FULL;
-                    else w2 = (w2 & ~(0x3FFu << 18)) | ((unsigned)ecand[0] << 18) | ((unsigned)ecand[1] << 23);
+                    else {
+                        w2 = (w2 & ~(0x3FFu << 18)) | ((unsigned)ecand[0] << 18) | ((unsigned)ecand[1] << 23);
+                        if (ne == 1) code |= AUV_GRID_POLY_ONE | ((unsigned)ecand[0] << 26);
+                    }
                 }
                 // obstacle circles (inflated radii): candidates = circles a point of the cell can hit
                 int nc = 0; unsigned cc3[3] = {0x3FF, 0x3FF, 0x3FF};
@@ -232,7 +253,10 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
                     if (hypot(mx - circles[3 * k], my - circles[3 * k + 1]) - rho <= reff[k]) { if (nc < 3) cc3[nc] = (unsigned)k; nc++; }
                 if (nc == 0) code |= 4u;
                 else if (nc > 3 || K > 1022) code |= AUV_GRID_CIRC_MANY;
-                else w1 = cc3[0] | (cc3[1] << 10) | (cc3[2] << 20);
+                else {
+                    w1 = cc3[0] | (cc3[1] << 10) | (cc3[2] << 20);
+                    if (nc == 1) code |= AUV_GRID_CIRC_ONE | (cc3[0] << 16);
+                }
                 // habitats: first match in list order
                 unsigned hc = AUV_GRID_HAB_NONE;
                 int nh = 0; unsigned hh3[3] = {0x3F, 0x3F, 0x3F};
@@ -241,68 +265,24 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
                     double d = hypot(mx - hab[3 * q], my - hab[3 * q + 1]);
                     if (d - rho <= hab[3 * q + 2]) {                       // the cell touches habitat q
                         const bool covers = d + rho < hab[3 * q + 2];
-                        if (nh == 0 && covers) { hc = (unsigned)q; break; }    // definitive
+                        if (nh == 0 && covers && q < 64) { hc = (unsigned)q; break; }    // definitive
                         hc = AUV_GRID_HAB_AMBIG;
                         if (nh < 3) hh3[nh] = (unsigned)q; else hmany = true;
                         nh++;
                         if (covers) break;                                 // later habitats can never be first
                     }
                 }
-                code |= hc << 3;
                 if (hc == AUV_GRID_HAB_AMBIG) {
                     if (hmany || H > 62) code |= AUV_GRID_HAB_MANY;
-                    else w2 = (w2 & ~0x3FFFFu) | hh3[0] | (hh3[1] << 6) | (hh3[2] << 12);
-                }
-                // shark cell: constant piece and constant first candidate over the whole grid cell?
-                unsigned cc = AUV_GRID_CELL_AMBIG;
-                if (NB == 0 || C >= 65534) { if (NB == 0) cc = AUV_GRID_CELL_NONE; }
-                else {
-                    const double xa = x0 - margin, xb_ = x0 + gs + margin, ya = y0 - margin, yb = y0 + gs + margin;
-                    if (xb_ < (double)brk[0] || xa > (double)brk[NB - 1]) cc = AUV_GRID_CELL_NONE;
                     else {
-                        int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)xa) - brk.begin()) - 1;   // last brk <= xa
-                        bool has_break = false;
-                        for (int i = std::max(lo_i, 0); i < NB && (double)brk[i] <= xb_; i++)
-                            if ((double)brk[i] >= xa) { has_break = true; break; }
-                        if (!has_break && lo_i >= 0 && lo_i + 1 < NB) {
-                            const int p = 2 * lo_i + 1;
-                            bool amb = false; int first = -1;
-                            for (int k = piece[p]; k < piece[p + 1]; k++) {
-                                double c1v = (double)cand_c1[k];
-                                if (c1v > ya && c1v <= yb) { amb = true; break; }
-                                if (c1v <= ya) { first = cand_cell[k]; break; }
-                            }
-                            if (!amb) cc = first >= 0 ? (unsigned)first : AUV_GRID_CELL_NONE;
-                        }
+                        w2 = (w2 & ~0x3FFFFu) | hh3[0] | (hh3[1] << 6) | (hh3[2] << 12);
+                        if (nh == 1) hc = AUV_GRID_HAB_ONE + hh3[0];      // only this habitat can hold a point of the cell
                     }
                 }
-                code |= cc << 16;
+                code |= hc << 3;
                 const size_t ncell = (size_t)h.gnx * h.gny, ci = (size_t)iy * h.gnx + ix;      // three planes
                 grid[ci] = code; grid[ncell + ci] = w1; grid[2 * ncell + ci] = w2;
             }
-    }
-    // --- fine x table: a bucket is decided when no breakpoint lies within `margin` of it (the rounding of the
-    // device's bucket index is orders of magnitude below the margin)
-    {
-        const double margin = sizeof(R) == 4 ? 2e-3 : 1e-6;
-        XCell<R> *xc = (XCell<R> *)(blob.data() + h.off_xcell);
-        for (int b = 0; b < h.nxc; b++) {
-            const double xa = h.xc0 + b * h.xcw - margin, xb_ = h.xc0 + (b + 1) * h.xcw + margin;
-            XCell<R> e; e.c1 = (R)0; e.v = -2;
-            if (xb_ < (double)brk[0] || xa > (double)brk[NB - 1]) e.v = -1;
-            else {
-                const int lo_i = (int)(std::upper_bound(brk.begin(), brk.end(), (R)xa) - brk.begin()) - 1;   // last brk <= xa
-                bool has_break = false;
-                for (int i = std::max(lo_i, 0); i < NB && (double)brk[i] <= xb_; i++)
-                    if ((double)brk[i] >= xa) { has_break = true; break; }
-                if (!has_break && lo_i >= 0 && lo_i + 1 < NB) {
-                    const int p = 2 * lo_i + 1, k0 = piece[p], k1 = piece[p + 1];
-                    if (k0 >= k1) e.v = -1;
-                    else if (cand_cell[k0] < (1 << 30)) { e.c1 = cand_c1[k0]; e.v = cand_cell[k0] | (k1 - k0 > 1 ? (1 << 30) : 0); }
-                }
-            }
-            xc[b] = e;
-        }
     }
     memcpy(blob.data(), &h, sizeof(h));
     *hout = h;
@@ -420,6 +400,22 @@ extern "C" int auvrrt_env_create(const double *circles, int K, const double *pol
     }
     *out = e;
     return AUVRRT_OK;
+}
+// The world-model blob as the kernels see it (EnvHeader + tables, env.cuh), built on the host only: what the
+// CPU-only tests validate the classification grid and the cell index against the exact predicates with.
+extern "C" int64_t auvrrt_env_host_blob(const double *circles, int K, const double *poly, int E, const double *habitats,
+                                        int H, const double *bins, int T, const double *cells, int C, const double *probs,
+                                        int precision, unsigned char *out, int64_t cap) {
+    if (K < 0 || E < 0 || H < 0 || T < 0 || C < 0 || H > 64 || (precision != AUVRRT_F32 && precision != AUVRRT_F64)) {
+        set_err(AUVRRT_ERR_ARG, "env_host_blob: bad argument");
+        return -1;
+    }
+    EnvHeader h;
+    std::vector<unsigned char> b = precision == AUVRRT_F32
+        ? build_blob<float>(circles, K, poly, E, habitats, H, bins, T, cells, C, probs, &h)
+        : build_blob<double>(circles, K, poly, E, habitats, H, bins, T, cells, C, probs, &h);
+    if (out && cap >= (int64_t)b.size()) memcpy(out, b.data(), b.size());
+    return (int64_t)b.size();
 }
 extern "C" void auvrrt_env_destroy(auvrrt_env_t *e) {
     if (!e) return;

@@ -33,9 +33,11 @@ namespace auv {
 #define AUV_TPE_BUCKETS 64
 #define AUV_TPE_MAXPAIRS 256      // all-pairs circle table in shared memory: up to 512 circles (6 KB)
 
-template <typename R, bool COST, bool ALLPAIRS>
+// STAGE: 1 = the hot part of the world model is in shared memory, 2 = the probability table too (always staged:
+// the launcher falls back to the warp-per-edge kernel when even the hot part does not fit)
+template <typename R, bool COST, bool ALLPAIRS, int STAGE>
 __global__ void __launch_bounds__(AUV_TPE_THREADS, sizeof(R) == 4 ? AUV_TPE_MINB : 1)
-k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *__restrict__ parents,
+k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const R *__restrict__ parents,
                 const uint64_t *__restrict__ seeds, long long n, SteerParams<R> sp, R w3, uint8_t *__restrict__ safe,
                 int32_t *__restrict__ counts, R *__restrict__ leaf, R *__restrict__ cost_out) {
     typedef typename Policy<R>::A A;
@@ -46,12 +48,12 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, int s
     __shared__ int s_next;
     __shared__ CircPair s_pairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_TPE_MAXPAIRS : 1];
     EnvView<R> env;
-    if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
-    else {
+    {
         uint64_t *bar = (uint64_t *)smem;
-        stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
-        env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
+        stage_env_tma(smem + 16, blob, STAGE == 2 ? total_bytes : hot_bytes, bar);
+        env.bind(smem + 16, STAGE == 2 ? smem + 16 : blob);
         env.bind_grid(blob, smem + 16);
+        env.assume_hot_shared(STAGE == 2);
     }
     CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
     if constexpr (ALLPAIRS && sizeof(R) == 4) {
@@ -133,10 +135,12 @@ static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t 
     // fp32: hot part + probability table in shared memory when they fit next to 3 resident CTAs' worth
     int budget = sizeof(R) == 4 ? 56 * 1024 : 100 * 1024;
     if (const char *ev = getenv("AUVRRT_TPE_STAGE_KB")) budget = atoi(ev) * 1024;
-    int sm = 16, mode = 0;
-    if (COST && b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
-    else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
-    auto kern = k_edges_arc_tpe<R, COST, ALLPAIRS>;
+    int sm = 16;
+    const bool probs_too = COST && b.total_bytes + 16 <= budget;
+    if (probs_too) sm = b.total_bytes + 16;
+    else if (b.hot_bytes + 16 <= 200 * 1024) sm = b.hot_bytes + 16;
+    else return AUVRRT_ERR_UNSUPPORTED;          // the caller falls back to the warp-per-edge kernel
+    auto kern = probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1>;
     AUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0, nsm = 0, dev = 0;
     AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AUV_TPE_THREADS, sm));
@@ -146,7 +150,7 @@ static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t 
     const int64_t batch = (int64_t)AUV_TPE_THREADS * AUV_TPE_EPT;
     int64_t blocks = (n + batch - 1) / batch;
     if (blocks > (int64_t)nsm * per_sm) blocks = (int64_t)nsm * per_sm;
-    kern<<<(unsigned)blocks, AUV_TPE_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, parents, seeds, (long long)n,
+    kern<<<(unsigned)blocks, AUV_TPE_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, parents, seeds, (long long)n,
                                                         make_steer_params<R>(params), (R)w3, safe, counts, leaf, cost_out);
     g_launches++;
     cudaError_t e = cudaGetLastError();

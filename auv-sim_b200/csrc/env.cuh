@@ -18,6 +18,9 @@
 //    which the set of x-admissible cells is constant; within a piece, a cell can only be the
 //    first match if its c1 is strictly below the c1 of every earlier admissible cell, so each
 //    piece keeps that strictly decreasing candidate list.  First candidate with c1 <= y wins.
+//    Lookup (find_cell): an x-bucket table (buckets no wider than 0.25 m) gives the last breakpoint left of the
+//    bucket; a bucket holds at most one breakpoint (else it is flagged and the breakpoints are walked), so one
+//    compare settles the piece; brk[NB] = +inf is a sentinel.  pfirst[piece] is the piece's first candidate.
 #pragma once
 #include "common.cuh"
 
@@ -34,19 +37,18 @@ struct EnvHeader {
     int off_b0, off_b1;
     int off_brk, off_piece, off_c1, off_cell;
     int off_probs;
-    int off_xb;        // x-bucket table for the shark-cell pieces (u16 per bucket), staged
+    int off_xb;        // x-bucket table for the shark-cell pieces (u16 per bucket, see find_cell), staged
     int nxb;           // number of x buckets (0: none)
+    int off_pfirst;    // first candidate of every piece (PFirst<R> per piece), staged
     int off_grid;      // classification grid (3 planes of u32, one word per cell each), not staged: read through L1/L2
     int gnx, gny;      // grid dimensions (0: no grid)
     int bins_uniform;  // 1: bins are [s0 + i w, s0 + (i+1) w], contiguous and in order
-    int off_xcell;     // fine x table for the shark-cell lookup (XCell<R> per bucket), bytes [total_bytes, ext_bytes)
-    int nxc;           // buckets in it (0: none)
-    int ext_bytes;     // a kernel with shared memory to spare stages [0, ext_bytes)
+    int pad_[2];
     double bbox[4];    // minx, miny, maxx, maxy of the polygon (Polygon.bounds, rrt_dubins.py:334)
     double gx0, gy0, gs;   // grid origin and cell size
     double bin_s0, bin_w;
     double xb0, xbw;       // x-bucket origin and width
-    double xc0, xcw;       // fine x table origin and bucket width
+    double pad2_[2];
 };
 static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignment of the arrays");
 
@@ -57,41 +59,43 @@ static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignmen
 // per-cell candidate list.  A code is only definitive when every point of the cell (plus a rounding
 // margin) gets the same answer from the exact test; candidate lists hold every object that can
 // decide a point of the cell.  Results are therefore identical to the exact tests by construction.
-//  word 0  bits 0-1  polygon: 0 ambiguous, 1 strictly inside, 2 outside
-//          bit  2    1: clear of every (inflated) obstacle circle
-//          bits 3-10 habitat: 0..63 first-match habitat, 254 none, 255 ambiguous
-//          bit  11   circles: more than 3 candidates -> full loop
-//          bit  12   habitats: more than 3 candidates -> full loop
-//          bit  13   polygon: convex fast path not applicable / more than 2 candidate edges -> full test
-//          bits 16-31 shark cell: first-match cell id, 0xFFFF none, 0xFFFE ambiguous
+//  word 0  bits 0-1   polygon: 0 ambiguous, 1 strictly inside, 2 outside
+//          bit  2     1: clear of every (inflated) obstacle circle
+//          bits 3-10  habitat: 0..63 first-match habitat (definitive); 64 + h: habitat h is the only one a point of
+//                     the cell can be in and must be tested; 254 none; 255 ambiguous (candidates in word 2)
+//          bit  11    circles: more than 3 candidates -> full loop
+//          bit  12    habitats: more than 3 candidates -> full loop
+//          bit  13    polygon: convex fast path not applicable / more than 2 candidate edges -> full test
+//          bit  14    circles: exactly ONE candidate, its index in bits 16-25
+//          bit  15    polygon ambiguous with exactly ONE candidate edge (convex ring), its index in bits 26-30
 //  word 1  three 10-bit circle indices (0x3FF = none): the only circles a point of the cell can hit
 //  word 2  bits 0-17 three 6-bit habitat indices (0x3F = none), in list order; bits 18-27 two 5-bit
 //          polygon edge indices (0x1F = none): the only edges whose half-plane is not already decided
+// The single-candidate forms keep the common boundary cells (one circle, one habitat or one polygon edge
+// nearby) on a short branch-free path: in a kernel that runs one edge per thread a rare slow path taken by one
+// lane stalls the other 31.
 #define AUV_GRID_HAB_NONE 254u
 #define AUV_GRID_HAB_AMBIG 255u
-#define AUV_GRID_CELL_NONE 0xFFFFu
-#define AUV_GRID_CELL_AMBIG 0xFFFEu
+#define AUV_GRID_HAB_ONE 64u
 #define AUV_GRID_CIRC_MANY (1u << 11)
 #define AUV_GRID_HAB_MANY (1u << 12)
 #define AUV_GRID_POLY_FULL (1u << 13)
-#define AUV_GRID_ALL_AMBIG ((AUV_GRID_CELL_AMBIG << 16) | (AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_CIRC_MANY | AUV_GRID_HAB_MANY | AUV_GRID_POLY_FULL)
+#define AUV_GRID_CIRC_ONE (1u << 14)
+#define AUV_GRID_POLY_ONE (1u << 15)
+#define AUV_GRID_ALL_AMBIG ((AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_CIRC_MANY | AUV_GRID_HAB_MANY | AUV_GRID_POLY_FULL)
 
 struct Cls { unsigned code; int idx; };   // word 0 and the cell index (-1 outside the grid)
 
-// Fine x table for the shark-cell lookup (cost.py:181-184, see the cell index above).  Bucket b covers
-// [xc0 + b w, xc0 + (b+1) w]; when no breakpoint lies within a margin of it, every x of the bucket is in the
-// same open piece and the entry holds that piece's FIRST candidate:
-//   v >= 0 : cell id (bits 0-29) of the first candidate, c1 its lower y bound; bit 30: more candidates follow
-//   v == -1: the piece has no candidate (no cell contains this x)
-//   v == -2: a breakpoint is near: walk the breakpoints (find_cell)
-template <typename R> struct alignas(8) XCell { R c1; int v; };
+// First candidate of a piece of the cell index (see the top of this file): v >= 0: cell id (bits 0-29), c1 its lower
+// y bound, bit 30: more candidates follow in the piece's list; v == -1: the piece has no candidate.
+template <typename R> struct alignas(8) PFirst { R c1; int v; };
 
 template <typename R> struct EnvView {
     int K, E, H, T, C, NB, NP, convex;
-    int gnx, gny, ncell, bins_uniform, nxb, nxc;
-    R gx0, gy0, ginv, gxo, gyo, bin_s0, bin_w, bin_winv, xb0, xbinv, xcinv, xco;
+    int gnx, gny, ncell, bins_uniform, nxb;
+    R gx0, gy0, ginv, gxo, gyo, bin_s0, bin_w, bin_winv, bin_off, bin_lo, bin_hi, xb0, xbinv, xbo;
     const unsigned *grid;
-    const XCell<R> *xcell;
+    const PFirst<R> *pfirst;
     const unsigned short *xb;
     R minx, miny, maxx, maxy;
     const R *cx, *cy, *cr, *creff, *creff2;
@@ -118,24 +122,32 @@ template <typename R> struct EnvView {
         brk = (const R *)(hot + h->off_brk); piece = (const int *)(hot + h->off_piece);
         c1 = (const R *)(hot + h->off_c1); cell = (const int *)(hot + h->off_cell);
         probs = (const R *)(probs_base + h->off_probs);
+        pfirst = (const PFirst<R> *)(hot + h->off_pfirst);
+        bin_lo = T > 0 ? b0[0] : (R)1; bin_hi = T > 0 ? b1[T - 1] : (R)0;      // [first b0, last b1]; empty when T == 0
+    }
+    // Tell the compiler that the staged arrays live in shared memory (the pointers are computed from offsets read
+    // at run time, so address-space inference cannot see it): loads become LDS with 32-bit addresses instead of
+    // generic loads with 64-bit address arithmetic.  Only for kernels that ALWAYS stage the hot part.
+    __device__ __forceinline__ void assume_hot_shared(bool probs_too) const {
+        __builtin_assume(__isShared(cx)); __builtin_assume(__isShared(cy)); __builtin_assume(__isShared(cr));
+        __builtin_assume(__isShared(creff)); __builtin_assume(__isShared(creff2));
+        __builtin_assume(__isShared(px)); __builtin_assume(__isShared(py));
+        __builtin_assume(__isShared(hx)); __builtin_assume(__isShared(hy)); __builtin_assume(__isShared(hr));
+        __builtin_assume(__isShared(hr2)); __builtin_assume(__isShared(b0)); __builtin_assume(__isShared(b1));
+        __builtin_assume(__isShared(brk)); __builtin_assume(__isShared(piece)); __builtin_assume(__isShared(c1));
+        __builtin_assume(__isShared(cell)); __builtin_assume(__isShared(pfirst)); __builtin_assume(__isShared(xb));
+        if (probs_too) __builtin_assume(__isShared(probs));
     }
     // the grid stays in global memory: bind it from the blob in HBM
     __device__ __forceinline__ void bind_grid(const unsigned char *blob_global, const unsigned char *hot) {
         const EnvHeader *h = (const EnvHeader *)hot;
         gnx = h->gnx; gny = h->gny; bins_uniform = h->bins_uniform; nxb = h->nxb;
-        xb0 = (R)h->xb0; xbinv = (R)(1.0 / h->xbw); xb = (const unsigned short *)(hot + h->off_xb);
+        xb0 = (R)h->xb0; xbinv = (R)(1.0 / h->xbw); xbo = (R)(-h->xb0 / h->xbw); xb = (const unsigned short *)(hot + h->off_xb);
         gx0 = (R)h->gx0; gy0 = (R)h->gy0; ginv = (R)(1.0 / h->gs);
         gxo = (R)(-h->gx0 / h->gs); gyo = (R)(-h->gy0 / h->gs);
-        bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w);
+        bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w); bin_off = (R)(-h->bin_s0 / h->bin_w);
         grid = (const unsigned *)(blob_global + h->off_grid);
         ncell = gnx * gny;
-        nxc = h->nxc; xcinv = (R)(1.0 / h->xcw); xco = (R)(-h->xc0 / h->xcw);
-        xcell = (const XCell<R> *)(blob_global + h->off_xcell);
-    }
-    // the fine x table staged in shared memory too (the kernel copied [0, ext_bytes))
-    __device__ __forceinline__ void bind_xcell_staged(const unsigned char *hot) {
-        const EnvHeader *h = (const EnvHeader *)hot;
-        xcell = (const XCell<R> *)(hot + h->off_xcell);
     }
     // classification of the cell containing (x, y); off the grid: outside the polygon, everything else ambiguous
     __device__ __forceinline__ Cls classify(R x, R y) const {

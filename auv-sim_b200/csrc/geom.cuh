@@ -106,6 +106,13 @@ template <typename R, bool OUTLINE = true> __device__ __forceinline__ bool point
     if (Policy<R>::VERIFY) return point_within<R>(env, px, py);
     if (cl.code & AUV_GRID_POLY_FULL)
         return OUTLINE ? point_within_outlined<R>(env.px, env.py, env.E, env.convex, px, py) : point_within<R>(env, px, py);
+    if (cl.code & AUV_GRID_POLY_ONE) {
+        // one undecided edge (every other half-plane is constant over the cell, on the inner side)
+        const int i = (int)((cl.code >> 26) & 0x1Fu), j = i + 1 == env.E ? 0 : i + 1;
+        const R ax = env.px[i], ay = env.py[i], bx = env.px[j], by = env.py[j];
+        const R det = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+        return env.convex > 0 ? det > (R)0 : det < (R)0;
+    }
     const unsigned w2 = env.word2(cl);
     bool in = true;
 #pragma unroll
@@ -147,6 +154,11 @@ __device__ __noinline__ bool point_hits_circles_outlined(const R *cx, const R *c
 template <typename R, bool OUTLINE = true> __device__ __forceinline__ bool point_hits_circles_c(const EnvView<R> &env, const Cls &cl, R x, R y) {
     typedef typename Policy<R>::A A;
     if (cl.code & 4u) return false;
+    if (cl.code & AUV_GRID_CIRC_ONE) {
+        const int k = (int)((cl.code >> 16) & 0x3FFu);
+        const R q = A::sq2(A::sub(x, env.cx[k]), A::sub(y, env.cy[k]));
+        return Policy<R>::VERIFY ? (A::sqrt(q) <= env.creff[k]) : (q <= env.creff2[k]);
+    }
     if (cl.code & AUV_GRID_CIRC_MANY) {
         if (Policy<R>::VERIFY || !OUTLINE) return point_hits_circles<R>(env, x, y);
         return point_hits_circles_outlined<R>(env.cx, env.cy, env.creff2, env.K, x, y);
@@ -173,44 +185,43 @@ struct Contrib {
     int hab;      // first habitat containing the point, -1: none
 };
 
+// the rare cases of find_cell: a bucket with several breakpoints, or a point below the first candidate of a piece
+// that has more
+template <typename R>
+__device__ __noinline__ int find_cell_walk(const R *brk, const int *piece, const R *c1, const int *cell, int NB, int lo, R x, R y) {
+    if (!(x >= brk[0]) || !(x <= brk[NB - 1])) return -1;
+    lo = lo < 0 ? 0 : lo;
+    while (lo > 0 && brk[lo] > x) lo--;
+    while (lo + 1 < NB && brk[lo + 1] <= x) lo++;
+    const int p = 2 * lo + (x == brk[lo] ? 0 : 1);
+    for (int k = piece[p]; k < piece[p + 1]; k++)
+        if (c1[k] <= y) return cell[k];
+    return -1;
+}
+
+// first cell (dict order) with x >= c0 and x <= c2 and y >= c1 and x <= c3 (sic), -1 if none     cost.py:181-184
+// Straight-line code but for two rare cases (a bucket with several breakpoints; a point below the first candidate
+// of a piece that has more): sentinels brk[-1] = -inf, brk[NB] = +inf, pfirst[-2] = pfirst[-1] = none (api.cu).
 template <typename R>
 __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
-    if (env.NB == 0) return -1;
-    if (env.nxc > 0) {
-        // fine x table: most buckets hold no breakpoint, so the piece and its first candidate are known
-        int b;
-        if (sizeof(R) == 4) b = __float_as_int(__fadd_rd(fmaf((float)x, (float)env.xcinv, (float)env.xco), 8388608.f)) - 0x4B000000;
-        else { const R fb = x * env.xcinv + env.xco; b = fb >= (R)0 ? (fb < (R)env.nxc ? (int)fb : env.nxc - 1) : 0; }
-        b = min(max(b, 0), env.nxc - 1);      // the first and last buckets lie outside every cell
-        const XCell<R> e = env.xcell[b];
-        if (e.v >= 0) {
-            if (y >= e.c1) return e.v & 0x3FFFFFFF;
-            if (!(e.v >> 30)) return -1;
-        } else if (e.v == -1) return -1;
-    }
-    if (!(x >= env.brk[0]) || !(x <= env.brk[env.NB - 1])) return -1;
-    int lo;                                   // largest i with brk[i] <= x
-    if (env.nxb > 0) {
-        // x-bucket table: index of the last breakpoint <= the bucket's left edge (0 if none), then a
-        // short walk; exact because the walk ends on the same comparison the binary search would
-        int b = (int)((x - env.xb0) * env.xbinv);
-        b = b < 0 ? 0 : (b >= env.nxb ? env.nxb - 1 : b);
-        lo = (int)env.xb[b];
-        while (lo > 0 && env.brk[lo] > x) lo--;
-        while (lo + 1 < env.NB && env.brk[lo + 1] <= x) lo++;
-    } else {
-        lo = 0;
-        int hi = env.NB - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (env.brk[mid] <= x) lo = mid; else hi = mid - 1;
-        }
-    }
-    int p = 2 * lo + (x == env.brk[lo] ? 0 : 1);
-    int bb = env.piece[p], ee = env.piece[p + 1];
-    for (int k = bb; k < ee; k++)
-        if (env.c1[k] <= y) return env.cell[k];
-    return -1;
+    if (env.nxb == 0) return env.NB == 0 ? -1 : find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, 0, x, y);
+    int b;
+    if (sizeof(R) == 4) b = __float_as_int(__fadd_rd(fmaf((float)x, (float)env.xbinv, (float)env.xbo), 8388608.f)) - 0x4B000000;
+    else { const R fb = (x - env.xb0) * env.xbinv; b = fb >= (R)0 ? (fb < (R)env.nxb ? (int)fb : env.nxb - 1) : 0; }
+    b = min(max(b, 0), env.nxb - 1);             // the first and last buckets lie outside every cell
+    const int e = (int)env.xb[b];
+    int lo = (e & 0x7FFF) - 1;                   // last breakpoint left of the bucket (-1: none)
+    if (__builtin_expect(e & 0x8000, 0)) return find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, lo, x, y);
+    // at most one breakpoint in the bucket: one compare settles the piece
+    const R nxt = env.brk[lo + 1];
+    R cur = env.brk[lo];
+    if (nxt <= x) { lo++; cur = nxt; }
+    const int p = 2 * lo + (x == cur ? 0 : 1);   // the point piece {brk[lo]} or the open interval after it; lo == -1: none
+    const PFirst<R> f = env.pfirst[p];
+    const bool hit = f.v >= 0 && y >= f.c1;
+    if (__builtin_expect(!hit && f.v >= (1 << 30), 0))
+        return find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, lo, x, y);
+    return hit ? (f.v & 0x3FFFFFFF) : -1;
 }
 
 // first shark-grid time bin (dict order) with b0 <= t <= b1, -1 if none          cost.py:173-177
@@ -219,11 +230,16 @@ __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin
     if (env.bins_uniform && bin_mask == 0xffffffffu) {
         // contiguous sorted bins: the containing bins are adjacent; guess (off by at most one), settle
         // on the FIRST containing bin, verify with the reference's own comparisons
-        int k = (int)((t - env.bin_s0) * env.bin_winv);
-        k = k < 0 ? 0 : (k > env.T - 1 ? env.T - 1 : k);
-        if (k > 0 && t <= env.b1[k - 1]) k--;
-        else if (k < env.T - 1 && t > env.b1[k]) k++;
-        return (t >= env.b0[k] && t <= env.b1[k]) ? k : -1;
+        // contiguous bins (b0[i+1] == b1[i]): the first containing bin is the first i with b1[i] >= t, if
+        // b0[0] <= t <= b1[T-1].  The arithmetic guess is off by at most one either way.
+        // (b1[-1] = b0[0] is a sentinel; beyond the last bin the range test below rejects)
+        int k;
+        if (sizeof(R) == 4) k = __float_as_int(__fadd_rd(fmaf((float)t, (float)env.bin_winv, (float)env.bin_off), 8388608.f)) - 0x4B000000;
+        else k = (int)((t - env.bin_s0) * env.bin_winv);
+        k = min(max(k, 0), env.T - 1);
+        const R up = env.b1[k], dn = env.b1[k - 1];
+        k += (t > up ? 1 : 0) - ((k > 0 && t <= dn) ? 1 : 0);   // t <= b1[k-1]: an earlier bin holds it; t > b1[k]: a later one
+        return (t >= env.bin_lo && t <= env.bin_hi) ? k : -1;
     }
     for (int b = 0; b < env.T; b++) {
         if (b < 32 && !((bin_mask >> b) & 1u)) continue;
@@ -241,11 +257,20 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
     c.bin = find_bin<R>(env, t, bin_mask);
     if (c.bin < 0) return c;
     const unsigned code = cl.code;
-    const unsigned cc = code >> 16;
-    if (cc == AUV_GRID_CELL_AMBIG) c.cell = find_cell(env, x, y);
-    else if (cc != AUV_GRID_CELL_NONE) c.cell = (int)cc;
+    c.cell = find_cell(env, x, y);
     const unsigned hc = (code >> 3) & 0xFFu;
-    if (hc == AUV_GRID_HAB_AMBIG && !(code & AUV_GRID_HAB_MANY)) {
+    if (hc < 128u) {
+        // definitive first match (hc < 64), or the one habitat a point of this cell can be in (64 + h)
+        const int h = (int)(hc & 63u);
+        if (h < n_hab) {
+            bool in = true;
+            if (hc >= AUV_GRID_HAB_ONE) {
+                R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
+                in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
+            }
+            if (in) c.hab = h;
+        }
+    } else if (hc == AUV_GRID_HAB_AMBIG && !(code & AUV_GRID_HAB_MANY)) {
         // the cell's candidate habitats, in list order (every habitat that touches the cell, up to
         // and including the first that covers it)
         const unsigned w2 = env.word2(cl);
@@ -264,8 +289,6 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
             bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
             if (in) { c.hab = h; break; }
         }
-    } else if (hc != AUV_GRID_HAB_NONE && (int)hc < n_hab) {
-        c.hab = (int)hc;
     }
     return c;
 }

@@ -581,9 +581,11 @@ int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *se
     // above (lower latency for a handful of edges); AUVRRT_EDGES_BRUTE=1 the all-pairs variant of the
     // thread-per-edge kernel (every waypoint against every circle / polygon edge / habitat: the roofline run).
     const char *variant = getenv("AUVRRT_EDGES_VARIANT"), *brute = getenv("AUVRRT_EDGES_BRUTE");
-    if (!(variant && variant[0] == 'w'))
-        return launch_edges_arc_tpe<R>(env, parents, seeds, n, params, safe, counts, leaf, s, w3, cost_out,
-                                       brute && brute[0] == '1');
+    if (!(variant && variant[0] == 'w')) {
+        int rc = launch_edges_arc_tpe<R>(env, parents, seeds, n, params, safe, counts, leaf, s, w3, cost_out,
+                                         brute && brute[0] == '1');
+        if (rc != AUVRRT_ERR_UNSUPPORTED) return rc;      // world model too large for shared memory: warp per edge
+    }
     return cost_out ? launch_edges_arc_t<R, true>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s)
                     : launch_edges_arc_t<R, false>(env, parents, seeds, n, params, w3, safe, counts, leaf, cost_out, s);
 }

@@ -65,6 +65,14 @@ int auvrrt_env_create(const double *circles, int K, const double *poly, int E,
                       const double *cells, int C, const double *probs, int device,
                       auvrrt_env_t **out);
 void auvrrt_env_destroy(auvrrt_env_t *env);
+/* The flattened world model exactly as the kernels read it (header + tables, csrc/env.cuh), built on the
+ * host without touching a device: returns its size in bytes (-1 on a bad argument) and copies it to `out`
+ * if cap is large enough.  For the CPU-only tests that check the classification grid and the shark-cell
+ * index against the reference's exact predicates (rrt_dubins.py:530-549, cost.py:173-191). */
+int64_t auvrrt_env_host_blob(const double *circles, int K, const double *poly, int E,
+                             const double *habitats, int H, const double *bins, int T,
+                             const double *cells, int C, const double *probs, int precision,
+                             unsigned char *out, int64_t cap);
 
 /* ---- RRT.get_closest_mps (rrt_dubins.py:505-513) ---------------------------------------------
  * nq queries against one tree of n nodes (SoA x[], y[]); strict <, lowest index wins ties;

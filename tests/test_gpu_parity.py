@@ -468,6 +468,19 @@ def test_plan_full_size_properties(api, env, oworld):
     assert rb["records"]["status"][0] == 1 and rb["records"]["n_nodes"][0] == 1
 
 
+def _flat_steer_draws(u, dist_to_end, diff_max, freq):
+    """the flat sequence RRT.steer reads from a slot-addressed stream block: position 0 is the
+    n_expand draw, primitive k owns positions 1 + 3k .. 3 + 3k and leaves the third unread unless abs(dist) > abs(diff)"""
+    n = int(np.floor(freq * u[0]))
+    flat = [u[0]]
+    for k in range(n):
+        d, f = u[1 + 3 * k], u[2 + 3 * k]
+        flat += [d, f]
+        if abs(0.0 + dist_to_end * d) > abs(-diff_max + (diff_max - -diff_max) * f):
+            flat.append(u[3 + 3 * k])
+    return np.array(flat)
+
+
 def test_edges_arc_cost_vs_oracle(api, env, oworld, edge_variant):
     """config 4 "cost on": the fused steer + collide + cost edge kernel; per-edge cost terms against
     cost.habitat_shark_cost_func restated by the oracle on the oracle's own waypoints"""
@@ -485,7 +498,7 @@ def test_edges_arc_cost_vs_oracle(api, env, oworld, edge_variant):
     nh = oworld.c.H
     n_pos = 0
     for i in range(n):
-        u = H.stream_block(int(seeds[i]), 0, 96)
+        u = _flat_steer_draws(H.stream_block(int(seeds[i]), 0, 96), 2.0, 0.5, 30.0)
         st, lf, wp, used = orc.steer_arc(parents[i], u, 2.0, 0.5, 30.0, 0.5, 2.0)
         assert st == 0 and len(wp) + 1 == counts[i]
         want = orc.cost(wp[:, [0, 1, 4]], 1.0, oworld, [float(nh), 1.0, w3]) if len(wp) else np.zeros(4)
