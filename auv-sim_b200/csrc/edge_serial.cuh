@@ -101,6 +101,13 @@ __device__ __forceinline__ bool point_unsafe(const EnvView<R> &env, const CircTa
     return !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
 }
 
+// the same out of line through the shared copy of the view (every cell that is not "inside and clear")
+template <typename R>
+__device__ __noinline__ bool point_unsafe_shared(const EnvView<R> *senv, unsigned code, int idx, R x, R y) {
+    Cls cl; cl.code = code; cl.idx = idx;
+    return !point_within_c<R>(*senv, cl, x, y) || point_hits_circles_c<R>(*senv, cl, x, y);
+}
+
 // what one thread carries along an edge
 template <typename R> struct ArcEdge {
     R x, y, th, t, len;
@@ -109,11 +116,14 @@ template <typename R> struct ArcEdge {
     bool bad, moved, degenerate, last_is_wp;
     R s2; uint32_t cnt; unsigned long long mask;     // cost sums over the APPENDED waypoints
     R self_s2; int self_hab;                         // contribution of the provisional leaf state
+    BinCursor<R> bins;                               // shark-grid time bin of the current traj_time_stamp (COST)
     int status;
 };
 
 // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
-template <typename R, bool ALLPAIRS>
+// FASTENV: contiguous equal time bins, the x-bucket table and a shared copy of the view are all present (the
+// launcher checked): the hot loop carries no run-time flags.
+template <typename R, bool ALLPAIRS, bool FASTENV = false>
 __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const CircTable &ct, ArcEdge<R> &e, R px, R py, R pth,
                                                R pt, R plen, R parent_self_s2, int parent_self_hab) {
     typedef typename Policy<R>::A A;
@@ -124,12 +134,15 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
     e.s2 = 0; e.cnt = 0; e.mask = 0ull; e.self_s2 = parent_self_s2; e.self_hab = parent_self_hab; e.status = 0;
     Cls pcl; pcl.code = 0; pcl.idx = -1;
     if (!ALLPAIRS) pcl = env.classify(px, py);
-    e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
+    if (FASTENV && !ALLPAIRS) e.bad = (pcl.code & 7u) != 5u && point_unsafe_shared<R>(env.shared_self, pcl.code, pcl.idx, px, py);
+    else e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
+    e.bins.k = 0; e.bins.up = 0;
+    if (FASTENV || env.bins_uniform) e.bins.start(env, pt);
 }
 
 // one arc primitive (rrt_dubins.py:264-284).  Returns false when the edge must stop (ZeroDivisionError in
 // the fp64 build; a degenerate 2^-23 draw in the fp32 build, which rejects the sample).
-template <typename R, bool COST, bool SELF, bool ALLPAIRS>
+template <typename R, bool COST, bool SELF, bool ALLPAIRS, bool FASTENV = false>
 __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircTable &ct, const SteerParams<R> &sp, R w3,
                                               SerialStream<R> &rng, ArcEdge<R> &e) {
     typedef typename Policy<R>::A A;
@@ -177,14 +190,20 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
         else {
             cl = env.classify(e.x, e.y);
             // the common cell: strictly inside the polygon (code 1) and clear of every circle (bit 2)
-            if (__builtin_expect((cl.code & 7u) != 5u, 0)) e.bad = e.bad || point_unsafe<R, false>(env, ct, cl, e.x, e.y);
+            if (__builtin_expect((cl.code & 7u) != 5u, 0))
+                e.bad = e.bad || ((FASTENV || env.shared_self) ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
+                                                               : point_unsafe<R, false>(env, ct, cl, e.x, e.y));
         }
         if (COST) {
-            const Contrib c = point_contrib<R>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl);
-            const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+            const Contrib c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl,
+                                                                     (FASTENV || env.bins_uniform) ? e.bins.at(env, e.t) : -2);
+            const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[c.bin * env.C + c.cell]) : (R)0;
             if (c.bin >= 0) {
-                e.s2 = A::add(e.s2, ps2);
-                if (c.hab >= 0) { e.cnt++; e.mask |= 1ull << c.hab; }
+                e.s2 = A::add(e.s2, ps2);          // (adds +0 when no cell matches: the sum is unchanged)
+                // c.hab is -1 when no habitat holds the point (point_contrib leaves it so when no bin does)
+                const unsigned hb = c.hab >= 0 ? 1u : 0u, sh = (unsigned)c.hab & 31u;
+                e.cnt += hb;
+                e.mask |= (unsigned long long)((c.hab & 32) ? 0u : (hb << sh)) | ((unsigned long long)((c.hab & 32) ? (hb << sh) : 0u) << 32);
             }
             if (SELF) { e.self_s2 = c.bin >= 0 ? ps2 : (R)0; e.self_hab = c.bin >= 0 ? c.hab : -1; }
         }

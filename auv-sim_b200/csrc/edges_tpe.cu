@@ -35,8 +35,8 @@ namespace auv {
 
 // STAGE: 1 = the hot part of the world model is in shared memory, 2 = the probability table too (always staged:
 // the launcher falls back to the warp-per-edge kernel when even the hot part does not fit)
-template <typename R, bool COST, bool ALLPAIRS, int STAGE>
-__global__ void __launch_bounds__(AUV_TPE_THREADS, sizeof(R) == 4 ? AUV_TPE_MINB : 1)
+template <typename R, bool COST, bool ALLPAIRS, int STAGE, bool FASTENV, int MINB>
+__global__ void __launch_bounds__(AUV_TPE_THREADS, MINB)
 k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const R *__restrict__ parents,
                 const uint64_t *__restrict__ seeds, long long n, SteerParams<R> sp, R w3, uint8_t *__restrict__ safe,
                 int32_t *__restrict__ counts, R *__restrict__ leaf, R *__restrict__ cost_out) {
@@ -55,6 +55,10 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
         env.bind_grid(blob, smem + 16);
         env.assume_hot_shared(STAGE == 2);
     }
+    __shared__ EnvView<R> s_env;                 // for the out-of-line slow paths
+    if (threadIdx.x == 0) s_env = env;
+    __syncthreads();
+    env.shared_self = &s_env;
     CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
     if constexpr (ALLPAIRS && sizeof(R) == 4) {
         if (env.K > 0 && env.K <= 2 * AUV_TPE_MAXPAIRS) {
@@ -115,9 +119,9 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
                 rng.init(stream_key(seeds[i]));
                 const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
                 ArcEdge<R> ed;
-                arc_edge_begin<R, ALLPAIRS>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1);
+                arc_edge_begin<R, ALLPAIRS, FASTENV>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1);
                 for (int k = 0; k < n_exp; k++)
-                    if (!arc_edge_step<R, COST, false, ALLPAIRS>(env, ct, sp, w3, rng, ed)) break;
+                    if (!arc_edge_step<R, COST, false, ALLPAIRS, FASTENV>(env, ct, sp, w3, rng, ed)) break;
                 safe[i] = (ed.status == 0 && !(ed.bad || ed.degenerate)) ? 1 : 0;
                 if (counts) counts[i] = ed.nwp;
                 if (leaf) { R *l = leaf + 5 * i; l[0] = ed.x; l[1] = ed.y; l[2] = ed.th; l[3] = ed.t; l[4] = ed.len; }
@@ -140,7 +144,25 @@ static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t 
     if (probs_too) sm = b.total_bytes + 16;
     else if (b.hot_bytes + 16 <= 200 * 1024) sm = b.hot_bytes + 16;
     else return AUVRRT_ERR_UNSUPPORTED;          // the caller falls back to the warp-per-edge kernel
-    auto kern = probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1>;
+    // FASTENV: equal contiguous time bins, x-bucket table and classification grid all present (any real map)
+    const EnvHeader &hd = sizeof(R) == 4 ? env->h32 : env->h64;
+    const bool fast = hd.gnx > 0 && (!COST || (hd.bins_uniform && hd.nxb > 0));
+    // resident CTAs per SM the register allocation targets: 3 (85 registers) or 4 (64 registers, 32 warps per SM)
+    int minb = sizeof(R) == 4 ? AUV_TPE_MINB : 1;
+    if (const char *ev = getenv("AUVRRT_TPE_MINB")) minb = atoi(ev);
+    void (*kern)(const unsigned char *, int, int, const R *, const uint64_t *, long long, SteerParams<R>, R, uint8_t *,
+                 int32_t *, R *, R *);
+    if constexpr (sizeof(R) == 4) {
+        if (minb >= 4)
+            kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 4> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 4>)
+                        : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 4> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 4>);
+        else
+            kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 3> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 3>)
+                        : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 3> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 3>);
+    } else {
+        kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 1> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 1>)
+                    : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 1> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 1>);
+    }
     AUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0, nsm = 0, dev = 0;
     AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AUV_TPE_THREADS, sm));

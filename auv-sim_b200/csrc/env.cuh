@@ -96,6 +96,10 @@ template <typename R> struct EnvView {
     R gx0, gy0, ginv, gxo, gyo, bin_s0, bin_w, bin_winv, bin_off, bin_lo, bin_hi, xb0, xbinv, xbo;
     const unsigned *grid;
     const PFirst<R> *pfirst;
+    // A copy of this view in shared memory, or nullptr.  Kernels that run one edge per thread publish one so that
+    // the rare slow paths (boundary cells, ambiguous habitats, buckets with several breakpoints) can live OUT OF LINE,
+    // taking just this pointer: the hot loop stays short and its registers free.
+    const EnvView<R> *shared_self;
     const unsigned short *xb;
     R minx, miny, maxx, maxy;
     const R *cx, *cy, *cr, *creff, *creff2;
@@ -111,6 +115,7 @@ template <typename R> struct EnvView {
     __device__ __forceinline__ void bind(const unsigned char *hot, const unsigned char *probs_base) {
         const EnvHeader *h = (const EnvHeader *)hot;
         K = h->K; E = h->E; H = h->H; T = h->T; C = h->C; NB = h->NB; NP = h->NP; convex = h->convex;
+        shared_self = nullptr;
         minx = (R)h->bbox[0]; miny = (R)h->bbox[1]; maxx = (R)h->bbox[2]; maxy = (R)h->bbox[3];
         cx = (const R *)(hot + h->off_cx); cy = (const R *)(hot + h->off_cy);
         cr = (const R *)(hot + h->off_cr); creff = (const R *)(hot + h->off_creff);

@@ -199,19 +199,30 @@ __device__ __noinline__ int find_cell_walk(const R *brk, const int *piece, const
     return -1;
 }
 
+template <typename R>
+__device__ __noinline__ int find_cell_walk_shared(const EnvView<R> *senv, int lo, R x, R y) {
+    return find_cell_walk<R>(senv->brk, senv->piece, senv->c1, senv->cell, senv->NB, lo, x, y);
+}
+template <typename R, bool SHARED = false>
+__device__ __forceinline__ int find_cell_rare(const EnvView<R> &env, int lo, R x, R y) {
+    if (SHARED || env.shared_self) return find_cell_walk_shared<R>(env.shared_self, lo, x, y);
+    return find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, lo, x, y);
+}
+
 // first cell (dict order) with x >= c0 and x <= c2 and y >= c1 and x <= c3 (sic), -1 if none     cost.py:181-184
 // Straight-line code but for two rare cases (a bucket with several breakpoints; a point below the first candidate
 // of a piece that has more): sentinels brk[-1] = -inf, brk[NB] = +inf, pfirst[-2] = pfirst[-1] = none (api.cu).
-template <typename R>
+// HAS_XB: the caller knows the bucket table exists (nxb > 0), checked once on the host
+template <typename R, bool HAS_XB = false>
 __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
-    if (env.nxb == 0) return env.NB == 0 ? -1 : find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, 0, x, y);
+    if (!HAS_XB && env.nxb == 0) return env.NB == 0 ? -1 : find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, 0, x, y);
     int b;
     if (sizeof(R) == 4) b = __float_as_int(__fadd_rd(fmaf((float)x, (float)env.xbinv, (float)env.xbo), 8388608.f)) - 0x4B000000;
     else { const R fb = (x - env.xb0) * env.xbinv; b = fb >= (R)0 ? (fb < (R)env.nxb ? (int)fb : env.nxb - 1) : 0; }
     b = min(max(b, 0), env.nxb - 1);             // the first and last buckets lie outside every cell
     const int e = (int)env.xb[b];
     int lo = (e & 0x7FFF) - 1;                   // last breakpoint left of the bucket (-1: none)
-    if (__builtin_expect(e & 0x8000, 0)) return find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, lo, x, y);
+    if (__builtin_expect(e & 0x8000, 0)) return find_cell_rare<R, HAS_XB>(env, lo, x, y);
     // at most one breakpoint in the bucket: one compare settles the piece
     const R nxt = env.brk[lo + 1];
     R cur = env.brk[lo];
@@ -219,8 +230,7 @@ __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
     const int p = 2 * lo + (x == cur ? 0 : 1);   // the point piece {brk[lo]} or the open interval after it; lo == -1: none
     const PFirst<R> f = env.pfirst[p];
     const bool hit = f.v >= 0 && y >= f.c1;
-    if (__builtin_expect(!hit && f.v >= (1 << 30), 0))
-        return find_cell_walk<R>(env.brk, env.piece, env.c1, env.cell, env.NB, lo, x, y);
+    if (__builtin_expect(!hit && f.v >= (1 << 30), 0)) return find_cell_rare<R, HAS_XB>(env, lo, x, y);
     return hit ? (f.v & 0x3FFFFFFF) : -1;
 }
 
@@ -248,16 +258,57 @@ __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin
     return -1;
 }
 
+// first habitat holding (x, y) in a cell whose habitat code is "ambiguous": out of line, for kernels with a shared view
 template <typename R>
+__device__ __noinline__ int first_habitat_ambiguous(const EnvView<R> *senv, unsigned code, int idx, int n_hab, R x, R y) {
+    typedef typename Policy<R>::A A;
+    if (!(code & AUV_GRID_HAB_MANY)) {
+        const unsigned w2 = __ldg(senv->grid + 2 * senv->ncell + idx);
+        for (int s = 0; s < 3; s++) {
+            const int h = (int)((w2 >> (6 * s)) & 0x3Fu);
+            if (h != 0x3F && h < n_hab) {
+                R q = A::sq2(A::sub(senv->hx[h], x), A::sub(senv->hy[h], y));
+                if (Policy<R>::VERIFY ? (A::sqrt(q) <= senv->hr[h]) : (q <= senv->hr2[h])) return h;
+            }
+        }
+        return -1;
+    }
+    for (int h = 0; h < n_hab; h++) {
+        R q = A::sq2(A::sub(senv->hx[h], x), A::sub(senv->hy[h], y));
+        if (Policy<R>::VERIFY ? (A::sqrt(q) <= senv->hr[h]) : (q <= senv->hr2[h])) return h;
+    }
+    return -1;
+}
+
+// Time bins along ONE edge: traj_time_stamp never decreases from waypoint to waypoint (rrt_dubins.py:281 adds
+// movement / velocity_temp >= 0), so for contiguous increasing bins the first containing bin can only move forward.
+// The cursor keeps k = the first bin with b1[k] >= t (T: none left) and up = b1[k]; most waypoints cost one compare.
+template <typename R> struct BinCursor {
+    int k; R up;
+    __device__ __forceinline__ void start(const EnvView<R> &env, R t) {
+        k = 0;
+        while (k < env.T && env.b1[k] < t) k++;
+        up = k < env.T ? env.b1[k] : Policy<R>::A::inf();
+    }
+    // first bin in dict order with b0 <= t <= b1 (cost.py:173-177), -1 if none; t must not decrease between calls
+    __device__ __forceinline__ int at(const EnvView<R> &env, R t) {
+        while (__builtin_expect(t > up, 0)) { k++; up = k < env.T ? env.b1[k] : Policy<R>::A::inf(); }
+        return (k < env.T && t >= env.bin_lo) ? k : -1;
+    }
+};
+
+// FASTENV (checked once on the host, edges_tpe.cu / plan_tpt.cu): the bucket table exists, the caller passes the bin
+// (known_bin) and published a shared copy of the view -- the run-time flags and the generic fallbacks drop out.
+template <typename R, bool FASTENV = false>
 __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y, R t,
-                                                 unsigned bin_mask, int n_hab, const Cls &cl) {
+                                                 unsigned bin_mask, int n_hab, const Cls &cl, int known_bin = -2) {
     typedef typename Policy<R>::A A;
     Contrib c;
     c.cell = -1; c.hab = -1;
-    c.bin = find_bin<R>(env, t, bin_mask);
+    c.bin = (FASTENV || known_bin != -2) ? known_bin : find_bin<R>(env, t, bin_mask);
     if (c.bin < 0) return c;
     const unsigned code = cl.code;
-    c.cell = find_cell(env, x, y);
+    c.cell = find_cell<R, FASTENV>(env, x, y);
     const unsigned hc = (code >> 3) & 0xFFu;
     if (hc < 128u) {
         // definitive first match (hc < 64), or the one habitat a point of this cell can be in (64 + h)
@@ -270,6 +321,8 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
             }
             if (in) c.hab = h;
         }
+    } else if (hc == AUV_GRID_HAB_AMBIG && (FASTENV || env.shared_self)) {
+        c.hab = first_habitat_ambiguous<R>(env.shared_self, code, cl.idx, n_hab, x, y);
     } else if (hc == AUV_GRID_HAB_AMBIG && !(code & AUV_GRID_HAB_MANY)) {
         // the cell's candidate habitats, in list order (every habitat that touches the cell, up to
         // and including the first that covers it)

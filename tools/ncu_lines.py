@@ -58,7 +58,8 @@ def main():
             text = src_cache[f][ln - 1].strip()[:90] if src_cache[f] else ""
         except Exception:
             pass
-        print("%5.2f%% inst %5.2f%% stall-samples  %-12s:%-4d %s" % (100.0 * v[0] / ti, 100.0 * v[1] / max(ts, 1), f, ln, text))
+        print("%5.2f%% inst %5.2f%% stall-samples %4.1f lanes  %-12s:%-4d %s" % (100.0 * v[0] / ti, 100.0 * v[1] / max(ts, 1),
+                                                                             v[2] / max(v[0], 1), f, ln, text))
 
 
 if __name__ == "__main__":
