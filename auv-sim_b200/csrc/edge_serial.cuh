@@ -13,6 +13,16 @@
 #pragma once
 #include "edge.cuh"
 
+// tuning switches of the one-edge-per-thread hot loop (measured in profiles/r02_tpe_*.txt)
+#ifndef AUV_OUTLINE_COLLIDE
+#define AUV_OUTLINE_COLLIDE 0     // boundary-cell collision tests out of line: measured SLOWER (4.1e9 vs 4.9e9 edges/s at Catalina
+                                  // scale): some lane of a warp is in a boundary cell on most steps, so the call overhead is paid often
+#endif
+#ifndef AUV_BIN_CURSOR
+#define AUV_BIN_CURSOR 0          // forward-only time-bin cursor instead of a lookup per waypoint: measured equal (5.0e9 vs 4.9e9);
+                                  // the heavy-tailed time steps make some lane advance the cursor on most steps
+#endif
+
 namespace auv {
 
 // circles for the all-pairs test of the fast build, relative to an origin o (the polygon's bounding-box
@@ -134,10 +144,10 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
     e.s2 = 0; e.cnt = 0; e.mask = 0ull; e.self_s2 = parent_self_s2; e.self_hab = parent_self_hab; e.status = 0;
     Cls pcl; pcl.code = 0; pcl.idx = -1;
     if (!ALLPAIRS) pcl = env.classify(px, py);
-    if (FASTENV && !ALLPAIRS) e.bad = (pcl.code & 7u) != 5u && point_unsafe_shared<R>(env.shared_self, pcl.code, pcl.idx, px, py);
+    if (AUV_OUTLINE_COLLIDE && FASTENV && !ALLPAIRS) e.bad = (pcl.code & 7u) != 5u && point_unsafe_shared<R>(env.shared_self, pcl.code, pcl.idx, px, py);
     else e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
     e.bins.k = 0; e.bins.up = 0;
-    if (FASTENV || env.bins_uniform) e.bins.start(env, pt);
+    if (AUV_BIN_CURSOR && (FASTENV || env.bins_uniform)) e.bins.start(env, pt);
 }
 
 // one arc primitive (rrt_dubins.py:264-284).  Returns false when the edge must stop (ZeroDivisionError in
@@ -191,12 +201,15 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
             cl = env.classify(e.x, e.y);
             // the common cell: strictly inside the polygon (code 1) and clear of every circle (bit 2)
             if (__builtin_expect((cl.code & 7u) != 5u, 0))
-                e.bad = e.bad || ((FASTENV || env.shared_self) ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
-                                                               : point_unsafe<R, false>(env, ct, cl, e.x, e.y));
+                e.bad = e.bad || ((AUV_OUTLINE_COLLIDE && (FASTENV || env.shared_self))
+                                      ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
+                                      : point_unsafe<R, false>(env, ct, cl, e.x, e.y));
         }
         if (COST) {
-            const Contrib c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl,
-                                                                     (FASTENV || env.bins_uniform) ? e.bins.at(env, e.t) : -2);
+            int kb = -2;
+            if (AUV_BIN_CURSOR) { if (FASTENV || env.bins_uniform) kb = e.bins.at(env, e.t); }
+            else if (FASTENV) kb = find_bin<R>(env, e.t, 0xffffffffu);
+            const Contrib c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
             const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[c.bin * env.C + c.cell]) : (R)0;
             if (c.bin >= 0) {
                 e.s2 = A::add(e.s2, ps2);          // (adds +0 when no cell matches: the sum is unchanged)

@@ -28,7 +28,7 @@ namespace auv {
 #define AUV_TPE_EPT 8             // edges per thread per batch: batch = 2048 edges
 #endif
 #ifndef AUV_TPE_MINB
-#define AUV_TPE_MINB 3
+#define AUV_TPE_MINB 4
 #endif
 #define AUV_TPE_BUCKETS 64
 #define AUV_TPE_MAXPAIRS 256      // all-pairs circle table in shared memory: up to 512 circles (6 KB)

@@ -258,6 +258,9 @@ __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin
     return -1;
 }
 
+#ifndef AUV_OUTLINE_HAB
+#define AUV_OUTLINE_HAB 1         // ambiguous-habitat cells out of line
+#endif
 // first habitat holding (x, y) in a cell whose habitat code is "ambiguous": out of line, for kernels with a shared view
 template <typename R>
 __device__ __noinline__ int first_habitat_ambiguous(const EnvView<R> *senv, unsigned code, int idx, int n_hab, R x, R y) {
@@ -321,7 +324,7 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
             }
             if (in) c.hab = h;
         }
-    } else if (hc == AUV_GRID_HAB_AMBIG && (FASTENV || env.shared_self)) {
+    } else if (AUV_OUTLINE_HAB && hc == AUV_GRID_HAB_AMBIG && (FASTENV || env.shared_self)) {
         c.hab = first_habitat_ambiguous<R>(env.shared_self, code, cl.idx, n_hab, x, y);
     } else if (hc == AUV_GRID_HAB_AMBIG && !(code & AUV_GRID_HAB_MANY)) {
         // the cell's candidate habitats, in list order (every habitat that touches the cell, up to
