@@ -63,7 +63,9 @@ __device__ __forceinline__ float sinc_small(float h) {
 // FLAT = true : an explicit recorded stream (e.g. a CPython Mersenne-Twister sequence) consumed back to back,
 //   2 or 3 uniforms per primitive: the per-position step goes to shared memory and log2(G) rounds of pointer
 //   doubling give each lane the offset of its primitive.
-template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP, bool FLAT = false>
+// ONE_CHUNK: the caller guarantees n_expand <= G (freq <= G, checked on the host): the chunk loop runs at most once
+//   and its loop-carried state disappears.
+template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP, bool FLAT = false, bool ONE_CHUNK = false>
 __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &sc, const EnvView<R> &env,
                                           const Stream<R> &rng, uint32_t ctr, const SteerParams<R> &sp,
                                           R px, R py, R pth, R pt, R plen, R w3, int n_hab,
@@ -312,6 +314,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             if (VERIFY) out.status = 2; else degenerate = true;
             break;
         }
+        if (ONE_CHUNK) break;
     }
     if (DO_COLLIDE && n_exp == 0 && env.K > 0 && !parent_clear && parent_many) {
         // the path is [parent] alone: test it against the circles

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include "launch.h"
 #include "dubins.cuh"
+#include "edge_serial.cuh"
 
 namespace auv {
 
@@ -348,11 +349,11 @@ template int launch_cost_point<double>(const auvrrt_env *, const double *, int64
 #define AUV_ED_THREADS 256
 #endif
 #ifndef AUV_ED_MINB
-#define AUV_ED_MINB 1
+#define AUV_ED_MINB 2
 #endif
 #define AUV_ED_TILE 512      // circles kept as float4 triples in shared memory (8 KB); more circles read the SoA arrays
-template <typename R, int WT>
-__global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(const unsigned char *blob, int hot_bytes, int total_bytes,
+template <typename R, int WT, int MB>
+__global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                       int stage_mode, const R *from, const R *to, int64_t n, R rho,
                                                       int W, uint8_t *safe, uint8_t *word, R *length) {
     typedef typename Policy<R>::A A;
@@ -403,40 +404,61 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, AUV_ED_MINB) k_edges_dubins(co
                 // The expansion cancels, so a result within `guard` of the decision is re-evaluated with
                 // the direct formula (far circles never get there: their |c|^2 dwarfs r^2).
                 const R ox = wx[0], oy = wy[0];
-                R pp[WT], ppmax = (R)0;
+                // waypoints packed in pairs for the Blackwell packed-FP32 pipe (fma.rn.f32x2 -> FFMA2): one instruction
+                // evaluates two (waypoint, circle) pairs, FMNMX3 folds both into the running minimum: 1.5 issue slots
+                // per pair instead of 3.  Two circles per iteration keep four independent chains in flight.
+                float2 wx2[WT / 2], wy2[WT / 2], pp2[WT / 2];
+                R ppmax = (R)0;
 #pragma unroll
-                for (int k = 0; k < WT; k++) {
-                    wx[k] -= ox; wy[k] -= oy;
-                    pp[k] = fmaf(wy[k], wy[k], wx[k] * wx[k]);
-                    ppmax = fmaxf(ppmax, pp[k]);
-                    wx[k] *= (R)-2; wy[k] *= (R)-2;            // exact scaling: -2 p.c = c.(-2p)
+                for (int k = 0; k < WT / 2; k++) {
+                    const R ax = wx[2 * k] - ox, ay = wy[2 * k] - oy, bx = wx[2 * k + 1] - ox, by = wy[2 * k + 1] - oy;
+                    pp2[k] = make_float2(fmaf(ay, ay, ax * ax), fmaf(by, by, bx * bx));
+                    ppmax = fmaxf(ppmax, fmaxf(pp2[k].x, pp2[k].y));
+                    wx2[k] = make_float2((R)-2 * ax, (R)-2 * bx);            // exact scaling: -2 p.c = c.(-2p)
+                    wy2[k] = make_float2((R)-2 * ay, (R)-2 * by);
                 }
                 const R g0 = (R)4e-6 * ppmax;
-                {
-                    for (int c = 0; c < env.K; c++) {
-                        // circles as (x, y, r_eff^2) in shared memory: one 16-byte load each (staged once per block below)
-                        const float4 ci = use_tile ? circ4[c]
-                                                   : make_float4((float)env.cx[c], (float)env.cy[c], (float)env.creff2[c], 0.f);
-                        const R cxr = ci.x - ox, cyr = ci.y - oy;
-                        const R cc = fmaf(cyr, cyr, cxr * cxr);
-                        R qa = A::inf(), qb = A::inf(), qc = A::inf(), qd4 = A::inf();    // 4 independent min chains
+                const int K2 = env.K & ~1;
+                for (int c = 0; c < env.K; c += 2) {
+                    // circles as (x, y, r_eff^2) in shared memory: one 16-byte load each; an odd last circle is paired with itself
+                    const int c1 = c + 1 < env.K ? c + 1 : c;
+                    const float4 ca = use_tile ? circ4[c] : make_float4((float)env.cx[c], (float)env.cy[c], (float)env.creff2[c], 0.f);
+                    const float4 cb = use_tile ? circ4[c1] : make_float4((float)env.cx[c1], (float)env.cy[c1], (float)env.creff2[c1], 0.f);
+                    const R axr = ca.x - ox, ayr = ca.y - oy, bxr = cb.x - ox, byr = cb.y - oy;
+                    const float2 ax2 = make_float2(axr, axr), ay2 = make_float2(ayr, ayr), bx2 = make_float2(bxr, bxr), by2 = make_float2(byr, byr);
+                    R qa0 = A::inf(), qa1 = A::inf(), qb0 = A::inf(), qb1 = A::inf();
 #pragma unroll
-                        for (int k = 0; k < WT; k += 4) {
-                            qa = fminf(qa, fmaf(cyr, wy[k], fmaf(cxr, wx[k], pp[k])));
-                            if (k + 1 < WT) qb = fminf(qb, fmaf(cyr, wy[k + 1], fmaf(cxr, wx[k + 1], pp[k + 1])));
-                            if (k + 2 < WT) qc = fminf(qc, fmaf(cyr, wy[k + 2], fmaf(cxr, wx[k + 2], pp[k + 2])));
-                            if (k + 3 < WT) qd4 = fminf(qd4, fmaf(cyr, wy[k + 3], fmaf(cxr, wx[k + 3], pp[k + 3])));
+                    for (int k = 0; k < WT / 2; k += 2) {
+                        const float2 a0 = ffma2(ay2, wy2[k], ffma2(ax2, wx2[k], pp2[k]));
+                        const float2 b0 = ffma2(by2, wy2[k], ffma2(bx2, wx2[k], pp2[k]));
+                        qa0 = fminf(qa0, fminf(a0.x, a0.y));
+                        qb0 = fminf(qb0, fminf(b0.x, b0.y));
+                        if (k + 1 < WT / 2) {
+                            const float2 a1 = ffma2(ay2, wy2[k + 1], ffma2(ax2, wx2[k + 1], pp2[k + 1]));
+                            const float2 b1 = ffma2(by2, wy2[k + 1], ffma2(bx2, wx2[k + 1], pp2[k + 1]));
+                            qa1 = fminf(qa1, fminf(a1.x, a1.y));
+                            qb1 = fminf(qb1, fminf(b1.x, b1.y));
                         }
-                        const R q = fminf(fminf(qa, qb), fminf(qc, qd4));
-                        const R t = (q + cc) - ci.z;                 // d^2 - r_eff^2
-                        const R guard = fmaf((R)4e-6, cc, g0);
-                        if (t <= guard) {
-                            if (t < -guard) hit = true;
-                            else {                                   // too close to call: direct formula
+                    }
+                    (void)K2;
+                    // d^2 - r_eff^2 for both circles; the expansion cancels, so a result within `guard` of the decision is
+                    // re-evaluated with the direct formula (far circles never get there: their |c|^2 dwarfs r^2)
+                    const R cca = fmaf(ayr, ayr, axr * axr), ccb = fmaf(byr, byr, bxr * bxr);
+                    const R ta = (fminf(qa0, qa1) + cca) - ca.z, tb = (fminf(qb0, qb1) + ccb) - cb.z;
+                    const R ga = fmaf((R)4e-6, cca, g0), gb = fmaf((R)4e-6, ccb, g0);
+                    if (ta <= ga || tb <= gb) {
+                        if (ta < -ga || tb < -gb) hit = true;
+                        else {
+#pragma unroll 1
+                            for (int s = 0; s < 2; s++) {                 // too close to call: direct formula
+                                const R cxr = s ? bxr : axr, cyr = s ? byr : ayr, r2 = s ? cb.z : ca.z;
                                 R qd = A::inf();
 #pragma unroll
-                                for (int k = 0; k < WT; k++) qd = fminf(qd, A::sq2((R)-0.5 * wx[k] - cxr, (R)-0.5 * wy[k] - cyr));
-                                hit = hit || (qd <= ci.z);
+                                for (int k = 0; k < WT / 2; k++) {
+                                    qd = fminf(qd, A::sq2((R)-0.5 * wx2[k].x - cxr, (R)-0.5 * wy2[k].x - cyr));
+                                    qd = fminf(qd, A::sq2((R)-0.5 * wx2[k].y - cxr, (R)-0.5 * wy2[k].y - cyr));
+                                }
+                                hit = hit || (qd <= r2);
                             }
                         }
                     }
@@ -506,16 +528,22 @@ int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64
     int smem, mode = env_stage_mode(b.hot_bytes, b.hot_bytes, 64 * 1024, &smem);
     mode = mode ? 1 : 0;
     int64_t blocks = (n + AUV_ED_THREADS - 1) / AUV_ED_THREADS;
-    if (blocks > AUV_SMS * 16 * (256 / AUV_ED_THREADS)) blocks = AUV_SMS * 16 * (256 / AUV_ED_THREADS);
-#define AUV_ED(WT)                                                                                                 \
+    if (blocks > AUV_SMS * 12 * (256 / AUV_ED_THREADS)) blocks = AUV_SMS * 12 * (256 / AUV_ED_THREADS);   // a multiple of 1, 2 and 3 CTAs per SM
+    // resident CTAs per SM the register allocation targets (fp32): 2 -> 118 registers, 3 -> 80 registers (48 B spilled)
+    int mb = AUV_ED_MINB;
+    if (const char *ev = getenv("AUVRRT_ED_MINB")) mb = atoi(ev);
+    if (sizeof(R) == 8) mb = 1;
+#define AUV_ED_L(WT, MB)                                                                                           \
     {                                                                                                              \
-        AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins<R, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-        k_edges_dubins<R, WT><<<(unsigned)blocks, AUV_ED_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, from,  \
+        AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins<R, WT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        k_edges_dubins<R, WT, MB><<<(unsigned)blocks, AUV_ED_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, from,  \
                                                                    to, n, (R)rho, W, safe, word, length);          \
     }
+#define AUV_ED(WT) { if (mb >= 3) AUV_ED_L(WT, 3) else if (mb == 2) AUV_ED_L(WT, 2) else AUV_ED_L(WT, 1) }
     if (W <= 8) AUV_ED(8) else if (W <= 12) AUV_ED(12) else if (W <= 16) AUV_ED(16) else if (W <= 20) AUV_ED(20)
     else if (W <= 24) AUV_ED(24) else AUV_ED(32)
 #undef AUV_ED
+#undef AUV_ED_L
     AUV_LAUNCH_CHECK();
     return AUVRRT_OK;
 }

@@ -80,7 +80,8 @@ template <typename R> struct Tree {
 template <typename R> struct BestPlan { R c0, c1, c2, len, t; int node, iter; };
 // MODE >= 0 compiles the kernel for that parent-pick mode alone (the other modes' code -- about 1000 instructions that
 // the compiler otherwise places inside the hot loop -- disappears); MODE < 0 reads P.mode at run time.
-template <typename R, int G, bool BS, int MODE>
+// ONE: freq <= G, every edge is a single chunk of primitives (eval_edge ONE_CHUNK)
+template <typename R, int G, bool BS, int MODE, bool ONE>
 __global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : (AUV_PLAN_MINB + 1) / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
@@ -219,8 +220,8 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             const R ppx = pr.x, ppy = pr.y, ppth = pr.th, ppt = pr.t, pplen = pr.len;
             const uint32_t ctr0 = ctr;
             EdgeOut<R> o;
-            eval_edge<R, G, true, true, false>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
-                                               nullptr, 0, o);
+            eval_edge<R, G, true, true, false, false, ONE>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
+                                                           nullptr, 0, o);
             ctr = o.ctr;
             n_waypoints += o.nwp; n_prims += o.n_exp;
             if (P.trace && g.gl == 0) {
@@ -419,7 +420,7 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <typename R, int G, bool BS, int MODE> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
+template <typename R, int G, bool BS, int MODE, bool ONE> static int plan_geometry(const auvrrt_env *env, int *grid, int *smem, int *stage_mode) {
     EnvBlob<R> b = env_blob<R>(env);
     // only the small hot part of the world model is staged in shared memory when it is tight: with 4
     // CTAs per SM the probability table (39 KB for Catalina) is better served by the larger L1
@@ -428,9 +429,9 @@ template <typename R, int G, bool BS, int MODE> static int plan_geometry(const a
     int sm = 16, mode = 0;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
-    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS, MODE, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE>, PLAN_THREADS, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE, ONE>, PLAN_THREADS, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan: kernel does not fit on an SM (smem %d)", sm);
     int nsm = 0, dev = 0;
     AUV_CUDA(cudaGetDevice(&dev));
@@ -439,7 +440,7 @@ template <typename R, int G, bool BS, int MODE> static int plan_geometry(const a
     return AUVRRT_OK;
 }
 
-template <typename R, int G, bool BS, int MODE>
+template <typename R, int G, bool BS, int MODE, bool ONE>
 static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t *seeds, int64_t Q,
                          const auvrrt_plan_params_t *p, void *workspace, int64_t workspace_bytes,
                          auvrrt_plan_record_t *records, uint32_t *chain, R *path, const auvrrt_plan_trace_t *trace,
@@ -448,7 +449,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     int rc = make_planp<R>(env, p, &P);
     if (rc) return rc;
     int grid, smem, mode;
-    rc = plan_geometry<R, G, BS, MODE>(env, &grid, &smem, &mode);
+    rc = plan_geometry<R, G, BS, MODE, ONE>(env, &grid, &smem, &mode);
     if (rc) return rc;
     WsLayout L = make_layout<R>(P.cap, P.nb, P.nchunks);
     const int gpc = PLAN_THREADS / G;
@@ -463,7 +464,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     auvrrt_plan_trace_t tr;
     if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
     EnvBlob<R> b = env_blob<R>(env);
-    k_plan<R, G, BS, MODE><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+    k_plan<R, G, BS, MODE, ONE><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
                                                   (unsigned char *)workspace + 256, (unsigned long long *)workspace,
                                                   records, chain, path, tr);
     AUV_LAUNCH_CHECK2();
@@ -480,10 +481,12 @@ static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t 
     // the fast build's default mode (time-bin pick) gets its own compilation of the kernel
 #define AUV_PLAN_ARGS env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes
     if constexpr (sizeof(R) == 4) {
-        if (p->mode == 0 && !getenv("AUVRRT_PLAN_GENERIC"))
-            return bs ? launch_plan_gb<R, G, true, 0>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, 0>(AUV_PLAN_ARGS);
+        if (p->mode == 0 && !getenv("AUVRRT_PLAN_GENERIC")) {
+            if (p->freq <= (double)G && bs) return launch_plan_gb<R, G, true, 0, true>(AUV_PLAN_ARGS);   // the common shape
+            return bs ? launch_plan_gb<R, G, true, 0, false>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, 0, false>(AUV_PLAN_ARGS);
+        }
     }
-    return bs ? launch_plan_gb<R, G, true, -1>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, -1>(AUV_PLAN_ARGS);
+    return bs ? launch_plan_gb<R, G, true, -1, false>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, -1, false>(AUV_PLAN_ARGS);
 #undef AUV_PLAN_ARGS
 }
 

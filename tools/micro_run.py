@@ -29,9 +29,17 @@ if what == "edges":
                       (torch.rand(n, device=dev, generator=g) * 2 - 1) * np.pi], 1).contiguous()
     safe = torch.zeros(n, dtype=torch.uint8, device=dev); word = torch.zeros(n, dtype=torch.uint8, device=dev)
     length = torch.zeros(n, device=dev)
+    ts = []
     for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         adev.edges_dubins_dev(env4, q0, q1, 1.0, 20, safe, word, length, "f32")
-    torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    import os
+    flop = 6 * 20 * K + 6 * 20 * 5 + 140 + 24 * 20
+    print("edges-dubins n", n, "edges/s %.4g" % (n / min(ts)), "algorithmic TFLOP/s %.2f" % (n * flop / min(ts) / 1e12), "safe", float(safe.float().mean()),
+          {k: os.environ[k] for k in os.environ if k.startswith("AUVRRT_")})
 elif what.startswith("catalina"):
     # python tools/micro_run.py catalina[-allpairs|-nocost] n : the thread-per-edge arc kernel at Catalina scale
     import os
