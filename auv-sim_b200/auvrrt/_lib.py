@@ -25,7 +25,9 @@ class PlanParams(C.Structure):
                 ("v", C.c_double), ("max_traj_time", C.c_double), ("dist_to_end", C.c_double),
                 ("diff_max", C.c_double), ("freq", C.c_double), ("min_dist", C.c_double),
                 ("weights", C.c_double * 3), ("chain_cap", C.c_int32), ("path_cap", C.c_int32),
-                ("trace", C.c_int32), ("group", C.c_int32), ("max_plan_time", C.c_double)]
+                ("trace", C.c_int32), ("group", C.c_int32), ("max_plan_time", C.c_double),
+                ("dubins_rho", C.c_double), ("dubins_eta", C.c_double), ("near_radius", C.c_double),
+                ("dubins_w", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PlanRecord(C.Structure):

@@ -254,11 +254,14 @@ def edges_arc_cost(env: Env, parents, seeds, params, w3, precision="f32"):
 
 def plan_params(iterations, mode=0, bin_interval=5.0, v=2.0, max_traj_time=500.0, dist_to_end=2.0,
                 diff_max=0.5, freq=30.0, min_dist=0.5, weights=(-3.0, -3.0, -4.0), chain_cap=96,
-                path_cap=0, trace=False, group=0, max_plan_time=5.0):
+                path_cap=0, trace=False, group=0, max_plan_time=5.0, dubins_rho=1.0, dubins_eta=20.0,
+                near_radius=15.0, dubins_w=12):
+    """mode 3 (Dubins-RRT with best-parent selection) reads dubins_rho / dubins_eta / near_radius / dubins_w"""
     return PlanParams(int(iterations), int(mode), float(bin_interval), float(v), float(max_traj_time),
                       float(dist_to_end), float(diff_max), float(freq), float(min_dist),
                       (C.c_double * 3)(*[float(x) for x in weights]), int(chain_cap), int(path_cap),
-                      int(bool(trace)), int(group), float(max_plan_time))
+                      int(bool(trace)), int(group), float(max_plan_time), float(dubins_rho), float(dubins_eta),
+                      float(near_radius), int(dubins_w), 0)
 
 
 RECORD_DTYPE = np.dtype([("status", "i4"), ("n_nodes", "i4"), ("best_node", "i4"), ("best_iter", "i4"),

@@ -355,15 +355,18 @@ template int launch_cost_point<double>(const auvrrt_env *, const double *, int64
 template <typename R, int WT, int MB>
 __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                       int stage_mode, const R *from, const R *to, int64_t n, R rho,
-                                                      int W, uint8_t *safe, uint8_t *word, R *length) {
+                                                      int W, uint8_t *safe, uint8_t *word, R *length, int wp_off) {
     typedef typename Policy<R>::A A;
     const bool VERIFY = Policy<R>::VERIFY;
     extern __shared__ __align__(16) unsigned char smem[];
     EnvView<R> env = load_env<R>(smem, blob, hot_bytes, total_bytes, stage_mode);
+    // fast build: the W waypoints of this thread's edge pass through shared memory, so that a ROLLED loop can compute
+    // them (the unrolled sampler + polygon test was 10 k instructions of straight-line code streamed from L2 for every
+    // edge: 15 % of the stall cycles were instruction fetch) and an unrolled one loads them into packed registers
+    float2 *s_wp = (float2 *)(smem + wp_off) + threadIdx.x;
     __shared__ float4 circ4[AUV_ED_TILE];
-    const bool use_tile = !VERIFY && env.K <= AUV_ED_TILE;
-    if (use_tile) {
-        for (int j = threadIdx.x; j < env.K; j += blockDim.x)
+    if (!VERIFY) {
+        for (int j = threadIdx.x; j < env.K && j < AUV_ED_TILE; j += blockDim.x)
             circ4[j] = make_float4((float)env.cx[j], (float)env.cy[j], (float)env.creff2[j], 0.f);
         __syncthreads();
     }
@@ -372,22 +375,22 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsig
         const R *a = from + 3 * i, *b = to + 3 * i;
         DubinsPath<R> d = dubins_shortest<R>(a[0], a[1], a[2], b[0], b[1], b[2], rho);
         bool ok = d.word >= 0;
-        R wx[WT], wy[WT];
         if (ok) {
             DubinsSampler<R> smp;
             smp.init(d, a[0], a[1], a[2], rho);
             R step = A::div(d.length, (R)(W - 1));
-#pragma unroll
-            for (int k = 0; k < WT; k++) {
-                R th;
-                if (k < W - 1) smp.at(A::mul((R)k, step), wx[k], wy[k], th);
-                else { wx[k] = b[0]; wy[k] = b[1]; }       // k == W-1 is `to`; k >= W duplicates it
-            }
-            bool in = true;             // polygon first: the fast circle loop below re-centres wx / wy in place
-#pragma unroll
-            for (int k = 0; k < WT; k++) in = in && point_within<R>(env, wx[k], wy[k]);
+            bool in = true;
             bool hit = false;
             if (VERIFY) {
+                R wx[WT], wy[WT];
+#pragma unroll
+                for (int k = 0; k < WT; k++) {
+                    R th;
+                    if (k < W - 1) smp.at(A::mul((R)k, step), wx[k], wy[k], th);
+                    else { wx[k] = b[0]; wy[k] = b[1]; }       // k == W-1 is `to`; k >= W duplicates it
+                }
+#pragma unroll
+                for (int k = 0; k < WT; k++) in = in && point_within<R>(env, wx[k], wy[k]);
                 for (int c = 0; c < env.K; c++) {
                     R ccx = env.cx[c], ccy = env.cy[c];
                     R q = A::inf();
@@ -403,7 +406,15 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsig
                 // waypoint: 2 FFMA + 1 FMNMX per (waypoint, circle) instead of 2 FADD + FMUL + FFMA + FMNMX.
                 // The expansion cancels, so a result within `guard` of the decision is re-evaluated with
                 // the direct formula (far circles never get there: their |c|^2 dwarfs r^2).
-                const R ox = wx[0], oy = wy[0];
+#pragma unroll 1
+                for (int k = 0; k < WT; k++) {
+                    R x, y, th;
+                    if (k < W - 1) smp.at(A::mul((R)k, step), x, y, th);
+                    else { x = b[0]; y = b[1]; }               // k == W-1 is `to`; k >= W duplicates it
+                    in = in && point_within<R>(env, x, y);
+                    s_wp[k * AUV_ED_THREADS] = make_float2((float)x, (float)y);
+                }
+                const R ox = s_wp[0].x, oy = s_wp[0].y;
                 // waypoints packed in pairs for the Blackwell packed-FP32 pipe (fma.rn.f32x2 -> FFMA2): one instruction
                 // evaluates two (waypoint, circle) pairs, FMNMX3 folds both into the running minimum: 1.5 issue slots
                 // per pair instead of 3.  Two circles per iteration keep four independent chains in flight.
@@ -411,19 +422,19 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsig
                 R ppmax = (R)0;
 #pragma unroll
                 for (int k = 0; k < WT / 2; k++) {
-                    const R ax = wx[2 * k] - ox, ay = wy[2 * k] - oy, bx = wx[2 * k + 1] - ox, by = wy[2 * k + 1] - oy;
+                    const float2 wa = s_wp[(2 * k) * AUV_ED_THREADS], wb = s_wp[(2 * k + 1) * AUV_ED_THREADS];
+                    const R ax = wa.x - ox, ay = wa.y - oy, bx = wb.x - ox, by = wb.y - oy;
                     pp2[k] = make_float2(fmaf(ay, ay, ax * ax), fmaf(by, by, bx * bx));
                     ppmax = fmaxf(ppmax, fmaxf(pp2[k].x, pp2[k].y));
                     wx2[k] = make_float2((R)-2 * ax, (R)-2 * bx);            // exact scaling: -2 p.c = c.(-2p)
                     wy2[k] = make_float2((R)-2 * ay, (R)-2 * by);
                 }
                 const R g0 = (R)4e-6 * ppmax;
-                const int K2 = env.K & ~1;
-                for (int c = 0; c < env.K; c += 2) {
+                const int KT = env.K < AUV_ED_TILE ? env.K : AUV_ED_TILE;       // circles in the shared-memory tile
+                for (int c = 0; c < KT; c += 2) {
                     // circles as (x, y, r_eff^2) in shared memory: one 16-byte load each; an odd last circle is paired with itself
-                    const int c1 = c + 1 < env.K ? c + 1 : c;
-                    const float4 ca = use_tile ? circ4[c] : make_float4((float)env.cx[c], (float)env.cy[c], (float)env.creff2[c], 0.f);
-                    const float4 cb = use_tile ? circ4[c1] : make_float4((float)env.cx[c1], (float)env.cy[c1], (float)env.creff2[c1], 0.f);
+                    const int c1 = c + 1 < KT ? c + 1 : c;
+                    const float4 ca = circ4[c], cb = circ4[c1];
                     const R axr = ca.x - ox, ayr = ca.y - oy, bxr = cb.x - ox, byr = cb.y - oy;
                     const float2 ax2 = make_float2(axr, axr), ay2 = make_float2(ayr, ayr), bx2 = make_float2(bxr, bxr), by2 = make_float2(byr, byr);
                     R qa0 = A::inf(), qa1 = A::inf(), qb0 = A::inf(), qb1 = A::inf();
@@ -440,7 +451,6 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsig
                             qb1 = fminf(qb1, fminf(b1.x, b1.y));
                         }
                     }
-                    (void)K2;
                     // d^2 - r_eff^2 for both circles; the expansion cancels, so a result within `guard` of the decision is
                     // re-evaluated with the direct formula (far circles never get there: their |c|^2 dwarfs r^2)
                     const R cca = fmaf(ayr, ayr, axr * axr), ccb = fmaf(byr, byr, bxr * bxr);
@@ -462,6 +472,17 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsig
                             }
                         }
                     }
+                }
+                // circles beyond the tile (K > 512): the direct formula on the SoA arrays
+                for (int c = KT; c < env.K; c++) {
+                    const R cxr = (R)env.cx[c] - ox, cyr = (R)env.cy[c] - oy;
+                    R qd = A::inf();
+#pragma unroll
+                    for (int k = 0; k < WT / 2; k++) {
+                        qd = fminf(qd, A::sq2((R)-0.5 * wx2[k].x - cxr, (R)-0.5 * wy2[k].x - cyr));
+                        qd = fminf(qd, A::sq2((R)-0.5 * wx2[k].y - cxr, (R)-0.5 * wy2[k].y - cyr));
+                    }
+                    hit = hit || (qd <= (R)env.creff2[c]);
                 }
             }
             ok = !hit && in;
@@ -535,9 +556,10 @@ int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64
     if (sizeof(R) == 8) mb = 1;
 #define AUV_ED_L(WT, MB)                                                                                           \
     {                                                                                                              \
-        AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins<R, WT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-        k_edges_dubins<R, WT, MB><<<(unsigned)blocks, AUV_ED_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, from,  \
-                                                                   to, n, (R)rho, W, safe, word, length);          \
+        const int wp_off = (smem + 15) & ~15, smem_all = wp_off + (sizeof(R) == 4 ? WT * AUV_ED_THREADS * 8 : 0);      \
+        AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins<R, WT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_all));  \
+        k_edges_dubins<R, WT, MB><<<(unsigned)blocks, AUV_ED_THREADS, smem_all, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, from,  \
+                                                                   to, n, (R)rho, W, safe, word, length, wp_off);  \
     }
 #define AUV_ED(WT) { if (mb >= 3) AUV_ED_L(WT, 3) else if (mb == 2) AUV_ED_L(WT, 2) else AUV_ED_L(WT, 1) }
     if (W <= 8) AUV_ED(8) else if (W <= 12) AUV_ED(12) else if (W <= 16) AUV_ED(16) else if (W <= 20) AUV_ED(20)

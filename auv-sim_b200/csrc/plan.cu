@@ -20,6 +20,7 @@
 // summation order (fp64: <= 1e-12 relative).
 #include <stdlib.h>
 #include "plan_common.cuh"
+#include "dubins.cuh"
 
 namespace auv {
 
@@ -76,6 +77,67 @@ template <typename R> struct Tree {
 // BS: keep the per-bin metadata (count / head chunk / tail chunk) of the group's tree in shared
 // memory as u16 (needs <= 126 time bins and <= 65535 nodes / chunks): the rejection loop of the
 // parent pick reads count[bin] once per draw, so this takes a global round trip off every draw.
+// ---- mode 3: one candidate edge = six-word Dubins path parent -> sample, cut at eta, W waypoints ---------------------
+// (the build's own definition, parity unpinned: DESIGN.md section 11; oracle/auvrrt_oracle.c orc_exploring_dubins)
+template <typename R> struct DubinsEdge {
+    bool ok;                  // a word exists and the parent may be extended
+    bool safe;                // check_collision over the W points
+    R x, y, th, t, len;       // the new node = waypoint W-1
+    R s2; uint32_t cnt; unsigned long long mask;   // cost sums over waypoints 1..W-1
+    R self_s2; int self_hab;                       // contribution of the new node's own state
+};
+// rows != nullptr: also write waypoints 1..W-1 as (x, y, theta, v, t, len) rows (at most `room` of them)
+template <typename R>
+__device__ __forceinline__ void dubins_edge_eval(const EnvView<R> &env, const PlanP<R> &P, R px, R py, R pth, R pt, R plen,
+                                                 R sx, R sy, R sth, bool do_tests, R *rows, int room, DubinsEdge<R> &e) {
+    typedef typename Policy<R>::A A;
+    e.ok = false; e.safe = false; e.x = px; e.y = py; e.th = pth; e.t = pt; e.len = plen;
+    e.s2 = 0; e.cnt = 0; e.mask = 0ull; e.self_s2 = 0; e.self_hab = -1;
+    const DubinsPath<R> d = dubins_shortest<R>(px, py, pth, sx, sy, sth, P.rho);
+    if (d.word < 0) return;
+    e.ok = true;
+    const R s_end = d.length < P.eta ? d.length : P.eta;
+    const R step = A::div(s_end, (R)(P.W - 1));
+    DubinsSampler<R> smp;
+    smp.init(d, px, py, pth, P.rho);
+    bool bad = false;
+    if (do_tests) {                                      // path[0] is the parent node object
+        const Cls pcl = env.classify(px, py);
+        bad = !point_within_c<R>(env, pcl, px, py) || point_hits_circles_c<R>(env, pcl, px, py);
+    }
+#pragma unroll 1
+    for (int k = 1; k < P.W; k++) {
+        const R sk = A::mul((R)k, step);
+        R x, y, th;
+        smp.at(sk, x, y, th);
+        const R t = A::add(pt, A::div(sk, P.vel)), len = A::add(plen, sk);
+        if (do_tests) {
+            const Cls cl = env.classify(x, y);
+            bad = bad || !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+            const Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, cl);
+            const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
+            if (c.bin >= 0) {
+                e.s2 = A::add(e.s2, ps2);
+                if (c.hab >= 0) { e.cnt++; e.mask |= 1ull << c.hab; }
+            }
+            e.self_s2 = c.bin >= 0 ? ps2 : (R)0; e.self_hab = c.bin >= 0 ? c.hab : -1;   // the last one is the new node
+        }
+        if (rows && k - 1 < room) {
+            R *w = rows + 6 * (size_t)(k - 1);
+            w[0] = x; w[1] = y; w[2] = th; w[3] = P.vel; w[4] = t; w[5] = len;
+        }
+        e.x = x; e.y = y; e.th = th; e.t = t; e.len = len;
+    }
+    e.safe = !bad;
+}
+// the sample of the iteration whose draws start at stream position ctr (get_random_mps, rrt_dubins.py:333-343)
+template <typename R>
+__device__ __forceinline__ void dubins_sample_at(const EnvView<R> &env, const Stream<R> &rng, uint32_t ctr, R &sx, R &sy, R &sth) {
+    sx = uniform_ab<R>(env.minx, env.maxx, rng.u(ctr));
+    sy = uniform_ab<R>(env.miny, env.maxy, rng.u(ctr + 1u));
+    sth = uniform_ab<R>((R)-3.141592653589793, (R)3.141592653589793, rng.u(ctr + 2u));     // + 3: size, unused
+}
+
 #define AUV_BINS_SMEM 128
 template <typename R> struct BestPlan { R c0, c1, c2, len, t; int node, iter; };
 // MODE >= 0 compiles the kernel for that parent-pick mode alone (the other modes' code -- about 1000 instructions that
@@ -137,7 +199,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
             r0.self_hab = c.bin >= 0 ? c.hab : -1;
             T.row[0] = r0;
-            if (pick_mode == 1) { T.nx[0] = sx; T.ny[0] = sy; }
+            if (pick_mode == 1 || pick_mode == 3) { T.nx[0] = sx; T.ny[0] = sy; }
         }
         g.sync();
         if (g.gl == 0) { SET_BIN_HEAD(1, 0); SET_BIN_TAIL(1, 0); SET_BIN_COUNT(1, 1); T.pool[0] = 0; T.next[0] = -1; }
@@ -157,6 +219,129 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
 
         while (it < P.I && guard++ < guard_max) {
             int parent;
+            if (pick_mode == 3) {
+                // ================= mode 3: Dubins-RRT with best-parent selection =================
+                // lane = candidate parent: each lane evaluates ONE candidate edge (steer + collide + cost), a warp
+                // min-reduction on (path cost, node index) picks the parent
+                const uint32_t ctr0 = ctr;
+                R smx, smy, smth;
+                dubins_sample_at<R>(env, rng, ctr, smx, smy, smth);
+                ctr += 4;
+                // nearest node (get_closest_mps :505-513) and the first G nodes within near_radius, in index order
+                int *near = (int *)sc.us;
+                R bq = A::inf(), bs = A::inf();
+                int bi = 0x7fffffff, nlist = 0;
+                for (int i0 = 0; i0 < n_nodes; i0 += G) {
+                    const int i = i0 + g.gl;
+                    bool in = false;
+                    if (i < n_nodes) {
+                        const R qq = A::sq2(A::sub(smx, T.nx[i]), A::sub(smy, T.ny[i]));
+                        if (qq < bq) {
+                            if (VERIFY) { R sd = A::sqrt(qq); if (sd < bs) { bs = sd; bi = i; } }
+                            else { bs = qq; bi = i; }
+                            bq = qq;
+                        }
+                        in = VERIFY ? (A::sqrt(qq) <= P.near_r) : (qq <= P.near_r2);
+                    }
+                    const unsigned m = g.ballot(in);
+                    if (in) {
+                        const int pos = nlist + __popc(m & ((1u << g.gl) - 1u));
+                        if (pos < G) near[pos] = i;
+                    }
+                    nlist += __popc(m);
+                }
+                nlist = min(nlist, G);
+#pragma unroll
+                for (int mm = G / 2; mm > 0; mm >>= 1) {
+                    R os = g.xorv(bs, mm);
+                    int oi = g.xorv(bi, mm);
+                    if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                }
+                const int nearest = bi;
+                g.sync();
+                if (T.row[nearest].t > P.max_traj) { upos_mark = ctr; continue; }          // :138-139
+                // candidates: [nearest] + the list without it, G at most
+                int pn = nlist;                                    // position of the nearest node in the list, if any
+                for (int j = g.gl; j < nlist; j += G) if (near[j] == nearest) pn = j;
+#pragma unroll
+                for (int mm = G / 2; mm > 0; mm >>= 1) pn = min(pn, g.xorv(pn, mm));
+                const int ncand = min(G, 1 + nlist - (pn < nlist ? 1 : 0));
+                int pidx = -1;
+                if (g.gl == 0) pidx = nearest;
+                else if (g.gl < ncand) { const int j = g.gl - 1; pidx = near[j < pn ? j : j + 1]; }
+                g.sync();
+                DubinsEdge<R> de;
+                de.ok = false; de.safe = false; de.x = de.y = de.th = de.t = de.len = 0; de.s2 = 0; de.cnt = 0; de.mask = 0ull;
+                de.self_s2 = 0; de.self_hab = -1;
+                NodeRow<R> pr;
+                pr.s2 = 0; pr.self_s2 = 0; pr.cnt = 0; pr.mask = 0ull; pr.self_hab = -1; pr.t = 0;
+                if (pidx >= 0) {
+                    pr = T.row[pidx];
+                    if (!(pr.t > P.max_traj))
+                        dubins_edge_eval<R>(env, P, pr.x, pr.y, pr.th, pr.t, pr.len, smx, smy, smth, true, nullptr, 0, de);
+                }
+                n_waypoints += (unsigned)(P.W * __popc(g.ballot(de.ok)));
+                // path cost root -> new node through this parent                            cost.py:145-207
+                R pre_s2 = 0, c0 = 0, c1 = 0, c2 = 0, total = A::inf();
+                uint32_t pre_cnt = 0; unsigned long long pre_mask = 0;
+                if (de.ok && de.safe) {
+                    const int ph = pr.self_hab;
+                    pre_s2 = A::add(A::add(pr.s2, pr.self_s2), de.s2);
+                    pre_cnt = pr.cnt + (ph >= 0 ? 1u : 0u) + de.cnt;
+                    pre_mask = pr.mask | (ph >= 0 ? (1ull << ph) : 0ull) | de.mask;
+                    const uint32_t cnt = pre_cnt + (de.self_hab >= 0 ? 1u : 0u);
+                    const unsigned long long mk = pre_mask | (de.self_hab >= 0 ? (1ull << de.self_hab) : 0ull);
+                    c1 = A::mul(P.w2, (R)cnt);
+                    c2 = A::add(pre_s2, de.self_s2);
+                    if (de.t > (R)0) { c1 = A::div(c1, de.t); c2 = A::div(c2, de.t); }
+                    if (env.H != 0) c0 = A::div(A::mul(P.w1, (R)__popcll(mk)), (R)env.H);
+                    total = py_sum3p<R>(c0, c1, c2);
+                }
+                // best parent: minimum (total, node index) over the lanes
+                R bt = total; int bp = (de.ok && de.safe) ? pidx : 0x7fffffff;
+#pragma unroll
+                for (int mm = G / 2; mm > 0; mm >>= 1) {
+                    R ot = g.xorv(bt, mm);
+                    int op = g.xorv(bp, mm);
+                    if (ot < bt || (ot == bt && op < bp)) { bt = ot; bp = op; }
+                }
+                const bool any_safe = bp != 0x7fffffff;
+                const unsigned wm = g.ballot(any_safe && pidx == bp && de.ok && de.safe);
+                const int bl = wm ? __ffs(wm) - 1 : 0;            // the winning lane (lane 0 = the nearest node otherwise)
+                const R nx_ = g.bcast(de.x, bl), ny_ = g.bcast(de.y, bl), nth_ = g.bcast(de.th, bl), nt_ = g.bcast(de.t, bl),
+                        nlen_ = g.bcast(de.len, bl);
+                if (P.trace && g.gl == 0) {
+                    size_t r = (size_t)q * P.I + it;
+                    tr.parent[r] = any_safe ? bp : -1; tr.safe[r] = any_safe ? 1 : 0; tr.nwp[r] = P.W; tr.upos[r] = upos_mark;
+                    R *lf = (R *)tr.leaf + 5 * r;
+                    lf[0] = nx_; lf[1] = ny_; lf[2] = nth_; lf[3] = nt_; lf[4] = nlen_;
+                }
+                if (any_safe) {
+                    const int id = n_nodes++;
+                    if (g.gl == bl) {
+                        NodeRow<R> nr;
+                        nr.x = de.x; nr.y = de.y; nr.th = de.th; nr.t = de.t; nr.len = de.len; nr.parent = bp; nr.ctr = ctr0;
+                        nr.s2 = pre_s2; nr.cnt = pre_cnt; nr.mask = pre_mask; nr.self_s2 = de.self_s2; nr.self_hab = de.self_hab;
+                        nr.born = it;
+                        T.row[id] = nr;
+                        T.nx[id] = de.x; T.ny[id] = de.y;
+                    }
+                    if (nt_ >= P.horizon) {                                                  // :158-171
+                        n_cost_evals++;
+                        if (bt < best_total) {
+                            best_total = bt;
+                            if (g.gl == bl) {
+                                BestPlan<R> b; b.c0 = c0; b.c1 = c1; b.c2 = c2; b.len = de.len; b.t = de.t; b.node = id; b.iter = it;
+                                best_s[threadIdx.x / G] = b;
+                            }
+                        }
+                    }
+                }
+                g.sync();
+                it++;
+                upos_mark = ctr;
+                continue;
+            }
             if (pick_mode == 0) {
                 // ---- pick a random non-empty time bin, then a random node in it           :122-127
                 int ran_bin = 0, bincnt = 0;
@@ -247,7 +432,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     nr.s2 = pre_s2; nr.cnt = pre_cnt; nr.mask = pre_mask; nr.self_s2 = self_s2n; nr.self_hab = self_habn;
                     nr.born = it;
                     T.row[id] = nr;
-                    if (pick_mode == 1) { T.nx[id] = o.x; T.ny[id] = o.y; }
+                    if (pick_mode == 1 || pick_mode == 3) { T.nx[id] = o.x; T.ny[id] = o.y; }
                 }
                 // ---- time-bin insert (decision is group-uniform, lane 0 writes)            :147-151
                 if (pick_mode != 2) {                   // `if traj_time_stamp:` -- mode 2 keeps no bins
@@ -338,11 +523,23 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                     const NodeRow<R> pn = T.row[T.row[id].parent];
                     if (g.gl == 0 && n_path < P.path_cap) {
                         R *w = rows + 6 * (size_t)n_path;
-                        w[0] = pn.x; w[1] = pn.y; w[2] = pn.th; w[3] = (R)0; w[4] = pn.t; w[5] = pn.len;
+                        w[0] = pn.x; w[1] = pn.y; w[2] = pn.th; w[3] = (pick_mode == 3 && pn.parent >= 0) ? P.vel : (R)0;
+                        w[4] = pn.t; w[5] = pn.len;
                     }
                     n_path++;
-                    EdgeOut<R> o;
                     int room = P.path_cap - n_path; if (room < 0) room = 0;
+                    if (pick_mode == 3) {
+                        if (g.gl == 0) {
+                            R smx, smy, smth;
+                            dubins_sample_at<R>(env, rng, T.row[id].ctr, smx, smy, smth);
+                            DubinsEdge<R> de;
+                            dubins_edge_eval<R>(env, P, pn.x, pn.y, pn.th, pn.t, pn.len, smx, smy, smth, false,
+                                                rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0), room, de);
+                        }
+                        n_path += P.W - 1;
+                        continue;
+                    }
+                    EdgeOut<R> o;
                     eval_edge<R, G, false, false, true>(g, sc, env, rng, T.row[id].ctr, P.sp, pn.x, pn.y, pn.th,
                                                         pn.t, pn.len, (R)0, 0,
                                                         rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0), room, o);
@@ -351,7 +548,8 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
                 if (g.gl == 0 && n_path < P.path_cap) {
                     R *w = rows + 6 * (size_t)n_path;
                     const NodeRow<R> bn = T.row[best_node];
-                    w[0] = bn.x; w[1] = bn.y; w[2] = bn.th; w[3] = (R)0; w[4] = bn.t; w[5] = bn.len;
+                    w[0] = bn.x; w[1] = bn.y; w[2] = bn.th; w[3] = (pick_mode == 3 && bn.parent >= 0) ? P.vel : (R)0;
+                    w[4] = bn.t; w[5] = bn.len;
                 }
                 n_path++;
                 if (n_path > P.path_cap && status == AUVRRT_ST_OK) status = AUVRRT_ST_OVERFLOW;
@@ -397,11 +595,21 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
         for (int e = 0; e < d; e++) {
             if (g.gl == 0 && n_path < P.path_cap) {
                 R *w = rows + 6 * (size_t)n_path;
-                w[0] = x; w[1] = y; w[2] = th; w[3] = (R)0; w[4] = t; w[5] = len;
+                w[0] = x; w[1] = y; w[2] = th; w[3] = (P.mode == 3 && e > 0) ? P.vel : (R)0; w[4] = t; w[5] = len;
             }
             n_path++;
-            EdgeOut<R> o;
             int room = P.path_cap - n_path; if (room < 0) room = 0;
+            if (P.mode == 3) {                      // every lane re-creates the same Dubins edge; lane 0 writes its rows
+                R smx, smy, smth;
+                dubins_sample_at<R>(env, rng, chain[(size_t)q * P.chain_cap + e], smx, smy, smth);
+                DubinsEdge<R> de;
+                dubins_edge_eval<R>(env, P, x, y, th, t, len, smx, smy, smth, false,
+                                    g.gl == 0 ? rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0) : nullptr, room, de);
+                n_path += P.W - 1;
+                x = de.x; y = de.y; th = de.th; t = de.t; len = de.len;
+                continue;
+            }
+            EdgeOut<R> o;
             eval_edge<R, G, false, false, true>(g, sc, env, rng, chain[(size_t)q * P.chain_cap + e], P.sp, x, y, th, t,
                                                 len, (R)0, 0, rows + 6 * (size_t)(n_path < P.path_cap ? n_path : 0),
                                                 room, o);
@@ -411,7 +619,7 @@ k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds,
         if (d >= 0) {
             if (g.gl == 0 && n_path < P.path_cap) {
                 R *w = rows + 6 * (size_t)n_path;
-                w[0] = x; w[1] = y; w[2] = th; w[3] = (R)0; w[4] = t; w[5] = len;
+                w[0] = x; w[1] = y; w[2] = th; w[3] = (P.mode == 3 && d > 0) ? P.vel : (R)0; w[4] = t; w[5] = len;
             }
             n_path++;
         }
@@ -497,7 +705,8 @@ int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, i
                 cudaStream_t s) {
     // group 0 = automatic: a warp per tree shortens the latency of a few thousand queries; from
     // ~3x10^4 queries on, the queries themselves fill the machine and one thread per tree wins
-    int G = p->group ? p->group : ((Q >= 32768 && !(path && p->path_cap > 0)) ? 1 : 32);
+    int G = p->group ? p->group : ((Q >= 32768 && !(path && p->path_cap > 0) && p->mode != 3) ? 1 : 32);
+    if (G == 1 && p->mode == 3) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: mode 3 evaluates one candidate parent per lane; group must be 32, 16 or 8");
     if (G == 1) {
         if (path && p->path_cap > 0) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: group 1 (thread per tree) writes no paths; use auvrrt_materialize");
         return launch_plan_tpt<R>(env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, trace, s, nullptr);
@@ -510,7 +719,7 @@ int launch_plan(const auvrrt_env *env, const R *starts, const uint64_t *seeds, i
 template <typename R>
 int64_t plan_workspace_bytes(const auvrrt_env *env, const auvrrt_plan_params_t *p, int64_t Q) {
     int64_t need = -1;
-    int G = p->group ? p->group : (Q >= 32768 ? 1 : 32), rc;
+    int G = p->group ? p->group : ((Q >= 32768 && p->mode != 3) ? 1 : 32), rc;
     if (G == 1) rc = launch_plan_tpt<R>(env, nullptr, nullptr, Q, p, nullptr, 0, nullptr, nullptr, nullptr, 0, &need);
     else if (G == 32) rc = launch_plan_g<R, 32>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);
     else if (G == 16) rc = launch_plan_g<R, 16>(env, nullptr, nullptr, 0, p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, &need);

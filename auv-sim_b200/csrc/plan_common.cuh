@@ -9,6 +9,8 @@ template <typename R> struct PlanP {
     int I, mode, nb, chain_cap, path_cap, trace, cap, nchunks;
     R bin_interval, max_traj, horizon, w1, w2, w3;
     R ran_time_max, plan_dt;      // mode 2: max_plan_time * freq (:129) and max_plan_time / iterations
+    R rho, eta, near_r, near_r2, vel;   // mode 3: turning radius, longest edge, neighbourhood radius (and its square), speed
+    int W;                              // mode 3: waypoints per edge, the parent included
     SteerParams<R> sp;
 };
 
@@ -30,7 +32,10 @@ template <typename R> __device__ __forceinline__ R py_sum3p(R c0, R c1, R c2) {
 
 template <typename R> static inline int make_planp(const auvrrt_env *env, const auvrrt_plan_params_t *p, PlanP<R> *out) {
     if (p->iterations < 1) return set_err(AUVRRT_ERR_ARG, "plan: iterations must be >= 1");
-    if (p->mode < 0 || p->mode > 2) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0, 1 or 2");
+    if (p->mode < 0 || p->mode > 3) return set_err(AUVRRT_ERR_ARG, "plan: mode must be 0, 1, 2 or 3");
+    if (p->mode == 3 && (p->dubins_w < 2 || p->dubins_w > 32 || !(p->dubins_rho > 0) || !(p->dubins_eta > 0) || !(p->v > 0) ||
+                         !(p->near_radius >= 0)))
+        return set_err(AUVRRT_ERR_ARG, "plan: mode 3 needs dubins_w in [2, 32], dubins_rho > 0, dubins_eta > 0, v > 0, near_radius >= 0");
     if (p->mode == 2 && !(p->max_plan_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: mode 2 needs max_plan_time > 0");
     if (!(p->bin_interval > 0) || !(p->max_traj_time > 0)) return set_err(AUVRRT_ERR_ARG, "plan: bin_interval and max_traj_time must be > 0");
     if (env->H > 64) return set_err(AUVRRT_ERR_UNSUPPORTED, "plan: more than 64 habitats");
@@ -45,6 +50,8 @@ template <typename R> static inline int make_planp(const auvrrt_env *env, const 
     P.ran_time_max = (R)(p->max_plan_time * p->freq);
     P.plan_dt = (R)(p->max_plan_time / (double)p->iterations);
     P.w1 = (R)p->weights[0]; P.w2 = (R)p->weights[1]; P.w3 = (R)p->weights[2];
+    P.rho = (R)p->dubins_rho; P.eta = (R)p->dubins_eta; P.near_r = (R)p->near_radius;
+    P.near_r2 = (R)(p->near_radius * p->near_radius); P.vel = (R)p->v; P.W = p->dubins_w;
     double sp[5] = {p->dist_to_end, p->diff_max, p->freq, p->min_dist, p->v};
     P.sp = make_steer_params<R>(sp);
     *out = P;

@@ -78,19 +78,29 @@ class RRT:
     # ------------------------------------------------------------------ planners
     def exploring(self, initial, habitats, plot_interval, bin_interval, v, shark_interval, traj_time_stamp=False,
                   max_plan_time=5, max_traj_time=200.0, plan_time=True, weights=[-1, -1, -1], *,
-                  iterations=None, seed=None, replicas=1):
+                  iterations=None, seed=None, replicas=1, steer="arc", dubins_rho=1.0, dubins_eta=20.0,
+                  near_radius=15.0, dubins_w=12):
         """reference :92-176.  Returns {"path length": float, "path": [list[MPS], {(t0,t1): list[MPS]}],
-        "cost": [sum, [c0, c1, c2]]}."""
+        "cost": [sum, [c0, c1, c2]]}.
+
+        steer="dubins" (an extra of this build, NOT reference behaviour: the reference's Dubins steer is a
+        commented-out call, :238-251) grows the tree with six-word Dubins edges toward sampled states and picks, among
+        the nearest node and the nodes within near_radius, the parent with the cheapest path cost (planner mode 3)."""
         # plan_time & traj_time_stamp: time-bin pick (:122-127); plan_time only: pick by wall-clock
         # plan_time_stamp (get_closest_mps_time, :129-132) replayed on a simulated clock that spends
         # max_plan_time evenly over the steer calls; neither: nearest node to a random state (:136-139)
         mode = (0 if traj_time_stamp else 2) if plan_time else 1
+        if steer == "dubins":
+            mode = 3
+        elif steer != "arc":
+            raise ValueError("steer must be 'arc' or 'dubins'")
         iters = int(iterations) if iterations is not None else max(1, int(math.ceil(max_plan_time * REFERENCE_STEER_CALLS_PER_SECOND)))
         seed = random.getrandbits(63) if seed is None else int(seed)
         env = self._env(self.obstacle_list, habitats)
         pp = api.plan_params(iters, mode=mode, bin_interval=bin_interval, v=v, max_traj_time=max_traj_time,
                              dist_to_end=self.dist_to_end, diff_max=self.diff_max, freq=self.freq, min_dist=0.5,
-                             weights=weights, chain_cap=255, path_cap=0, max_plan_time=max_plan_time)
+                             weights=weights, chain_cap=255, path_cap=0, max_plan_time=max_plan_time,
+                             dubins_rho=dubins_rho, dubins_eta=dubins_eta, near_radius=near_radius, dubins_w=dubins_w)
         start = [initial.x, initial.y, initial.theta, initial.traj_time_stamp, initial.length]
         R = max(1, int(replicas))
         starts = np.tile(np.array(start, dtype=np.float64), (R, 1))

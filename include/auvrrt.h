@@ -169,7 +169,15 @@ typedef struct {
                                 1: plan_time False (get_random_mps + get_closest_mps, :136-139)
                                 2: plan_time & not traj_time_stamp (get_closest_mps_time, :129-132,
                                    :515-528) on a simulated clock: steer call i happens at
-                                   plan time i * max_plan_time / iterations */
+                                   plan time i * max_plan_time / iterations
+                                3: Dubins-RRT with best-parent selection -- NOT executed by the reference (its
+                                   Dubins steer is a commented-out call into the absent PyPI `dubins` module,
+                                   :238-251, under the nearest-node branch :136-141); the build's own definition,
+                                   parity unpinned: sample a state (:333-343), candidate
+                                   parents = the nearest node + the nodes within near_radius (32 at most), per
+                                   candidate a six-word Dubins path cut at dubins_eta with dubins_w waypoints,
+                                   check_collision, path cost through that parent (cost.py:145-207); the
+                                   cheapest safe candidate becomes the parent (warp min-reduction) */
     double bin_interval, v, max_traj_time;
     double dist_to_end, diff_max, freq, min_dist;   /* RRT.__init__ defaults 2, 0.5, 30; 0.5 (:141) */
     double weights[3];
@@ -179,6 +187,11 @@ typedef struct {
     int32_t group;           /* lanes cooperating on one tree: 32 (default when 0), 16 or 8; 1 = one thread
                                 per tree, the throughput planner for >= 10^5 queries (no in-kernel paths) */
     double max_plan_time;    /* the reference's wall-clock budget in seconds; only mode 2 reads it */
+    /* mode 3 only (see above): turning radius, longest edge, neighbourhood radius, waypoints per edge (2..32,
+     * the parent included) */
+    double dubins_rho, dubins_eta, near_radius;
+    int32_t dubins_w;
+    int32_t reserved;
 } auvrrt_plan_params_t;
 
 /* one fixed-size record per query: the unit the multi-GPU gather moves */

@@ -361,6 +361,9 @@ typedef struct {
     double dist_to_end, diff_max, freq, min_dist;   /* RRT.__init__ defaults 2, .5, 30; 0.5 (:141) */
     double weights[3];
     double max_plan_time;
+    /* mode 3 (Dubins-RRT with best-parent selection, see orc_exploring_dubins) */
+    double dubins_rho, dubins_eta, near_radius;
+    int dubins_w;
 } orc_plan_params_t;
 
 typedef struct {
@@ -402,8 +405,12 @@ static int final_course(const node_t *nodes, const wp_t *wps, int leaf, wp_t *ou
     return n;
 }
 
+int orc_exploring_dubins(const orc_world_t *w, const double start[5], orc_stream_t *rng,
+                         const orc_plan_params_t *p, orc_trace_t *out);
+
 int orc_exploring(const orc_world_t *w, const double start[5], orc_stream_t *rng,
                   const orc_plan_params_t *p, orc_trace_t *out) {
+    if (p->mode == 3) return orc_exploring_dubins(w, start, rng, p, out);
     const int I = p->iterations;
     const int maxp = (int)ceil(p->freq) + 2;          /* most waypoints one steer call can append */
     node_t *nodes = (node_t *)malloc(sizeof(node_t) * (size_t)(I + 1));
@@ -646,6 +653,157 @@ int orc_edge_dubins(const orc_world_t *w, const double q0[3], const double q1[3]
     for (int k = 0; k < W; k++) { pts[2 * k] = wp[3 * k]; pts[2 * k + 1] = wp[3 * k + 1]; }
     return orc_check_collision(pts, W, w);
 }
+/* ---------------------------------------------------------------- mode 3: Dubins-RRT, best parent ------ */
+/* PARITY UNPINNED.  The reference only hints at a Dubins steer (commented-out call into the absent PyPI `dubins`
+ * module, path_planning/rrt_dubins.py:238-251) driven from the nearest-node branch of the loop (:136-141); the
+ * north star asks for "the six-word Dubins steer from each tree node to each sampled AUV state ... with
+ * min-reductions for best-parent selection".  This is the build's own definition, restated
+ * here independently of csrc/plan.cu and the straightforward way: every candidate's path cost is evaluated by
+ * generate_final_course + habitat_shark_cost_func on the explicit waypoint list, not incrementally.
+ *
+ * One iteration:
+ *  1. sample = get_random_mps (:333-343): x, y uniform in the boundary's bounding box, theta in [-pi, pi], size
+ *     (4 draws, size unused).
+ *  2. candidate parents: the nearest node (get_closest_mps :505-513, strict <, lowest index) and, in index order,
+ *     the nodes within near_radius of the sample, at most 32 candidates in all.  If the nearest node's
+ *     traj_time_stamp exceeds max_traj_time the iteration is skipped (`continue`, :138-139); other candidates past
+ *     it are dropped.
+ *  3. per candidate: six-word Dubins path (turning radius dubins_rho) to the sample, cut at arclength
+ *     s_end = min(L, dubins_eta); W = dubins_w waypoints at s_k = k s_end / (W-1), k = 0..W-1 (k = 0 is the parent);
+ *     the new node is the last waypoint; traj_time_stamp advances by s / v, length by s.
+ *  4. RRT.check_collision on the W points; unsafe candidates are out.
+ *  5. cost of the path root -> new node through that parent (cost.habitat_shark_cost_func on generate_final_course,
+ *     with the planner's bin filter :161-166); the candidate with the smallest total wins, ties to the lowest node
+ *     index.  The node is appended with that parent.
+ *  6. if its traj_time_stamp >= max_traj_time - 30 it is a candidate plan (:158-171, strict <).
+ * Trace rows: parent = chosen parent (-1: no safe candidate), safe, nwp = W, leaf = the new node (through the
+ * nearest node when nothing was safe), upos = stream position before the iteration's draws. */
+int orc_exploring_dubins(const orc_world_t *w, const double start[5], orc_stream_t *rng,
+                         const orc_plan_params_t *p, orc_trace_t *out) {
+    const int I = p->iterations, W = p->dubins_w, NC = 32;
+    if (W < 2 || W > 32 || !(p->dubins_rho > 0) || !(p->dubins_eta > 0) || !(p->v > 0)) return ORC_KEY_ERROR;
+    node_t *nodes = (node_t *)malloc(sizeof(node_t) * (size_t)(I + 2));
+    wp_t *wps = (wp_t *)malloc(sizeof(wp_t) * ((size_t)I + 2) * (size_t)W);
+    wp_t *course = (wp_t *)malloc(sizeof(wp_t) * ((size_t)(I + 2) * (size_t)(W + 1) + 2));
+    double *cpts = (double *)malloc(sizeof(double) * 3 * ((size_t)(I + 2) * (size_t)(W + 1) + 2));
+    uint8_t *bin_mask = (uint8_t *)malloc((size_t)(w->T > 0 ? w->T : 1));
+    int n_nodes = 0, n_wps = 0, status = ORC_OK;
+    nodes[n_nodes++] = (node_t){{start[0], start[1], start[2], 0.0, start[3], start[4]}, -1, 0, 0, 0.0};
+    double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+    for (int i = 0; i < w->E; i++) {
+        minx = fmin(minx, w->poly[2 * i]); maxx = fmax(maxx, w->poly[2 * i]);
+        miny = fmin(miny, w->poly[2 * i + 1]); maxy = fmax(maxy, w->poly[2 * i + 1]);
+    }
+    double opt_cost[4] = {INFINITY, 0, 0, 0}, opt_len = 0.0;
+    int opt_node = -1, opt_iter = -1;
+    out->n_cost_evals = 0; out->n_waypoints_total = 0;
+    int it = 0;
+    int64_t upos0 = 0, guard = 0, guard_max = 64LL * I + 1024;
+    while (it < I && guard++ < guard_max) {
+        const double sx = uniform(rng, minx, maxx), sy = uniform(rng, miny, maxy);     /* :336-339 */
+        const double sth = uniform(rng, -M_PI, M_PI);
+        (void)uniform(rng, 0.0, 15.0);
+        int nearest = 0;                                                               /* :505-513 */
+        {
+            double dx = sx - nodes[0].s.x, dy = sy - nodes[0].s.y, md = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+            for (int i = 0; i < n_nodes; i++) {
+                dx = sx - nodes[i].s.x; dy = sy - nodes[i].s.y;
+                double d = sqrt(pow(dx, 2.0) + pow(dy, 2.0));
+                if (d < md) { md = d; nearest = i; }
+            }
+        }
+        if (nodes[nearest].s.t > p->max_traj_time) { upos0 = rng->pos; continue; }     /* :138-139 */
+        int cand[32], nc = 0;
+        cand[nc++] = nearest;
+        for (int i = 0; i < n_nodes && nc < NC; i++) {
+            if (i == nearest) continue;
+            double dx = sx - nodes[i].s.x, dy = sy - nodes[i].s.y;
+            if (sqrt(pow(dx, 2.0) + pow(dy, 2.0)) <= p->near_radius) cand[nc++] = i;
+        }
+        int best = -1; double best_c[4] = {INFINITY, 0, 0, 0}; wp_t best_wp[32]; double best_send = 0.0;
+        wp_t near_leaf = nodes[nearest].s;
+        const double q1[3] = {sx, sy, sth};
+        for (int c = 0; c < nc; c++) {
+            const int pi_ = cand[c];
+            const node_t *pn = &nodes[pi_];
+            if (pn->s.t > p->max_traj_time) continue;
+            const double q0[3] = {pn->s.x, pn->s.y, pn->s.th};
+            double prm[3], L;
+            const int word = orc_dubins_shortest(q0, q1, p->dubins_rho, prm, &L, NULL);
+            if (word < 0) continue;
+            const double s_end = L < p->dubins_eta ? L : p->dubins_eta;
+            wp_t wp[32]; double pts[64];
+            for (int k = 0; k < W; k++) {
+                const double sk = (double)k * (s_end / (double)(W - 1));
+                double q[3];
+                orc_dubins_sample(q0, p->dubins_rho, word, prm, sk, q);
+                wp[k] = (wp_t){q[0], q[1], q[2], p->v, pn->s.t + sk / p->v, pn->s.len + sk};
+                pts[2 * k] = q[0]; pts[2 * k + 1] = q[1];
+            }
+            out->n_waypoints_total += W;
+            if (pi_ == nearest) near_leaf = wp[W - 1];
+            if (!orc_check_collision(pts, W, w)) continue;
+            /* tentatively hang the node under this parent and cost the whole path */
+            nodes[n_nodes] = (node_t){wp[W - 1], pi_, W - 1, n_wps, 0.0};
+            memcpy(wps + n_wps, wp + 1, sizeof(wp_t) * (size_t)(W - 1));
+            const int n = final_course(nodes, wps, n_nodes, course);
+            const double t0 = start[3], t1 = wp[W - 1].t;
+            for (int b = 0; b < w->T; b++) {                                           /* :164-166 */
+                double b0 = w->bins[2 * b], b1 = w->bins[2 * b + 1];
+                bin_mask[b] = (uint8_t)((t0 >= b0 && t0 <= b1) || (b0 >= t0 && b1 <= t1) || (t1 >= b0 && t1 <= b1));
+            }
+            for (int k = 0; k < n; k++) { cpts[3 * k] = course[k].x; cpts[3 * k + 1] = course[k].y; cpts[3 * k + 2] = course[k].t; }
+            double cc[4];
+            orc_cost(cpts, n, t1, w, bin_mask, p->weights, cc);
+            if (cc[0] < best_c[0] || (cc[0] == best_c[0] && best >= 0 && pi_ < best)) {
+                memcpy(best_c, cc, sizeof(cc)); best = pi_; memcpy(best_wp, wp, sizeof(wp_t) * (size_t)W); best_send = s_end;
+            }
+        }
+        (void)best_send;
+        if (out->parent) out->parent[it] = best;
+        if (out->safe) out->safe[it] = (uint8_t)(best >= 0);
+        if (out->nwp) out->nwp[it] = W;
+        if (out->upos) out->upos[it] = upos0;
+        if (out->leaf) {
+            const wp_t lf = best >= 0 ? best_wp[W - 1] : near_leaf;
+            double *o = out->leaf + 5 * (size_t)it;
+            o[0] = lf.x; o[1] = lf.y; o[2] = lf.th; o[3] = lf.t; o[4] = lf.len;
+        }
+        if (best >= 0) {
+            const int id = n_nodes++;
+            nodes[id] = (node_t){best_wp[W - 1], best, W - 1, n_wps, 0.0};
+            memcpy(wps + n_wps, best_wp + 1, sizeof(wp_t) * (size_t)(W - 1));
+            n_wps += W - 1;
+            if (best_wp[W - 1].t >= p->max_traj_time - 30) {                           /* :158 */
+                if (out->cost_evals) {
+                    double *r = out->cost_evals + 6 * (size_t)out->n_cost_evals;
+                    r[0] = it; r[1] = best_c[0]; r[2] = best_c[1]; r[3] = best_c[2]; r[4] = best_c[3];
+                    r[5] = final_course(nodes, wps, id, course);
+                }
+                out->n_cost_evals++;
+                if (best_c[0] < opt_cost[0]) {                                         /* :169 */
+                    memcpy(opt_cost, best_c, sizeof(best_c)); opt_len = best_wp[W - 1].len; opt_node = id; opt_iter = it;
+                }
+            }
+        }
+        it++;
+        upos0 = rng->pos;
+        if (rng->exhausted) { status = ORC_STREAM_END; break; }
+    }
+    out->n_nodes = n_nodes; out->n_uniforms = rng->pos;
+    out->best_iter = opt_iter; out->best_node = opt_node; out->n_path = 0;
+    if (status == ORC_OK && opt_node < 0) status = ORC_NO_PATH;
+    if (opt_node >= 0) {
+        out->result[0] = opt_len; memcpy(out->result + 1, opt_cost, sizeof(opt_cost));
+        const int n = final_course(nodes, wps, opt_node, course);
+        out->n_path = n;
+        if (out->path) for (int k = 0; k < n && k < out->path_cap; k++)
+            memcpy(out->path + 6 * (size_t)k, &course[n - 1 - k], sizeof(wp_t));
+    }
+    free(nodes); free(wps); free(course); free(cpts); free(bin_mask);
+    return status;
+}
+
 typedef struct {
     const orc_world_t *w; const double *q0, *q1; double rho; int W; uint8_t *safe, *word; double *length;
 } orc_db_t;

@@ -48,7 +48,9 @@ class PlanParams(C.Structure):
     _fields_ = [("iterations", C.c_int), ("mode", C.c_int), ("bin_interval", C.c_double),
                 ("v", C.c_double), ("max_traj_time", C.c_double), ("dist_to_end", C.c_double),
                 ("diff_max", C.c_double), ("freq", C.c_double), ("min_dist", C.c_double),
-                ("weights", C.c_double * 3), ("max_plan_time", C.c_double)]
+                ("weights", C.c_double * 3), ("max_plan_time", C.c_double),
+                ("dubins_rho", C.c_double), ("dubins_eta", C.c_double), ("near_radius", C.c_double),
+                ("dubins_w", C.c_int)]
 
 
 class Trace(C.Structure):
@@ -183,9 +185,11 @@ def cost_point(x, y, world: OracleWorld, visited, tb, weights):
 
 
 def plan_params(iterations, mode=0, bin_interval=5.0, v=2.0, max_traj_time=500.0, dist_to_end=2.0,
-                diff_max=0.5, freq=30.0, min_dist=0.5, weights=(-3.0, -3.0, -4.0), max_plan_time=5.0):
+                diff_max=0.5, freq=30.0, min_dist=0.5, weights=(-3.0, -3.0, -4.0), max_plan_time=5.0,
+                dubins_rho=1.0, dubins_eta=20.0, near_radius=15.0, dubins_w=12):
     return PlanParams(int(iterations), int(mode), bin_interval, v, max_traj_time, dist_to_end,
-                      diff_max, freq, min_dist, (C.c_double * 3)(*[float(x) for x in weights]), float(max_plan_time))
+                      diff_max, freq, min_dist, (C.c_double * 3)(*[float(x) for x in weights]), float(max_plan_time),
+                      float(dubins_rho), float(dubins_eta), float(near_radius), int(dubins_w))
 
 
 def exploring(world: OracleWorld, start, params: PlanParams, seed=None, u=None, f32u=False,

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(auvrrt):
 def test_struct_layouts_match_header(auvrrt):
     import ctypes as C
     assert C.sizeof(auvrrt._lib.PlanRecord) == 96
-    assert C.sizeof(auvrrt._lib.PlanParams) == 2 * 4 + 10 * 8 + 4 * 4 + 8
+    assert C.sizeof(auvrrt._lib.PlanParams) == 2 * 4 + 10 * 8 + 4 * 4 + 8 + 3 * 8 + 2 * 4
     assert auvrrt.api.RECORD_DTYPE.itemsize == 96
 
 

