@@ -28,7 +28,11 @@ def mods():
 def test_signatures_match_reference(mods):
     import inspect
     rrt_dubins, cost, catalina, mps = mods
-    sig = lambda f: [p for p in inspect.signature(f).parameters if p not in ("iterations", "seed", "replicas")]
+    # keyword-only extras of the drop-in (iteration budget, seed, replicas, the Dubins steer of planner mode 3) do not
+    # change how the reference's callers call it
+    extras = ("iterations", "seed", "replicas", "steer", "dubins_rho", "dubins_eta", "near_radius", "dubins_w")
+    assert all(inspect.signature(rrt_dubins.RRT.exploring).parameters[k].kind is inspect.Parameter.KEYWORD_ONLY for k in extras)
+    sig = lambda f: [p for p in inspect.signature(f).parameters if p not in extras]
     R = rrt_dubins.RRT
     assert sig(R.__init__) == ["self", "boundary", "obstacles", "sharkGrid", "cell_list", "exp_rate", "dist_to_end", "diff_max", "freq"]
     assert sig(R.exploring) == ["self", "initial", "habitats", "plot_interval", "bin_interval", "v", "shark_interval",
