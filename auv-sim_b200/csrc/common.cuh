@@ -188,7 +188,9 @@ template <> __device__ __forceinline__ float uniform_ab<float>(float a, float b,
 // floor of the EXACT quotient, not of the rounded one.
 template <typename R> __device__ __forceinline__ R floordiv_pos(R t, R w) {
     typedef typename Policy<R>::A A;
-    R q = A::floor(t / w);
+    // fp32: any quotient within one of the true floor will do (the residual tests below settle it), so the fast
+    // reciprocal replaces the IEEE division
+    R q = sizeof(R) == 4 ? A::floor(A::div(t, w)) : A::floor(t / w);
     // exact residual via FMA: r = q*w - t
     if (A::fma(q, w, -t) > (R)0) q -= (R)1;            // rounded quotient overshot
     else if (A::fma(q + (R)1, w, -t) <= (R)0) q += (R)1;  // or undershot
@@ -201,7 +203,11 @@ template <int G> struct Grp {
     int lane, gl, gbase;
     unsigned gmask;
     __device__ __forceinline__ Grp() {
-        lane = threadIdx.x & 31;
+        // %laneid through a volatile asm: the compiler may not rematerialise it (it re-read SR_TID.X and masked it all
+        // over the planner's hot loop: 3 % of its instructions)
+        unsigned l;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+        lane = (int)l;
         gl = lane & (G - 1);
         gbase = lane - gl;
         gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);

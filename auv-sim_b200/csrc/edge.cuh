@@ -290,8 +290,14 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             acc_cnt += __popc(hm);
             // visited-habitat set: OR of (1 << hab) over counting lanes
             unsigned long long mbits = (counts && c.hab >= 0) ? (1ull << c.hab) : 0ull;
+            if (G == 32) {
+                // full warp: two REDUX.OR instead of ten shuffles
+                const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mbits), hi = __reduce_or_sync(0xffffffffu, (unsigned)(mbits >> 32));
+                mbits = ((unsigned long long)hi << 32) | lo;
+            } else {
 #pragma unroll
-            for (int m = G / 2; m > 0; m >>= 1) mbits |= g.xorv(mbits, m);
+                for (int m = G / 2; m > 0; m >>= 1) mbits |= g.xorv(mbits, m);
+            }
             acc_mask |= mbits;
             if (last_valid >= 0) {
                 self_s2 = g.bcast((c.bin >= 0) ? ps2 : (R)0, last_valid);

@@ -164,6 +164,8 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
             env.bind_grid(blob, smem + 16);
         }
+        // the single-chunk variant is only launched with the hot part staged (launch_plan_g): its loads are LDS
+        if (ONE) env.assume_hot_shared(false);
     }
     Grp<G> g;
     GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
@@ -690,7 +692,9 @@ static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t 
 #define AUV_PLAN_ARGS env, starts, seeds, Q, p, workspace, workspace_bytes, records, chain, path, trace, s, need_bytes
     if constexpr (sizeof(R) == 4) {
         if (p->mode == 0 && !getenv("AUVRRT_PLAN_GENERIC")) {
-            if (p->freq <= (double)G && bs) return launch_plan_gb<R, G, true, 0, true>(AUV_PLAN_ARGS);   // the common shape
+            // the common shape: every edge one chunk, bins in shared memory, hot part of the world model staged
+            if (p->freq <= (double)G && bs && env->h32.hot_bytes + 16 <= 24 * 1024 && !getenv("AUVRRT_PLAN_STAGE_KB"))
+                return launch_plan_gb<R, G, true, 0, true>(AUV_PLAN_ARGS);
             return bs ? launch_plan_gb<R, G, true, 0, false>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, 0, false>(AUV_PLAN_ARGS);
         }
     }

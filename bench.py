@@ -10,8 +10,9 @@ A "step" is one pass of the planner over the batch.  `value` has the queries res
 N > 1 (torchrun): queries are sharded across ranks (weak scaling, no data-path collective) and the
 96-byte plan records are gathered to rank 0 over NCCL inside the timed region.
 
---impl reference times the reference's CPU algorithm (the fp64 C oracle port of the pure-Python
-reference, all host threads) on a bounded sample of the same workload.
+--impl reference times the reference's own pure-Python planner (the unmodified modules installed into baseline/_ref
+by baseline/install_ref.py) on all host cores, one query of the workload per process per step; without that install it
+falls back to the fp64 C port of the reference (oracle/auvrrt_oracle.c).
 """
 import argparse
 import json
@@ -116,6 +117,81 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+PORT_THREADS = 16            # the C port is always timed on this many threads, so BENCH and SCALE ratios are comparable
+
+
+def python_reference_available():
+    return os.path.isfile(os.path.join(REF_DIR, "path_planning", "rrt_dubins.py"))
+
+
+_py_ref_state = {}
+
+
+def _py_ref_worker(qids):
+    """one process of the pure-Python reference arm: plan the given queries with the UNMODIFIED reference modules
+    (baseline/_ref, installed by baseline/install_ref.py) under the iteration-budget clock; returns
+    (steer calls, seconds inside RRT.exploring, plans found)"""
+    st = _py_ref_state
+    if not st:
+        os.environ["AUVRRT_REFERENCE"] = REF_DIR
+        import importlib
+        from oracle import harness as H
+        H = importlib.reload(H)
+        ref = H.load_reference()
+        world = H.catalina_world(ref)
+        csv = os.path.join(REF_DIR, "path_planning", "shark_data", "AUVGrid_prob_500_turn.csv")
+        obstacles, poly, habitats, cells, shark = H.world_objects(ref, world, grid_csv=csv)
+        st.update(H=H, ref=ref, habitats=habitats, rrt=ref.RRT(poly, obstacles, shark, cells))
+    H, ref = st["H"], st["ref"]
+    calls = found = 0
+    secs = 0.0
+    for qid, sx, sy in qids:
+        res, c, dt = H.timed_exploring(ref, st["rrt"], ref.MPS(sx, sy), list(st["habitats"]), iterations=ITERS, seed=int(qid))
+        calls += c; secs += dt; found += res is not None
+    return calls, secs, found
+
+
+class PythonReference:
+    """the reference's own pure-Python planner on the host cores: a pool of processes, one query of the workload each
+    per step (queries are independent: the embarrassingly parallel way its authors would run many)"""
+
+    def __init__(self, procs=0):
+        import multiprocessing as mp
+        self.procs = procs or (os.cpu_count() or 1)
+        self.pool = mp.get_context("spawn").Pool(self.procs)
+        self.starts, _ = make_queries(0, max(self.procs, 1) * 4)
+
+    def step(self, k):
+        """plan `procs` queries concurrently (query ids k*procs ...); -> (edges/s over all processes, plans/s, wall, found)"""
+        ids = [(k * self.procs + j) % len(self.starts) for j in range(self.procs)]
+        jobs = [[(i, float(self.starts[i, 0]), float(self.starts[i, 1]))] for i in ids]
+        t0 = time.perf_counter()
+        out = self.pool.map(_py_ref_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        calls = sum(o[0] for o in out)
+        return calls / wall, len(ids) / wall, wall, sum(o[2] for o in out), max(o[1] for o in out)
+
+    def single(self):
+        """one query in one process: the single-core figure"""
+        calls, secs, _ = self.pool.apply(_py_ref_worker, ([(0, float(self.starts[0, 0]), float(self.starts[0, 1]))],))
+        return calls / secs
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for l in f:
+                if l.startswith("model name"):
+                    return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(nthreads=0, sample_queries=None):
     """the oracle port (fp64 C restatement of the pure-Python reference) on the host cores"""
     from oracle import orc
@@ -143,11 +219,42 @@ def config_dict(n_gpus):
 
 
 def run_reference(args, rank, world_size):
+    """the reference arm: the UNMODIFIED pure-Python planner (baseline/_ref) on all host cores when it is installed,
+    else its fp64 C port.  A step = every host core plans one query of the workload (2048 steer calls)."""
     if rank != 0:
+        return
+    port = cpu_baseline(nthreads=PORT_THREADS)
+    port_obj = {"value": port["value"], "unit": UNIT, "cores": port["cores"], "kind": "port", "sample": port["sample"]}
+    if python_reference_available():
+        pr = PythonReference()
+        try:
+            single = pr.single()
+            vals = []
+            for i in range(args.warmup + args.steps):
+                r = pr.step(i)
+                if i >= args.warmup:
+                    vals.append(r)
+        finally:
+            pr.close()
+        v = float(np.mean([r[0] for r in vals]))
+        ms = float(np.mean([r[2] for r in vals])) * 1e3
+        sample = ("%d of the %d queries x %d steer calls per step (one query per process, %d processes), unmodified "
+                  "path_planning/rrt_dubins.py + cost.py from baseline/_ref under the iteration-budget clock, CPython %s, %s"
+                  % (pr.procs, Q_PER_GPU, ITERS, pr.procs, sys.version.split()[0], cpu_model()))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+                "plans_per_s": float(np.mean([r[1] for r in vals])),
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": pr.procs, "kind": "reference", "sample": sample,
+                                 "single_process_edges_per_s": single, "cpu_model": cpu_model(), "port": port_obj},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "the reference's own pure-Python planner; `port` is its fp64 C restatement (oracle/auvrrt_oracle.c) "
+                        "on %d threads for comparison" % PORT_THREADS}
+        print(json.dumps(line))
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        b = cpu_baseline()
+        b = cpu_baseline(nthreads=PORT_THREADS)
         if i >= args.warmup:
             vals.append(b)
     v = float(np.mean([b["value"] for b in vals]))
@@ -158,9 +265,8 @@ def run_reference(args, rank, world_size):
             "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": b["cores"], "kind": "port", "sample": b["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference is pure Python (no native code to compile into oracle/_ref); this arm times its "
-                    "fp64 C port on all host threads. The unmodified Python reference measured in the build "
-                    "container: ~0.41 k edges/s per core with cost active (BASELINE.md section 2)."}
+            "note": "baseline/_ref is not installed (python baseline/install_ref.py in the build container): this arm "
+                    "times the fp64 C port of the pure-Python reference"}
     print(json.dumps(line))
 
 
@@ -175,6 +281,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip micro-benchmarks / cpu baseline")
     ap.add_argument("--micro-edges", type=int, default=100_000_000)
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU (default: the configs[1] size, 4096)")
+    ap.add_argument("--config5-queries", type=int, default=1 << 20,
+                    help="total queries of the sharded config-5 run (strong scaling, part of every line; 0 skips it)")
     args = ap.parse_args()
     global Q_PER_GPU
     if args.queries > 0:
@@ -260,6 +368,15 @@ def main():
     e2e_s = float(te.item())
     rsz = 4 if args.precision == "f32" else 8
 
+    c5 = None
+    if args.config5_queries > 0 and not args.no_extras:
+        try:
+            del planner
+            torch.cuda.empty_cache()
+            c5 = config5(env, dev, args, api, adev, rank, world_size)
+        except Exception as ex:
+            c5 = {"error": repr(ex)}
+
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -299,8 +416,27 @@ def main():
                         "waypoints_per_edge": W / (len(rec) * ITERS), "primitives_per_edge": P / (len(rec) * ITERS),
                         "note": "no tensor cores: no dense contraction on this path (BASELINE.json north_star)"}
 
+    if c5 is not None:
+        line["config5"] = c5
     if not args.no_extras and world_size == 1:
-        line["cpu_baseline"] = {k: v for k, v in cpu_baseline().items() if k in ("value", "unit", "cores", "kind", "sample")}
+        port = cpu_baseline(nthreads=PORT_THREADS)
+        port_obj = {k: v for k, v in port.items() if k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = port_obj
+        if python_reference_available():
+            try:
+                pr = PythonReference()
+                try:
+                    single = pr.single()
+                    r = pr.step(0)
+                finally:
+                    pr.close()
+                line["cpu_baseline"] = {
+                    "value": r[0], "unit": UNIT, "cores": pr.procs, "kind": "reference",
+                    "sample": "%d of the %d queries x %d steer calls, one query per process on %d processes, unmodified "
+                              "reference modules from baseline/_ref, %.1f s wall; %s" % (pr.procs, Q_PER_GPU, ITERS, pr.procs, r[2], cpu_model()),
+                    "single_process_edges_per_s": single, "plans_per_s": r[1], "port": port_obj}
+            except Exception as ex:
+                line["cpu_baseline"]["python_reference_error"] = repr(ex)
         try:
             line["extras"] = extras(env, dev, args, api, adev)
         except Exception as ex:   # extras never invalidate the headline line
@@ -410,6 +546,69 @@ def micro_catalina(env, dev, n_edges, api, adev, cal_flops, timed):
     return out
 
 
+def config5(env, dev, args, api, adev, rank, world_size):
+    """BASELINE.json configs[4]: Q planning queries (default 2^20) sharded contiguously over the ranks, planned by the
+    thread-per-tree kernel with everything resident in HBM, one NCCL all-gather of the 96-byte records, the global
+    minimum-cost plan by two 8-byte MIN all-reduces, the winner's path re-created on its owner and broadcast
+    (auvrrt.multi.plan_sharded_device).  STRONG scaling: the same Q at every N."""
+    import torch
+    import torch.distributed as dist
+    from auvrrt import multi
+    Q = int(args.config5_queries)
+    own_pg = False
+    if not dist.is_initialized():
+        import socket
+        sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1, device_id=dev)
+        own_pg = True
+    try:
+        pp5 = api.plan_params(ITERS, group=1)
+        starts, seeds = make_queries(0, Q)
+        lo, hi = multi.shard_range(Q, rank, world_size)
+        cap = max(multi.shard_range(Q, r, world_size)[1] - multi.shard_range(Q, r, world_size)[0] for r in range(world_size))
+        planner = adev.DevicePlanner(env, pp5, "f32", cap, want_chain=True)
+
+        def sync():
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        multi.plan_sharded_device(env, starts, seeds, pp5, "f32", want_path=False, planner=planner)      # warm-up
+        reps, ts = 2, []
+        for _ in range(reps):
+            sync()
+            t0 = time.perf_counter()
+            r = multi.plan_sharded_device(env, starts, seeds, pp5, "f32", want_path=True, planner=planner)
+            sync()
+            ts.append(time.perf_counter() - t0)
+        t = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+        out = None
+        if rank == 0:
+            rec = r["records"]
+            n = rec.shape[0]
+            status = rec.view(torch.int32).view(n, 24)[:, 0]
+            best = r["best"]
+            # a fixed sample of query ids, planned again by this rank alone with the same kernel: identical records?
+            ids = np.linspace(0, Q - 1, 64).astype(np.int64)
+            sp = adev.DevicePlanner(env, pp5, "f32", len(ids), want_chain=False)
+            sp.set_queries(starts[ids], seeds[ids]); sp.launch(); torch.cuda.synchronize()
+            same = bool(torch.equal(sp.records[:len(ids)], rec[torch.from_numpy(ids).to(dev)]))
+            bc = rec[best:best + 1].cpu().numpy().view(api.RECORD_DTYPE)["cost"][0, 0] if best >= 0 else None
+            out = {"queries": Q, "iterations": ITERS, "n_gpus": world_size, "scaling": "strong", "seconds": secs,
+                   "plans_per_s": Q / secs, "edges_per_s": Q * ITERS / secs, "queries_ok": int((status == 0).sum().item()),
+                   "best_query": best, "best_cost": None if bc is None else float(bc),
+                   "best_path_rows": None if r["path"] is None else int(len(r["path"])),
+                   "gather_bytes_per_rank": int(cap * 96), "sample_records_equal_single_gpu": same,
+                   "kernel": "k_plan_tpt<float> (one thread per tree)",
+                   "includes": "planner launch on every rank, NCCL all-gather of records, 2 MIN all-reduces, winner's path "
+                               "materialised on its owner and broadcast; wall clock, max over ranks"}
+        del planner
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        if own_pg:
+            dist.destroy_process_group()
+
+
 def extras(env, dev, args, api, adev):
     """secondary measurements: NN scan against the HBM roofline, config-4 micro-benchmark, fp64 build"""
     import torch
@@ -478,6 +677,27 @@ def extras(env, dev, args, api, adev):
         torch.cuda.empty_cache()
     except Exception as ex:
         out["throughput_planner_group1"] = {"error": repr(ex)}
+
+    # planner mode 3: Dubins-RRT with best-parent selection (row X1; the build's own definition, parity unpinned)
+    try:
+        Q3, I3, W3 = 4096, 1024, 12
+        pp3 = api.plan_params(I3, mode=3, v=1.0, max_traj_time=200.0, dubins_rho=1.0, dubins_eta=20.0, near_radius=15.0, dubins_w=W3)
+        st3, sd3 = make_queries(0, Q3)
+        pl3 = adev.DevicePlanner(env, pp3, "f32", Q3, want_chain=True)
+        pl3.set_queries(st3, sd3)
+        mean_s, _ = timed(lambda: pl3.launch(), reps=3, warm=1)
+        rec3 = pl3.records_numpy()
+        cand = float(rec3["n_waypoints"].sum()) / W3
+        out["planner_mode3_dubins"] = {"queries": Q3, "iterations": I3, "waypoints_per_edge": W3, "seconds": mean_s,
+                                       "plans_per_s": Q3 / mean_s, "iterations_per_s": Q3 * I3 / mean_s,
+                                       "candidate_edges_per_s": cand / mean_s, "candidates_per_iteration": cand / (Q3 * I3),
+                                       "queries_ok": int((rec3["status"] == 0).sum()), "nodes_mean": float(rec3["n_nodes"].mean()),
+                                       "kernel": "k_plan<float,32,mode 3> (lane = candidate parent, warp min-reduction)",
+                                       "note": "sample -> nearest + near nodes -> six-word Dubins steer + collide + cost per lane -> best parent"}
+        del pl3
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["planner_mode3_dubins"] = {"error": repr(ex)}
 
     # config 4: Dubins edges vs 500 synthetic circles, 20 waypoints per edge
     rs = np.random.RandomState(1234)

@@ -721,3 +721,39 @@ def traced_astar(aref, start, circles, boundary, habitats, bins, cells, probs, *
     elif "raised" not in out:
         out["exhausted"] = True      # open list ran empty: astar() returns None
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Timing the unmodified planner (bench.py --impl reference): no tracing, Python's own Mersenne Twister
+# ---------------------------------------------------------------------------------------------
+def timed_exploring(ref, rrt, initial, habitats, *, iterations, seed, bin_interval=5, v=2, shark_interval=50,
+                    max_plan_time=10.0, max_traj_time=500.0, weights=(-3, -3, -4), plot_interval=0.5):
+    """RRT.exploring (/root/reference/path_planning/rrt_dubins.py:92-176) in its default mode for exactly `iterations`
+    steer calls (the wall-clock budget is replaced by BudgetClock, nothing else is touched) on `random.Random(seed)`.
+    Returns (result dict or None, steer calls, seconds spent inside exploring)."""
+    import random as _random
+    import time as _time
+    mod = ref.rrt_dubins
+    clock = BudgetClock(iterations)
+    saved = (mod.random, mod.time)
+    orig_cc = rrt.check_collision
+
+    def check_collision(mps, obstacles):          # exactly one call per steer call (:141-143): the iteration counter
+        clock.done += 1
+        return orig_cc(mps, obstacles)
+
+    rrt.check_collision = check_collision
+    mod.random, mod.time = _random.Random(seed), clock
+    t0 = _time.perf_counter()
+    try:
+        try:
+            res = rrt.exploring(initial, habitats, plot_interval, bin_interval, v, shark_interval, traj_time_stamp=True,
+                                max_plan_time=max_plan_time, max_traj_time=max_traj_time, plan_time=True,
+                                weights=list(weights))
+        except TypeError:
+            res = None                            # no node reached the horizon (rrt_dubins.py:174)
+    finally:
+        dt = _time.perf_counter() - t0
+        mod.random, mod.time = saved
+        del rrt.check_collision
+    return res, clock.done, dt
