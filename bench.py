@@ -592,7 +592,7 @@ def config5(env, dev, args, api, adev, rank, world_size):
             sp = adev.DevicePlanner(env, pp5, "f32", len(ids), want_chain=False)
             sp.set_queries(starts[ids], seeds[ids]); sp.launch(); torch.cuda.synchronize()
             same = bool(torch.equal(sp.records[:len(ids)], rec[torch.from_numpy(ids).to(dev)]))
-            bc = rec[best:best + 1].cpu().numpy().view(api.RECORD_DTYPE)["cost"][0, 0] if best >= 0 else None
+            bc = rec[best:best + 1].cpu().numpy().view(api.RECORD_DTYPE)["cost"].reshape(-1)[0] if best >= 0 else None
             out = {"queries": Q, "iterations": ITERS, "n_gpus": world_size, "scaling": "strong", "seconds": secs,
                    "plans_per_s": Q / secs, "edges_per_s": Q * ITERS / secs, "queries_ok": int((status == 0).sum().item()),
                    "best_query": best, "best_cost": None if bc is None else float(bc),
