@@ -25,12 +25,19 @@ class RRTEnv:
         self.rrt_planner = None
         self.precision = "f32"
         self.seed_value = None
+        # nodes one episode may hold (start included).  The reference's tree is unbounded and its RL drivers step an
+        # episode up to 1000 times (2000 at test time, solveRL-RRT.py:35-36), each step adding at most one node, so the
+        # default leaves room for the longest of those; init_env(max_steps=...) changes it.
+        self.max_steps = 2000
+        self._episode = 0
 
     def seed(self, seed=None):
         self.seed_value = seed
 
     def init_env(self, auv_init_pos, shark_init_pos, boundary_array, grid_cell_side_length, num_of_subsections,
-                 obstacle_array=[], habitat_grid=None):
+                 obstacle_array=[], habitat_grid=None, max_steps=None):
+        if max_steps is not None:
+            self.max_steps = int(max_steps)
         self.auv_init_pos = auv_init_pos
         self.shark_init_pos = shark_init_pos
         self.obstacle_array_for_rendering = obstacle_array
@@ -61,7 +68,9 @@ class RRTEnv:
         self.rrt_planner = Planner_RRT(a, s, self.boundary_array, self.obstacle_array_for_rendering,
                                        self.habitats_array_for_rendering, cell_side_length=self.cell_side_length,
                                        freq=RRT_PLANNER_FREQ, subsections_in_cell=self.num_of_subsections,
-                                       seed=self.seed_value, precision=self.precision, track_counts=True)
+                                       seed=None if self.seed_value is None else self.seed_value + self._episode,
+                                       precision=self.precision, track_counts=True, node_cap=self.max_steps + 1)
+        self._episode += 1            # a seeded env replays a different stream every episode
         self._static_grid = self._grid_rows()
         self.state = {'auv_pos': np.array([a.x, a.y, a.z, a.theta]), 'shark_pos': np.array([s.x, s.y, s.z, s.theta]),
                       'obstacles_pos': self.obstacle_array, 'path': None}

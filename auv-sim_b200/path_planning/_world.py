@@ -50,7 +50,12 @@ def grid_of(shark_dict):
     probs = np.zeros((len(bins), len(keys)))
     for i, g in enumerate(shark_dict.values()):
         if len(g) != len(keys) or (g is not first and list(g.keys()) != keys):
-            raise NotImplementedError("shark grid bins must list the same cells in the same order")
+            raise NotImplementedError(
+                "shark grid bins must list the same cells in the same order (bin %d lists %d cells, bin 0 lists %d). "
+                "The first-match scan of cost.py:181-184 depends on each bin's own dict order, and the device cell "
+                "index is built once for all bins.  createSharkGrid (rrt_dubins.py:612-630) always satisfies this; "
+                "SharkOccupancyGrid.convert drops zero-probability cells per bin (as the reference's convert2DArr does): "
+                "pass convert(..., keep_zero_cells=True) to get planner-ready grids." % (i, len(g), len(keys)))
         probs[i] = np.fromiter((float(p) for p in g.values()), dtype=np.float64, count=len(keys))
     return bins, cells, probs
 
@@ -76,7 +81,15 @@ class EnvCache:
 
 
 def grid_fingerprint(shark_dict):
+    """Content key of a shark grid {(t0, t1): {cell_bounds: p}}: a digest of its bins, cell bounds (in dict order) and
+    probabilities.  Never the object's id(): CPython reuses the id of a freed dict, and a dict can be mutated in place,
+    so an identity key silently served costs computed with a previous grid's probabilities."""
     if not shark_dict:
         return None
-    first = next(iter(shark_dict.values()))
-    return (id(shark_dict), len(shark_dict), len(first), tuple(shark_dict.keys()))
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for k, g in shark_dict.items():
+        h.update(np.array([float(k[0]), float(k[1]), float(len(g))], dtype=np.float64).tobytes())
+        h.update(np.fromiter((float(v) for b in g.keys() for v in b), dtype=np.float64, count=4 * len(g)).tobytes())
+        h.update(np.fromiter((float(p) for p in g.values()), dtype=np.float64, count=len(g)).tobytes())
+    return ("grid", h.hexdigest())

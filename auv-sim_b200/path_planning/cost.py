@@ -34,8 +34,7 @@ def habitat_shark_cost_func(path, total_traj_time, habitats, shark_dict, weight)
 def habitat_shark_cost_point(mps, habitats, visited, AUVGrid, weight):
     """single-state variant; `visited` is returned unchanged, as in the reference (:234 compares
     instead of assigning)"""
-    env = _env_for(habitats, {(0, 0): AUVGrid} if AUVGrid else {},
-                   fingerprint=("point", id(AUVGrid), len(AUVGrid) if AUVGrid else 0))
+    env = _env_for(habitats, {(0, 0): AUVGrid} if AUVGrid else {})      # keyed by the grid's CONTENT (_world.grid_fingerprint)
     vis = [1 if visited[i] else 0 for i in range(len(habitats))]
     s = api.cost_point(env, [[mps.x, mps.y]], vis, 0, [float(w) for w in weight[:3]], precision="f64")[0]
     return float(s), visited

@@ -112,7 +112,8 @@ class RRT:
             raise _STATUS_EXC.get(int(rec["status"][0]), lambda: RuntimeError("planner failed"))()
         best = int(np.argmin(np.where(ok, rec["cost"][:, 0], np.inf)))        # strict <: first minimum wins
         # re-create the optimal path from its chain of stream positions (the planner stores no waypoints)
-        pp.path_cap = 32 * (int(rec["depth"][best]) + 1)
+        # rows per edge: the parent node object + at most ceil(freq) arc waypoints (dubins_w - 1 Dubins samples)
+        pp.path_cap = (max(int(math.ceil(self.freq)), int(dubins_w)) + 2) * (int(rec["depth"][best]) + 1) + 2
         path_rows, n_path = api.materialize(env, starts[best:best + 1], seeds[best:best + 1], r["chain"][best:best + 1],
                                             rec["depth"][best:best + 1], pp, self.precision)
         rows = path_rows[0, :n_path[0]]
@@ -126,7 +127,11 @@ class RRT:
 
     def replanning(self, start, habitats, plan_time_budget, traj_time_length, replan_time_interval, weight):
         """reference :51-90: receding-horizon loop over `exploring`.  `initial` is detached from any
-        previous tree (the reference sometimes walks on into the old tree)."""
+        previous tree (the reference sometimes walks on into the old tree): a segment whose
+        start point was a NODE of the previous tree is costed without that tree's older waypoints.
+        Deterministic replay: set `self.replan_seed` (inner call k uses seed + k) and `self.replan_iterations`."""
+        replan_seed = getattr(self, "replan_seed", None)
+        replan_iterations = getattr(self, "replan_iterations", None)
         traj = [start]
         time_dict = {}
         final_traj_time = list(self.sharkGrid.keys())[-1][1]
@@ -139,7 +144,8 @@ class RRT:
             temp = self.exploring(traj[-1], habitats, 0.5, 5, 2, plan_time, traj_time_stamp=True,
                                   max_plan_time=plan_time_budget,
                                   max_traj_time=(traj_time_length + traj[-1].traj_time_stamp), plan_time=True,
-                                  weights=weight)
+                                  weights=weight, iterations=replan_iterations,
+                                  seed=None if replan_seed is None else replan_seed + count - 1)
             temp_path = temp["path"][1][list(temp["path"][1].keys())[0]]
             traj.extend(temp_path)
             time_dict[count] = [temp_path, habitats.copy()]

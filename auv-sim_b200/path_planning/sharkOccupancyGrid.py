@@ -125,8 +125,14 @@ class SharkOccupancyGrid:
         lowx, lowy = cell.bounds[:2]
         return int((lowy - miny) / self.cell_size), int((lowx - minx) / self.cell_size)
 
-    def convert(self, shark_dict):
-        """-> (resultArr {bin: 2-D list}, resultCell {bin: {cell.bounds: p}}), reference :47-71"""
+    def convert(self, shark_dict, keep_zero_cells=False):
+        """-> (resultArr {bin: 2-D list}, resultCell {bin: {cell.bounds: p}}), reference :47-71.
+
+        Like the reference's convert2DArr (:284-292) the per-bin dicts drop zero-probability cells, so different bins
+        generally list different cells.  The planner / cost entry points need every bin to list the same cells in the
+        same order (their first-match scan depends on dict order, see _world.grid_of): keep_zero_cells=True (an extra
+        of this build) keeps every cell of cell_list in every bin, in cell_list order -- the layout createSharkGrid
+        (rrt_dubins.py:612-630) produces from the reference's CSV files."""
         self.data = shark_dict
         self.bin_list = self.createBinList()
         polys = [_cell_vertices(c) for c in self.cell_list]
@@ -140,7 +146,7 @@ class SharkOccupancyGrid:
             cells = {}
             for c, (row, col) in zip(self.cell_list, idx):                      # convert2DArr :284-292
                 v = float(grid[b, row, col])
-                if v != 0:
+                if v != 0 or keep_zero_cells:
                     cells[c.bounds] = v
             resultCell[key] = cells
         return resultArr, resultCell

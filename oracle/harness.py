@@ -757,3 +757,67 @@ def timed_exploring(ref, rrt, initial, habitats, *, iterations, seed, bin_interv
         mod.random, mod.time = saved
         del rrt.check_collision
     return res, clock.done, dt
+
+
+# ---------------------------------------------------------------------------------------------
+# RRT.replanning (/root/reference/path_planning/rrt_dubins.py:51-90) under the harness
+# ---------------------------------------------------------------------------------------------
+class _RandomProxy:
+    """`random` stand-in whose player is swapped for every exploring call of a replanning run"""
+
+    def __init__(self):
+        self.player = None
+
+    def uniform(self, a, b):
+        return self.player.uniform(a, b)
+
+    def random(self):
+        return self.player.random()
+
+
+def traced_replanning(ref, rrt, start, habitats, plan_time_budget, traj_time_length, replan_time_interval, weight, *,
+                      iterations, seed):
+    """Run the unmodified RRT.replanning with every inner exploring call k = 0, 1, ... limited to `iterations` steer
+    calls on the slot-addressed stream of seed + k.  Returns (traj, time_dict, cost, segments) where segments[k] holds
+    the initial state of call k, whether that object had a live .parent (a node of the previous tree: the reference
+    then walks on into the old tree), the call's result cost and its first-interval points."""
+    mod = ref.rrt_dubins
+    proxy = _RandomProxy()
+    clock = BudgetClock(iterations)
+    saved = (mod.random, mod.time)
+    segs = []
+    orig_steer, orig_cc, orig_expl = rrt.steer, rrt.check_collision, rrt.exploring
+
+    def steer(mps, *a, **k):
+        proxy.player.begin_steer()
+        try:
+            return orig_steer(mps, *a, **k)
+        finally:
+            proxy.player.end_steer()
+
+    def check_collision(mps, obstacles):
+        clock.done += 1
+        return orig_cc(mps, obstacles)
+
+    def exploring(initial, *a, **k):
+        clock.done = 0
+        proxy.player = StreamPlayer(seed=seed + len(segs))
+        seg = {"initial": (initial.x, initial.y, initial.theta, initial.traj_time_stamp, initial.length),
+               "has_parent": initial.parent is not None, "max_traj_time": k.get("max_traj_time")}
+        segs.append(seg)
+        res = orig_expl(initial, *a, **k)
+        seg["cost"] = [res["cost"][0]] + list(res["cost"][1])
+        seg["path_length"] = res["path length"]
+        first = res["path"][1][list(res["path"][1].keys())[0]]
+        seg["first_interval"] = path_to_array(first)
+        seg["n_path"] = len(res["path"][0])
+        return res
+
+    rrt.steer, rrt.check_collision, rrt.exploring = steer, check_collision, exploring
+    mod.random, mod.time = proxy, clock
+    try:
+        traj, time_dict, cost = rrt.replanning(start, habitats, plan_time_budget, traj_time_length, replan_time_interval, weight)
+    finally:
+        mod.random, mod.time = saved
+        del rrt.steer, rrt.check_collision, rrt.exploring
+    return traj, time_dict, cost, segs

@@ -169,3 +169,30 @@ def test_vec_env_and_replicas(g):
     assert isinstance(path, list) and step <= 200
     assert np.hypot(path[0].x - 35.0, path[0].y - 40.0) <= 1.0 + 1e-3
     assert abs(path[-1].x - 10.0) < 1e-3 and abs(path[-1].y - 10.0) < 1e-3
+
+
+@pytest.mark.gpu
+def test_rrt_env_long_episode_does_not_overflow(g):
+    """the reference's RL drivers step an episode up to 1000 times (2000 at test time); the tree must hold that many
+    nodes (round 1 capped it at 257 and raised OverflowError mid-episode), and a seeded env must not replay the same
+    stream every episode"""
+    envs, rd, M, _ = g
+    env = envs.RRTEnv()
+    env.seed(3)
+    state = env.init_env(M(5.0, 5.0, theta=0.0), M(45.0, 45.0), [M(0.0, 0.0), M(50.0, 50.0)], 2, 8, [])
+    rs = np.random.RandomState(0)
+    steps = 0
+    for s in range(700):
+        occ = np.flatnonzero(state["has_node"])
+        state, reward, done, _ = env.step(int(occ[rs.randint(len(occ))]), step_num=s)
+        steps += 1
+        if done:
+            break
+    assert steps > 300 or done
+    first = state["rrt_grid_num_of_nodes_only"].copy()
+    state = env.reset()
+    occ = np.flatnonzero(state["has_node"])
+    for s in range(40):
+        occ = np.flatnonzero(state["has_node"])
+        state, reward, done, _ = env.step(int(occ[0]), step_num=s)
+    assert env._episode == 2

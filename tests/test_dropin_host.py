@@ -112,3 +112,30 @@ def test_no_gpu_fails_loudly(mods):
             M(1, 1), [], 0.5, 5, 2, 50, traj_time_stamp=True, max_traj_time=100)
     with pytest.raises(AuvrrtError, match="no CUDA device"):
         cost.habitat_shark_cost_func([M(1, 1)], 1.0, [M(0, 0, size=2)], {}, [-1, -1, -1])
+
+
+def test_env_cache_is_keyed_by_grid_content(mods):
+    """the world-model cache must notice a NEW grid with the same time bins and cells but other probabilities (CPython
+    reuses the id() of a freed dict) and an in-place mutation"""
+    import _world
+    cells = [(0.0, 0.0, 10.0, 10.0), (10.0, 0.0, 20.0, 10.0)]
+    fps = set()
+    for i in range(12):
+        g = {(0, 100): {c: 0.1 * (i + 1) + j for j, c in enumerate(cells)}}       # fresh dict every time, same keys
+        fps.add(_world.grid_fingerprint(g))
+    assert len(fps) == 12
+    g = {(0, 100): {c: 0.5 for c in cells}}
+    a = _world.grid_fingerprint(g)
+    assert a == _world.grid_fingerprint({(0, 100): {c: 0.5 for c in cells}})      # same content, other object: same key
+    g[(0, 100)][cells[0]] = 0.75
+    assert _world.grid_fingerprint(g) != a                                        # in-place mutation changes the key
+    assert _world.grid_fingerprint({}) is None
+
+
+def test_sparse_bins_are_rejected_with_directions(mods):
+    """per-bin dicts that list different cells (what SharkOccupancyGrid.convert emits when a cell's probability is 0 in
+    some bin) cannot share one device cell index: the error says what to do"""
+    import _world
+    g = {(0, 50): {(0.0, 0.0, 10.0, 10.0): 0.5, (10.0, 0.0, 20.0, 10.0): 0.25}, (50, 100): {(10.0, 0.0, 20.0, 10.0): 0.125}}
+    with pytest.raises(NotImplementedError, match="keep_zero_cells=True"):
+        _world.grid_of(g)

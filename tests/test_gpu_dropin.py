@@ -136,3 +136,39 @@ def test_replanning_runs(world):
     assert len(traj) > 10 and len(time_dict) >= 2 and len(cost) == 2 and len(cost[1]) == 3
     ts = [p.traj_time_stamp for p in traj]
     assert ts[-1] > 200
+
+
+def test_replanning_matches_reference_trace(world, golden_dir):
+    """RRT.replanning (rrt_dubins.py:51-90) against traces of the unmodified reference (tests/golden/pins.npz): every
+    inner exploring call on the slot-addressed stream of seed + k with the same iteration budget.  The drop-in detaches
+    `initial` from the previous tree; the reference walks on into the old tree when the start point was one of its
+    NODES (has_parent in the fixture), so segments are compared up to the first such start, the whole run when none."""
+    rrt, M = world["rrt"], world["M"]
+    z = np.load(os.path.join(golden_dir, "pins.npz"))
+    meta = json.loads(str(z["meta"]))
+    rrt.precision = "f64"
+    checked_all = 0
+    try:
+        for ci, c in enumerate(meta):
+            tag = "rp%d_" % ci
+            rrt.replan_seed, rrt.replan_iterations = c["seed"], c["iterations"]
+            traj, time_dict, cost = rrt.replanning(M(c["start"][0], c["start"][1]), list(world["habitats"]), c["budget"], c["length"],
+                                                   c["interval"], [-3, -3, -4])
+            hp = z[tag + "has_parent"]
+            n_ok = int(np.argmax(hp)) + 1 if hp.any() else len(hp)       # the flagged segment itself still starts alike
+            off = z[tag + "first_off"]
+            want = z[tag + "first"]
+            got = np.array([[p.x, p.y, p.theta, p.v, p.traj_time_stamp, p.length] for p in traj])
+            n_pts = int(off[n_ok - 1]) if hp.any() else int(off[-1])       # points of the segments before the flagged one
+            assert len(got) >= n_pts
+            assert np.allclose(got[:n_pts], want[:n_pts], rtol=1e-9, atol=1e-9), ci
+            assert [len(v[1]) for v in time_dict.values()][:n_ok - 1 if hp.any() else None] == \
+                list(z[tag + "habitats_left"])[:n_ok - 1 if hp.any() else None]
+            if not hp.any():
+                assert len(got) == len(z[tag + "traj"]) and np.allclose(got, z[tag + "traj"], rtol=1e-9, atol=1e-9)
+                assert np.allclose([cost[0]] + list(cost[1]), z[tag + "cost"], rtol=1e-9, atol=1e-12)
+                checked_all += 1
+        assert checked_all >= 1
+    finally:
+        rrt.replan_seed = rrt.replan_iterations = None
+        rrt.precision = "f32"

@@ -526,3 +526,51 @@ def test_edges_arc_cost_vs_oracle(api, env, oworld, edge_variant):
         n_sum += ints and abs(s32[3][i, 0] - want[3]) <= 1e-5 * max(1.0, abs(want[3]))
     assert n_int > 0.99 * same.sum() and n_sum > 0.98 * same.sum()
     assert (s32[3][:, 0] != 0).sum() > 100
+
+
+# ------------------------------------------------------------------------------------ reference-pinned K2 / C2 / bin filter
+def test_pins_from_the_unmodified_reference(api, env, golden_dir):
+    """tests/golden/pins.npz (oracle/make_golden_pins.py, outputs of the unmodified reference): check_collision_obstacle
+    (rrt_dubins.py:551-556), habitat_shark_cost_point (cost.py:209-241) and habitat_shark_cost_func on the planner's
+    filtered shark dict (rrt_dubins.py:161-166) through the C ABI, fp64 build: exact"""
+    z = np.load(os.path.join(golden_dir, "pins.npz"))
+    assert np.array_equal(api.collide_points(env, z["k2_points"], "f64"), z["k2_safe"])
+    assert np.mean(api.collide_points(env, z["k2_points"], "f32") != z["k2_safe"]) < 0.01       # rim points may flip in fp32
+    pts, vis, tb, w = z["c2_points"], z["c2_visited"], z["c2_tb"], z["c2_weights"]
+    got = np.array([api.cost_point(env, pts[i:i + 1], vis[i], int(tb[i]), w[i], "f64")[0] for i in range(len(pts))])
+    assert np.array_equal(got, z["c2_out"])
+    off = z["bm_off"]
+    paths = [z["bm_pts"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    for i, p in enumerate(paths):
+        out = api.cost(env, [p], [z["bm_T"][i]], [-3, -3, -4], bin_mask=z["bm_mask"][i], precision="f64")
+        assert np.array_equal(out[0], z["bm_out"][i]), i
+        out32 = api.cost(env, [p], [z["bm_T"][i]], [-3, -3, -4], bin_mask=z["bm_mask"][i], precision="f32")
+        assert np.allclose(out32[0], z["bm_out"][i], rtol=2e-4, atol=1e-6), i
+
+
+def test_fp32_planner_first_divergence_rate(api, env):
+    """How long does the fp32 build follow the fp64 build decision for decision?  Same seeds, same stream (the fp32
+    build reads the top 23 bits of each word), traces compared on (parent, collision flag, waypoint count).  The first
+    difference comes from a draw that falls within 2^-23 of a decision threshold (bin / index pick, abs(dist) >
+    abs(diff), movement >= min_dist) or a waypoint within fp32 rounding of a circle / boundary / cell border; after
+    it the two trees differ (statistical parity only).  A regression in the fp32 fast paths (sinc polynomial, MUFU
+    sine, reciprocal division, grid margins) shows up here as a much earlier first divergence."""
+    Q, I = 96, 1024
+    starts = np.tile([-200.0, 0.0, 0.0, 0.0, 0.0], (Q, 1))
+    starts[:, 0] += np.linspace(-30, 30, Q)
+    seeds = np.arange(Q) + 31000
+    r64 = api.plan_batch(env, starts, seeds, api.plan_params(I, trace=True), "f64")["trace"]
+    r32 = api.plan_batch(env, starts, seeds, api.plan_params(I, trace=True), "f32")["trace"]
+    first = np.full(Q, I)
+    for q in range(Q):
+        d = (r64["parent"][q] != r32["parent"][q]) | (r64["safe"][q] != r32["safe"][q]) | (r64["nwp"][q] != r32["nwp"][q])
+        if d.any():
+            first[q] = int(np.argmax(d))
+    hist = np.histogram(first, bins=[0, 16, 64, 256, 512, 1024, 1025])[0]
+    print("first divergence of the fp32 trace from the fp64 trace (iterations):", dict(zip(["<16", "<64", "<256", "<512", "<1024", "never"], hist)))
+    # before they diverge the leaves agree to the fp32 tolerance
+    for q in range(Q):
+        n = first[q]
+        if n > 0:
+            assert close(r32["leaf"][q][:n, :2], r64["leaf"][q][:n, :2], 2e-5, scale=100.0)
+    assert np.median(first) >= 256 and (first < 16).mean() <= 0.05

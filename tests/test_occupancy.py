@@ -119,3 +119,37 @@ def test_config3_grid_from_shark_tracking_data(golden, golden_dir, catalina_map)
                         weights=[-3, -3, -4], iterations=1024, seed=4, replicas=16)
     assert res["cost"][1][2] < 0 and res["path"][0][-1].traj_time_stamp >= 420      # the shark term is active
     sys.path.remove(PP)
+
+
+@pytest.mark.gpu
+def test_sparse_tracks_need_keep_zero_cells(golden, catalina_map):
+    """two sharks in one corner: most cells have zero detection probability in some bins, so convert()'s per-bin dicts
+    (zero cells dropped, like the reference's convert2DArr) differ from bin to bin.  The cost entry refuses such a grid
+    with directions; keep_zero_cells=True gives the planner-ready layout, and grids with equal keys but different
+    probabilities are never confused (the world-model cache is keyed by content)."""
+    sys.path.insert(0, PP)
+    for n in ("sharkOccupancyGrid", "_world", "motion_plan_state", "rrt_dubins", "cost"):
+        sys.modules.pop(n, None)
+    import sharkOccupancyGrid as sog
+    import cost
+    from motion_plan_state import Motion_plan_state as M
+    boundary = [tuple(p) for p in catalina_map["boundary"]]
+    cells = sog.splitCell(boundary, 10)
+    shark = {1: [M(-300.0 + 0.5 * i, 20.0, traj_time_stamp=2.0 * i) for i in range(60)],
+             2: [M(-280.0, 40.0 - 0.5 * i, traj_time_stamp=2.0 * i) for i in range(60)]}
+    g = sog.SharkOccupancyGrid(10, boundary, 50, 50, cells)
+    arr, sparse = g.convert(shark)
+    assert len({len(v) for v in sparse.values()}) > 1 or min(len(v) for v in sparse.values()) < len(cells)
+    path = [M(-300.0 + i, 20.0, traj_time_stamp=5.0 * i) for i in range(20)]
+    with pytest.raises(NotImplementedError, match="keep_zero_cells"):
+        cost.habitat_shark_cost_func(path, 95.0, [], sparse, [-3, -3, -4])
+    arr2, dense = g.convert(shark, keep_zero_cells=True)
+    assert all(list(v.keys()) == [c.bounds for c in cells] for v in dense.values())
+    a = cost.habitat_shark_cost_func(path, 95.0, [], dense, [-3, -3, -4])
+    assert a[1][2] < 0
+    # a FRESH grid with the same bins and cells but doubled probabilities: twice the shark term, not a cached answer
+    for k in range(6):
+        doubled = {tb: {c: (k + 2) * p for c, p in v.items()} for tb, v in dense.items()}
+        b = cost.habitat_shark_cost_func(path, 95.0, [], doubled, [-3, -3, -4])
+        assert abs(b[1][2] - (k + 2) * a[1][2]) <= 1e-12 * abs(a[1][2]) * (k + 2)
+    sys.path.remove(PP)
