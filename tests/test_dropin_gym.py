@@ -31,7 +31,7 @@ def g():
 
 def test_signatures_match_reference(g):
     envs, rd, M, gc = g
-    extras = ("seed", "replicas", "node_cap", "precision", "device", "track_counts")
+    extras = ("seed", "replicas", "node_cap", "precision", "device", "track_counts", "max_steps")
     sig = lambda f: [p for p in inspect.signature(f).parameters if p not in extras]
     P = rd.Planner_RRT
     assert sig(P.__init__) == ["self", "start", "goal", "boundary", "obstacles", "habitats", "exp_rate", "dist_to_end",
