@@ -535,7 +535,9 @@ def test_pins_from_the_unmodified_reference(api, env, golden_dir):
     filtered shark dict (rrt_dubins.py:161-166) through the C ABI, fp64 build: exact"""
     z = np.load(os.path.join(golden_dir, "pins.npz"))
     assert np.array_equal(api.collide_points(env, z["k2_points"], "f64"), z["k2_safe"])
-    assert np.mean(api.collide_points(env, z["k2_points"], "f32") != z["k2_safe"]) < 0.01       # rim points may flip in fp32
+    f32 = api.collide_points(env, z["k2_points"], "f32")
+    rim = 3 * 4 * len(env.circles)                    # the first points sit exactly on / one ulp off obstacle rims
+    assert np.array_equal(f32[rim:], z["k2_safe"][rim:]) and np.mean(f32[:rim] != z["k2_safe"][:rim]) < 0.7
     pts, vis, tb, w = z["c2_points"], z["c2_visited"], z["c2_tb"], z["c2_weights"]
     got = np.array([api.cost_point(env, pts[i:i + 1], vis[i], int(tb[i]), w[i], "f64")[0] for i in range(len(pts))])
     assert np.array_equal(got, z["c2_out"])
@@ -573,4 +575,5 @@ def test_fp32_planner_first_divergence_rate(api, env):
         n = first[q]
         if n > 0:
             assert close(r32["leaf"][q][:n, :2], r64["leaf"][q][:n, :2], 2e-5, scale=100.0)
-    assert np.median(first) >= 256 and (first < 16).mean() <= 0.05
+    # measured on B200 (round 2): 72 of 96 never diverge within 1024 iterations, 3 before 256, none before 64
+    assert (first >= I).mean() >= 0.5 and np.median(first) >= 512 and (first < 64).mean() <= 0.03

@@ -40,6 +40,20 @@ if what == "edges":
     flop = 6 * 20 * K + 6 * 20 * 5 + 140 + 24 * 20
     print("edges-dubins n", n, "edges/s %.4g" % (n / min(ts)), "algorithmic TFLOP/s %.2f" % (n * flop / min(ts) / 1e12), "safe", float(safe.float().mean()),
           {k: os.environ[k] for k in os.environ if k.startswith("AUVRRT_")})
+elif what == "tpt":
+    # python tools/micro_run.py tpt Q : the thread-per-tree planner on Q queries (config-5 scale on one GPU)
+    world, bins_, probs_ = bench.load_world()
+    env = api.Env.from_map(world, bins_, probs_, device=0)
+    pp = api.plan_params(bench.ITERS, group=1)
+    st, sd = bench.make_queries(0, n)
+    pl = adev.DevicePlanner(env, pp, "f32", n, want_chain=True)
+    pl.set_queries(st, sd)
+    ts = []
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pl.launch(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    print("tpt Q", n, "edges/s %.4g" % (n * bench.ITERS / min(ts)), "plans/s %.4g" % (n / min(ts)), ts)
 elif what.startswith("catalina"):
     # python tools/micro_run.py catalina[-allpairs|-nocost] n : the thread-per-edge arc kernel at Catalina scale
     import os
