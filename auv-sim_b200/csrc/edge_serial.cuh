@@ -38,7 +38,14 @@ struct CircTable {
     int npair;
     float ox, oy;           // origin
     float ccmax;            // max |c'|^2: scale of the rounding error of the expansion
+    // the same packed form for the habitats (first match in list order; a missing second habitat has k = +inf) ...
+    const CircPair *hpair; int nhpair; float hccmax;
+    // ... and for the edges of a convex boundary ring: det_i(p') = A_i x' + B_i y' + C_i as (m2x, m2y, k) = (A, B, C) pairs,
+    // signs normalised so that "strictly inside" is det < 0 for every edge; a missing second edge has (0, 0, -1)
+    const CircPair *epair; int nepair; float escale, eoff;   // |det| <= escale (|x'| + |y'|) + eoff: too close to call
 };
+#define AUV_AP_MAXH 32       // habitat pairs (64 habitats)
+#define AUV_AP_MAXE 16       // polygon edge pairs (32 edges)
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     float2 d;
@@ -69,6 +76,78 @@ __device__ __forceinline__ float circ_table_ccmax(const EnvView<float> &env, flo
         m = fmaxf(m, fmaf(ay, ay, ax * ax));
     }
     return m;
+}
+
+// habitats and boundary edges in the packed form (all threads of the CTA; caller syncs)
+__device__ __forceinline__ void allpairs_tables_fill(CircPair *hdst, CircPair *edst, const EnvView<float> &env, float ox, float oy) {
+    const int nh = (env.H + 1) >> 1, ne = (env.E + 1) >> 1;
+    for (int j = threadIdx.x; j < nh; j += blockDim.x) {
+        const int a = 2 * j, b = 2 * j + 1;
+        const float ax = env.hx[a] - ox, ay = env.hy[a] - oy;
+        CircPair p;
+        p.m2x = make_float2(-2.f * ax, 0.f); p.m2y = make_float2(-2.f * ay, 0.f);
+        p.k = make_float2(fmaf(ay, ay, ax * ax) - env.hr2[a], Ar<float, false>::inf());
+        if (b < env.H) {
+            const float bx = env.hx[b] - ox, by = env.hy[b] - oy;
+            p.m2x.y = -2.f * bx; p.m2y.y = -2.f * by; p.k.y = fmaf(by, by, bx * bx) - env.hr2[b];
+        }
+        hdst[j] = p;
+    }
+    const float sgn = env.convex > 0 ? -1.f : 1.f;       // CCW ring: inside is det > 0 -> flip
+    for (int j = threadIdx.x; j < ne; j += blockDim.x) {
+        CircPair p;
+        p.m2x = make_float2(0.f, 0.f); p.m2y = make_float2(0.f, 0.f); p.k = make_float2(-1.f, -1.f);
+        for (int s2 = 0; s2 < 2; s2++) {
+            const int i = 2 * j + s2;
+            if (i >= env.E) break;
+            const int i1 = i + 1 == env.E ? 0 : i + 1;
+            const float ax = env.px[i] - ox, ay = env.py[i] - oy, bx = env.px[i1] - ox, by = env.py[i1] - oy;
+            const float A = -(by - ay) * sgn, B = (bx - ax) * sgn, Cc = -(B * ay + A * ax);
+            if (s2 == 0) { p.m2x.x = A; p.m2y.x = B; p.k.x = Cc; } else { p.m2x.y = A; p.m2y.y = B; p.k.y = Cc; }
+        }
+        edst[j] = p;
+    }
+}
+
+// first habitat (list order) holding (x, y): every habitat, packed pairs; -1 none
+__device__ __forceinline__ int first_habitat_all_f32(const EnvView<float> &env, const CircTable &ct, float x, float y) {
+    const float xr = x - ct.ox, yr = y - ct.oy;
+    const float pp = fmaf(yr, yr, xr * xr);
+    const float2 x2 = make_float2(xr, xr), y2 = make_float2(yr, yr);
+    const float guard = 4e-6f * (pp + ct.hccmax);
+    int hab = -1;
+    bool amb = false;
+    for (int j = ct.nhpair - 1; j >= 0; j--) {            // last to first: the earliest match ends up in `hab`
+        const CircPair a = ct.hpair[j];
+        const float2 q = ffma2(a.m2y, y2, ffma2(a.m2x, x2, a.k));
+        const float ta = q.x + pp, tb = q.y + pp;         // d^2 - r^2
+        if (tb <= 0.f) hab = 2 * j + 1;
+        if (ta <= 0.f) hab = 2 * j;
+        amb = amb || fabsf(ta) <= guard || fabsf(tb) <= guard;
+    }
+    if (__builtin_expect(amb, 0)) {                       // too close to a rim to call: the direct formula, in order
+        hab = -1;
+        for (int h = 0; h < env.H; h++) {
+            const float q = Ar<float, false>::sq2(env.hx[h] - x, env.hy[h] - y);
+            if (q <= env.hr2[h]) { hab = h; break; }
+        }
+    }
+    return hab;
+}
+
+// strictly inside the convex boundary ring: every edge, packed pairs
+__device__ __forceinline__ bool point_within_all_f32(const EnvView<float> &env, const CircTable &ct, float x, float y) {
+    const float xr = x - ct.ox, yr = y - ct.oy;
+    const float2 x2 = make_float2(xr, xr), y2 = make_float2(yr, yr);
+    float dmax = -Ar<float, false>::inf();
+    for (int j = 0; j < ct.nepair; j++) {
+        const CircPair a = ct.epair[j];
+        const float2 d = ffma2(a.m2y, y2, ffma2(a.m2x, x2, a.k));
+        dmax = fmaxf(dmax, fmaxf(d.x, d.y));
+    }
+    // inside <=> every det < 0 <=> dmax < 0; within the rounding error of the expansion: the direct formula
+    if (__builtin_expect(fabsf(dmax) <= fmaf(ct.escale, fabsf(xr) + fabsf(yr), ct.eoff), 0)) return point_within<float>(env, x, y);
+    return dmax < 0.f;
 }
 
 // does (x, y) hit any (inflated) circle: every circle, no culling
@@ -105,9 +184,16 @@ __device__ __forceinline__ bool point_hits_circles_all<float>(const EnvView<floa
 }
 
 // unsafe point?  (outside the polygon, on its boundary, or inside an inflated circle)
+template <typename R> __device__ __forceinline__ bool point_within_all(const EnvView<R> &env, const CircTable &ct, R x, R y) {
+    return point_within<R>(env, x, y);
+}
+template <> __device__ __forceinline__ bool point_within_all<float>(const EnvView<float> &env, const CircTable &ct, float x, float y) {
+    if (ct.epair == nullptr) return point_within<float>(env, x, y);
+    return point_within_all_f32(env, ct, x, y);
+}
 template <typename R, bool ALLPAIRS>
 __device__ __forceinline__ bool point_unsafe(const EnvView<R> &env, const CircTable &ct, const Cls &cl, R x, R y) {
-    if (ALLPAIRS) return !point_within<R>(env, x, y) || point_hits_circles_all<R>(env, ct, x, y);
+    if (ALLPAIRS) return !point_within_all<R>(env, ct, x, y) || point_hits_circles_all<R>(env, ct, x, y);
     return !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
 }
 
@@ -209,7 +295,15 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
             int kb = -2;
             if (AUV_BIN_CURSOR) { if (FASTENV || env.bins_uniform) kb = e.bins.at(env, e.t); }
             else if (FASTENV) kb = find_bin<R>(env, e.t, 0xffffffffu);
-            const Contrib c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
+            Contrib c;
+            if constexpr (ALLPAIRS && sizeof(R) == 4) {
+                // every habitat in the packed form (the grid code for "no habitat test needed" keeps point_contrib off them)
+                if (ct.hpair != nullptr) cl.code = (cl.code & ~(0xFFu << 3)) | (AUV_GRID_HAB_NONE << 3);
+                c = point_contrib<R, false>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
+                if (ct.hpair != nullptr && c.bin >= 0) c.hab = first_habitat_all_f32(env, ct, (float)e.x, (float)e.y);
+            } else {
+                c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
+            }
             const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[c.bin * env.C + c.cell]) : (R)0;
             if (c.bin >= 0) {
                 e.s2 = A::add(e.s2, ps2);          // (adds +0 when no cell matches: the sum is unchanged)

@@ -47,6 +47,7 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     __shared__ int s_hist[AUV_TPE_BUCKETS];
     __shared__ int s_next;
     __shared__ CircPair s_pairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_TPE_MAXPAIRS : 1];
+    __shared__ CircPair s_hpairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_AP_MAXH : 1], s_epairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_AP_MAXE : 1];
     EnvView<R> env;
     {
         uint64_t *bar = (uint64_t *)smem;
@@ -60,13 +61,30 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     __syncthreads();
     env.shared_self = &s_env;
     CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
+    ct.hpair = nullptr; ct.nhpair = 0; ct.hccmax = 0.f; ct.epair = nullptr; ct.nepair = 0; ct.escale = 0.f; ct.eoff = 0.f;
     if constexpr (ALLPAIRS && sizeof(R) == 4) {
+        ct.ox = 0.5f * (float)(env.minx + env.maxx); ct.oy = 0.5f * (float)(env.miny + env.maxy);
         if (env.K > 0 && env.K <= 2 * AUV_TPE_MAXPAIRS) {
-            ct.ox = 0.5f * (float)(env.minx + env.maxx); ct.oy = 0.5f * (float)(env.miny + env.maxy);
             circ_table_fill(s_pairs, env, ct.ox, ct.oy);
             ct.ccmax = circ_table_ccmax(env, ct.ox, ct.oy);
             ct.pair = s_pairs; ct.npair = (env.K + 1) >> 1;
         }
+        allpairs_tables_fill(s_hpairs, s_epairs, env, ct.ox, ct.oy);
+        if (env.H > 0 && env.H <= 2 * AUV_AP_MAXH) {
+            float m = 0.f;
+            for (int h = 0; h < env.H; h++) { const float ax = env.hx[h] - ct.ox, ay = env.hy[h] - ct.oy; m = fmaxf(m, fmaf(ay, ay, ax * ax)); }
+            ct.hpair = s_hpairs; ct.nhpair = (env.H + 1) >> 1; ct.hccmax = m;
+        }
+        if (env.convex != 0 && env.E >= 3 && env.E <= 2 * AUV_AP_MAXE) {
+            float m = 0.f;                                  // largest edge coefficient: scale of the rounding error
+            for (int i = 0; i < env.E; i++) {
+                const int i1 = i + 1 == env.E ? 0 : i + 1;
+                m = fmaxf(m, fmaxf(fabsf((float)(env.px[i1] - env.px[i])), fabsf((float)(env.py[i1] - env.py[i]))));
+            }
+            ct.epair = s_epairs; ct.nepair = (env.E + 1) >> 1;
+            ct.escale = 1e-6f * m; ct.eoff = ct.escale * ((float)(env.maxx - env.minx) + (float)(env.maxy - env.miny));
+        }
+        __syncthreads();
     }
     const int tid = threadIdx.x, lane = tid & 31;
     const long long n_batches = (n + BATCH - 1) / BATCH;

@@ -59,6 +59,11 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
     __shared__ int s_nnodes[T], s_nchunks[T], s_it[T], s_status[T], s_bestnode[T], s_bestiter[T], s_ncost[T], s_nwp[T],
         s_guard[T], s_active[T], s_parent[T], s_nexp[T], s_order[T], s_hist[64];
     __shared__ R s_bc0[T], s_bc1[T], s_bc2[T], s_bc3[T], s_blen[T], s_bt[T];
+    // which time bins of each tree are non-empty (<= 128 bins): the rejection loop of the parent pick probes bins until
+    // it finds one (rrt_dubins.py:123-125); testing a bit in shared memory instead of reading count[bin] from the tree's
+    // workspace takes a dependent global load (and a 32-byte sector) off every probe
+    __shared__ unsigned s_nonempty[T][4];
+    const bool bin_bits = P.nb + 2 <= 128;
     EnvView<R> env;
     if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
     else {
@@ -96,6 +101,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 const uint32_t ctr0 = rng.ctr - 1;                 // position of the n_expand draw
                 ArcEdge<R> ed;
                 CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
+                ct.hpair = nullptr; ct.nhpair = 0; ct.hccmax = 0.f; ct.epair = nullptr; ct.nepair = 0; ct.escale = 0.f; ct.eoff = 0.f;
                 arc_edge_begin<R, false>(env, ct, ed, pr.x, pr.y, pr.th, pr.t, pr.len, pr.self_s2, pr.self_hab);
                 for (int k = 0; k < n_exp; k++)
                     if (!arc_edge_step<R, true, true, false>(env, ct, sp, P.w3, rng, ed)) break;
@@ -147,6 +153,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                             }
                             pool[tail[bidx] * 32 + (c & 31)] = id;
                             count[bidx] = c + 1;
+                            if (bin_bits) s_nonempty[slot][bidx >> 5] |= 1u << (bidx & 31);
                         }
                         if (!status && t >= P.horizon) {                                // :158-171
                             const uint32_t cnt = nr.cnt + (self_hab >= 0 ? 1u : 0u);
@@ -209,6 +216,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     r0.self_hab = c.bin >= 0 ? c.hab : -1;
                     nodes[0] = r0;
                     head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
+                    s_nonempty[slot][0] = 2u; s_nonempty[slot][1] = s_nonempty[slot][2] = s_nonempty[slot][3] = 0u;     // bin 1 holds `initial`
                     s_z[slot] = stream_key(seeds[q]); s_ctr[slot] = 0; s_upos[slot] = 0; s_q[slot] = q; s_nprims[slot] = 0;
                     s_nnodes[slot] = 1; s_nchunks[slot] = 1; s_it[slot] = 0; s_status[slot] = AUVRRT_ST_OK;
                     s_bestnode[slot] = -1; s_bestiter[slot] = -1; s_ncost[slot] = 0; s_nwp[slot] = 0; s_guard[slot] = 0;
@@ -227,6 +235,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     for (;;) {
                         rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), rng.next());
                         if (rb > P.nb || rb < 1) { status = AUVRRT_ST_KEY_ERROR; break; }
+                        if (bin_bits && !((s_nonempty[slot][rb >> 5] >> (rb & 31)) & 1u)) continue;      // empty: draw again
                         cn = count[rb];
                         if (cn > 0) break;
                     }

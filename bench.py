@@ -678,6 +678,32 @@ def extras(env, dev, args, api, adev):
     except Exception as ex:
         out["throughput_planner_group1"] = {"error": repr(ex)}
 
+    # planner mode 1 (get_random_mps + get_closest_mps, rrt_dubins.py:136-139, :505-513): the IN-PLANNER nearest-node scan.
+    # Every steer call scans the query's own tree (x[], y[] SoA, 8 B per node, lane-strided, coalesced); 4096 trees of
+    # <= 2049 nodes are 64 MB of coordinates, resident in the 126 MB L2, so the scan is L2-bandwidth work.
+    try:
+        Q1, I1 = 4096, ITERS
+        pp1 = api.plan_params(I1, mode=1)
+        st1, sd1 = make_queries(0, Q1)
+        pl1 = adev.DevicePlanner(env, pp1, "f32", Q1, want_chain=True)
+        pl1.set_queries(st1, sd1)
+        mean_s, _ = timed(lambda: pl1.launch(), reps=3, warm=1)
+        rec1 = pl1.records_numpy()
+        # nodes scanned: the tree grows by one node per accepted edge, about linearly over the I steer calls
+        scanned = float(((rec1["n_nodes"].astype(np.float64) + 1.0) * 0.5 * I1).sum())
+        out["planner_mode1_nn_scan"] = {"queries": Q1, "iterations": I1, "seconds": mean_s, "edges_per_s": Q1 * I1 / mean_s,
+                                        "nodes_scanned": scanned, "scan_bytes": 8.0 * scanned,
+                                        "scan_gbs_over_whole_kernel": 8.0 * scanned / mean_s / 1e9,
+                                        "nodes_mean_final": float(rec1["n_nodes"].mean()),
+                                        "kernel": "k_plan<float,32,mode 1> (warp-cooperative scan of the tree's x[], y[] SoA)",
+                                        "note": "GB/s of node coordinates read by the nearest-node scans, over the duration of the WHOLE "
+                                                "planner kernel (steer / collide / cost included); the L2 throughput ncu measures for "
+                                                "this kernel is in profiles/r02_plan_mode1_nn.txt"}
+        del pl1
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["planner_mode1_nn_scan"] = {"error": repr(ex)}
+
     # planner mode 3: Dubins-RRT with best-parent selection (row X1; the build's own definition, parity unpinned)
     try:
         Q3, I3, W3 = 4096, 1024, 12

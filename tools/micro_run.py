@@ -40,6 +40,17 @@ if what == "edges":
     flop = 6 * 20 * K + 6 * 20 * 5 + 140 + 24 * 20
     print("edges-dubins n", n, "edges/s %.4g" % (n / min(ts)), "algorithmic TFLOP/s %.2f" % (n * flop / min(ts) / 1e12), "safe", float(safe.float().mean()),
           {k: os.environ[k] for k in os.environ if k.startswith("AUVRRT_")})
+elif what.startswith("mode"):
+    # python tools/micro_run.py mode1|mode3 Q : the warp-per-tree planner in nearest-node mode / Dubins best-parent mode
+    world, bins_, probs_ = bench.load_world()
+    env = api.Env.from_map(world, bins_, probs_, device=0)
+    pp = api.plan_params(bench.ITERS, mode=1) if what == "mode1" else api.plan_params(1024, mode=3, v=1.0, max_traj_time=200.0)
+    st, sd = bench.make_queries(0, n)
+    pl = adev.DevicePlanner(env, pp, "f32", n, want_chain=True)
+    pl.set_queries(st, sd)
+    for _ in range(3):
+        pl.launch()
+    torch.cuda.synchronize()
 elif what == "tpt":
     # python tools/micro_run.py tpt Q : the thread-per-tree planner on Q queries (config-5 scale on one GPU)
     world, bins_, probs_ = bench.load_world()
