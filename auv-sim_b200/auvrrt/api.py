@@ -92,7 +92,7 @@ _HEADER_INTS = ["K", "E", "H", "T", "C", "NB", "NP", "NCAND", "convex", "hot_byt
                 "off_cx", "off_cy", "off_cr", "off_creff", "off_creff2", "off_px", "off_py",
                 "off_hx", "off_hy", "off_hr", "off_hr2", "off_b0", "off_b1",
                 "off_brk", "off_piece", "off_c1", "off_cell", "off_probs", "off_xb", "nxb", "off_pfirst",
-                "off_grid", "gnx", "gny", "bins_uniform", "pad0", "pad1"]
+                "off_grid", "gnx", "gny", "bins_uniform", "off_one", "pad1"]
 _HEADER_DOUBLES = ["minx", "miny", "maxx", "maxy", "gx0", "gy0", "gs", "bin_s0", "bin_w", "xb0", "xbw", "pad2", "pad3"]
 
 

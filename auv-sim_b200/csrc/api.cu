@@ -81,8 +81,9 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     size_t o = sizeof(EnvHeader);
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return (int)r; };
     const size_t sr = sizeof(R);
-    h.off_cx = take(sr * K); h.off_cy = take(sr * K); h.off_cr = take(sr * K); h.off_creff = take(sr * K);
-    h.off_creff2 = take(sr * K);
+    // circles: K rows + one "always hit" row (radius +inf) that grid cells wholly inside a circle point at
+    h.off_cx = take(sr * (K + 1)); h.off_cy = take(sr * (K + 1)); h.off_cr = take(sr * (K + 1)); h.off_creff = take(sr * (K + 1));
+    h.off_creff2 = take(sr * (K + 1));
     h.off_px = take(sr * E); h.off_py = take(sr * E);
     h.off_hx = take(sr * H); h.off_hy = take(sr * H); h.off_hr = take(sr * H); h.off_hr2 = take(sr * H);
     // sentinels in front of / behind three arrays keep the lookups of geom.cuh free of bounds branches:
@@ -104,6 +105,8 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         h.nxb = nin + 2;
     }
     h.off_xb = take(2 * (size_t)h.nxb);
+    h.off_one = take(sizeof(One<R>) * (size_t)((K + 1) + std::max(E, 1) + std::max(H, 1)));
+    h.pad_ = 0;
     h.hot_bytes = (int)o;
     h.off_probs = take(sr * (size_t)T * C);
     h.total_bytes = (int)o;          // what may be staged in shared memory ends here
@@ -143,7 +146,35 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         arr(h.off_cx)[k] = (R)circles[3 * k]; arr(h.off_cy)[k] = (R)circles[3 * k + 1]; arr(h.off_cr)[k] = r;
         arr(h.off_creff)[k] = suffix; arr(h.off_creff2)[k] = suffix * suffix;
     }
+    arr(h.off_cx)[K] = (R)0; arr(h.off_cy)[K] = (R)0; arr(h.off_cr)[K] = (R)INFINITY;
+    arr(h.off_creff)[K] = (R)INFINITY; arr(h.off_creff2)[K] = (R)INFINITY;
     for (int i = 0; i < E; i++) { arr(h.off_px)[i] = (R)poly[2 * i]; arr(h.off_py)[i] = (R)poly[2 * i + 1]; }
+    {
+        // single-candidate tables (env.cuh, One<R>): the same numbers the SoA arrays hold, one row per object; the edge
+        // differences are formed in R exactly as the kernels' direct formula forms them
+        One<R> *one = (One<R> *)(blob.data() + h.off_one);
+        for (int k = 0; k <= K; k++) {
+            One<R> r; r.x = arr(h.off_cx)[k]; r.y = arr(h.off_cy)[k]; r.z = arr(h.off_creff2)[k]; r.w = arr(h.off_creff)[k];
+            one[k] = r;
+        }
+        One<R> *pone = one + (K + 1);
+        { One<R> z; z.x = z.y = z.z = z.w = (R)0; pone[0] = z; }
+        const R sgn = h.convex < 0 ? (R)-1 : (R)1;
+        for (int i = 0; i < E; i++) {
+            const int j = (i + 1) % E;
+            const R ax = (R)poly[2 * i], ay = (R)poly[2 * i + 1], bx = (R)poly[2 * j], by = (R)poly[2 * j + 1];
+            volatile R ex = bx - ax, ey = by - ay;
+            One<R> r; r.x = ax; r.y = ay; r.z = sgn * ex; r.w = sgn * ey;
+            pone[i] = r;
+        }
+        One<R> *hone = pone + std::max(E, 1);
+        { One<R> z; z.x = z.y = (R)0; z.z = z.w = (R)-1; hone[0] = z; }
+        for (int i = 0; i < H; i++) {
+            const R r0 = (R)hab[3 * i + 2];
+            One<R> r; r.x = (R)hab[3 * i]; r.y = (R)hab[3 * i + 1]; r.z = r0 * r0; r.w = r0;
+            hone[i] = r;
+        }
+    }
     for (int i = 0; i < H; i++) {
         R r = (R)hab[3 * i + 2];
         arr(h.off_hx)[i] = (R)hab[3 * i]; arr(h.off_hy)[i] = (R)hab[3 * i + 1]; arr(h.off_hr)[i] = r;
@@ -249,14 +280,23 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
                 }
                 // obstacle circles (inflated radii): candidates = circles a point of the cell can hit
                 int nc = 0; unsigned cc3[3] = {0x3FF, 0x3FF, 0x3FF};
-                for (int k = 0; k < K; k++)
-                    if (hypot(mx - circles[3 * k], my - circles[3 * k + 1]) - rho <= reff[k]) { if (nc < 3) cc3[nc] = (unsigned)k; nc++; }
+                bool covered = false;                    // some circle holds the whole cell: every point is a hit
+                for (int k = 0; k < K; k++) {
+                    const double d = hypot(mx - circles[3 * k], my - circles[3 * k + 1]);
+                    if (d - rho <= reff[k]) { if (nc < 3) cc3[nc] = (unsigned)k; nc++; }
+                    if (d + rho < reff[k]) covered = true;
+                }
+                const bool poly_general = (code & 3u) == 0u && !(code & AUV_GRID_POLY_ONE);
+                bool circ_general = false;
                 if (nc == 0) code |= 4u;
-                else if (nc > 3 || K > 1022) code |= AUV_GRID_CIRC_MANY;
+                else if (covered && K <= 1022) code |= AUV_GRID_CIRC_ONE | ((unsigned)K << 16);
+                else if (nc > 3 || K > 1022) { code |= AUV_GRID_CIRC_MANY; circ_general = true; }
                 else {
                     w1 = cc3[0] | (cc3[1] << 10) | (cc3[2] << 20);
                     if (nc == 1) code |= AUV_GRID_CIRC_ONE | (cc3[0] << 16);
+                    else circ_general = true;
                 }
+                if (poly_general || circ_general) code |= AUV_GRID_SLOW;
                 // habitats: first match in list order
                 unsigned hc = AUV_GRID_HAB_NONE;
                 int nh = 0; unsigned hh3[3] = {0x3F, 0x3F, 0x3F};

@@ -94,10 +94,12 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
         // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
         if (g.gl == 0) { sc.wx[G] = px; sc.wy[G] = py; }
         const Cls pcl = env.classify(px, py);
-        outside = !point_within_c<R>(env, pcl, px, py);
         parent_clear = (pcl.code & 4u) != 0u;
         parent_many = (pcl.code & AUV_GRID_CIRC_MANY) != 0u;
-        if (!parent_clear && !parent_many) hit = point_hits_circles_c<R>(env, pcl, px, py);
+        if (VERIFY || (pcl.code & AUV_GRID_SLOW)) {
+            outside = !point_within_c<R>(env, pcl, px, py);
+            if (!parent_clear && !parent_many) hit = point_hits_circles_c<R>(env, pcl, px, py);
+        } else outside = point_unsafe_one<R>(env, pcl.code, px, py);     // (either flag makes the edge unsafe)
     }
 
     for (int base = 0; base < n_exp; base += G) {
@@ -244,8 +246,17 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             // lane = waypoint: polygon and the cell's candidate circles
             bool in = true, h1 = false;
             if (is_wp) {
-                in = point_within_c<R>(env, cl, x, y);
-                if (!(cl.code & AUV_GRID_CIRC_MANY)) h1 = point_hits_circles_c<R>(env, cl, x, y);
+                if (VERIFY) {
+                    in = point_within_c<R>(env, cl, x, y);
+                    if (!(cl.code & AUV_GRID_CIRC_MANY)) h1 = point_hits_circles_c<R>(env, cl, x, y);
+                } else {
+                    // decided cells and single-candidate boundary cells in straight-line code; `in` carries the verdict
+                    in = !point_unsafe_one<R>(env, cl.code, x, y);
+                    if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u, 0)) {
+                        in = point_within_c<R>(env, cl, x, y);
+                        if (!(cl.code & AUV_GRID_CIRC_MANY)) h1 = point_hits_circles_c<R>(env, cl, x, y);
+                    }
+                }
             }
             if (g.ballot(!in)) outside = true;
             if (g.ballot(h1)) hit = true;

@@ -194,7 +194,7 @@ template <> __device__ __forceinline__ bool point_within_all<float>(const EnvVie
 template <typename R, bool ALLPAIRS>
 __device__ __forceinline__ bool point_unsafe(const EnvView<R> &env, const CircTable &ct, const Cls &cl, R x, R y) {
     if (ALLPAIRS) return !point_within_all<R>(env, ct, x, y) || point_hits_circles_all<R>(env, ct, x, y);
-    return !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+    return point_unsafe_c<R>(env, cl, x, y);
 }
 
 // the same out of line through the shared copy of the view (every cell that is not "inside and clear")
@@ -219,7 +219,7 @@ template <typename R> struct ArcEdge {
 // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
 // FASTENV: contiguous equal time bins, the x-bucket table and a shared copy of the view are all present (the
 // launcher checked): the hot loop carries no run-time flags.
-template <typename R, bool ALLPAIRS, bool FASTENV = false>
+template <typename R, bool ALLPAIRS, bool FASTENV = false, bool GRIDS = false>
 __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const CircTable &ct, ArcEdge<R> &e, R px, R py, R pth,
                                                R pt, R plen, R parent_self_s2, int parent_self_hab) {
     typedef typename Policy<R>::A A;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
     e.nwp = 1; e.moved = false; e.degenerate = false; e.last_is_wp = false;
     e.s2 = 0; e.cnt = 0; e.mask = 0ull; e.self_s2 = parent_self_s2; e.self_hab = parent_self_hab; e.status = 0;
     Cls pcl; pcl.code = 0; pcl.idx = -1;
-    if (!ALLPAIRS) pcl = env.classify(px, py);
+    if (!ALLPAIRS) pcl = env.template classify<GRIDS>(px, py);
     if (AUV_OUTLINE_COLLIDE && FASTENV && !ALLPAIRS) e.bad = (pcl.code & 7u) != 5u && point_unsafe_shared<R>(env.shared_self, pcl.code, pcl.idx, px, py);
     else e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
     e.bins.k = 0; e.bins.up = 0;
@@ -238,7 +238,7 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
 
 // one arc primitive (rrt_dubins.py:264-284).  Returns false when the edge must stop (ZeroDivisionError in
 // the fp64 build; a degenerate 2^-23 draw in the fp32 build, which rejects the sample).
-template <typename R, bool COST, bool SELF, bool ALLPAIRS, bool FASTENV = false>
+template <typename R, bool COST, bool SELF, bool ALLPAIRS, bool FASTENV = false, bool GRIDS = false>
 __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircTable &ct, const SteerParams<R> &sp, R w3,
                                               SerialStream<R> &rng, ArcEdge<R> &e) {
     typedef typename Policy<R>::A A;
@@ -284,12 +284,18 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
         Cls cl; cl.code = AUV_GRID_ALL_AMBIG; cl.idx = -1;
         if (ALLPAIRS) e.bad = e.bad || point_unsafe<R, true>(env, ct, cl, e.x, e.y);
         else {
-            cl = env.classify(e.x, e.y);
-            // the common cell: strictly inside the polygon (code 1) and clear of every circle (bit 2)
-            if (__builtin_expect((cl.code & 7u) != 5u, 0))
-                e.bad = e.bad || ((AUV_OUTLINE_COLLIDE && (FASTENV || env.shared_self))
-                                      ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
-                                      : point_unsafe<R, false>(env, ct, cl, e.x, e.y));
+            cl = env.template classify<GRIDS>(e.x, e.y);
+            if (Policy<R>::VERIFY) {
+                // the common cell: strictly inside the polygon (code 1) and clear of every circle (bit 2)
+                if (__builtin_expect((cl.code & 7u) != 5u, 0)) e.bad = e.bad || point_unsafe<R, false>(env, ct, cl, e.x, e.y);
+            } else {
+                // decided cells and single-candidate boundary cells in straight-line code (point_unsafe_one)
+                bool bad1 = point_unsafe_one<R>(env, cl.code, e.x, e.y);
+                if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u, 0))
+                    bad1 = (AUV_OUTLINE_COLLIDE && (FASTENV || env.shared_self)) ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
+                                                                                 : (!point_within_c<R>(env, cl, e.x, e.y) || point_hits_circles_c<R>(env, cl, e.x, e.y));
+                e.bad = e.bad || bad1;
+            }
         }
         if (COST) {
             int kb = -2;
@@ -305,13 +311,13 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
                 c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
             }
             const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[c.bin * env.C + c.cell]) : (R)0;
-            if (c.bin >= 0) {
-                e.s2 = A::add(e.s2, ps2);          // (adds +0 when no cell matches: the sum is unchanged)
-                // c.hab is -1 when no habitat holds the point (point_contrib leaves it so when no bin does)
-                const unsigned hb = c.hab >= 0 ? 1u : 0u, sh = (unsigned)c.hab & 31u;
-                e.cnt += hb;
-                e.mask |= (unsigned long long)((c.hab & 32) ? 0u : (hb << sh)) | ((unsigned long long)((c.hab & 32) ? (hb << sh) : 0u) << 32);
-            }
+            // no bin holds the time stamp: the point is skipped (cost.py:178); point_contrib then reports no cell and no
+            // habitat, so the sums below do not move (s2 only ever grows from +0)
+            e.s2 = A::add(e.s2, ps2);
+            const unsigned hb = c.hab >= 0 ? 1u : 0u, sh = (unsigned)c.hab & 31u;
+            e.cnt += hb;
+            if (FASTENV) e.mask |= (unsigned long long)(hb << sh);             // FASTENV: at most 32 habitats (checked by the launcher)
+            else e.mask |= (unsigned long long)((c.hab & 32) ? 0u : (hb << sh)) | ((unsigned long long)((c.hab & 32) ? (hb << sh) : 0u) << 32);
             if (SELF) { e.self_s2 = c.bin >= 0 ? ps2 : (R)0; e.self_hab = c.bin >= 0 ? c.hab : -1; }
         }
     }

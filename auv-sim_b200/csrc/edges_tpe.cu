@@ -11,7 +11,7 @@
 // bulk copy per CTA.
 //
 // Divergence control.  n_expand is uniform in [0, freq): 32 arbitrary edges in a warp would leave half
-// the lanes idle in the primitive loop.  Each CTA therefore takes a batch of 256 x AUV_TPE_EPT consecutive
+// the lanes idle in the primitive loop.  Each CTA therefore takes a batch of NT x AUV_TPE_EPT consecutive
 // edges, (1) draws n_expand for all of them with coalesced loads, (2) counting-sorts the batch by
 // n_expand in shared memory, (3) lets its warps pull groups of 32 edges of (nearly) equal n_expand off a
 // shared counter, longest first.  Inputs and outputs stay in the caller's order.
@@ -21,11 +21,8 @@
 
 namespace auv {
 
-#ifndef AUV_TPE_THREADS
-#define AUV_TPE_THREADS 256
-#endif
 #ifndef AUV_TPE_EPT
-#define AUV_TPE_EPT 8             // edges per thread per batch: batch = 2048 edges
+#define AUV_TPE_EPT 8             // edges per thread per batch: batch = 8 x threads edges
 #endif
 #ifndef AUV_TPE_MINB
 #define AUV_TPE_MINB 4
@@ -35,13 +32,16 @@ namespace auv {
 
 // STAGE: 1 = the hot part of the world model is in shared memory, 2 = the probability table too (always staged:
 // the launcher falls back to the warp-per-edge kernel when even the hot part does not fit)
-template <typename R, bool COST, bool ALLPAIRS, int STAGE, bool FASTENV, int MINB>
-__global__ void __launch_bounds__(AUV_TPE_THREADS, MINB)
+// NT x MINB: threads per CTA x resident CTAs per SM the register allocation targets (256 x 4, 512 x 2 and 1024 x 1 are all
+// 32 warps per SM at 64 registers; fewer, larger CTAs share one staged copy of the world model)
+// GRIDS: plane 0 of the classification grid is staged behind the world model (one more bulk copy) and read with LDS
+template <typename R, bool COST, bool ALLPAIRS, int STAGE, bool FASTENV, int NT, int MINB, bool GRIDS>
+__global__ void __launch_bounds__(NT, MINB)
 k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const R *__restrict__ parents,
                 const uint64_t *__restrict__ seeds, long long n, SteerParams<R> sp, R w3, uint8_t *__restrict__ safe,
                 int32_t *__restrict__ counts, R *__restrict__ leaf, R *__restrict__ cost_out) {
     typedef typename Policy<R>::A A;
-    const int T = AUV_TPE_THREADS, BATCH = AUV_TPE_THREADS * AUV_TPE_EPT;
+    const int T = NT, BATCH = NT * AUV_TPE_EPT;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned short s_order[BATCH];
     __shared__ int s_hist[AUV_TPE_BUCKETS];
@@ -51,10 +51,25 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     EnvView<R> env;
     {
         uint64_t *bar = (uint64_t *)smem;
-        stage_env_tma(smem + 16, blob, STAGE == 2 ? total_bytes : hot_bytes, bar);
+        const int staged = STAGE == 2 ? total_bytes : hot_bytes;          // multiples of 16 (api.cu)
+        if (GRIDS) {
+            // world model + plane 0 of the grid: two regions, one barrier
+            const EnvHeader *gh = (const EnvHeader *)blob;
+            const int plane = (gh->gnx * gh->gny * 4 + 15) & ~15;          // (the blob holds three planes: rounding up stays inside)
+            if (threadIdx.x == 0) mbar_init(bar, 1);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)(staged + plane));
+                for (int o = 0; o < staged; o += 65536) tma_bulk_g2s(smem + 16 + o, blob + o, (uint32_t)(staged - o < 65536 ? staged - o : 65536), bar);
+                const unsigned char *gsrc = blob + gh->off_grid;
+                for (int o = 0; o < plane; o += 65536) tma_bulk_g2s(smem + 16 + staged + o, gsrc + o, (uint32_t)(plane - o < 65536 ? plane - o : 65536), bar);
+            }
+            mbar_wait(bar, 0);
+        } else stage_env_tma(smem + 16, blob, staged, bar);
         env.bind(smem + 16, STAGE == 2 ? smem + 16 : blob);
         env.bind_grid(blob, smem + 16);
         env.assume_hot_shared(STAGE == 2);
+        if (GRIDS) { env.grid0s = (const unsigned *)(smem + 16 + staged); __builtin_assume(__isShared(env.grid0s)); }
     }
     __shared__ EnvView<R> s_env;                 // for the out-of-line slow paths
     if (threadIdx.x == 0) s_env = env;
@@ -137,9 +152,9 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
                 rng.init(stream_key(seeds[i]));
                 const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
                 ArcEdge<R> ed;
-                arc_edge_begin<R, ALLPAIRS, FASTENV>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1);
+                arc_edge_begin<R, ALLPAIRS, FASTENV, GRIDS>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1);
                 for (int k = 0; k < n_exp; k++)
-                    if (!arc_edge_step<R, COST, false, ALLPAIRS, FASTENV>(env, ct, sp, w3, rng, ed)) break;
+                    if (!arc_edge_step<R, COST, false, ALLPAIRS, FASTENV, GRIDS>(env, ct, sp, w3, rng, ed)) break;
                 safe[i] = (ed.status == 0 && !(ed.bad || ed.degenerate)) ? 1 : 0;
                 if (counts) counts[i] = ed.nwp;
                 if (leaf) { R *l = leaf + 5 * i; l[0] = ed.x; l[1] = ed.y; l[2] = ed.th; l[3] = ed.t; l[4] = ed.len; }
@@ -150,48 +165,90 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     }
 }
 
+typedef void (*tpe_kernel_f32)(const unsigned char *, int, int, const float *, const uint64_t *, long long, SteerParams<float>, float,
+                               uint8_t *, int32_t *, float *, float *);
+typedef void (*tpe_kernel_f64)(const unsigned char *, int, int, const double *, const uint64_t *, long long, SteerParams<double>, double,
+                               uint8_t *, int32_t *, double *, double *);
+
+// the fp32 instantiations: (threads x resident CTAs) in {256 x 4, 256 x 3, 512 x 2, 1024 x 1}; the grid plane in shared
+// memory only for the grid-classified kernel on a map with all the lookup tables (FASTENV)
+template <bool COST, bool ALLPAIRS>
+static tpe_kernel_f32 pick_f32(bool fast, bool probs_too, int nt, int minb, bool grids) {
+#define AUV_TPE_K(ST, F, NT_, MB, G) k_edges_arc_tpe<float, COST, ALLPAIRS, ST, F, NT_, MB, G>
+#define AUV_TPE_ST(F, NT_, MB, G) (probs_too ? AUV_TPE_K(2, F, NT_, MB, G) : AUV_TPE_K(1, F, NT_, MB, G))
+    if constexpr (!ALLPAIRS) {
+        if (fast && grids) {
+            if (nt == 1024) return AUV_TPE_ST(true, 1024, 1, true);
+            if (nt == 512) return AUV_TPE_ST(true, 512, 2, true);
+            return minb >= 4 ? AUV_TPE_ST(true, 256, 4, true) : AUV_TPE_ST(true, 256, 3, true);
+        }
+        if (fast) {
+            if (nt == 1024) return AUV_TPE_ST(true, 1024, 1, false);
+            if (nt == 512) return AUV_TPE_ST(true, 512, 2, false);
+        }
+    }
+    if (minb >= 4) return fast ? AUV_TPE_ST(true, 256, 4, false) : AUV_TPE_ST(false, 256, 4, false);
+    return fast ? AUV_TPE_ST(true, 256, 3, false) : AUV_TPE_ST(false, 256, 3, false);
+#undef AUV_TPE_ST
+#undef AUV_TPE_K
+}
+
 template <typename R, bool COST, bool ALLPAIRS>
 static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n, const double params[5],
                         double w3, uint8_t *safe, int32_t *counts, R *leaf, R *cost_out, cudaStream_t s) {
     EnvBlob<R> b = env_blob<R>(env);
-    // fp32: hot part + probability table in shared memory when they fit next to 3 resident CTAs' worth
-    int budget = sizeof(R) == 4 ? 56 * 1024 : 100 * 1024;
+    // FASTENV: equal contiguous time bins, x-bucket table and classification grid all present (any real map)
+    const EnvHeader &hd = sizeof(R) == 4 ? env->h32 : env->h64;
+    const bool fast = hd.gnx > 0 && (!COST || (hd.bins_uniform && hd.nxb > 0 && hd.H <= 32));
+    // CTA shape: threads x resident CTAs per SM (fp32: 32 warps per SM at 64 registers, or 24 at 85 with 256 x 3)
+    // fp32, measured on the Catalina map at 3.4e7 edges, cost on (profiles/r02_tpe_shapes.txt): 256 x 4: 5.5e9 edges/s,
+    // 512 x 2: 6.3e9, 1024 x 1: 6.6e9, 1024 x 1 with the grid plane in shared memory: 6.8e9 -- one staged copy of the
+    // world model per SM instead of four leaves the L1 to the grid and the outputs.  Small batches keep 256-thread CTAs
+    // (a CTA works on 8 edges per thread at a time).
+    int nt = 256, minb = sizeof(R) == 4 ? AUV_TPE_MINB : 1;
+    bool grids = false;
+    if (sizeof(R) == 4) {
+        int nsm_ = 148, dev_ = 0;
+        if (cudaGetDevice(&dev_) == cudaSuccess) cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, dev_);
+        if (n >= (int64_t)nsm_ * 1024 * AUV_TPE_EPT) { nt = 1024; grids = true; }
+        if (const char *ev = getenv("AUVRRT_TPE_THREADS")) { const int v = atoi(ev); if (v == 256 || v == 512 || v == 1024) nt = v; }
+        if (const char *ev = getenv("AUVRRT_TPE_MINB")) minb = atoi(ev);
+        if (const char *ev = getenv("AUVRRT_TPE_GRIDS")) grids = atoi(ev) != 0;
+        if (nt == 512) minb = 2; else if (nt == 1024) minb = 1; else minb = minb >= 4 ? 4 : 3;
+        if (ALLPAIRS || !fast) { grids = false; nt = 256; minb = minb >= 4 ? 4 : 3; }
+        // the grid plane must fit next to the hot part
+        if (grids && ((hd.gnx * hd.gny * 4 + 15) & ~15) + b.hot_bytes + 16 > (int)((227 * 1024) / minb) - 2048 - (int)(2 * nt * AUV_TPE_EPT)) grids = false;
+    }
+    const int plane = grids ? ((hd.gnx * hd.gny * 4 + 15) & ~15) : 0;
+    // shared memory per CTA: the hot part, + the probability table when the resident CTAs still fit, + the grid plane
+    const int per_cta_max = (int)((227 * 1024) / minb) - 1024 - (int)(2 * nt * AUV_TPE_EPT) - 1024;   // less the static arrays
+    int budget = per_cta_max - plane;
     if (const char *ev = getenv("AUVRRT_TPE_STAGE_KB")) budget = atoi(ev) * 1024;
     int sm = 16;
     const bool probs_too = COST && b.total_bytes + 16 <= budget;
     if (probs_too) sm = b.total_bytes + 16;
-    else if (b.hot_bytes + 16 <= 200 * 1024) sm = b.hot_bytes + 16;
+    else if (b.hot_bytes + 16 + plane <= 200 * 1024) sm = b.hot_bytes + 16;
     else return AUVRRT_ERR_UNSUPPORTED;          // the caller falls back to the warp-per-edge kernel
-    // FASTENV: equal contiguous time bins, x-bucket table and classification grid all present (any real map)
-    const EnvHeader &hd = sizeof(R) == 4 ? env->h32 : env->h64;
-    const bool fast = hd.gnx > 0 && (!COST || (hd.bins_uniform && hd.nxb > 0));
-    // resident CTAs per SM the register allocation targets: 3 (85 registers) or 4 (64 registers, 32 warps per SM)
-    int minb = sizeof(R) == 4 ? AUV_TPE_MINB : 1;
-    if (const char *ev = getenv("AUVRRT_TPE_MINB")) minb = atoi(ev);
+    sm += plane;
     void (*kern)(const unsigned char *, int, int, const R *, const uint64_t *, long long, SteerParams<R>, R, uint8_t *,
                  int32_t *, R *, R *);
     if constexpr (sizeof(R) == 4) {
-        if (minb >= 4)
-            kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 4> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 4>)
-                        : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 4> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 4>);
-        else
-            kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 3> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 3>)
-                        : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 3> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 3>);
+        kern = pick_f32<COST, ALLPAIRS>(fast, probs_too, nt, minb, grids);
     } else {
-        kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 1> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 1>)
-                    : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 1> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 1>);
+        kern = fast ? (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, true, 256, 1, false> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, true, 256, 1, false>)
+                    : (probs_too ? k_edges_arc_tpe<R, COST, ALLPAIRS, 2, false, 256, 1, false> : k_edges_arc_tpe<R, COST, ALLPAIRS, 1, false, 256, 1, false>);
     }
     AUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0, nsm = 0, dev = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AUV_TPE_THREADS, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "edges_arc (thread per edge): kernel does not fit on an SM (smem %d)", sm);
     AUV_CUDA(cudaGetDevice(&dev));
     AUV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t batch = (int64_t)AUV_TPE_THREADS * AUV_TPE_EPT;
+    const int64_t batch = (int64_t)nt * AUV_TPE_EPT;
     int64_t blocks = (n + batch - 1) / batch;
     if (blocks > (int64_t)nsm * per_sm) blocks = (int64_t)nsm * per_sm;
-    kern<<<(unsigned)blocks, AUV_TPE_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, parents, seeds, (long long)n,
-                                                        make_steer_params<R>(params), (R)w3, safe, counts, leaf, cost_out);
+    kern<<<(unsigned)blocks, nt, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, parents, seeds, (long long)n,
+                                          make_steer_params<R>(params), (R)w3, safe, counts, leaf, cost_out);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(AUVRRT_ERR_CUDA, "edges_arc (thread per edge) launch: %s", cudaGetErrorString(e));

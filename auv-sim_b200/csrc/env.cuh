@@ -43,7 +43,8 @@ struct EnvHeader {
     int off_grid;      // classification grid (3 planes of u32, one word per cell each), not staged: read through L1/L2
     int gnx, gny;      // grid dimensions (0: no grid)
     int bins_uniform;  // 1: bins are [s0 + i w, s0 + (i+1) w], contiguous and in order
-    int pad_[2];
+    int off_one;       // single-candidate tables (One<R> rows, staged): K+1 circles, then max(E,1) boundary edges, then max(H,1) habitats
+    int pad_;
     double bbox[4];    // minx, miny, maxx, maxy of the polygon (Polygon.bounds, rrt_dubins.py:334)
     double gx0, gy0, gs;   // grid origin and cell size
     double bin_s0, bin_w;
@@ -62,27 +63,32 @@ static_assert(sizeof(EnvHeader) % 16 == 0, "EnvHeader must keep 16-byte alignmen
 //  word 0  bits 0-1   polygon: 0 ambiguous, 1 strictly inside, 2 outside
 //          bit  2     1: clear of every (inflated) obstacle circle
 //          bits 3-10  habitat: 0..63 first-match habitat (definitive); 64 + h: habitat h is the only one a point of
-//                     the cell can be in and must be tested; 254 none; 255 ambiguous (candidates in word 2)
+//                     the cell can be in and must be tested; 128 none; 192 ambiguous (candidates in word 2)
+//                     (the low six bits always index a valid row of the habitat table)
 //          bit  11    circles: more than 3 candidates -> full loop
 //          bit  12    habitats: more than 3 candidates -> full loop
 //          bit  13    polygon: convex fast path not applicable / more than 2 candidate edges -> full test
-//          bit  14    circles: exactly ONE candidate, its index in bits 16-25
+//          bit  14    circles: exactly ONE candidate, its index in bits 16-25; index K (a row with radius +inf) says
+//                     "every point of the cell is inside some circle"
 //          bit  15    polygon ambiguous with exactly ONE candidate edge (convex ring), its index in bits 26-30
+//          bit  31    the collision test of this cell needs the general path (words 1 / 2 or the full loops); clear:
+//                     bits 0-2 and the two single candidates decide it (point_unsafe_one, geom.cuh)
 //  word 1  three 10-bit circle indices (0x3FF = none): the only circles a point of the cell can hit
 //  word 2  bits 0-17 three 6-bit habitat indices (0x3F = none), in list order; bits 18-27 two 5-bit
 //          polygon edge indices (0x1F = none): the only edges whose half-plane is not already decided
 // The single-candidate forms keep the common boundary cells (one circle, one habitat or one polygon edge
 // nearby) on a short branch-free path: in a kernel that runs one edge per thread a rare slow path taken by one
 // lane stalls the other 31.
-#define AUV_GRID_HAB_NONE 254u
-#define AUV_GRID_HAB_AMBIG 255u
+#define AUV_GRID_HAB_NONE 128u
+#define AUV_GRID_HAB_AMBIG 192u
 #define AUV_GRID_HAB_ONE 64u
 #define AUV_GRID_CIRC_MANY (1u << 11)
 #define AUV_GRID_HAB_MANY (1u << 12)
 #define AUV_GRID_POLY_FULL (1u << 13)
 #define AUV_GRID_CIRC_ONE (1u << 14)
 #define AUV_GRID_POLY_ONE (1u << 15)
-#define AUV_GRID_ALL_AMBIG ((AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_CIRC_MANY | AUV_GRID_HAB_MANY | AUV_GRID_POLY_FULL)
+#define AUV_GRID_SLOW (1u << 31)
+#define AUV_GRID_ALL_AMBIG ((AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_CIRC_MANY | AUV_GRID_HAB_MANY | AUV_GRID_POLY_FULL | AUV_GRID_SLOW)
 
 struct Cls { unsigned code; int idx; };   // word 0 and the cell index (-1 outside the grid)
 
@@ -90,12 +96,20 @@ struct Cls { unsigned code; int idx; };   // word 0 and the cell index (-1 outsi
 // y bound, bit 30: more candidates follow in the piece's list; v == -1: the piece has no candidate.
 template <typename R> struct alignas(8) PFirst { R c1; int v; };
 
+// One row of the single-candidate tables, fetched with one 16-byte load (fp32):
+//   circle   {cx, cy, r_eff^2, r_eff}      (row K: {0, 0, +inf, +inf})
+//   edge i   {ax, ay, s (bx - ax), s (by - ay)}, s = +1 for a CCW ring, -1 for CW: strictly inside the half-plane <=> det > 0
+//   habitat  {hx, hy, r^2, r}
+template <typename R> struct alignas(16) One { R x, y, z, w; };
+
 template <typename R> struct EnvView {
     int K, E, H, T, C, NB, NP, convex;
     int gnx, gny, ncell, bins_uniform, nxb;
     R gx0, gy0, ginv, gxo, gyo, bin_s0, bin_w, bin_winv, bin_off, bin_lo, bin_hi, xb0, xbinv, xbo;
     const unsigned *grid;
+    const unsigned *grid0s;        // plane 0 of the grid in shared memory (kernels that stage it), else nullptr
     const PFirst<R> *pfirst;
+    const One<R> *cone, *pone, *hone;
     // A copy of this view in shared memory, or nullptr.  Kernels that run one edge per thread publish one so that
     // the rare slow paths (boundary cells, ambiguous habitats, buckets with several breakpoints) can live OUT OF LINE,
     // taking just this pointer: the hot loop stays short and its registers free.
@@ -128,6 +142,7 @@ template <typename R> struct EnvView {
         c1 = (const R *)(hot + h->off_c1); cell = (const int *)(hot + h->off_cell);
         probs = (const R *)(probs_base + h->off_probs);
         pfirst = (const PFirst<R> *)(hot + h->off_pfirst);
+        cone = (const One<R> *)(hot + h->off_one); pone = cone + (K + 1); hone = pone + (E > 0 ? E : 1);
         bin_lo = T > 0 ? b0[0] : (R)1; bin_hi = T > 0 ? b1[T - 1] : (R)0;      // [first b0, last b1]; empty when T == 0
     }
     // Tell the compiler that the staged arrays live in shared memory (the pointers are computed from offsets read
@@ -141,6 +156,7 @@ template <typename R> struct EnvView {
         __builtin_assume(__isShared(hr2)); __builtin_assume(__isShared(b0)); __builtin_assume(__isShared(b1));
         __builtin_assume(__isShared(brk)); __builtin_assume(__isShared(piece)); __builtin_assume(__isShared(c1));
         __builtin_assume(__isShared(cell)); __builtin_assume(__isShared(pfirst)); __builtin_assume(__isShared(xb));
+        __builtin_assume(__isShared(cone)); __builtin_assume(__isShared(pone)); __builtin_assume(__isShared(hone));
         if (probs_too) __builtin_assume(__isShared(probs));
     }
     // the grid stays in global memory: bind it from the blob in HBM
@@ -152,9 +168,12 @@ template <typename R> struct EnvView {
         gxo = (R)(-h->gx0 / h->gs); gyo = (R)(-h->gy0 / h->gs);
         bin_s0 = (R)h->bin_s0; bin_w = (R)h->bin_w; bin_winv = (R)(1.0 / h->bin_w); bin_off = (R)(-h->bin_s0 / h->bin_w);
         grid = (const unsigned *)(blob_global + h->off_grid);
+        grid0s = nullptr;
         ncell = gnx * gny;
     }
     // classification of the cell containing (x, y); off the grid: outside the polygon, everything else ambiguous
+    // GRIDS: plane 0 is read from its shared-memory copy (grid0s)
+    template <bool GRIDS = false>
     __device__ __forceinline__ Cls classify(R x, R y) const {
         Cls c;
         int ix, iy;
@@ -175,7 +194,7 @@ template <typename R> struct EnvView {
             c.code = AUV_GRID_ALL_AMBIG | (gnx > 0 ? 2u : 0u); c.idx = -1; return c;
         }
         c.idx = iy * gnx + ix;
-        c.code = __ldg(grid + c.idx);
+        c.code = GRIDS ? grid0s[c.idx] : __ldg(grid + c.idx);
         return c;
     }
     __device__ __forceinline__ unsigned word1(const Cls &c) const { return __ldg(grid + ncell + c.idx); }

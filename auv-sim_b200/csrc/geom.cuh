@@ -177,6 +177,32 @@ template <typename R, bool OUTLINE = true> __device__ __forceinline__ bool point
     return hit;
 }
 
+// Fast build, branch-free: the collision test of a cell that is decided by its code or by ONE circle and / or ONE
+// boundary edge (code bit 31 clear).  Both candidates are always fetched (a cell without one names row 0) and
+// their results masked by the code: on the Catalina map 17 % of the free cells are boundary cells of this kind, so in a
+// kernel that runs 32 edges per warp some lane is in one on nearly every step -- a branch would be taken every time,
+// for two or three lanes.  Same arithmetic as point_within_c / point_hits_circles_c.
+template <typename R>
+__device__ __forceinline__ bool point_unsafe_one(const EnvView<R> &env, unsigned code, R x, R y) {
+    typedef typename Policy<R>::A A;
+    const One<R> ce = env.cone[(code >> 16) & 0x3FFu];
+    const One<R> pe = env.pone[(code >> 26) & 0x1Fu];
+    const R q = A::sq2(A::sub(x, ce.x), A::sub(y, ce.y));
+    const R det = pe.z * (y - pe.y) - pe.w * (x - pe.x);
+    const bool hit = (code & AUV_GRID_CIRC_ONE) && q <= ce.z;
+    const bool in = (code & 3u) == 1u || ((code & AUV_GRID_POLY_ONE) && det > (R)0);
+    return !in || hit;
+}
+// collision test of a classified point: the branch-free form, the general one only for cells flagged AUV_GRID_SLOW
+template <typename R>
+__device__ __forceinline__ bool point_unsafe_c(const EnvView<R> &env, const Cls &cl, R x, R y) {
+    if (Policy<R>::VERIFY) return !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+    bool bad = point_unsafe_one<R>(env, cl.code, x, y);
+    if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u, 0))
+        bad = !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+    return bad;
+}
+
 // ---------------------------------------------------------------- cost contribution of a point
 // One iteration of the `for mps in path` loop of habitat_shark_cost_func (cost.py:171-191).
 struct Contrib {
@@ -309,43 +335,55 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
     Contrib c;
     c.cell = -1; c.hab = -1;
     c.bin = (FASTENV || known_bin != -2) ? known_bin : find_bin<R>(env, t, bin_mask);
-    if (c.bin < 0) return c;
+    if (!FASTENV && c.bin < 0) return c;             // (FASTENV: straight-line code, the result is masked at the end)
     const unsigned code = cl.code;
     c.cell = find_cell<R, FASTENV>(env, x, y);
     const unsigned hc = (code >> 3) & 0xFFu;
-    if (hc < 128u) {
+    if (!Policy<R>::VERIFY) {
+        // branch-free: definitive first match (hc < 64), the one habitat a point of this cell can be in (64 + h), or
+        // none (128: row 0 is fetched and the result masked)
+        const int h = (int)(hc & 63u);
+        const One<R> ho = env.hone[h];
+        const R q = A::sq2(A::sub(ho.x, x), A::sub(ho.y, y));
+        const bool take = (hc < AUV_GRID_HAB_ONE || (hc < 128u && q <= ho.z)) && (FASTENV || h < n_hab);
+        c.hab = take ? h : -1;
+    } else if (hc < 128u) {
         // definitive first match (hc < 64), or the one habitat a point of this cell can be in (64 + h)
         const int h = (int)(hc & 63u);
         if (h < n_hab) {
             bool in = true;
             if (hc >= AUV_GRID_HAB_ONE) {
                 R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
-                in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
+                in = A::sqrt(q) <= env.hr[h];
             }
             if (in) c.hab = h;
         }
-    } else if (AUV_OUTLINE_HAB && hc == AUV_GRID_HAB_AMBIG && (FASTENV || env.shared_self)) {
-        c.hab = first_habitat_ambiguous<R>(env.shared_self, code, cl.idx, n_hab, x, y);
-    } else if (hc == AUV_GRID_HAB_AMBIG && !(code & AUV_GRID_HAB_MANY)) {
-        // the cell's candidate habitats, in list order (every habitat that touches the cell, up to
-        // and including the first that covers it)
-        const unsigned w2 = env.word2(cl);
+    }
+    if (__builtin_expect(hc == AUV_GRID_HAB_AMBIG, 0)) {
+        if (AUV_OUTLINE_HAB && (FASTENV || env.shared_self)) {
+            c.hab = first_habitat_ambiguous<R>(env.shared_self, code, cl.idx, n_hab, x, y);
+        } else if (!(code & AUV_GRID_HAB_MANY)) {
+            // the cell's candidate habitats, in list order (every habitat that touches the cell, up to
+            // and including the first that covers it)
+            const unsigned w2 = env.word2(cl);
 #pragma unroll
-        for (int s = 0; s < 3; s++) {
-            const int h = (int)((w2 >> (6 * s)) & 0x3Fu);
-            if (h != 0x3F && h < n_hab && c.hab < 0) {
+            for (int s = 0; s < 3; s++) {
+                const int h = (int)((w2 >> (6 * s)) & 0x3Fu);
+                if (h != 0x3F && h < n_hab && c.hab < 0) {
+                    R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
+                    bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
+                    if (in) c.hab = h;
+                }
+            }
+        } else {
+            for (int h = 0; h < n_hab; h++) {
                 R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
                 bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
-                if (in) c.hab = h;
+                if (in) { c.hab = h; break; }
             }
         }
-    } else if (hc == AUV_GRID_HAB_AMBIG) {
-        for (int h = 0; h < n_hab; h++) {
-            R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
-            bool in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
-            if (in) { c.hab = h; break; }
-        }
     }
+    if (FASTENV && c.bin < 0) { c.hab = -1; c.cell = -1; }
     return c;
 }
 

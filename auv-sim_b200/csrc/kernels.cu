@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) k_collide(const unsigned char *blob, int 
         for (int64_t k = b + g.gl; k < e; k += 32) {
             R x = pts[2 * k], y = pts[2 * k + 1];
             const Cls cl = env.classify(x, y);
-            bad = bad || point_hits_circles_c<R>(env, cl, x, y) || !point_within_c<R>(env, cl, x, y);
+            bad = bad || point_unsafe_c<R>(env, cl, x, y);
         }
         unsigned any = g.ballot(bad);
         if (g.gl == 0) safe[i] = (e == b && env.K > 0) ? 255 : (any ? 0 : 1);

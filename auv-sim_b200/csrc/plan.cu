@@ -103,7 +103,7 @@ __device__ __forceinline__ void dubins_edge_eval(const EnvView<R> &env, const Pl
     bool bad = false;
     if (do_tests) {                                      // path[0] is the parent node object
         const Cls pcl = env.classify(px, py);
-        bad = !point_within_c<R>(env, pcl, px, py) || point_hits_circles_c<R>(env, pcl, px, py);
+        bad = point_unsafe_c<R>(env, pcl, px, py);
     }
 #pragma unroll 1
     for (int k = 1; k < P.W; k++) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void dubins_edge_eval(const EnvView<R> &env, const Pl
         const R t = A::add(pt, A::div(sk, P.vel)), len = A::add(plen, sk);
         if (do_tests) {
             const Cls cl = env.classify(x, y);
-            bad = bad || !point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y);
+            bad = bad || point_unsafe_c<R>(env, cl, x, y);
             const Contrib c = point_contrib<R>(env, x, y, t, 0xffffffffu, env.H, cl);
             const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
             if (c.bin >= 0) {

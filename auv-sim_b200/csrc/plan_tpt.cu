@@ -44,7 +44,9 @@ template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchu
 // steer / collide / cost / append part for the i-th slot in that order, so the lanes of a warp loop
 // over nearly the same number of primitives.  The per-tree registers that survive an iteration
 // live in shared memory (struct-of-arrays) because a different thread owns the tree every trip.
-template <typename R>
+// FAST: the hot part of the world model is staged and the map has every lookup table (classification grid, x-bucket
+// table, equal contiguous time bins, <= 32 habitats): the edge loop runs the straight-line forms of edge_serial.cuh
+template <typename R, bool FAST>
 __global__ void __launch_bounds__(TPT_THREADS, AUV_TPT_MINB)
 k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
            const uint64_t *seeds, long long Q, PlanP<R> P, TptLayout L, unsigned char *ws, unsigned long long *qcounter,
@@ -71,7 +73,11 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
         env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
         env.bind_grid(blob, smem + 16);
+        if (FAST) env.assume_hot_shared(stage_mode == 2);
     }
+    __shared__ EnvView<R> s_env;                 // for the out-of-line slow paths
+    if (threadIdx.x == 0) s_env = env;
+    env.shared_self = &s_env;
     const SteerParams<R> sp = P.sp;
     const int tid = threadIdx.x;
     unsigned char *block_ws = ws + (size_t)blockIdx.x * T * L.slot_bytes;
@@ -102,9 +108,9 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 ArcEdge<R> ed;
                 CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
                 ct.hpair = nullptr; ct.nhpair = 0; ct.hccmax = 0.f; ct.epair = nullptr; ct.nepair = 0; ct.escale = 0.f; ct.eoff = 0.f;
-                arc_edge_begin<R, false>(env, ct, ed, pr.x, pr.y, pr.th, pr.t, pr.len, pr.self_s2, pr.self_hab);
+                arc_edge_begin<R, false, FAST>(env, ct, ed, pr.x, pr.y, pr.th, pr.t, pr.len, pr.self_s2, pr.self_hab);
                 for (int k = 0; k < n_exp; k++)
-                    if (!arc_edge_step<R, true, true, false>(env, ct, sp, P.w3, rng, ed)) break;
+                    if (!arc_edge_step<R, true, true, false, FAST>(env, ct, sp, P.w3, rng, ed)) break;
                 status = ed.status;
                 const R x = ed.x, y = ed.y, th = ed.th, t = ed.t, len = ed.len;
                 const int nwp = ed.nwp;
@@ -315,9 +321,12 @@ int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seed
     int budget = 24 * 1024, sm = 16, mode = 0;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
-    AUV_CUDA(cudaFuncSetAttribute(k_plan_tpt<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    const EnvHeader &hd = sizeof(R) == 4 ? env->h32 : env->h64;
+    const bool fast = sizeof(R) == 4 && mode >= 1 && hd.gnx > 0 && hd.bins_uniform && hd.nxb > 0 && hd.H <= 32;
+    auto kern = fast ? k_plan_tpt<R, true> : k_plan_tpt<R, false>;
+    AUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0, nsm = 0, dev = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan_tpt<R>, TPT_THREADS, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPT_THREADS, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan_tpt: kernel does not fit on an SM");
     AUV_CUDA(cudaGetDevice(&dev));
     AUV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -336,7 +345,7 @@ int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seed
     AUV_CUDA(cudaMemsetAsync(workspace, 0, 256, s));
     auvrrt_plan_trace_t tr;
     if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
-    k_plan_tpt<R><<<grid, TPT_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+    kern<<<grid, TPT_THREADS, sm, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
                                                 (unsigned char *)workspace + 256, (unsigned long long *)workspace, records,
                                                 chain, tr);
     g_launches++;

@@ -15,7 +15,8 @@ import pytest
 
 from auvrrt import api
 
-HAB_NONE, HAB_AMBIG, HAB_ONE = 254, 255, 64
+HAB_NONE, HAB_AMBIG, HAB_ONE = 128, 192, 64
+SLOW = 1 << 31
 CIRC_MANY, HAB_MANY, POLY_FULL, CIRC_ONE, POLY_ONE = 1 << 11, 1 << 12, 1 << 13, 1 << 14, 1 << 15
 
 
@@ -29,8 +30,11 @@ class Blob:
         def arr(off, n, dt=None):
             dt = dt or self.R
             return self.raw[off:off + n * np.dtype(dt).itemsize].view(dt)
-        self.cx, self.cy = arr(h["off_cx"], h["K"]).astype(np.float64), arr(h["off_cy"], h["K"]).astype(np.float64)
-        self.creff = arr(h["off_creff"], h["K"]).astype(np.float64)
+        # K circles + the "always hit" row K (radius +inf) that cells wholly inside a circle name as their one candidate
+        self.cx, self.cy = arr(h["off_cx"], h["K"] + 1).astype(np.float64), arr(h["off_cy"], h["K"] + 1).astype(np.float64)
+        self.creff = arr(h["off_creff"], h["K"] + 1).astype(np.float64)
+        one = arr(h["off_one"], 4 * (h["K"] + 1 + max(h["E"], 1) + max(h["H"], 1))).astype(np.float64).reshape(-1, 4)
+        self.cone, self.pone, self.hone = one[:h["K"] + 1], one[h["K"] + 1:h["K"] + 1 + max(h["E"], 1)], one[h["K"] + 1 + max(h["E"], 1):]
         self.px, self.py = arr(h["off_px"], h["E"]).astype(np.float64), arr(h["off_py"], h["E"]).astype(np.float64)
         self.hx, self.hy = arr(h["off_hx"], h["H"]).astype(np.float64), arr(h["off_hy"], h["H"]).astype(np.float64)
         self.hr = arr(h["off_hr"], h["H"]).astype(np.float64)
@@ -112,12 +116,13 @@ def test_classification_grid_is_exact(blob):
         assert np.array_equal(inside[two], ok[two])
         # circles (inflated radii)
         dist = np.hypot(xs[:, None] - blob.cx[None], ys[:, None] - blob.cy[None])
-        hitk = dist <= blob.creff[None]
-        hit = hitk.any(1)
+        hitk = dist <= blob.creff[None]                  # column K: the always-hit row
+        assert hitk[:, h["K"]].all()
+        hit = hitk[:, :h["K"]].any(1)
         assert not hit[(code & 4) != 0].any()
         c1 = ((code & 4) == 0) & ((code & CIRC_ONE) != 0)
         kk = ((code >> 16) & 0x3FF).astype(np.int64)
-        assert np.array_equal(hit[c1], hitk[np.arange(len(xs)), np.minimum(kk, h["K"] - 1)][c1])
+        assert np.array_equal(hit[c1], hitk[np.arange(len(xs)), np.minimum(kk, h["K"])][c1])
         c3 = ((code & 4) == 0) & ((code & (CIRC_ONE | CIRC_MANY)) == 0)
         h3 = np.zeros(len(xs), bool)
         for s in range(3):
@@ -139,11 +144,21 @@ def test_classification_grid_is_exact(blob):
             hs = ((w2 >> (6 * s)) & 0x3F).astype(np.int64)
             f3 = np.where((hs != 0x3F) & inh[np.arange(len(xs)), np.minimum(hs, h["H"] - 1)], hs, f3)
         assert np.array_equal(first[a3], f3[a3])
-        # the fast single-load cases must dominate, or a thread-per-edge warp always takes a slow path
+        # the branch-free collision rule of point_unsafe_one (geom.cuh) for every cell not flagged SLOW: both single
+        # candidates are always fetched (row 0 when the cell has none) and masked by the code
+        ce = blob.cone[((code >> 16) & 0x3FF).astype(np.int64)]
+        pe = blob.pone[((code >> 26) & 0x1F).astype(np.int64)]
+        q = (xs - ce[:, 0]) ** 2 + (ys - ce[:, 1]) ** 2
+        det1 = pe[:, 2] * (ys - pe[:, 1]) - pe[:, 3] * (xs - pe[:, 0])
+        hit1 = ((code & CIRC_ONE) != 0) & (np.sqrt(q) <= ce[:, 3])
+        in1 = (pc == 1) | (((code & POLY_ONE) != 0) & (det1 > 0))
+        fast = (code & SLOW) == 0
+        assert np.array_equal((~in1 | hit1)[fast], (~inside | hit)[fast])
+        assert np.array_equal(blob.cone[:, 3], blob.creff) and np.array_equal(blob.hone[:h["H"], 3], blob.hr)
+        # the straight-line cases must dominate, or a thread-per-edge warp always takes a slow path
         inside_free = inside & ~hit
-        fastc = ((code & 7) == 5) | ((code & 3) == 1) & ((code & CIRC_ONE) != 0)
-        assert fastc[inside_free].mean() > 0.95
-        assert ((hc < 128) | (hc == HAB_NONE))[inside_free].mean() > 0.97
+        assert fast[inside_free].mean() > 0.97
+        assert (hc != HAB_AMBIG)[inside_free].mean() > 0.97
 
 
 def _find_cell_tables(b, x, y, nudge):
