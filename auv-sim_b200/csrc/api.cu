@@ -87,7 +87,7 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
     h.off_px = take(sr * E); h.off_py = take(sr * E);
     h.off_hx = take(sr * H); h.off_hy = take(sr * H); h.off_hr = take(sr * H); h.off_hr2 = take(sr * H);
     // sentinels in front of / behind three arrays keep the lookups of geom.cuh free of bounds branches:
-    // b1[-1] = b0[0];  brk[-1] = -inf, brk[NB] = +inf;  pfirst[-2] = pfirst[-1] = "no candidate"
+    // b1[-1] = just below b0[0];  brk[-1] = -inf, brk[NB] = +inf;  pfirst[-2] = pfirst[-1] = "no candidate"
     h.off_b0 = take(sr * T); h.off_b1 = take(sr * (T + 2)) + 2 * (int)sr;
     h.off_brk = take(sr * (NB + 4)) + 2 * (int)sr;
     h.off_piece = take(4 * (size_t)(NP + 1)); h.off_c1 = take(sr * cand_c1.size());
@@ -181,7 +181,7 @@ std::vector<unsigned char> build_blob(const double *circles, int K, const double
         arr(h.off_hr2)[i] = r * r;
     }
     for (int i = 0; i < T; i++) { arr(h.off_b0)[i] = (R)bins[2 * i]; arr(h.off_b1)[i] = (R)bins[2 * i + 1]; }
-    arr(h.off_b1)[-1] = T > 0 ? (R)bins[0] : (R)0;
+    arr(h.off_b1)[-1] = T > 0 ? std::nextafter((R)bins[0], (R)-INFINITY) : (R)0;
     for (int i = 0; i < NB; i++) arr(h.off_brk)[i] = brk[i];
     arr(h.off_brk)[NB] = (R)INFINITY;
     arr(h.off_brk)[-1] = (R)-INFINITY;

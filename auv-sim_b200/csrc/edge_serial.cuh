@@ -44,6 +44,21 @@ struct CircTable {
     // signs normalised so that "strictly inside" is det < 0 for every edge; a missing second edge has (0, 0, -1)
     const CircPair *epair; int nepair; float escale, eoff;   // |det| <= escale (|x'| + |y'|) + eoff: too close to call
 };
+// Deferred slow cases of the thread-per-edge kernel.  Whether a waypoint collides, and which habitat holds it, only
+// feed commutative updates of the edge's result (bad |=, cnt +=, mask |=): nothing the rest of the edge depends on.
+// A lane that meets a cell needing the general tests (2 % of the waypoints on the Catalina map, i.e. some lane on
+// every other step) therefore queues the point and goes on; the warp resolves the queue after its 32 edges, one
+// entry per lane, and every lane folds its slot of the result arrays into its edge.
+struct SlowEntry { float x, y; int idx; int meta; };      // meta: owner lane | 32: collision test wanted | 64: habitat wanted
+#define AUV_SLOWQ_CAP 48
+struct SlowQ {               // per warp, shared memory; one pointer (a register) in the hot loop, everything at fixed offsets
+    unsigned char *base;     // AUV_SLOWQ_CAP entries | n (entries pushed; beyond the capacity they were resolved in place) | bad[32] cnt[32] mask[32]
+    __device__ __forceinline__ SlowEntry *ent() const { return (SlowEntry *)base; }
+    __device__ __forceinline__ int *n() const { return (int *)(base + AUV_SLOWQ_CAP * sizeof(SlowEntry)); }
+    __device__ __forceinline__ unsigned *bad() const { return (unsigned *)(base + AUV_SLOWQ_CAP * sizeof(SlowEntry) + 16); }
+    __device__ __forceinline__ unsigned *cnt() const { return bad() + 32; }
+    __device__ __forceinline__ unsigned *mask() const { return bad() + 64; }
+};
 #define AUV_AP_MAXH 32       // habitat pairs (64 habitats)
 #define AUV_AP_MAXE 16       // polygon edge pairs (32 edges)
 
@@ -204,6 +219,39 @@ __device__ __noinline__ bool point_unsafe_shared(const EnvView<R> *senv, unsigne
     return !point_within_c<R>(*senv, cl, x, y) || point_hits_circles_c<R>(*senv, cl, x, y);
 }
 
+// one queued point: the general tests, results into the owner's slots
+template <typename R>
+__device__ __forceinline__ void slowq_resolve(const EnvView<R> &env, const SlowQ &q, const SlowEntry &en) {
+    const int owner = en.meta & 31;
+    Cls cl; cl.idx = en.idx;
+    cl.code = en.idx >= 0 ? __ldg(env.grid + en.idx) : ((AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_HAB_MANY | AUV_GRID_CIRC_MANY | AUV_GRID_POLY_FULL | 2u);
+    const R x = (R)en.x, y = (R)en.y;
+    if (en.meta & 32) {
+        if (!point_within_c<R>(env, cl, x, y) || point_hits_circles_c<R>(env, cl, x, y)) atomicOr(&q.bad()[owner], 1u);
+    } else {
+        const int hab = first_habitat_ambiguous<R>(env.shared_self, cl.code, cl.idx, env.H, x, y);
+        if (hab >= 0) { atomicAdd(&q.cnt()[owner], 1u); atomicOr(&q.mask()[owner], 1u << (hab & 31)); }
+    }
+}
+// queue a point (out of line: the hot loop only sees a call); a full queue resolves the point on the spot
+template <typename R>
+__device__ __noinline__ void slowq_push(const EnvView<R> *senv, unsigned char *qbase, float x, float y, int idx, int meta) {
+    SlowQ q; q.base = qbase;
+    __builtin_assume(__isShared(qbase));
+    SlowEntry en; en.x = x; en.y = y; en.idx = idx; en.meta = meta;
+    const int slot = atomicAdd(q.n(), 1);
+    if (slot < AUV_SLOWQ_CAP) q.ent()[slot] = en;
+    else slowq_resolve<R>(*senv, q, en);
+}
+// resolve the queued points: all 32 lanes of the warp, converged; afterwards lane l owns bad[l], cnt[l], mask[l]
+template <typename R>
+__device__ __forceinline__ void slowq_drain(const EnvView<R> &env, const SlowQ &q) {
+    __syncwarp();
+    const int lane = threadIdx.x & 31, n = min(*q.n(), AUV_SLOWQ_CAP);
+    for (int j = lane; j < n; j += 32) slowq_resolve<R>(env, q, q.ent()[j]);
+    __syncwarp();
+}
+
 // what one thread carries along an edge
 template <typename R> struct ArcEdge {
     R x, y, th, t, len;
@@ -219,9 +267,9 @@ template <typename R> struct ArcEdge {
 // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
 // FASTENV: contiguous equal time bins, the x-bucket table and a shared copy of the view are all present (the
 // launcher checked): the hot loop carries no run-time flags.
-template <typename R, bool ALLPAIRS, bool FASTENV = false, bool GRIDS = false>
+template <typename R, bool ALLPAIRS, bool FASTENV = false, bool GRIDS = false, bool DEFER = false>
 __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const CircTable &ct, ArcEdge<R> &e, R px, R py, R pth,
-                                               R pt, R plen, R parent_self_s2, int parent_self_hab) {
+                                               R pt, R plen, R parent_self_s2, int parent_self_hab, const SlowQ sq = SlowQ()) {
     typedef typename Policy<R>::A A;
     e.x = px; e.y = py; e.th = pth; e.t = pt; e.len = plen;
     e.sin0 = 0; e.cos0 = 0;
@@ -231,22 +279,30 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
     Cls pcl; pcl.code = 0; pcl.idx = -1;
     if (!ALLPAIRS) pcl = env.template classify<GRIDS>(px, py);
     if (AUV_OUTLINE_COLLIDE && FASTENV && !ALLPAIRS) e.bad = (pcl.code & 7u) != 5u && point_unsafe_shared<R>(env.shared_self, pcl.code, pcl.idx, px, py);
-    else e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
+    else if (DEFER && !ALLPAIRS && !Policy<R>::VERIFY) {
+        e.bad = point_unsafe_one<R>(env, pcl.code, px, py);
+        if (__builtin_expect((pcl.code & AUV_GRID_SLOW) != 0u, 0)) {
+            slowq_push<R>(env.shared_self, sq.base, (float)px, (float)py, pcl.idx, (int)(threadIdx.x & 31u) | 32);
+            e.bad = false;
+        }
+    } else e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
     e.bins.k = 0; e.bins.up = 0;
     if (AUV_BIN_CURSOR && (FASTENV || env.bins_uniform)) e.bins.start(env, pt);
 }
 
 // one arc primitive (rrt_dubins.py:264-284).  Returns false when the edge must stop (ZeroDivisionError in
 // the fp64 build; a degenerate 2^-23 draw in the fp32 build, which rejects the sample).
-template <typename R, bool COST, bool SELF, bool ALLPAIRS, bool FASTENV = false, bool GRIDS = false>
+// DEFER: queue the slow cases in *sq (see SlowQ) instead of resolving them in place
+template <typename R, bool COST, bool SELF, bool ALLPAIRS, bool FASTENV = false, bool GRIDS = false, bool DEFER = false>
 __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircTable &ct, const SteerParams<R> &sp, R w3,
-                                              SerialStream<R> &rng, ArcEdge<R> &e) {
+                                              SerialStream<R> &rng, ArcEdge<R> &e, const SlowQ sq = SlowQ()) {
     typedef typename Policy<R>::A A;
     const bool VERIFY = Policy<R>::VERIFY;
-    const R dist = uniform_ab<R>((R)0, sp.d2e, rng.next());                          // :264
-    const R diff = uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next());                  // :265
+    // (fp32: uniform_ab with its two invariants b - a and a - (b - a) taken from the parameter block)
+    const R dist = VERIFY ? uniform_ab<R>((R)0, sp.d2e, rng.next()) : A::fma(sp.d2e, rng.next(), sp.o_dist);             // :264
+    const R diff = VERIFY ? uniform_ab<R>(sp.neg_dmax, sp.dmax, rng.next()) : A::fma(sp.w_diff, rng.next(), sp.o_diff);  // :265
     if (!(A::fabs(dist) > A::fabs(diff))) { rng.skip(1u); return true; }             // :266; the velocity slot stays unread
-    const R vt = uniform_ab<R>((R)0, sp.two_vel, rng.next());                        // :279
+    const R vt = VERIFY ? uniform_ab<R>((R)0, sp.two_vel, rng.next()) : A::fma(sp.two_vel, rng.next(), sp.o_vel);        // :279
     R movement;
     if (VERIFY) {
         R s1 = A::add(dist, diff), s2 = A::sub(dist, diff), den = A::add(-s1, s2), num = A::add(s1, s2);
@@ -291,16 +347,18 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
             } else {
                 // decided cells and single-candidate boundary cells in straight-line code (point_unsafe_one)
                 bool bad1 = point_unsafe_one<R>(env, cl.code, e.x, e.y);
-                if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u, 0))
-                    bad1 = (AUV_OUTLINE_COLLIDE && (FASTENV || env.shared_self)) ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
-                                                                                 : (!point_within_c<R>(env, cl, e.x, e.y) || point_hits_circles_c<R>(env, cl, e.x, e.y));
+                if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u, 0)) {
+                    if (DEFER) { slowq_push<R>(env.shared_self, sq.base, (float)e.x, (float)e.y, cl.idx, (int)(threadIdx.x & 31u) | 32); bad1 = false; }
+                    else bad1 = (AUV_OUTLINE_COLLIDE && (FASTENV || env.shared_self)) ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
+                                                                                      : (!point_within_c<R>(env, cl, e.x, e.y) || point_hits_circles_c<R>(env, cl, e.x, e.y));
+                }
                 e.bad = e.bad || bad1;
             }
         }
         if (COST) {
             int kb = -2;
             if (AUV_BIN_CURSOR) { if (FASTENV || env.bins_uniform) kb = e.bins.at(env, e.t); }
-            else if (FASTENV) kb = find_bin<R>(env, e.t, 0xffffffffu);
+            else if (FASTENV) kb = find_bin<R, true>(env, e.t, 0xffffffffu);
             Contrib c;
             if constexpr (ALLPAIRS && sizeof(R) == 4) {
                 // every habitat in the packed form (the grid code for "no habitat test needed" keeps point_contrib off them)
@@ -308,7 +366,13 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
                 c = point_contrib<R, false>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
                 if (ct.hpair != nullptr && c.bin >= 0) c.hab = first_habitat_all_f32(env, ct, (float)e.x, (float)e.y);
             } else {
-                c = point_contrib<R, FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
+                c = point_contrib<R, FASTENV && !ALLPAIRS, DEFER && FASTENV && !ALLPAIRS>(env, e.x, e.y, e.t, 0xffffffffu, env.H, cl, kb);
+                if (DEFER && FASTENV && !ALLPAIRS) {
+                    if (__builtin_expect(c.hab == -2, 0)) {          // ambiguous habitat cell (the point lies in a time bin)
+                        slowq_push<R>(env.shared_self, sq.base, (float)e.x, (float)e.y, cl.idx, (int)(threadIdx.x & 31u) | 64);
+                        c.hab = -1;
+                    }
+                }
             }
             const R ps2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(w3, env.probs[c.bin * env.C + c.cell]) : (R)0;
             // no bin holds the time stamp: the point is skipped (cost.py:178); point_contrib then reports no cell and no

@@ -27,7 +27,16 @@ namespace auv {
 #ifndef AUV_TPE_MINB
 #define AUV_TPE_MINB 4
 #endif
+// Queue the waypoints that need the general collision / habitat tests (2 % on the Catalina map) per warp and resolve them
+// after the warp's 32 edges (edge_serial.cuh, SlowQ).  Measured on B200, Catalina map, 3.4e7 edges, cost on: off 6.8e9
+// edges/s; on, push inline 6.2e9; on, push out of line 5.9e9.  The slow-path share of the executed instructions does
+// fall from 14.7 % to 5.5 % and the active lanes rise from 22.3 to 24.7, but at 64 registers the extra live state makes
+// the compiler duplicate and spill in the hot loop (+14 % instructions on the main path).  Kept for larger register budgets.
+#ifndef AUV_TPE_DEFER
+#define AUV_TPE_DEFER 0
+#endif
 #define AUV_TPE_BUCKETS 64
+#define AUV_TPE_QBYTES (AUV_SLOWQ_CAP * 16 + 16 + 3 * 128)      // SlowQ of one warp
 #define AUV_TPE_MAXPAIRS 256      // all-pairs circle table in shared memory: up to 512 circles (6 KB)
 
 // STAGE: 1 = the hot part of the world model is in shared memory, 2 = the probability table too (always staged:
@@ -49,6 +58,7 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     __shared__ CircPair s_pairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_TPE_MAXPAIRS : 1];
     __shared__ CircPair s_hpairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_AP_MAXH : 1], s_epairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_AP_MAXE : 1];
     EnvView<R> env;
+    unsigned char *q_base;
     {
         uint64_t *bar = (uint64_t *)smem;
         const int staged = STAGE == 2 ? total_bytes : hot_bytes;          // multiples of 16 (api.cu)
@@ -70,9 +80,21 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
         env.bind_grid(blob, smem + 16);
         env.assume_hot_shared(STAGE == 2);
         if (GRIDS) { env.grid0s = (const unsigned *)(smem + 16 + staged); __builtin_assume(__isShared(env.grid0s)); }
+        q_base = smem + 16 + staged + (GRIDS ? ((((const EnvHeader *)blob)->gnx * ((const EnvHeader *)blob)->gny * 4 + 15) & ~15) : 0);
+    }
+    // deferred slow cases (edge_serial.cuh, SlowQ): one queue per warp behind the staged data
+    constexpr bool DEFER = AUV_TPE_DEFER && FASTENV && !ALLPAIRS && sizeof(R) == 4 && NT >= 512;     // (256 x 4: no room next to four staged probability tables)
+    SlowQ sq; sq.base = nullptr;
+    if (DEFER) {
+        sq.base = q_base + (size_t)(threadIdx.x >> 5) * AUV_TPE_QBYTES;
+        __builtin_assume(__isShared(sq.base));
+        const int l = threadIdx.x & 31;
+        sq.bad()[l] = 0u; sq.cnt()[l] = 0u; sq.mask()[l] = 0u;
+        if (l == 0) *sq.n() = 0;
+        __syncwarp();
     }
     __shared__ EnvView<R> s_env;                 // for the out-of-line slow paths
-    if (threadIdx.x == 0) s_env = env;
+    if (threadIdx.x == 0) { s_env = env; s_env.shared_self = &s_env; }
     __syncthreads();
     env.shared_self = &s_env;
     CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
@@ -144,17 +166,32 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
             g = __shfl_sync(0xffffffffu, g, 0);
             const int pos = cnt - 1 - (g * 32 + lane);
             if (cnt - 1 - g * 32 < 0) break;
+            long long i = -1;
+            ArcEdge<R> ed;
             if (pos >= 0) {
-                const long long i = base + (long long)s_order[pos];
+                i = base + (long long)s_order[pos];
                 const R *p = parents + 5 * i;
                 const R px = p[0], py = p[1], pth = p[2], pt = p[3], plen = p[4];
                 SerialStream<R> rng;
                 rng.init(stream_key(seeds[i]));
                 const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
-                ArcEdge<R> ed;
-                arc_edge_begin<R, ALLPAIRS, FASTENV, GRIDS>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1);
+                arc_edge_begin<R, ALLPAIRS, FASTENV, GRIDS, DEFER>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1, sq);
                 for (int k = 0; k < n_exp; k++)
-                    if (!arc_edge_step<R, COST, false, ALLPAIRS, FASTENV, GRIDS>(env, ct, sp, w3, rng, ed)) break;
+                    if (!arc_edge_step<R, COST, false, ALLPAIRS, FASTENV, GRIDS, DEFER>(env, ct, sp, w3, rng, ed, sq)) break;
+            }
+            if (DEFER) {
+                // the queued slow cases of these 32 edges, one per lane; then every lane folds its results in
+                __syncwarp();
+                if (*(volatile int *)sq.n() > 0) {
+                    slowq_drain<R>(env, sq);
+                    if (pos >= 0) { ed.bad = ed.bad || sq.bad()[lane] != 0u; ed.cnt += sq.cnt()[lane]; ed.mask |= (unsigned long long)sq.mask()[lane]; }
+                    __syncwarp();
+                    sq.bad()[lane] = 0u; sq.cnt()[lane] = 0u; sq.mask()[lane] = 0u;
+                    if (lane == 0) *sq.n() = 0;
+                    __syncwarp();
+                }
+            }
+            if (pos >= 0) {
                 safe[i] = (ed.status == 0 && !(ed.bad || ed.degenerate)) ? 1 : 0;
                 if (counts) counts[i] = ed.nwp;
                 if (leaf) { R *l = leaf + 5 * i; l[0] = ed.x; l[1] = ed.y; l[2] = ed.th; l[3] = ed.t; l[4] = ed.len; }
@@ -221,8 +258,9 @@ static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t 
     }
     const int plane = grids ? ((hd.gnx * hd.gny * 4 + 15) & ~15) : 0;
     // shared memory per CTA: the hot part, + the probability table when the resident CTAs still fit, + the grid plane
+    const int qbytes = (AUV_TPE_DEFER && sizeof(R) == 4 && fast && !ALLPAIRS && nt >= 512) ? (nt / 32) * AUV_TPE_QBYTES : 0;       // the warps' SlowQ
     const int per_cta_max = (int)((227 * 1024) / minb) - 1024 - (int)(2 * nt * AUV_TPE_EPT) - 1024;   // less the static arrays
-    int budget = per_cta_max - plane;
+    int budget = per_cta_max - plane - qbytes;
     if (const char *ev = getenv("AUVRRT_TPE_STAGE_KB")) budget = atoi(ev) * 1024;
     int sm = 16;
     const bool probs_too = COST && b.total_bytes + 16 <= budget;
@@ -230,6 +268,7 @@ static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t 
     else if (b.hot_bytes + 16 + plane <= 200 * 1024) sm = b.hot_bytes + 16;
     else return AUVRRT_ERR_UNSUPPORTED;          // the caller falls back to the warp-per-edge kernel
     sm += plane;
+    sm += qbytes;
     void (*kern)(const unsigned char *, int, int, const R *, const uint64_t *, long long, SteerParams<R>, R, uint8_t *,
                  int32_t *, R *, R *);
     if constexpr (sizeof(R) == 4) {

@@ -191,7 +191,9 @@ template <typename R> struct EnvView {
         if (!((unsigned)ix < (unsigned)gnx && (unsigned)iy < (unsigned)gny)) {
             // the grid covers the polygon's bounding box plus one cell all round: a point off the grid is outside the
             // polygon (code 2) whatever else is undecided about it
-            c.code = AUV_GRID_ALL_AMBIG | (gnx > 0 ? 2u : 0u); c.idx = -1; return c;
+            // (code 2 settles the collision test: no SLOW flag; without a grid everything takes the general path)
+            c.code = gnx > 0 ? (((AUV_GRID_HAB_AMBIG << 3) | AUV_GRID_HAB_MANY | AUV_GRID_CIRC_MANY | AUV_GRID_POLY_FULL) | 2u) : AUV_GRID_ALL_AMBIG;
+            c.idx = -1; return c;
         }
         c.idx = iy * gnx + ix;
         c.code = GRIDS ? grid0s[c.idx] : __ldg(grid + c.idx);

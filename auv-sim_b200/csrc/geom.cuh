@@ -177,6 +177,9 @@ template <typename R, bool OUTLINE = true> __device__ __forceinline__ bool point
     return hit;
 }
 
+__device__ __forceinline__ void keep_unconditional(float &a, float &b) { asm volatile("" : "+f"(a), "+f"(b)); }
+__device__ __forceinline__ void keep_unconditional(double &, double &) {}
+
 // Fast build, branch-free: the collision test of a cell that is decided by its code or by ONE circle and / or ONE
 // boundary edge (code bit 31 clear).  Both candidates are always fetched (a cell without one names row 0) and
 // their results masked by the code: on the Catalina map 17 % of the free cells are boundary cells of this kind, so in a
@@ -187,11 +190,13 @@ __device__ __forceinline__ bool point_unsafe_one(const EnvView<R> &env, unsigned
     typedef typename Policy<R>::A A;
     const One<R> ce = env.cone[(code >> 16) & 0x3FFu];
     const One<R> pe = env.pone[(code >> 26) & 0x1Fu];
-    const R q = A::sq2(A::sub(x, ce.x), A::sub(y, ce.y));
-    const R det = pe.z * (y - pe.y) - pe.w * (x - pe.x);
-    const bool hit = (code & AUV_GRID_CIRC_ONE) && q <= ce.z;
-    const bool in = (code & 3u) == 1u || ((code & AUV_GRID_POLY_ONE) && det > (R)0);
-    return !in || hit;
+    R q = A::sq2(A::sub(x, ce.x), A::sub(y, ce.y));
+    R det = pe.z * (y - pe.y) - pe.w * (x - pe.x);
+    // (the compiler would otherwise sink the two fetches under the code bits that use them: a branch for two or three lanes)
+    keep_unconditional(q, det);
+    const unsigned hit = ((code >> 14) & 1u) & (q <= ce.z ? 1u : 0u);
+    const unsigned in = ((code & 3u) == 1u ? 1u : 0u) | (((code >> 15) & 1u) & (det > (R)0 ? 1u : 0u));
+    return ((in ^ 1u) | hit) != 0u;
 }
 // collision test of a classified point: the branch-free form, the general one only for cells flagged AUV_GRID_SLOW
 template <typename R>
@@ -261,21 +266,23 @@ __device__ __forceinline__ int find_cell(const EnvView<R> &env, R x, R y) {
 }
 
 // first shark-grid time bin (dict order) with b0 <= t <= b1, -1 if none          cost.py:173-177
-template <typename R>
+// UNIFORM: the caller knows the bins are contiguous and equally wide (checked once on the host) and asks for all of them
+template <typename R, bool UNIFORM = false>
 __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin_mask) {
-    if (env.bins_uniform && bin_mask == 0xffffffffu) {
+    if (UNIFORM || (env.bins_uniform && bin_mask == 0xffffffffu)) {
         // contiguous sorted bins: the containing bins are adjacent; guess (off by at most one), settle
         // on the FIRST containing bin, verify with the reference's own comparisons
         // contiguous bins (b0[i+1] == b1[i]): the first containing bin is the first i with b1[i] >= t, if
         // b0[0] <= t <= b1[T-1].  The arithmetic guess is off by at most one either way.
-        // (b1[-1] = b0[0] is a sentinel; beyond the last bin the range test below rejects)
+        // (b1[-1] = the number just below b0[0] is a sentinel: t < b0[0] steps down to -1 like any "an earlier bin
+        // holds it"; beyond the last bin the range test below rejects)
         int k;
         if (sizeof(R) == 4) k = __float_as_int(__fadd_rd(fmaf((float)t, (float)env.bin_winv, (float)env.bin_off), 8388608.f)) - 0x4B000000;
         else k = (int)((t - env.bin_s0) * env.bin_winv);
         k = min(max(k, 0), env.T - 1);
         const R up = env.b1[k], dn = env.b1[k - 1];
-        k += (t > up ? 1 : 0) - ((k > 0 && t <= dn) ? 1 : 0);   // t <= b1[k-1]: an earlier bin holds it; t > b1[k]: a later one
-        return (t >= env.bin_lo && t <= env.bin_hi) ? k : -1;
+        k += (t > up ? 1 : 0) - (t <= dn ? 1 : 0);              // t <= b1[k-1]: an earlier bin holds it; t > b1[k]: a later one
+        return t <= env.bin_hi ? k : -1;
     }
     for (int b = 0; b < env.T; b++) {
         if (b < 32 && !((bin_mask >> b) & 1u)) continue;
@@ -328,7 +335,9 @@ template <typename R> struct BinCursor {
 
 // FASTENV (checked once on the host, edges_tpe.cu / plan_tpt.cu): the bucket table exists, the caller passes the bin
 // (known_bin) and published a shared copy of the view -- the run-time flags and the generic fallbacks drop out.
-template <typename R, bool FASTENV = false>
+// DEFER: a cell whose habitat code is "ambiguous" is reported as hab = -2 and left to the caller (the thread-per-edge
+// kernel queues such points and resolves them warp-wide after the edge, edge_serial.cuh)
+template <typename R, bool FASTENV = false, bool DEFER = false>
 __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y, R t,
                                                  unsigned bin_mask, int n_hab, const Cls &cl, int known_bin = -2) {
     typedef typename Policy<R>::A A;
@@ -344,7 +353,8 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
         // none (128: row 0 is fetched and the result masked)
         const int h = (int)(hc & 63u);
         const One<R> ho = env.hone[h];
-        const R q = A::sq2(A::sub(ho.x, x), A::sub(ho.y, y));
+        R q = A::sq2(A::sub(ho.x, x), A::sub(ho.y, y)), q_ = q;
+        keep_unconditional(q, q_);      // (or the compiler branches around the fetch for the lanes with a definitive code)
         const bool take = (hc < AUV_GRID_HAB_ONE || (hc < 128u && q <= ho.z)) && (FASTENV || h < n_hab);
         c.hab = take ? h : -1;
     } else if (hc < 128u) {
@@ -359,7 +369,8 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
             if (in) c.hab = h;
         }
     }
-    if (__builtin_expect(hc == AUV_GRID_HAB_AMBIG, 0)) {
+    if (DEFER) { if (hc == AUV_GRID_HAB_AMBIG) c.hab = -2; }
+    else if (__builtin_expect(hc == AUV_GRID_HAB_AMBIG, 0)) {
         if (AUV_OUTLINE_HAB && (FASTENV || env.shared_self)) {
             c.hab = first_habitat_ambiguous<R>(env.shared_self, code, cl.idx, n_hab, x, y);
         } else if (!(code & AUV_GRID_HAB_MANY)) {

@@ -33,11 +33,15 @@ template <> SteerParams<float> make_steer_params<float>(const double p[5]) {
     SteerParams<float> s;
     s.d2e = (float)p[0]; s.dmax = (float)p[1]; s.neg_dmax = (float)(-p[1]); s.freq = (float)p[2];
     s.min_dist = (float)p[3]; s.two_vel = (float)(2.0 * p[4]);
+    { volatile float w = s.d2e - 0.f, o = 0.f - w; s.o_dist = o; }
+    { volatile float w = s.dmax - s.neg_dmax, o = s.neg_dmax - w; s.w_diff = w; s.o_diff = o; }
+    { volatile float w = s.two_vel - 0.f, o = 0.f - w; s.o_vel = o; }
     return s;
 }
 template <> SteerParams<double> make_steer_params<double>(const double p[5]) {
     SteerParams<double> s;
     s.d2e = p[0]; s.dmax = p[1]; s.neg_dmax = -p[1]; s.freq = p[2]; s.min_dist = p[3]; s.two_vel = 2.0 * p[4];
+    s.w_diff = s.dmax - s.neg_dmax; s.o_dist = -s.d2e; s.o_diff = s.neg_dmax - s.w_diff; s.o_vel = -s.two_vel;    // (fp32 build only)
     return s;
 }
 

@@ -76,7 +76,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         if (FAST) env.assume_hot_shared(stage_mode == 2);
     }
     __shared__ EnvView<R> s_env;                 // for the out-of-line slow paths
-    if (threadIdx.x == 0) s_env = env;
+    if (threadIdx.x == 0) { s_env = env; s_env.shared_self = &s_env; }
     env.shared_self = &s_env;
     const SteerParams<R> sp = P.sp;
     const int tid = threadIdx.x;

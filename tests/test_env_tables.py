@@ -39,6 +39,7 @@ class Blob:
         self.hx, self.hy = arr(h["off_hx"], h["H"]).astype(np.float64), arr(h["off_hy"], h["H"]).astype(np.float64)
         self.hr = arr(h["off_hr"], h["H"]).astype(np.float64)
         self.b0, self.b1 = arr(h["off_b0"], h["T"]).astype(np.float64), arr(h["off_b1"], h["T"]).astype(np.float64)
+        self.b1m1 = float(arr(h["off_b1"] - np.dtype(self.R).itemsize, 1)[0])
         self.brk = arr(h["off_brk"], h["NB"] + 1).astype(np.float64)
         self.piece = arr(h["off_piece"], h["NP"] + 1, np.int32)
         self.c1 = arr(h["off_c1"], h["NCAND"]).astype(np.float64)
@@ -246,10 +247,7 @@ def test_time_bin_guess_matches_first_match_scan(blob):
         for nudge in (0.0, 1e-3, -1e-3):
             k = int(np.floor((ti - h["bin_s0"]) / h["bin_w"] + nudge))
             k = min(max(k, 0), T - 1)
-            up, dn = blob.b1[k], (blob.b1[k - 1] if k > 0 else blob.b0[0])
-            if k > 0 and ti <= dn:
-                k -= 1
-            elif ti > up:
-                k += 1
-            got = k if (k < T and ti >= blob.b0[0] and ti <= blob.b1[T - 1]) else -1
+            up, dn = blob.b1[k], (blob.b1[k - 1] if k > 0 else blob.b1m1)     # b1[-1]: the sentinel just below b0[0]
+            k += int(ti > up) - int(ti <= dn)
+            got = k if ti <= blob.b1[T - 1] else -1
             assert got == want, (ti, nudge, got, want)

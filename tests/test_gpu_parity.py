@@ -308,15 +308,19 @@ def test_edges_dubins_vs_oracle(api):
     assert 0.05 < want_safe.mean() < 0.95
 
 
-EDGE_VARIANTS = {"thread_per_edge": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "0"},
+EDGE_VARIANTS = {"thread_per_edge": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "0", "AUVRRT_TPE_THREADS": "256"},
+                 # the shape large batches get: 1024-thread CTAs, grid plane in shared memory, slow cases deferred
+                 "thread_per_edge_1024": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "0", "AUVRRT_TPE_THREADS": "1024",
+                                          "AUVRRT_TPE_GRIDS": "1"},
+                 "thread_per_edge_512": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "0", "AUVRRT_TPE_THREADS": "512"},
                  "thread_per_edge_allpairs": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "1"},
                  "warp_per_edge": {"AUVRRT_EDGES_VARIANT": "warp", "AUVRRT_EDGES_BRUTE": "0"}}
 
 
 @pytest.fixture(params=sorted(EDGE_VARIANTS))
 def edge_variant(request, monkeypatch):
-    """the arc-edge kernels behind auvrrt_edges_arc*: one thread per edge (default, classification grid), the same
-    with every waypoint against every circle / polygon edge / habitat, and the warp-per-edge kernel"""
+    """the arc-edge kernels behind auvrrt_edges_arc*: one thread per edge (classification grid) in its three CTA shapes,
+    the same with every waypoint against every circle / polygon edge / habitat, and the warp-per-edge kernel"""
     for k, v in EDGE_VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)
     return request.param
@@ -526,6 +530,28 @@ def test_edges_arc_cost_vs_oracle(api, env, oworld, edge_variant):
         n_sum += ints and abs(s32[3][i, 0] - want[3]) <= 1e-5 * max(1.0, abs(want[3]))
     assert n_int > 0.99 * same.sum() and n_sum > 0.98 * same.sum()
     assert (s32[3][:, 0] != 0).sum() > 100
+
+
+def test_edges_arc_cta_shapes_agree(api, env, monkeypatch):
+    """the thread-per-edge kernel gives the same bits in every CTA shape: 256-thread CTAs (slow cells resolved in
+    place) against 1024-thread CTAs (grid plane in shared memory, slow cells queued per warp and resolved after the
+    edges -- including the overflow of the queue, forced here by parents packed around the obstacles)"""
+    rs = np.random.RandomState(28)
+    n = 300_000
+    parents = np.stack([rs.uniform(-300, -100, n), rs.uniform(-60, 100, n), rs.uniform(-6, 6, n),
+                        rs.uniform(0, 520, n), rs.uniform(0, 500, n)], 1)
+    parents = parents.astype(np.float32).astype(np.float64)
+    seeds = np.arange(n) + 99
+    params, w3 = [2.0, 0.5, 30.0, 0.5, 2.0], -4.0
+    out = {}
+    for shape in ("256", "512", "1024"):
+        monkeypatch.setenv("AUVRRT_EDGES_VARIANT", "tpe"); monkeypatch.setenv("AUVRRT_EDGES_BRUTE", "0")
+        monkeypatch.setenv("AUVRRT_TPE_THREADS", shape); monkeypatch.setenv("AUVRRT_TPE_GRIDS", "1" if shape == "1024" else "0")
+        out[shape] = api.edges_arc_cost(env, parents, seeds, params, w3, "f32")
+    for shape in ("512", "1024"):
+        for a, b in zip(out["256"], out[shape]):
+            assert np.array_equal(a, b), shape
+    assert 0.05 < 1.0 - out["256"][0].mean() < 0.5 and (out["256"][3][:, 1] > 0).mean() > 0.05
 
 
 # ------------------------------------------------------------------------------------ reference-pinned K2 / C2 / bin filter
