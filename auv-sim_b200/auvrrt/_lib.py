@@ -77,6 +77,7 @@ EXPORTS = [
     "auvrrt_gym_step_dev", "auvrrt_gym_tree", "auvrrt_gym_counts", "auvrrt_gym_counts_dev", "auvrrt_gym_path",
     "auvrrt_astar_env_create", "auvrrt_astar_env_destroy", "auvrrt_astar_batch", "auvrrt_astar_workspace_bytes",
     "auvrrt_astar_batch_dev", "auvrrt_edges_arc_cost_dev", "auvrrt_edges_arc_cost", "auvrrt_env_host_blob",
+    "auvrrt_edges_dubins_cost_dev", "auvrrt_edges_dubins_cost",
 ]
 
 _lib = None
@@ -123,6 +124,10 @@ def lib():
     L.auvrrt_edges_arc.argtypes = [vp, _dp, _u64p, C.c_int64, _dp, C.c_int, _u8p, _i32p, _dp]
     L.auvrrt_edges_arc_cost_dev.argtypes = [vp, vp, vp, C.c_int64, _dp, C.c_double, C.c_int, vp, vp, vp, vp, vp]
     L.auvrrt_edges_arc_cost.argtypes = [vp, _dp, _u64p, C.c_int64, _dp, C.c_double, C.c_int, _u8p, _i32p, _dp, _dp]
+    L.auvrrt_edges_dubins_cost_dev.argtypes = [vp, vp, vp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                                               vp, vp, vp, vp, vp]
+    L.auvrrt_edges_dubins_cost.argtypes = [vp, _dp, _dp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                                           _u8p, _u8p, _dp, _dp]
     L.auvrrt_stream_u.restype = C.c_double
     L.auvrrt_stream_u.argtypes = [C.c_uint64, C.c_int64, C.c_int]
     L.auvrrt_plan_batch.argtypes = [vp, _dp, _u64p, C.c_int64, C.POINTER(PlanParams), C.c_int,

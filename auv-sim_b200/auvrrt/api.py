@@ -223,6 +223,20 @@ def edges_dubins(env: Env, q0, q1, rho=1.0, W=20, precision="f32"):
     return safe, word, length
 
 
+def edges_dubins_cost(env: Env, q0, q1, rho=1.0, W=20, velocity=1.0, w3=-4.0, precision="f32"):
+    """edges_dubins + each edge's share of the path cost over waypoints 1..W-1 (traj_time_stamp = arclength / velocity):
+    cost [n][3] = sum of w3 * prob, waypoints inside a habitat, distinct habitats visited"""
+    q0, q1 = _f64(q0, (-1, 3)), _f64(q1, (-1, 3))
+    n = len(q0)
+    safe = np.zeros(n, np.uint8)
+    word = np.zeros(n, np.uint8)
+    length = np.zeros(n)
+    cost = np.zeros((n, 3))
+    check(lib().auvrrt_edges_dubins_cost(env.handle, _p(q0), _p(q1), n, float(rho), int(W), float(velocity), float(w3),
+                                         _prec(precision), _p(safe, C.c_uint8), _p(word, C.c_uint8), _p(length), _p(cost)))
+    return safe, word, length, cost
+
+
 def edges_arc(env: Env, parents, seeds, params, precision="f32"):
     parents = _f64(parents, (-1, 5))
     n = len(parents)

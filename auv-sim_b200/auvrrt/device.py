@@ -82,6 +82,12 @@ def edges_dubins_dev(env: Env, q0, q1, rho, W, out_safe, out_word, out_length, p
                                         _stream_ptr(stream)))
 
 
+def edges_dubins_cost_dev(env: Env, q0, q1, rho, W, velocity, w3, out_safe, out_word, out_length, out_cost, precision, stream=None):
+    check(lib().auvrrt_edges_dubins_cost_dev(env.handle, _vp(q0), _vp(q1), q0.shape[0], float(rho), int(W), float(velocity),
+                                             float(w3), _prec(precision), _vp(out_safe), _vp(out_word), _vp(out_length),
+                                             _vp(out_cost), _stream_ptr(stream)))
+
+
 def edges_arc_cost_dev(env: Env, parents, seeds, params5, w3, out_safe, out_counts, out_leaf, out_cost, precision, stream=None):
     p = (C.c_double * 5)(*[float(x) for x in params5])
     check(lib().auvrrt_edges_arc_cost_dev(env.handle, _vp(parents), _vp(seeds), parents.shape[0], p, float(w3),

@@ -682,14 +682,17 @@ extern "C" int auvrrt_edges_arc_dev(const auvrrt_env_t *env, const void *parents
 }
 template <typename R>
 static int edges_dubins_host(const auvrrt_env *env, const double *from, const double *to, int64_t n, double rho, int W,
-                             uint8_t *safe, uint8_t *word, double *length) {
+                             uint8_t *safe, uint8_t *word, double *length, double vel = 1.0, double w3 = 0.0, double *cost = nullptr) {
     cudaStream_t s = 0;
-    DBuf df, dt, t0, t1, dsafe, dword, dlen, t2;
+    DBuf df, dt, t0, t1, dsafe, dword, dlen, t2, dcost, t3;
     AUV_TRY(upload_real<R>(df, from, 3 * n, s, t0)); AUV_TRY(upload_real<R>(dt, to, 3 * n, s, t1));
     AUV_TRY(dsafe.alloc((size_t)n)); AUV_TRY(dword.alloc((size_t)n)); AUV_TRY(dlen.alloc(sizeof(R) * (size_t)n));
-    AUV_TRY(launch_edges_dubins<R>(env, df.as<R>(), dt.as<R>(), n, rho, W, dsafe.as<uint8_t>(), dword.as<uint8_t>(), dlen.as<R>(), s));
+    if (cost) AUV_TRY(dcost.alloc(sizeof(R) * 3 * (size_t)n));
+    AUV_TRY(launch_edges_dubins<R>(env, df.as<R>(), dt.as<R>(), n, rho, W, dsafe.as<uint8_t>(), dword.as<uint8_t>(), dlen.as<R>(), s,
+                                   vel, w3, cost ? dcost.as<R>() : nullptr));
     AUV_TRY(download_raw<uint8_t>(safe, dsafe, n, s)); AUV_TRY(download_raw<uint8_t>(word, dword, n, s));
     AUV_TRY(download_real<R>(length, dlen, n, s, t2));
+    if (cost) AUV_TRY(download_real<R>(cost, dcost, 3 * n, s, t3));
     AUV_CUDA(cudaStreamSynchronize(s));
     return AUVRRT_OK;
 }
@@ -701,6 +704,30 @@ extern "C" int auvrrt_edges_dubins(const auvrrt_env_t *env, const double *from, 
     if (n <= 0) return AUVRRT_OK;
     return precision == AUVRRT_F32 ? edges_dubins_host<float>(env, from, to, n, rho, W, out_safe, out_word, out_length)
                                    : edges_dubins_host<double>(env, from, to, n, rho, W, out_safe, out_word, out_length);
+}
+extern "C" int auvrrt_edges_dubins_cost_dev(const auvrrt_env_t *env, const void *from, const void *to, int64_t n, double rho,
+                                            int W, double velocity, double w3, int precision, uint8_t *out_safe,
+                                            uint8_t *out_word, void *out_length, void *out_cost, void *stream) {
+    AUV_TRY(check_precision(precision));
+    if (!env) return set_err(AUVRRT_ERR_ARG, "edges_dubins_cost: env is NULL");
+    if (!out_cost) return set_err(AUVRRT_ERR_ARG, "edges_dubins_cost: out_cost is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == AUVRRT_F32)
+        return launch_edges_dubins<float>(env, (const float *)from, (const float *)to, n, rho, W, out_safe, out_word, (float *)out_length, s,
+                                          velocity, w3, (float *)out_cost);
+    return launch_edges_dubins<double>(env, (const double *)from, (const double *)to, n, rho, W, out_safe, out_word, (double *)out_length, s,
+                                       velocity, w3, (double *)out_cost);
+}
+extern "C" int auvrrt_edges_dubins_cost(const auvrrt_env_t *env, const double *from, const double *to, int64_t n, double rho,
+                                        int W, double velocity, double w3, int precision, uint8_t *out_safe,
+                                        uint8_t *out_word, double *out_length, double *out_cost) {
+    AUV_TRY(check_precision(precision));
+    if (!env) return set_err(AUVRRT_ERR_ARG, "edges_dubins_cost: env is NULL");
+    if (!out_cost) return set_err(AUVRRT_ERR_ARG, "edges_dubins_cost: out_cost is NULL");
+    AUV_TRY(need_device(env->device));
+    if (n <= 0) return AUVRRT_OK;
+    return precision == AUVRRT_F32 ? edges_dubins_host<float>(env, from, to, n, rho, W, out_safe, out_word, out_length, velocity, w3, out_cost)
+                                   : edges_dubins_host<double>(env, from, to, n, rho, W, out_safe, out_word, out_length, velocity, w3, out_cost);
 }
 template <typename R>
 static int edges_arc_host(const auvrrt_env *env, const double *parents, const uint64_t *seeds, int64_t n,

@@ -499,10 +499,13 @@ __global__ void __launch_bounds__(AUV_ED_THREADS, MB) k_edges_dubins(const unsig
 // Same edges, same booleans, with the broad-phase cull of the classification grid: every waypoint
 // is tested only against the <= 3 circles that can touch its grid cell (all circles if the cell has
 // more).  Exact by construction (env.cuh); ~70x fewer instructions than the all-pairs loop at K=500.
-template <typename R>
+// COST: also the edge's share of cost.habitat_shark_cost_func (cost.py:171-191) over the appended waypoints 1..W-1
+// (waypoint 0 is the parent), with traj_time_stamp = arclength / vel from 0 -- config 4 "cost on" for Dubins edges.
+template <typename R, bool COST>
 __global__ void __launch_bounds__(256, 4) k_edges_dubins_culled(const unsigned char *blob, int hot_bytes, int total_bytes,
                                                              int stage_mode, const R *from, const R *to, int64_t n,
-                                                             R rho, int W, uint8_t *safe, uint8_t *word, R *length) {
+                                                             R rho, int W, uint8_t *safe, uint8_t *word, R *length,
+                                                             R vel, R w3, R *cost_out) {
     typedef typename Policy<R>::A A;
     extern __shared__ __align__(16) unsigned char smem[];
     EnvView<R> env = load_env<R>(smem, blob, hot_bytes, total_bytes, stage_mode);
@@ -511,6 +514,7 @@ __global__ void __launch_bounds__(256, 4) k_edges_dubins_culled(const unsigned c
         const R *a = from + 3 * i, *b = to + 3 * i;
         DubinsPath<R> d = dubins_shortest<R>(a[0], a[1], a[2], b[0], b[1], b[2], rho);
         bool ok = d.word >= 0;
+        R s2 = 0; unsigned cnt = 0; unsigned long long mask = 0ull;
         if (ok) {
             DubinsSampler<R> smp;
             smp.init(d, a[0], a[1], a[2], rho);
@@ -518,34 +522,51 @@ __global__ void __launch_bounds__(256, 4) k_edges_dubins_culled(const unsigned c
             bool bad = false;
             for (int k = 0; k < W; k++) {
                 R x, y, th;
-                if (k < W - 1) smp.at(A::mul((R)k, step), x, y, th); else { x = b[0]; y = b[1]; }
+                const R sk = k < W - 1 ? A::mul((R)k, step) : d.length;
+                if (k < W - 1) smp.at(sk, x, y, th); else { x = b[0]; y = b[1]; }
                 const Cls cl = env.classify(x, y);
                 bad = bad || !point_within_c<R, false>(env, cl, x, y) || point_hits_circles_c<R, false>(env, cl, x, y);   // polygon first: one grid code decides most points
+                if (COST && k > 0) {
+                    const Contrib c = point_contrib<R>(env, x, y, A::div(sk, vel), 0xffffffffu, env.H, cl);
+                    if (c.bin >= 0) {
+                        if (c.cell >= 0) s2 = A::add(s2, A::mul(w3, env.probs[(size_t)c.bin * env.C + c.cell]));
+                        if (c.hab >= 0) { cnt++; mask |= 1ull << c.hab; }
+                    }
+                }
             }
             ok = !bad;
         }
         safe[i] = ok ? 1 : 0;
         word[i] = d.word < 0 ? 255 : (uint8_t)d.word;
         length[i] = d.length;
+        if (COST) { R *c = cost_out + 3 * i; c[0] = s2; c[1] = (R)cnt; c[2] = (R)__popcll(mask); }
     }
 }
 template <typename R>
 int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64_t n, double rho, int W,
-                        uint8_t *safe, uint8_t *word, R *length, cudaStream_t s) {
+                        uint8_t *safe, uint8_t *word, R *length, cudaStream_t s, double vel, double w3, R *cost_out) {
     if (n <= 0) return AUVRRT_OK;
     EnvBlob<R> b = env_blob<R>(env);
     // default: broad-phase culled kernel; AUVRRT_EDGES_BRUTE=1 selects the all-pairs kernel (the
     // config-4 roofline measurement: every waypoint against every circle)
     const char *brute = getenv("AUVRRT_EDGES_BRUTE");
-    if (!(brute && brute[0] == '1') && env->h32.gnx > 0) {
+    if (cost_out && !(env->h32.gnx > 0)) return set_err(AUVRRT_ERR_UNSUPPORTED, "edges_dubins_cost: the world has no classification grid (no boundary polygon)");
+    if (cost_out && !(vel > 0.0)) return set_err(AUVRRT_ERR_ARG, "edges_dubins_cost: velocity must be positive, got %g", vel);
+    if ((cost_out || !(brute && brute[0] == '1')) && env->h32.gnx > 0) {
         if (W < 2) return set_err(AUVRRT_ERR_ARG, "edges_dubins: W must be >= 2, got %d", W);
         int smem_c, mode_c = env_stage_mode(b.hot_bytes, b.hot_bytes, 64 * 1024, &smem_c);
         mode_c = mode_c ? 1 : 0;
-        AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins_culled<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
         int64_t blocks_c = (n + 255) / 256;
         if (blocks_c > AUV_SMS * 16) blocks_c = AUV_SMS * 16;
-        k_edges_dubins_culled<R><<<(unsigned)blocks_c, 256, smem_c, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode_c, from, to,
-                                                                        n, (R)rho, W, safe, word, length);
+        if (cost_out) {
+            AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins_culled<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+            k_edges_dubins_culled<R, true><<<(unsigned)blocks_c, 256, smem_c, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode_c, from, to,
+                                                                                  n, (R)rho, W, safe, word, length, (R)vel, (R)w3, cost_out);
+        } else {
+            AUV_CUDA(cudaFuncSetAttribute(k_edges_dubins_culled<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+            k_edges_dubins_culled<R, false><<<(unsigned)blocks_c, 256, smem_c, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode_c, from, to,
+                                                                                   n, (R)rho, W, safe, word, length, (R)1, (R)0, nullptr);
+        }
         AUV_LAUNCH_CHECK();
         return AUVRRT_OK;
     }
@@ -574,9 +595,9 @@ int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64
     return AUVRRT_OK;
 }
 template int launch_edges_dubins<float>(const auvrrt_env *, const float *, const float *, int64_t, double, int,
-                                        uint8_t *, uint8_t *, float *, cudaStream_t);
+                                        uint8_t *, uint8_t *, float *, cudaStream_t, double, double, float *);
 template int launch_edges_dubins<double>(const auvrrt_env *, const double *, const double *, int64_t, double, int,
-                                         uint8_t *, uint8_t *, double *, cudaStream_t);
+                                         uint8_t *, uint8_t *, double *, cudaStream_t, double, double, double *);
 
 // ------------------------------------------------------------------ fused arc edges on the counter stream
 // COST: also the edge's share of cost.habitat_shark_cost_func over its appended waypoints (cost.py:171-191):

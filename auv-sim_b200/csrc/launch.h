@@ -51,7 +51,8 @@ int launch_cost_point(const auvrrt_env *env, const R *points, int64_t n, unsigne
                       const double weights[3], R *out, cudaStream_t s);
 template <typename R>
 int launch_edges_dubins(const auvrrt_env *env, const R *from, const R *to, int64_t n, double rho, int W,
-                        uint8_t *safe, uint8_t *word, R *length, cudaStream_t s);
+                        uint8_t *safe, uint8_t *word, R *length, cudaStream_t s, double vel = 1.0, double w3 = 0.0,
+                        R *cost_out = nullptr);
 template <typename R>
 int launch_edges_arc(const auvrrt_env *env, const R *parents, const uint64_t *seeds, int64_t n,
                      const double params[5], uint8_t *safe, int32_t *counts, R *leaf, cudaStream_t s, double w3 = 0.0,

@@ -22,6 +22,14 @@
 #include "plan_common.cuh"
 #include "dubins.cuh"
 
+// Rehearse the next iteration's parent pick and prefetch its row (k_plan, default parent pick).  Measured on B200,
+// config 2: 9.77 ms per step with it, 8.89 ms without -- the parent-row load is 17 % of the stall samples, but the
+// rehearsal costs ~50 instructions per iteration in a kernel whose issue slots are 68 % busy, and the prefetched line
+// competes with the tree's own lines in a 28-warp L1.  Off.
+#ifndef AUV_PLAN_PREFETCH
+#define AUV_PLAN_PREFETCH 0
+#endif
+
 namespace auv {
 
 #define AUV_LAUNCH_CHECK2()                                                                 \
@@ -406,9 +414,34 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             const NodeRow<R> pr = T.row[parent];           // every lane reads the same row: broadcast
             const R ppx = pr.x, ppy = pr.y, ppth = pr.th, ppt = pr.t, pplen = pr.len;
             const uint32_t ctr0 = ctr;
+#if AUV_PLAN_PREFETCH
+            // Look ahead.  Slot addressing makes the next iteration's stream position known now (this edge owns
+            // 1 + 3 n_expand positions), so its parent pick can be rehearsed on the bins as they stand: the pool entry is
+            // requested here and the parent's row prefetched behind the edge, while this edge is being evaluated.  The
+            // real pick of the next iteration runs unchanged (an append into a rehearsed bin changes it) and finds both
+            // lines in cache.
+            int spec_parent = -1;
+            if (ONE && BS && pick_mode == 0) {
+                const int n_exp_now = (int)A::floor(uniform_ab<R>((R)0, P.sp.freq, rng.u(ctr)));
+                const uint32_t cn0 = ctr + 1u + 3u * (uint32_t)(n_exp_now > 0 ? n_exp_now : 0);
+                const int rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), rng.u(cn0 + (uint32_t)g.gl));
+                const int cn = (rb >= 1 && rb <= P.nb) ? (int)s_count[rb] : 0;
+                const unsigned m = g.ballot(cn > 0);
+                if (m) {
+                    const int f = __ffs(m) - 1;
+                    const int sb = g.bcast(rb, f), sc_ = g.bcast(cn, f);
+                    const int idx = (int)uniform_ab<R>((R)0, (R)sc_, rng.u(cn0 + (uint32_t)f + 1u));
+                    if (idx < 32 && idx < sc_) spec_parent = T.pool[(int)s_head[sb] * 32 + idx];
+                }
+            }
+#endif
             EdgeOut<R> o;
             eval_edge<R, G, true, true, false, false, ONE>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
                                                            nullptr, 0, o);
+#if AUV_PLAN_PREFETCH
+            if (ONE && BS && pick_mode == 0 && spec_parent >= 0 && g.gl < 2)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"((const char *)&T.row[spec_parent] + 32 * g.gl));
+#endif
             ctr = o.ctr;
             n_waypoints += o.nwp; n_prims += o.n_exp;
             if (P.trace && g.gl == 0) {

@@ -11,6 +11,7 @@
 //
 // Per-tree workspace (private to the thread): AoS node rows (one 64-byte row in fp32: x,y,theta,t |
 // len,s2,self_s2,ctr | parent,cnt,self_hab | mask) and the chunked time bins of plan.cu.
+#include <stdlib.h>
 #include "plan_common.cuh"
 #include "edge_serial.cuh"
 
@@ -20,9 +21,20 @@ namespace auv {
 #define AUV_TPT_THREADS 128   // finer work units than 256 (measured +1..4 % at 1.3e5 - 2.6e5 queries)
 #endif
 static const int TPT_THREADS = AUV_TPT_THREADS;
-#ifndef AUV_TPT_MINB
-#define AUV_TPT_MINB 8
+// Tree slots per thread.  With 2, a CTA of T threads owns 2T trees; every trip sorts them by n_expand into 2T/32 groups
+// and warp w runs group w and then group 2T/32 - 1 - w (shortest with longest), so that the warps of a CTA reach the
+// barrier behind the sort at about the same time: with one group per warp the warp holding the short edges waits
+// for the one holding the long ones (29 % of the stall samples in profiles/r02_tpt_fast.txt).
+// Measured on B200, 262 144 queries x 2048: one slot per thread 2.04e9 edges/s, two 1.85e9 (2.02e9 at 524 288 queries):
+// the barrier stalls do fall (29 % -> 13 % of the samples) and so do the executed instructions (-15 %), but the shared
+// memory of 256 slots leaves 4 CTAs = 16 warps per SM, too few for the kernel's dependent global loads.
+#ifndef AUV_TPT_SPT
+#define AUV_TPT_SPT 1
 #endif
+#ifndef AUV_TPT_MINB
+#define AUV_TPT_MINB (AUV_TPT_SPT == 2 ? 4 : 8)
+#endif
+static const int TPT_SLOTS = AUV_TPT_THREADS * AUV_TPT_SPT;
 
 struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count; };
 
@@ -53,18 +65,18 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
            auvrrt_plan_record_t *records, uint32_t *chain_out, auvrrt_plan_trace_t tr) {
     typedef typename Policy<R>::A A;
     const bool VERIFY = Policy<R>::VERIFY;
-    const int T = TPT_THREADS;
+    const int T = TPT_THREADS, S = TPT_SLOTS, SPT = AUV_TPT_SPT;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ unsigned long long s_z[T];
-    __shared__ long long s_q[T], s_nprims[T];
-    __shared__ uint32_t s_ctr[T], s_upos[T];
-    __shared__ int s_nnodes[T], s_nchunks[T], s_it[T], s_status[T], s_bestnode[T], s_bestiter[T], s_ncost[T], s_nwp[T],
-        s_guard[T], s_active[T], s_parent[T], s_nexp[T], s_order[T], s_hist[64];
-    __shared__ R s_bc0[T], s_bc1[T], s_bc2[T], s_bc3[T], s_blen[T], s_bt[T];
+    __shared__ unsigned long long s_z[S];
+    __shared__ long long s_q[S], s_nprims[S];
+    __shared__ uint32_t s_ctr[S], s_upos[S];
+    __shared__ int s_nnodes[S], s_nchunks[S], s_it[S], s_status[S], s_bestnode[S], s_bestiter[S], s_ncost[S], s_nwp[S],
+        s_guard[S], s_active[S], s_parent[S], s_nexp[S], s_order[S], s_hist[64];
+    __shared__ R s_bc0[S], s_bc1[S], s_bc2[S], s_bc3[S], s_blen[S], s_bt[S];
     // which time bins of each tree are non-empty (<= 128 bins): the rejection loop of the parent pick probes bins until
     // it finds one (rrt_dubins.py:123-125); testing a bit in shared memory instead of reading count[bin] from the tree's
     // workspace takes a dependent global load (and a 32-byte sector) off every probe
-    __shared__ unsigned s_nonempty[T][4];
+    __shared__ unsigned s_nonempty[S][4];
     const bool bin_bits = P.nb + 2 <= 128;
     EnvView<R> env;
     if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
@@ -80,15 +92,20 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
     env.shared_self = &s_env;
     const SteerParams<R> sp = P.sp;
     const int tid = threadIdx.x;
-    unsigned char *block_ws = ws + (size_t)blockIdx.x * T * L.slot_bytes;
-    s_active[tid] = 0; s_q[tid] = -1; s_nexp[tid] = -2; s_order[tid] = tid;
+    unsigned char *block_ws = ws + (size_t)blockIdx.x * S * L.slot_bytes;
+    for (int i = tid; i < S; i += T) { s_active[i] = 0; s_q[i] = -1; s_nexp[i] = -2; s_order[i] = i; }
     bool queue_empty = false;
     const int guard_max = 64 * P.I + 1024;
     __syncthreads();
 
     for (;;) {
-        // ============ phase B: thread i runs the edge of the i-th slot in n_expand order ===============
-        const int slot = s_order[tid];
+        // this trip's slots of the thread: position tid of group w, then of group 2T/32 - 1 - w (read before anyone rewrites s_order)
+        const int slot0 = s_order[tid], slot1 = SPT == 2 ? s_order[(2 * (T / 32) - 1 - (tid >> 5)) * 32 + (tid & 31)] : 0;
+        int key0 = 63, key1 = 63, any_active = 0;
+#pragma unroll 1
+        for (int j = 0; j < SPT; j++) {
+        // ============ phase B: the thread runs the edge of its j-th slot ===============================
+        const int slot = j == 0 ? slot0 : slot1;
         unsigned char *base = block_ws + (size_t)slot * L.slot_bytes;
         NodeRow<R> *nodes = (NodeRow<R> *)(base + L.nodes);
         int *pool = (int *)(base + L.pool), *next = (int *)(base + L.next);
@@ -282,6 +299,8 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));     // :259-260
                     key = n_exp < 62 ? n_exp : 62;
                 }
+                // the thread that runs this tree's edge after the sort (any thread of this CTA) finds the parent's row in L1
+                if (parent >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(&nodes[parent]));
                 s_z[slot] = (unsigned long long)rng.wa | ((unsigned long long)rng.wb << 32); s_ctr[slot] = rng.ctr; s_parent[slot] = parent; s_nexp[slot] = n_exp;
                 if (status) { s_status[slot] = status; key = 62; s_nexp[slot] = -1; }    // phase B finalises it
                 if (skip) {
@@ -289,21 +308,25 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     if (++s_guard[slot] >= guard_max) { key = 62; s_nexp[slot] = -1; }
                 }
             }
-            // ============================ counting sort of the slots by n_expand ======================
-            if (tid < 64) s_hist[tid] = 0;
-            __syncthreads();
-            const int rank = atomicAdd(&s_hist[key], 1);
-            __syncthreads();
-            if (tid < 32) {                       // exclusive scan of 64 buckets by one warp
-                int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1], v = a0 + a1;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (tid >= d) v += o; }
-                s_hist[2 * tid] = v - a0 - a1; s_hist[2 * tid + 1] = v - a1;
-            }
-            __syncthreads();
-            s_order[s_hist[key] + rank] = slot;
+            if (j == 0) key0 = key; else key1 = key;
+            any_active |= s_active[slot];
         }
-        if (__syncthreads_count(s_active[slot]) == 0) break;      // also publishes s_order
+        }   // j
+        // ============================ counting sort of the slots by n_expand ======================
+        if (tid < 64) s_hist[tid] = 0;
+        __syncthreads();
+        const int rank0 = atomicAdd(&s_hist[key0], 1), rank1 = SPT == 2 ? atomicAdd(&s_hist[key1], 1) : 0;
+        __syncthreads();
+        if (tid < 32) {                       // exclusive scan of 64 buckets by one warp
+            int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1], v = a0 + a1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (tid >= d) v += o; }
+            s_hist[2 * tid] = v - a0 - a1; s_hist[2 * tid + 1] = v - a1;
+        }
+        __syncthreads();
+        s_order[s_hist[key0] + rank0] = slot0;
+        if (SPT == 2) s_order[s_hist[key1] + rank1] = slot1;
+        if (__syncthreads_count(any_active) == 0) break;      // also publishes s_order
     }
 }
 
@@ -319,6 +342,7 @@ int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seed
     // only the hot part of the world model is staged: the per-tree state of 256 trees already takes
     // ~27 KB of shared memory per CTA and 4 CTAs per SM must fit
     int budget = 24 * 1024, sm = 16, mode = 0;
+    if (const char *ev = getenv("AUVRRT_TPT_STAGE_KB")) budget = atoi(ev) * 1024;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
     const EnvHeader &hd = sizeof(R) == 4 ? env->h32 : env->h64;
@@ -334,10 +358,10 @@ int launch_plan_tpt(const auvrrt_env *env, const R *starts, const uint64_t *seed
     TptLayout L = make_tpt_layout<R>(P.cap, P.nb, P.nchunks);
     // the workspace is sized for the full machine unless the batch (Q > 0) is smaller
     if (Q > 0) {
-        int64_t blocks = (Q + TPT_THREADS - 1) / TPT_THREADS;
+        int64_t blocks = (Q + TPT_SLOTS - 1) / TPT_SLOTS;
         if (blocks < grid) grid = (int)blocks;
     }
-    int64_t need = 256 + (int64_t)grid * TPT_THREADS * (int64_t)L.slot_bytes;
+    int64_t need = 256 + (int64_t)grid * TPT_SLOTS * (int64_t)L.slot_bytes;
     if (need_bytes) { *need_bytes = need; return AUVRRT_OK; }
     if (Q <= 0) return AUVRRT_OK;
     if (workspace_bytes < need) return set_err(AUVRRT_ERR_ARG, "plan_tpt: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);

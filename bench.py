@@ -758,7 +758,7 @@ def extras(env, dev, args, api, adev):
                                    "identical_booleans": bool(torch.equal(safe, safe_brute)),
                                    "equivalent_all_pairs_tflops": ne * flop_edge / mean_c / 1e12,
                                    "note": "same results as the all-pairs kernel; the grid skips circles that cannot touch a waypoint's cell"}
-    del q0, q1, safe, word, length
+    safe_culled = safe.clone()
 
     # config 4 with the reference's own steer (S1 random arcs, P = 14.5 primitives, W = 11.9 waypoints on average)
     # against the same 500 circles + the Catalina polygon, cost off and cost on (habitats + shark grid)
@@ -766,6 +766,18 @@ def extras(env, dev, args, api, adev):
         world, bins_, probs_ = load_world()
         env4c = api.Env(circles=circles, boundary=world["boundary"], habitats=world["habitats"], bins=bins_,
                         cells=world["cells"], probs=probs_, device=dev.index)
+        # the Dubins edges with cost on (habitats + shark grid at every waypoint, t = arclength / v): SURVEY 8(d) "cost off and on"
+        cost_d = torch.zeros((ne, 3), device=dev)
+        mean_dc, _ = timed(lambda: adev.edges_dubins_cost_dev(env4c, q0, q1, 1.0, 20, 1.0, -4.0, safe, word, length, cost_d, "f32"),
+                           reps=3, warm=1)
+        flop_dc = flop_edge + 19 * (2 * 10 + 2 * 35 + 6 * 10 + 3)
+        out["micro_config4_culled_cost"] = {"edges": ne, "edges_per_s": ne / mean_dc, "kernel": "k_edges_dubins_culled<float,COST>",
+                                            "identical_booleans": bool(torch.equal(safe, safe_culled)),
+                                            "algorithmic_flop_per_edge": flop_dc,
+                                            "equivalent_all_pairs_tflops": ne * flop_dc / mean_dc / 1e12,
+                                            "edges_with_shark_cost": float((cost_d[:, 0] != 0).float().mean().item()),
+                                            "edges_touching_a_habitat": float((cost_d[:, 1] > 0).float().mean().item())}
+        del cost_d
         na = int(args.micro_edges)
         g = torch.Generator(device=dev); g.manual_seed(2)
         par = torch.stack([torch.rand(na, device=dev, generator=g) * 549.8 - 467.4,
@@ -787,17 +799,45 @@ def extras(env, dev, args, api, adev):
         out["micro_config4_arc"] = {"edges": na, "circles": K, "waypoints_mean": W_mean, "edges_per_s": na / mean_off,
                                     "algorithmic_flop_per_edge": flop_off, "equivalent_all_pairs_tflops": na * flop_off / mean_off / 1e12,
                                     "equivalent_frac": na * flop_off / mean_off / cal, "safe_fraction": float(safe_off.float().mean().item()),
-                                    "kernel": "k_edges_arc<float,32,false> (warp per edge, classification grid)",
+                                    "kernel": "k_edges_arc_tpe<float,no cost,grid> (one thread per edge, classification grid)",
                                     "note": "the grid skips circles that cannot touch a waypoint's cell, so the all-pairs FLOP count is an equivalent, not executed work"}
         out["micro_config4_arc_cost"] = {"edges": na, "edges_per_s": na / mean_on, "algorithmic_flop_per_edge": flop_on,
                                          "equivalent_all_pairs_tflops": na * flop_on / mean_on / 1e12, "equivalent_frac": na * flop_on / mean_on / cal,
                                          "identical_booleans": bool(torch.equal(safe_a, safe_off)),
                                          "edges_with_shark_cost": float((cost_a[:, 0] != 0).float().mean().item()),
-                                         "kernel": "k_edges_arc<float,32,true> (steer + collide + cost)"}
+                                         "kernel": "k_edges_arc_tpe<float,COST,grid> (steer + collide + cost, one thread per edge)"}
+        # the same edges all pairs (every waypoint against all 500 circles, the boundary edges and the habitats, packed
+        # FFMA2 loops): executed work = the FLOP formula, so this is the arc kernel's executed-work roofline at K = 500
+        nb_ = max(1 << 20, na // 16)
+        saved_b = os.environ.get("AUVRRT_EDGES_BRUTE")
+        try:
+            os.environ["AUVRRT_EDGES_BRUTE"] = "1"
+            safe_b = torch.zeros(nb_, dtype=torch.uint8, device=dev); cnt_b = torch.zeros(nb_, dtype=torch.int32, device=dev)
+            cost_b = torch.zeros((nb_, 3), device=dev)
+            mean_ap, _ = timed(lambda: adev.edges_arc_cost_dev(env4c, par[:nb_], sd[:nb_], sp5, -4.0, safe_b, cnt_b, None, cost_b, "f32"),
+                               reps=2, warm=1)
+            Wb = float(cnt_b.float().mean().item())
+            flop_ap = 6 * Wb * K + 6 * Wb * 5 + 30 * Pm + (Wb - 1) * (2 * 10 + 2 * 35 + 6 * 10 + 3)
+            out["micro_config4_arc_cost_allpairs"] = {
+                "edges": nb_, "circles": K, "edges_per_s": nb_ / mean_ap, "seconds": mean_ap,
+                "kernel": "k_edges_arc_tpe<float,COST,all pairs> (FFMA2 over circle / habitat / boundary-edge pairs)",
+                "roofline": {"bound": "fp32", "achieved": nb_ * flop_ap / mean_ap / 1e12, "peak": cal / 1e12, "unit": "TFLOP/s",
+                             "frac": nb_ * flop_ap / mean_ap / cal, "algorithmic_flop_per_edge": flop_ap,
+                             "peak_source": "FFMA calibration kernel measured live in this run"},
+                "booleans_differ_fraction": float((safe_b != safe_a[:nb_]).float().mean().item()),
+                "counts_identical": bool(torch.equal(cnt_b, cnt_a[:nb_]))}
+            del safe_b, cnt_b, cost_b
+        finally:
+            if saved_b is None:
+                os.environ.pop("AUVRRT_EDGES_BRUTE", None)
+            else:
+                os.environ["AUVRRT_EDGES_BRUTE"] = saved_b
         del par, sd, safe_a, cnt_a, cost_a, safe_off
         torch.cuda.empty_cache()
     except Exception as ex:
         out["micro_config4_arc"] = {"error": repr(ex)}
+    del q0, q1, safe, word, length, safe_culled
+    torch.cuda.empty_cache()
 
     # vectorised gym_rrt Planner_RRT (RRTEnv's planner, freq = 10), one thread per episode
     try:

@@ -146,6 +146,16 @@ int auvrrt_edges_dubins(const auvrrt_env_t *env, const double *from, const doubl
 int auvrrt_edges_arc(const auvrrt_env_t *env, const double *parents, const uint64_t *seeds,
                      int64_t n, const double params[5], int precision, uint8_t *out_safe,
                      int32_t *out_counts, double *out_leaf);
+/* Dubins edges with cost on: traj_time_stamp of waypoint k = arclength_k / velocity from 0 at `from`; out_cost as for the
+ * arc edges, over waypoints 1..W-1 (waypoint 0 is the parent node, rrt_dubins.py:537 tests it, cost.py never sees it
+ * as an appended point).  The world must have a boundary polygon (the culled kernel runs). */
+int auvrrt_edges_dubins_cost_dev(const auvrrt_env_t *env, const void *from, const void *to, int64_t n,
+                                 double rho, int W, double velocity, double w3, int precision,
+                                 uint8_t *out_safe, uint8_t *out_word, void *out_length, void *out_cost,
+                                 void *stream);
+int auvrrt_edges_dubins_cost(const auvrrt_env_t *env, const double *from, const double *to, int64_t n,
+                             double rho, int W, double velocity, double w3, int precision,
+                             uint8_t *out_safe, uint8_t *out_word, double *out_length, double *out_cost);
 int auvrrt_edges_arc_cost_dev(const auvrrt_env_t *env, const void *parents, const uint64_t *seeds,
                               int64_t n, const double params[5], double w3, int precision,
                               uint8_t *out_safe, int32_t *out_counts, void *out_leaf, void *out_cost,

@@ -308,6 +308,42 @@ def test_edges_dubins_vs_oracle(api):
     assert 0.05 < want_safe.mean() < 0.95
 
 
+def test_edges_dubins_cost_vs_oracle(api, env, oworld):
+    """config 4 "cost on" for Dubins edges (auvrrt_edges_dubins_cost): booleans / words / lengths as auvrrt_edges_dubins,
+    cost terms against cost.habitat_shark_cost_func restated by the oracle (orc.cost) on the oracle's own waypoints
+    1..W-1 with traj_time_stamp = arclength / velocity"""
+    rs = np.random.RandomState(12)
+    n, W, rho, vel, w3 = 1200, 12, 1.5, 0.7, -4.0
+    q0 = np.stack([rs.uniform(-300, -100, n), rs.uniform(-60, 100, n), rs.uniform(-np.pi, np.pi, n)], 1)
+    ang = rs.uniform(-np.pi, np.pi, n); dist = rs.uniform(2, 60, n)
+    q1 = np.stack([q0[:, 0] + dist * np.cos(ang), q0[:, 1] + dist * np.sin(ang), rs.uniform(-np.pi, np.pi, n)], 1)
+    s0, w0, l0 = api.edges_dubins(env, q0, q1, rho, W, "f64")
+    safe, word, length, cost = api.edges_dubins_cost(env, q0, q1, rho, W, vel, w3, "f64")
+    assert np.array_equal(safe, s0) and np.array_equal(word, w0) and np.array_equal(length, l0)
+    nh = oworld.c.H
+    n_pos = n_cell = 0
+    for i in range(n):
+        osafe, oword, _prm, olen, wp = orc.edge_dubins(oworld, q0[i], q1[i], rho, W)
+        if oword != word[i]:
+            continue                                        # two words of equal length within rounding (see test_edges_dubins_vs_oracle)
+        assert osafe == safe[i]
+        s = np.concatenate([np.arange(W - 1) * (olen / (W - 1)), [olen]])
+        pts = np.stack([wp[1:, 0], wp[1:, 1], s[1:] / vel], 1)
+        want = orc.cost(pts, 1.0, oworld, [float(nh), 1.0, w3])
+        assert cost[i, 2] == want[1] and cost[i, 1] == want[2], i
+        assert abs(cost[i, 0] - want[3]) <= 1e-12 * max(1.0, abs(want[3])), i
+        n_pos += cost[i, 1] > 0; n_cell += cost[i, 0] != 0
+    assert n_pos > 20 and n_cell > 100
+    q0f, q1f = q0.astype(np.float32).astype(np.float64), q1.astype(np.float32).astype(np.float64)
+    s64 = api.edges_dubins_cost(env, q0f, q1f, rho, W, vel, w3, "f64")
+    s32 = api.edges_dubins_cost(env, q0f, q1f, rho, W, vel, w3, "f32")
+    same = (s32[0] == s64[0]) & (s32[1] == s64[1])
+    assert same.mean() > 0.98
+    ints = (s32[3][same][:, 1:] == s64[3][same][:, 1:]).all(1)
+    assert ints.mean() > 0.98                                  # a waypoint within rounding distance of a habitat rim may flip
+    assert close(s32[3][same][ints][:, 0], s64[3][same][ints][:, 0], 1e-4, scale=1.0)
+
+
 EDGE_VARIANTS = {"thread_per_edge": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "0", "AUVRRT_TPE_THREADS": "256"},
                  # the shape large batches get: 1024-thread CTAs, grid plane in shared memory, slow cases deferred
                  "thread_per_edge_1024": {"AUVRRT_EDGES_VARIANT": "tpe", "AUVRRT_EDGES_BRUTE": "0", "AUVRRT_TPE_THREADS": "1024",
