@@ -13,6 +13,10 @@
 #pragma once
 #include "geom.cuh"
 
+#ifndef AUV_EDGE_ONE
+#define AUV_EDGE_ONE 1     // warp-per-edge evaluation: single-candidate boundary cells in straight-line code (point_unsafe_one)
+#endif
+
 namespace auv {
 
 template <typename R> struct SteerParams {
@@ -100,7 +104,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
         const Cls pcl = env.classify(px, py);
         parent_clear = (pcl.code & 4u) != 0u;
         parent_many = (pcl.code & AUV_GRID_CIRC_MANY) != 0u;
-        if (VERIFY || (pcl.code & AUV_GRID_SLOW)) {
+        if (VERIFY || !AUV_EDGE_ONE || (pcl.code & AUV_GRID_SLOW)) {
             outside = !point_within_c<R>(env, pcl, px, py);
             if (!parent_clear && !parent_many) hit = point_hits_circles_c<R>(env, pcl, px, py);
         } else outside = point_unsafe_one<R>(env, pcl.code, px, py);     // (either flag makes the edge unsafe)
@@ -250,7 +254,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
             // lane = waypoint: polygon and the cell's candidate circles
             bool in = true, h1 = false;
             if (is_wp) {
-                if (VERIFY) {
+                if (VERIFY || !AUV_EDGE_ONE) {
                     in = point_within_c<R>(env, cl, x, y);
                     if (!(cl.code & AUV_GRID_CIRC_MANY)) h1 = point_hits_circles_c<R>(env, cl, x, y);
                 } else {

@@ -291,6 +291,9 @@ __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin
     return -1;
 }
 
+#ifndef AUV_HAB_ONE
+#define AUV_HAB_ONE 1             // warp-per-edge kernels too fetch the single candidate habitat unconditionally
+#endif
 #ifndef AUV_OUTLINE_HAB
 #define AUV_OUTLINE_HAB 1         // ambiguous-habitat cells out of line
 #endif
@@ -348,7 +351,7 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
     const unsigned code = cl.code;
     c.cell = find_cell<R, FASTENV>(env, x, y);
     const unsigned hc = (code >> 3) & 0xFFu;
-    if (!Policy<R>::VERIFY) {
+    if (!Policy<R>::VERIFY && (FASTENV || AUV_HAB_ONE)) {
         // branch-free: definitive first match (hc < 64), the one habitat a point of this cell can be in (64 + h), or
         // none (128: row 0 is fetched and the result masked)
         const int h = (int)(hc & 63u);
@@ -364,7 +367,7 @@ __device__ __forceinline__ Contrib point_contrib(const EnvView<R> &env, R x, R y
             bool in = true;
             if (hc >= AUV_GRID_HAB_ONE) {
                 R q = A::sq2(A::sub(env.hx[h], x), A::sub(env.hy[h], y));
-                in = A::sqrt(q) <= env.hr[h];
+                in = Policy<R>::VERIFY ? (A::sqrt(q) <= env.hr[h]) : (q <= env.hr2[h]);
             }
             if (in) c.hab = h;
         }

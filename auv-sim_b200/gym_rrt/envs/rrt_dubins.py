@@ -71,6 +71,7 @@ class Planner_RRT:
         self._batch.reset(starts, goals, seeds)
         self._episode = 0            # the replica `mps_list`, `env_grid` and generate_one_node talk about
         self._tree_cache = None
+        self._nodes = [self.start]   # Motion_plan_state per node, extended step by step (None: rebuild from the device tree)
         self._steps = 0
 
     # ------------------------------------------------------------------ grid (read-only views)
@@ -90,17 +91,24 @@ class Planner_RRT:
     def _tree(self):
         if self._tree_cache is None:
             t = self._batch.tree(self._episode)
-            nodes = [self.start]
-            for i in range(1, len(t["nodes"])):
-                x, y, th, tt = t["nodes"][i]
-                m = Motion_plan_state(x, y, theta=th, traj_time_stamp=tt)
-                m.parent = nodes[t["parents"][i]]
-                nodes.append(m)
+            nodes = self._nodes if (self._nodes is not None and len(self._nodes) == len(t["nodes"])) else None
+            if nodes is None:
+                nodes = [self.start]
+                for i in range(1, len(t["nodes"])):
+                    x, y, th, tt = t["nodes"][i]
+                    m = Motion_plan_state(x, y, theta=th, traj_time_stamp=tt)
+                    m.parent = nodes[t["parents"][i]]
+                    nodes.append(m)
+                self._nodes = nodes
             self._tree_cache = (t, nodes)
         return self._tree_cache
 
     @property
     def mps_list(self):
+        """the tree's nodes in creation order.  generate_one_node extends the list from the step's record (the new
+        node and its parent index), so an RL episode does not download the whole tree on every step."""
+        if self._nodes is not None and self._tree_cache is None:
+            return self._nodes
         return self._tree()[1]
 
     @property
@@ -140,6 +148,7 @@ class Planner_RRT:
             raise OverflowError("max_step %d needs node_cap >= %d" % (max_step, max_step + self._steps + 1))
         recs = self._batch.plan(max_step)
         self._tree_cache = None
+        self._nodes = None
         done = np.flatnonzero(recs["done"])
         q = int(done[0]) if len(done) else 0
         self._episode = q
@@ -171,7 +180,14 @@ class Planner_RRT:
             path[0].length = float(rec["arc_length"])
             return True, path
         if rec["last_accepted"]:
-            node = self.mps_list[-1]
+            if self._nodes is not None and len(self._nodes) == int(rec["n_nodes"]) - 1:
+                x, y, th, tt = (float(v) for v in rec["cand"])
+                node = Motion_plan_state(x, y, theta=th, traj_time_stamp=tt)
+                node.parent = self._nodes[int(rec["last_parent"])]
+                self._nodes.append(node)
+            else:
+                self._nodes = None
+                node = self.mps_list[-1]
             node.rl_state_id = step_num
             return False, node
         return False, None

@@ -160,12 +160,14 @@ class PythonReference:
         import multiprocessing as mp
         self.procs = procs or (os.cpu_count() or 1)
         self.pool = mp.get_context("spawn").Pool(self.procs)
-        self.starts, _ = make_queries(0, max(self.procs, 1) * 4)
+        self.starts, _ = make_queries(0, max(self.procs, 1) * 16)
 
-    def step(self, k):
-        """plan `procs` queries concurrently (query ids k*procs ...); -> (edges/s over all processes, plans/s, wall, found)"""
-        ids = [(k * self.procs + j) % len(self.starts) for j in range(self.procs)]
-        jobs = [[(i, float(self.starts[i, 0]), float(self.starts[i, 1]))] for i in ids]
+    def step(self, k, per_proc=1):
+        """plan `per_proc` queries on each of the `procs` processes concurrently (query ids k*procs*per_proc ...);
+        -> (edges/s over all processes, plans/s, wall, found)"""
+        n = self.procs * per_proc
+        ids = [(k * n + j) % len(self.starts) for j in range(n)]
+        jobs = [[(i, float(self.starts[i, 0]), float(self.starts[i, 1])) for i in ids[p::self.procs]] for p in range(self.procs)]
         t0 = time.perf_counter()
         out = self.pool.map(_py_ref_worker, jobs, chunksize=1)
         wall = time.perf_counter() - t0
@@ -427,13 +429,14 @@ def main():
                 pr = PythonReference()
                 try:
                     single = pr.single()
-                    r = pr.step(0)
+                    PER_PROC = 8                       # ~10 s of wall clock: 8 queries x 2048 steer calls per process
+                    r = pr.step(0, per_proc=PER_PROC)
                 finally:
                     pr.close()
                 line["cpu_baseline"] = {
                     "value": r[0], "unit": UNIT, "cores": pr.procs, "kind": "reference",
-                    "sample": "%d of the %d queries x %d steer calls, one query per process on %d processes, unmodified "
-                              "reference modules from baseline/_ref, %.1f s wall; %s" % (pr.procs, Q_PER_GPU, ITERS, pr.procs, r[2], cpu_model()),
+                    "sample": "%d of the %d queries x %d steer calls, %d queries per process on %d processes, unmodified "
+                              "reference modules from baseline/_ref, %.1f s wall; %s" % (pr.procs * PER_PROC, Q_PER_GPU, ITERS, PER_PROC, pr.procs, r[2], cpu_model()),
                     "single_process_edges_per_s": single, "plans_per_s": r[1], "port": port_obj}
             except Exception as ex:
                 line["cpu_baseline"]["python_reference_error"] = repr(ex)

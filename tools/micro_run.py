@@ -65,12 +65,23 @@ elif what == "tpt":
         e0.record(); pl.launch(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)
     print("tpt Q", n, "edges/s %.4g" % (n * bench.ITERS / min(ts)), "plans/s %.4g" % (n / min(ts)), ts)
-elif what.startswith("catalina"):
+elif what.startswith("catalina") or what.startswith("config4"):
     # python tools/micro_run.py catalina[-allpairs|-nocost] n : the thread-per-edge arc kernel at Catalina scale
+    # python tools/micro_run.py config4[-allpairs|-nocost] n  : the same on config 4's 500 random circles (bench.py micro_config4_arc*)
     import os
     world, bins_, probs_ = bench.load_world()
-    env = api.Env.from_map(world, bins_, probs_, device=0)
-    par = bench.catalina_parents(world, n, dev)
+    if what.startswith("config4"):
+        rs = np.random.RandomState(1234)
+        circles = np.stack([rs.uniform(-467.4, 82.4, 500), rs.uniform(-153.5, 191.2, 500), rs.uniform(1, 5, 500)], 1)
+        env = api.Env(circles=circles, boundary=world["boundary"], habitats=world["habitats"], bins=bins_, cells=world["cells"],
+                      probs=probs_, device=0)
+        g = torch.Generator(device=dev); g.manual_seed(2)
+        par = torch.stack([torch.rand(n, device=dev, generator=g) * 549.8 - 467.4, torch.rand(n, device=dev, generator=g) * 344.7 - 153.5,
+                           (torch.rand(n, device=dev, generator=g) * 2 - 1) * np.pi, torch.rand(n, device=dev, generator=g) * 400.0,
+                           torch.zeros(n, device=dev)], 1).contiguous()
+    else:
+        env = api.Env.from_map(world, bins_, probs_, device=0)
+        par = bench.catalina_parents(world, n, dev)
     sd = torch.arange(n, device=dev, dtype=torch.int64)
     safe = torch.zeros(n, dtype=torch.uint8, device=dev); cnt = torch.zeros(n, dtype=torch.int32, device=dev)
     leaf = torch.zeros((n, 5), device=dev); cost = torch.zeros((n, 3), device=dev)
