@@ -14,7 +14,11 @@
 #include "geom.cuh"
 
 #ifndef AUV_EDGE_ONE
-#define AUV_EDGE_ONE 1     // warp-per-edge evaluation: single-candidate boundary cells in straight-line code (point_unsafe_one)
+// warp-per-edge evaluation: single-candidate boundary cells in straight-line code (point_unsafe_one).  Measured on B200,
+// k_plan config 2: 8.89 ms per step with it (and AUV_HAB_ONE), 8.71 with this one off, 8.65 with both off -- the lanes of a
+// warp are consecutive waypoints of ONE edge, mostly in cells of one kind, so the branches cost little here and the
+// unconditional fetches cost their instructions.  Off; the thread-per-edge kernels (32 unrelated edges per warp) use it.
+#define AUV_EDGE_ONE 0
 #endif
 
 namespace auv {

@@ -347,7 +347,7 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
             } else {
                 // decided cells and single-candidate boundary cells in straight-line code (point_unsafe_one)
                 bool bad1 = point_unsafe_one<R>(env, cl.code, e.x, e.y);
-                if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u, 0)) {
+                if (__builtin_expect((cl.code & AUV_GRID_SLOW) != 0u && !e.bad, 0)) {       // (an edge that is already unsafe skips the general tests)
                     if (DEFER) { slowq_push<R>(env.shared_self, sq.base, (float)e.x, (float)e.y, cl.idx, (int)(threadIdx.x & 31u) | 32); bad1 = false; }
                     else bad1 = (AUV_OUTLINE_COLLIDE && (FASTENV || env.shared_self)) ? point_unsafe_shared<R>(env.shared_self, cl.code, cl.idx, e.x, e.y)
                                                                                       : (!point_within_c<R>(env, cl, e.x, e.y) || point_hits_circles_c<R>(env, cl, e.x, e.y));

@@ -292,7 +292,7 @@ __device__ __forceinline__ int find_bin(const EnvView<R> &env, R t, unsigned bin
 }
 
 #ifndef AUV_HAB_ONE
-#define AUV_HAB_ONE 1             // warp-per-edge kernels too fetch the single candidate habitat unconditionally
+#define AUV_HAB_ONE 0             // warp-per-edge kernels too fetch the single candidate habitat unconditionally: measured slower (edge.cuh, AUV_EDGE_ONE)
 #endif
 #ifndef AUV_OUTLINE_HAB
 #define AUV_OUTLINE_HAB 1         // ambiguous-habitat cells out of line
