@@ -525,6 +525,15 @@ def micro_catalina(env, dev, n_edges, api, adev, cal_flops, timed):
             "edges_with_shark_cost": float((cost_grid[:, 0] != 0).float().mean().item()),
             "note": "the grid decides most waypoint tests with one load, so the all-pairs FLOP count is an equivalent here; "
                     "the executed-work roofline is micro_catalina_arc_cost_allpairs (same edges, same results)"}
+        # what bounds the grid kernel is instruction issue, not FLOPs: executed warp-instructions per edge (ncu, profiles/
+        # r02_tpe_final.txt) x measured edges/s against 148 SMs x 4 schedulers x 1 instruction per clock
+        wi = ncu_traffic("k_edges_arc_tpe_f32_cost_grid_warp_instr_per_edge")
+        if wi:
+            issue_peak = 148 * 4 * 1.965e9
+            out["micro_catalina_arc_cost"]["roofline"] = {
+                "bound": "issue", "achieved": n_edges / t_on * wi / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-instr/s",
+                "frac": n_edges / t_on * wi / issue_peak, "warp_instructions_per_edge": wi,
+                "source": "smsp__inst_executed.sum / edges from the committed ncu capture of this kernel; peak = 148 SMs x 4 schedulers x 1.965 GHz"}
         out["micro_catalina_arc"] = {"edges": n_edges, "edges_per_s": n_edges / t_off, "seconds": t_off, "identical_booleans": same_off,
                                      "algorithmic_flop_per_edge": flop_geo, "equivalent_frac": n_edges * flop_geo / t_off / cal_flops,
                                      "kernel": "k_edges_arc_tpe<float,no cost,grid>"}

@@ -20,7 +20,7 @@ RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
 
 def main():
     rep, out, title = sys.argv[1:4]
-    lines = ["# " + title, "# source: %s (ncu --set full --clock-control none --import-source on)" % rep.split("/")[-1], ""]
+    lines = ["# " + title, "# source: %s (ncu --set full --clock-control none)" % rep.split("/")[-1], ""]
     det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout.splitlines()
     for l in det:
         if any(k in l for k in KEEP) or ("(" in l and ")x(" in l):
