@@ -33,9 +33,10 @@ struct CircPair {           // two circles a, b
     float2 m2x, m2y;        // -2 c'_x, -2 c'_y
     float2 k;               // |c'|^2 - r_eff^2
 };
+struct alignas(16) CircQuad { float4 m2x, m2y, k; };     // four circles: three 16-byte loads feed four FFMA2
 struct CircTable {
-    const CircPair *pair;   // ceil(K / 2) entries in shared memory; a missing second circle repeats the first
-    int npair;
+    const CircQuad *pair;   // ceil(K / 4) entries in shared memory; missing circles repeat the quad's first
+    int npair;              // number of quads
     float ox, oy;           // origin
     float ccmax;            // max |c'|^2: scale of the rounding error of the expansion
     // the same packed form for the habitats (first match in list order; a missing second habitat has k = +inf) ...
@@ -72,16 +73,20 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 }
 
 // fill a CircTable from the staged world model (all threads of the CTA; caller syncs)
-__device__ __forceinline__ void circ_table_fill(CircPair *dst, const EnvView<float> &env, float ox, float oy) {
-    const int np = (env.K + 1) >> 1;
-    for (int j = threadIdx.x; j < np; j += blockDim.x) {
-        const int a = 2 * j, b = (2 * j + 1 < env.K) ? 2 * j + 1 : 2 * j;
-        const float ax = env.cx[a] - ox, ay = env.cy[a] - oy, bx = env.cx[b] - ox, by = env.cy[b] - oy;
-        CircPair p;
-        p.m2x = make_float2(-2.f * ax, -2.f * bx);
-        p.m2y = make_float2(-2.f * ay, -2.f * by);
-        p.k = make_float2(fmaf(ay, ay, ax * ax) - env.creff2[a], fmaf(by, by, bx * bx) - env.creff2[b]);
-        dst[j] = p;
+__device__ __forceinline__ void circ_table_fill(CircQuad *dst, const EnvView<float> &env, float ox, float oy) {
+    const int nq = (env.K + 3) >> 2;
+    for (int j = threadIdx.x; j < nq; j += blockDim.x) {
+        float mx[4], my[4], kk[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int a = (4 * j + c < env.K) ? 4 * j + c : 4 * j;
+            const float ax = env.cx[a] - ox, ay = env.cy[a] - oy;
+            mx[c] = -2.f * ax; my[c] = -2.f * ay; kk[c] = fmaf(ay, ay, ax * ax) - env.creff2[a];
+        }
+        CircQuad q;
+        q.m2x = make_float4(mx[0], mx[1], mx[2], mx[3]); q.m2y = make_float4(my[0], my[1], my[2], my[3]);
+        q.k = make_float4(kk[0], kk[1], kk[2], kk[3]);
+        dst[j] = q;
     }
 }
 __device__ __forceinline__ float circ_table_ccmax(const EnvView<float> &env, float ox, float oy) {
@@ -129,7 +134,7 @@ __device__ __forceinline__ int first_habitat_all_f32(const EnvView<float> &env, 
     const float xr = x - ct.ox, yr = y - ct.oy;
     const float pp = fmaf(yr, yr, xr * xr);
     const float2 x2 = make_float2(xr, xr), y2 = make_float2(yr, yr);
-    const float guard = 4e-6f * (pp + ct.hccmax);
+    const float guard = 8e-7f * (pp + ct.hccmax);        // (see point_hits_circles_all)
     int hab = -1;
     bool amb = false;
     for (int j = ct.nhpair - 1; j >= 0; j--) {            // last to first: the earliest match ends up in `hab`
@@ -177,25 +182,23 @@ __device__ __forceinline__ bool point_hits_circles_all<float>(const EnvView<floa
     const float pp = fmaf(yr, yr, xr * xr);
     const float2 x2 = make_float2(xr, xr), y2 = make_float2(yr, yr);
     float q0 = Ar<float, false>::inf(), q1 = q0;
-    int j = 0;
 #pragma unroll 4
-    for (; j + 1 < ct.npair; j += 2) {
-        const CircPair a = ct.pair[j], b = ct.pair[j + 1];
-        const float2 qa = ffma2(a.m2y, y2, ffma2(a.m2x, x2, a.k));
-        const float2 qb = ffma2(b.m2y, y2, ffma2(b.m2x, x2, b.k));
+    for (int j = 0; j < ct.npair; j++) {
+        const CircQuad a = ct.pair[j];
+        const float2 qa = ffma2(make_float2(a.m2y.x, a.m2y.y), y2, ffma2(make_float2(a.m2x.x, a.m2x.y), x2, make_float2(a.k.x, a.k.y)));
+        const float2 qb = ffma2(make_float2(a.m2y.z, a.m2y.w), y2, ffma2(make_float2(a.m2x.z, a.m2x.w), x2, make_float2(a.k.z, a.k.w)));
         q0 = fminf(q0, fminf(qa.x, qa.y));
         q1 = fminf(q1, fminf(qb.x, qb.y));
     }
-    if (j < ct.npair) {
-        const CircPair a = ct.pair[j];
-        const float2 qa = ffma2(a.m2y, y2, ffma2(a.m2x, x2, a.k));
-        q0 = fminf(q0, fminf(qa.x, qa.y));
-    }
     const float t = fminf(q0, q1) + pp;                // min_k (d_k^2 - r_k^2)
-    const float guard = 4e-6f * (pp + ct.ccmax);
+    // Rounding error of the expansion: seven roundings (k: 3, pp: 2, the two fused multiply-adds) of terms bounded by
+    // M = |p'|^2 + max |c'|^2, i.e. <= 7 x 2^-24 M = 4.2e-7 M; the guard is twice that.  (A guard of 4e-6 M, as first
+    // written, is 0.7 m^2 on the Catalina map -- a 12 cm band around every rim -- and with 500 circles sent 1 % of the
+    // waypoints, hence every fourth warp step, through the scalar loop below: 85 % of the executed instructions.)
+    const float guard = 8e-7f * (pp + ct.ccmax);
     if (t > guard) return false;
     if (t < -guard) return true;
-    return point_hits_circles<float>(env, x, y);       // too close to call: the direct formula
+    return point_hits_circles_outlined<float>(env.cx, env.cy, env.creff2, env.K, x, y);       // too close to call: the direct formula
 }
 
 // unsafe point?  (outside the polygon, on its boundary, or inside an inflated circle)
@@ -208,7 +211,10 @@ template <> __device__ __forceinline__ bool point_within_all<float>(const EnvVie
 }
 template <typename R, bool ALLPAIRS>
 __device__ __forceinline__ bool point_unsafe(const EnvView<R> &env, const CircTable &ct, const Cls &cl, R x, R y) {
-    if (ALLPAIRS) return !point_within_all<R>(env, ct, x, y) || point_hits_circles_all<R>(env, ct, x, y);
+    if (ALLPAIRS) {
+        const bool out = !point_within_all<R>(env, ct, x, y), hit = point_hits_circles_all<R>(env, ct, x, y);     // both, always
+        return out || hit;
+    }
     return point_unsafe_c<R>(env, cl, x, y);
 }
 
@@ -338,7 +344,12 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
     if (e.last_is_wp) {
         e.nwp++;
         Cls cl; cl.code = AUV_GRID_ALL_AMBIG; cl.idx = -1;
-        if (ALLPAIRS) e.bad = e.bad || point_unsafe<R, true>(env, ct, cl, e.x, e.y);
+        if (ALLPAIRS) {
+            // every waypoint against everything, also on an edge that is already unsafe: the executed work is the FLOP
+            // count the roofline figure uses
+            const bool u = point_unsafe<R, true>(env, ct, cl, e.x, e.y);
+            e.bad = e.bad || u;
+        }
         else {
             cl = env.template classify<GRIDS>(e.x, e.y);
             if (Policy<R>::VERIFY) {

@@ -37,7 +37,7 @@ namespace auv {
 #endif
 #define AUV_TPE_BUCKETS 64
 #define AUV_TPE_QBYTES (AUV_SLOWQ_CAP * 16 + 16 + 3 * 128)      // SlowQ of one warp
-#define AUV_TPE_MAXPAIRS 256      // all-pairs circle table in shared memory: up to 512 circles (6 KB)
+#define AUV_TPE_MAXPAIRS 128      // all-pairs circle table in shared memory: 128 quads = up to 512 circles (6 KB)
 
 // STAGE: 1 = the hot part of the world model is in shared memory, 2 = the probability table too (always staged:
 // the launcher falls back to the warp-per-edge kernel when even the hot part does not fit)
@@ -55,7 +55,7 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     __shared__ unsigned short s_order[BATCH];
     __shared__ int s_hist[AUV_TPE_BUCKETS];
     __shared__ int s_next;
-    __shared__ CircPair s_pairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_TPE_MAXPAIRS : 1];
+    __shared__ CircQuad s_pairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_TPE_MAXPAIRS : 1];
     __shared__ CircPair s_hpairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_AP_MAXH : 1], s_epairs[(ALLPAIRS && sizeof(R) == 4) ? AUV_AP_MAXE : 1];
     EnvView<R> env;
     unsigned char *q_base;
@@ -101,10 +101,10 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     ct.hpair = nullptr; ct.nhpair = 0; ct.hccmax = 0.f; ct.epair = nullptr; ct.nepair = 0; ct.escale = 0.f; ct.eoff = 0.f;
     if constexpr (ALLPAIRS && sizeof(R) == 4) {
         ct.ox = 0.5f * (float)(env.minx + env.maxx); ct.oy = 0.5f * (float)(env.miny + env.maxy);
-        if (env.K > 0 && env.K <= 2 * AUV_TPE_MAXPAIRS) {
+        if (env.K > 0 && env.K <= 4 * AUV_TPE_MAXPAIRS) {
             circ_table_fill(s_pairs, env, ct.ox, ct.oy);
             ct.ccmax = circ_table_ccmax(env, ct.ox, ct.oy);
-            ct.pair = s_pairs; ct.npair = (env.K + 1) >> 1;
+            ct.pair = s_pairs; ct.npair = (env.K + 3) >> 2;
         }
         allpairs_tables_fill(s_hpairs, s_epairs, env, ct.ox, ct.oy);
         if (env.H > 0 && env.H <= 2 * AUV_AP_MAXH) {
@@ -224,6 +224,10 @@ static tpe_kernel_f32 pick_f32(bool fast, bool probs_too, int nt, int minb, bool
             if (nt == 512) return AUV_TPE_ST(true, 512, 2, false);
         }
     }
+    if constexpr (ALLPAIRS) {
+        // the all-pairs loops are unrolled four quads deep (48 registers of circle data in flight): 2 CTAs per SM = 128 registers
+        if (minb <= 2) return fast ? AUV_TPE_ST(true, 256, 2, false) : AUV_TPE_ST(false, 256, 2, false);
+    }
     if (minb >= 4) return fast ? AUV_TPE_ST(true, 256, 4, false) : AUV_TPE_ST(false, 256, 4, false);
     return fast ? AUV_TPE_ST(true, 256, 3, false) : AUV_TPE_ST(false, 256, 3, false);
 #undef AUV_TPE_ST
@@ -251,8 +255,10 @@ static int launch_tpe_t(const auvrrt_env *env, const R *parents, const uint64_t 
         if (const char *ev = getenv("AUVRRT_TPE_THREADS")) { const int v = atoi(ev); if (v == 256 || v == 512 || v == 1024) nt = v; }
         if (const char *ev = getenv("AUVRRT_TPE_MINB")) minb = atoi(ev);
         if (const char *ev = getenv("AUVRRT_TPE_GRIDS")) grids = atoi(ev) != 0;
-        if (nt == 512) minb = 2; else if (nt == 1024) minb = 1; else minb = minb >= 4 ? 4 : 3;
-        if (ALLPAIRS || !fast) { grids = false; nt = 256; minb = minb >= 4 ? 4 : 3; }
+        // (all pairs, measured at 256 x 2 / 3 / 4: Catalina 3.14 / 3.54 / 3.50e9 edges/s, config 4 6.37 / 6.35 / 6.16e8: 3 unless asked otherwise)
+        const int minb256 = ALLPAIRS ? ((getenv("AUVRRT_TPE_MINB") && minb <= 2) ? 2 : ((getenv("AUVRRT_TPE_MINB") && minb >= 4) ? 4 : 3)) : (minb >= 4 ? 4 : 3);
+        if (ALLPAIRS || !fast) { grids = false; nt = 256; }
+        minb = nt == 512 ? 2 : (nt == 1024 ? 1 : minb256);
         // the grid plane must fit next to the hot part
         if (grids && ((hd.gnx * hd.gny * 4 + 15) & ~15) + b.hot_bytes + 16 > (int)((227 * 1024) / minb) - 2048 - (int)(2 * nt * AUV_TPE_EPT)) grids = false;
     }
