@@ -25,9 +25,27 @@ for prec in ("f32", "f64"):
     parents = np.stack([rs.uniform(-300, -100, 200), rs.uniform(-60, 100, 200), rs.uniform(-6, 6, 200), rs.uniform(0, 400, 200), rs.uniform(0, 500, 200)], 1)
     api.edges_arc(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], prec)
     api.edges_arc_cost(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, prec)
+    # round 2: the thread-per-edge kernel in its other CTA shapes (grid plane in shared memory), all pairs, warp per edge
+    for shape, grids in (("512", "0"), ("1024", "1"), ("1024", "0")):
+        os.environ["AUVRRT_TPE_THREADS"] = shape; os.environ["AUVRRT_TPE_GRIDS"] = grids
+        api.edges_arc_cost(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, prec)
+        api.edges_arc(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], prec)
+    os.environ.pop("AUVRRT_TPE_THREADS"); os.environ.pop("AUVRRT_TPE_GRIDS")
+    os.environ["AUVRRT_EDGES_BRUTE"] = "1"
+    api.edges_arc_cost(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, prec)
+    os.environ["AUVRRT_EDGES_BRUTE"] = "0"
+    os.environ["AUVRRT_EDGES_VARIANT"] = "warp"
+    api.edges_arc_cost(env, parents, np.arange(200), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, prec)
+    os.environ.pop("AUVRRT_EDGES_VARIANT")
+    # round 2: Dubins-RRT with best parent (mode 3), Dubins edges with cost on
+    p3 = api.plan_params(48, mode=3, v=1.0, max_traj_time=120.0, dubins_rho=3.0, dubins_eta=8.0, near_radius=15.0, dubins_w=6,
+                         trace=True, path_cap=512)
+    r3 = api.plan_batch(env, starts[:8], seeds[:8], p3, prec)
+    assert (r3["records"]["status"] <= 1).all()
     q0 = np.stack([rs.uniform(-400, 50, 300), rs.uniform(-100, 120, 300), rs.uniform(-3, 3, 300)], 1)
     q1 = q0 + rs.uniform(-20, 20, (300, 3))
     api.edges_dubins(env, q0, q1, 1.0, 20, prec)
+    api.edges_dubins_cost(env, q0, q1, 1.0, 20, 1.0, -4.0, prec)
     os.environ["AUVRRT_EDGES_BRUTE"] = "1"
     api.edges_dubins(env, q0, q1, 1.0, 20, prec)
     os.environ["AUVRRT_EDGES_BRUTE"] = "0"
