@@ -39,6 +39,8 @@ struct CircTable {
     int npair;              // number of quads
     float ox, oy;           // origin
     float ccmax;            // max |c'|^2: scale of the rounding error of the expansion
+    float rmax1;            // largest inflated radius + 1 m (circ_guard)
+    bool buf2;              // enough circles for two waypoints per pass over the table to pay (circles_hit2)
     // the same packed form for the habitats (first match in list order; a missing second habitat has k = +inf) ...
     const CircPair *hpair; int nhpair; float hccmax;
     // ... and for the edges of a convex boundary ring: det_i(p') = A_i x' + B_i y' + C_i as (m2x, m2y, k) = (A, B, C) pairs,
@@ -61,6 +63,9 @@ struct SlowQ {               // per warp, shared memory; one pointer (a register
     __device__ __forceinline__ unsigned *mask() const { return bad() + 64; }
 };
 #define AUV_AP_MAXH 32       // habitat pairs (64 habitats)
+#ifndef AUV_AP_BUFFER
+#define AUV_AP_BUFFER 1      // all-pairs fp32 build: two waypoints per pass over the circle table (circles_hit2)
+#endif
 #define AUV_AP_MAXE 16       // polygon edge pairs (32 edges)
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -170,6 +175,18 @@ __device__ __forceinline__ bool point_within_all_f32(const EnvView<float> &env, 
     return dmax < 0.f;
 }
 
+// How close to zero the minimum of the expanded form min_k (|p'|^2 - 2 c_k'.p' + |c_k'|^2 - r_k^2) may be and still be
+// trusted.  Circle k's value carries seven roundings of terms bounded by |p'|^2 + |c_k'|^2: an error below
+// 4.2e-7 (|p'|^2 + |c_k'|^2).  A circle that can be within 1 m of the point has |c_k'| <= |p'| + r_max + 1; every other
+// circle's true value exceeds 2 r + 1 >= 1 m^2, far above its error (< 0.1 m^2 on a 1 km map).  Twice the bound for the
+// near circles is therefore a rigorous guard -- about half of 8e-7 (|p'|^2 + max_k |c_k'|^2) for a typical point.
+__device__ __forceinline__ float circ_guard(const CircTable &ct, float pp) {
+    float root;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(pp));          // one MUFU; its 2^-22 relative error is nothing next to the factor two
+    const float reach = root + ct.rmax1;
+    return fminf(8e-7f * fmaf(reach, reach, pp), 8e-7f * (pp + ct.ccmax));
+}
+
 // does (x, y) hit any (inflated) circle: every circle, no culling
 template <typename R>
 __device__ __forceinline__ bool point_hits_circles_all(const EnvView<R> &env, const CircTable &ct, R x, R y) {
@@ -195,7 +212,7 @@ __device__ __forceinline__ bool point_hits_circles_all<float>(const EnvView<floa
     // M = |p'|^2 + max |c'|^2, i.e. <= 7 x 2^-24 M = 4.2e-7 M; the guard is twice that.  (A guard of 4e-6 M, as first
     // written, is 0.7 m^2 on the Catalina map -- a 12 cm band around every rim -- and with 500 circles sent 1 % of the
     // waypoints, hence every fourth warp step, through the scalar loop below: 85 % of the executed instructions.)
-    const float guard = 8e-7f * (pp + ct.ccmax);
+    const float guard = circ_guard(ct, pp);
     if (t > guard) return false;
     if (t < -guard) return true;
     return point_hits_circles_outlined<float>(env.cx, env.cy, env.creff2, env.K, x, y);       // too close to call: the direct formula
@@ -216,6 +233,35 @@ __device__ __forceinline__ bool point_unsafe(const EnvView<R> &env, const CircTa
         return out || hit;
     }
     return point_unsafe_c<R>(env, cl, x, y);
+}
+
+// what one thread carries along an edge
+template <typename R> struct ArcEdge;
+// Two waypoints per pass over the circle table (all-pairs fp32 build): the three 16-byte loads of a quad feed eight FFMA2
+// instead of four.  A warp flushes its lanes' buffers together as soon as one of them holds two waypoints
+// (edges_tpe.cu); a lane holding one tests it twice.  Returns "some buffered waypoint hits a circle".
+__device__ __forceinline__ bool circles_hit2(const EnvView<float> &env, const CircTable &ct, float xa, float ya, float xb, float yb) {
+    const float xra = xa - ct.ox, yra = ya - ct.oy, xrb = xb - ct.ox, yrb = yb - ct.oy;
+    const float ppa = fmaf(yra, yra, xra * xra), ppb = fmaf(yrb, yrb, xrb * xrb);
+    const float2 xa2 = make_float2(xra, xra), ya2 = make_float2(yra, yra), xb2 = make_float2(xrb, xrb), yb2 = make_float2(yrb, yrb);
+    float a0 = Ar<float, false>::inf(), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll 2
+    for (int j = 0; j < ct.npair; j++) {
+        const CircQuad q = ct.pair[j];
+        const float2 mxl = make_float2(q.m2x.x, q.m2x.y), mxh = make_float2(q.m2x.z, q.m2x.w);
+        const float2 myl = make_float2(q.m2y.x, q.m2y.y), myh = make_float2(q.m2y.z, q.m2y.w);
+        const float2 kl = make_float2(q.k.x, q.k.y), kh = make_float2(q.k.z, q.k.w);
+        const float2 al = ffma2(myl, ya2, ffma2(mxl, xa2, kl)), ah = ffma2(myh, ya2, ffma2(mxh, xa2, kh));
+        const float2 bl = ffma2(myl, yb2, ffma2(mxl, xb2, kl)), bh = ffma2(myh, yb2, ffma2(mxh, xb2, kh));
+        a0 = fminf(a0, fminf(al.x, al.y)); a1 = fminf(a1, fminf(ah.x, ah.y));
+        b0 = fminf(b0, fminf(bl.x, bl.y)); b1 = fminf(b1, fminf(bh.x, bh.y));
+    }
+    const float ta = fminf(a0, a1) + ppa, tb = fminf(b0, b1) + ppb;
+    const float ga = circ_guard(ct, ppa), gb = circ_guard(ct, ppb);
+    bool hit = ta < -ga || tb < -gb;
+    if (__builtin_expect(!hit && fabsf(ta) <= ga, 0)) hit = point_hits_circles_outlined<float>(env.cx, env.cy, env.creff2, env.K, xa, ya);
+    if (__builtin_expect(!hit && fabsf(tb) <= gb, 0)) hit = point_hits_circles_outlined<float>(env.cx, env.cy, env.creff2, env.K, xb, yb);
+    return hit;
 }
 
 // the same out of line through the shared copy of the view (every cell that is not "inside and clear")
@@ -268,7 +314,25 @@ template <typename R> struct ArcEdge {
     R self_s2; int self_hab;                         // contribution of the provisional leaf state
     BinCursor<R> bins;                               // shark-grid time bin of the current traj_time_stamp (COST)
     int status;
+    // all-pairs fp32 build: waypoints waiting for the circle loop (circles_flush2 takes two per pass over the circle table)
+    float pbx0, pby0, pbx1, pby1; int nbuf;
 };
+
+// queue a waypoint for the circle loop / run the loop over whatever the lane holds (all-pairs fp32 build)
+template <typename R> __device__ __forceinline__ void circles_push(ArcEdge<R> &e, R x, R y) {
+    if (e.nbuf == 0) { e.pbx0 = (float)x; e.pby0 = (float)y; } else { e.pbx1 = (float)x; e.pby1 = (float)y; }
+    e.nbuf++;
+}
+template <typename R> __device__ __forceinline__ void circles_flush2(const EnvView<R> &env, const CircTable &ct, ArcEdge<R> &e) {
+    if constexpr (sizeof(R) == 4) {
+        if (e.nbuf > 0) {
+            const bool two = e.nbuf > 1;
+            const bool hit = circles_hit2(env, ct, e.pbx0, e.pby0, two ? e.pbx1 : e.pbx0, two ? e.pby1 : e.pby0);
+            e.bad = e.bad || hit;
+            e.nbuf = 0;
+        }
+    }
+}
 
 // path[0] = the parent node object: tested like any other path point (rrt_dubins.py:537,544)
 // FASTENV: contiguous equal time bins, the x-bucket table and a shared copy of the view are all present (the
@@ -282,6 +346,7 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
     if (Policy<R>::VERIFY) A::sincos(pth, &e.sin0, &e.cos0);
     e.nwp = 1; e.moved = false; e.degenerate = false; e.last_is_wp = false;
     e.s2 = 0; e.cnt = 0; e.mask = 0ull; e.self_s2 = parent_self_s2; e.self_hab = parent_self_hab; e.status = 0;
+    e.nbuf = 0; e.pbx0 = e.pby0 = e.pbx1 = e.pby1 = 0.f;
     Cls pcl; pcl.code = 0; pcl.idx = -1;
     if (!ALLPAIRS) pcl = env.template classify<GRIDS>(px, py);
     if (AUV_OUTLINE_COLLIDE && FASTENV && !ALLPAIRS) e.bad = (pcl.code & 7u) != 5u && point_unsafe_shared<R>(env.shared_self, pcl.code, pcl.idx, px, py);
@@ -291,6 +356,9 @@ __device__ __forceinline__ void arc_edge_begin(const EnvView<R> &env, const Circ
             slowq_push<R>(env.shared_self, sq.base, (float)px, (float)py, pcl.idx, (int)(threadIdx.x & 31u) | 32);
             e.bad = false;
         }
+    } else if (ALLPAIRS && sizeof(R) == 4 && AUV_AP_BUFFER && ct.buf2) {
+        e.bad = !point_within_all<R>(env, ct, px, py);          // the boundary now, the circles together with the next waypoint
+        circles_push<R>(e, px, py);
     } else e.bad = point_unsafe<R, ALLPAIRS>(env, ct, pcl, px, py);
     e.bins.k = 0; e.bins.up = 0;
     if (AUV_BIN_CURSOR && (FASTENV || env.bins_uniform)) e.bins.start(env, pt);
@@ -347,8 +415,15 @@ __device__ __forceinline__ bool arc_edge_step(const EnvView<R> &env, const CircT
         if (ALLPAIRS) {
             // every waypoint against everything, also on an edge that is already unsafe: the executed work is the FLOP
             // count the roofline figure uses
-            const bool u = point_unsafe<R, true>(env, ct, cl, e.x, e.y);
-            e.bad = e.bad || u;
+            if (sizeof(R) == 4 && AUV_AP_BUFFER && ct.buf2) {
+                const bool out = !point_within_all<R>(env, ct, e.x, e.y);
+                e.bad = e.bad || out;
+                if (e.nbuf >= 2) circles_flush2<R>(env, ct, e);       // (the caller flushes earlier, warp-wide; this keeps the buffer bounded)
+                circles_push<R>(e, e.x, e.y);
+            } else {
+                const bool u = point_unsafe<R, true>(env, ct, cl, e.x, e.y);
+                e.bad = e.bad || u;
+            }
         }
         else {
             cl = env.template classify<GRIDS>(e.x, e.y);

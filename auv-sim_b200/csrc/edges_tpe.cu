@@ -97,7 +97,7 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
     if (threadIdx.x == 0) { s_env = env; s_env.shared_self = &s_env; }
     __syncthreads();
     env.shared_self = &s_env;
-    CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
+    CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f; ct.rmax1 = 1.f; ct.buf2 = false;
     ct.hpair = nullptr; ct.nhpair = 0; ct.hccmax = 0.f; ct.epair = nullptr; ct.nepair = 0; ct.escale = 0.f; ct.eoff = 0.f;
     if constexpr (ALLPAIRS && sizeof(R) == 4) {
         ct.ox = 0.5f * (float)(env.minx + env.maxx); ct.oy = 0.5f * (float)(env.miny + env.maxy);
@@ -105,6 +105,12 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
             circ_table_fill(s_pairs, env, ct.ox, ct.oy);
             ct.ccmax = circ_table_ccmax(env, ct.ox, ct.oy);
             ct.pair = s_pairs; ct.npair = (env.K + 3) >> 2;
+            float rm = 0.f;
+            for (int k = 0; k < env.K; k++) rm = fmaxf(rm, (float)env.creff[k]);
+            ct.rmax1 = rm + 1.f;
+            // two waypoints per pass over the table from 64 circles up (measured: Catalina's 27 circles 3.54e9 edges/s
+            // without, 3.40e9 with; config 4's 500 circles 6.35e8 without, 7.9e8 with)
+            ct.buf2 = ct.npair >= 16;
         }
         allpairs_tables_fill(s_hpairs, s_epairs, env, ct.ox, ct.oy);
         if (env.H > 0 && env.H <= 2 * AUV_AP_MAXH) {
@@ -176,8 +182,14 @@ k_edges_arc_tpe(const unsigned char *blob, int hot_bytes, int total_bytes, const
                 rng.init(stream_key(seeds[i]));
                 const int n_exp = (int)A::floor(uniform_ab<R>((R)0, sp.freq, rng.next()));
                 arc_edge_begin<R, ALLPAIRS, FASTENV, GRIDS, DEFER>(env, ct, ed, px, py, pth, pt, plen, (R)0, -1, sq);
-                for (int k = 0; k < n_exp; k++)
+                for (int k = 0; k < n_exp; k++) {
                     if (!arc_edge_step<R, COST, false, ALLPAIRS, FASTENV, GRIDS, DEFER>(env, ct, sp, w3, rng, ed, sq)) break;
+                    if constexpr (ALLPAIRS && sizeof(R) == 4 && AUV_AP_BUFFER) {
+                        // the lanes that are here together run the circle loop together as soon as one of them holds two waypoints
+                        if (__any_sync(__activemask(), ed.nbuf >= 2)) circles_flush2<R>(env, ct, ed);
+                    }
+                }
+                if constexpr (ALLPAIRS && sizeof(R) == 4 && AUV_AP_BUFFER) circles_flush2<R>(env, ct, ed);
             }
             if (DEFER) {
                 // the queued slow cases of these 32 edges, one per lane; then every lane folds its results in

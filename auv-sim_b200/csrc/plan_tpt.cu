@@ -123,7 +123,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 const NodeRow<R> pr = nodes[parent];
                 const uint32_t ctr0 = rng.ctr - 1;                 // position of the n_expand draw
                 ArcEdge<R> ed;
-                CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f;
+                CircTable ct; ct.pair = nullptr; ct.npair = 0; ct.ox = ct.oy = ct.ccmax = 0.f; ct.rmax1 = 1.f; ct.buf2 = false;
                 ct.hpair = nullptr; ct.nhpair = 0; ct.hccmax = 0.f; ct.epair = nullptr; ct.nepair = 0; ct.escale = 0.f; ct.eoff = 0.f;
                 arc_edge_begin<R, false, FAST>(env, ct, ed, pr.x, pr.y, pr.th, pr.t, pr.len, pr.self_s2, pr.self_hab);
                 for (int k = 0; k < n_exp; k++)
