@@ -32,11 +32,15 @@ static const int TPT_THREADS = AUV_TPT_THREADS;
 #define AUV_TPT_SPT 1
 #endif
 #ifndef AUV_TPT_MINB
-#define AUV_TPT_MINB (AUV_TPT_SPT == 2 ? 4 : 8)
+#define AUV_TPT_MINB (AUV_TPT_SPT == 2 ? 6 : 8)
 #endif
 static const int TPT_SLOTS = AUV_TPT_THREADS * AUV_TPT_SPT;
 
-struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count; };
+struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count, hdr; };
+
+// the part of a tree's bookkeeping that is touched rarely (a new best plan, a skipped trip, the trace): in the tree's
+// workspace, not in shared memory -- every byte of per-tree shared state costs resident warps
+template <typename R> struct TptHdr { int bestnode, bestiter, ncost, guard; uint32_t upos; int pad_; R bc1, bc2, bc3, blen, bt; };
 
 template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchunks) {
     TptLayout L;
@@ -45,6 +49,7 @@ template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchu
     L.nodes = take(sizeof(NodeRow<R>) * (size_t)cap);
     L.pool = take(4 * 32 * (size_t)nchunks); L.next = take(4 * (size_t)nchunks);
     L.head = take(4 * (size_t)(nb + 2)); L.tail = take(4 * (size_t)(nb + 2)); L.count = take(4 * (size_t)(nb + 2));
+    L.hdr = take(sizeof(TptHdr<R>));
     L.slot_bytes = o;
     return L;
 }
@@ -68,11 +73,11 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
     const int T = TPT_THREADS, S = TPT_SLOTS, SPT = AUV_TPT_SPT;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long s_z[S];
-    __shared__ long long s_q[S], s_nprims[S];
-    __shared__ uint32_t s_ctr[S], s_upos[S];
-    __shared__ int s_nnodes[S], s_nchunks[S], s_it[S], s_status[S], s_bestnode[S], s_bestiter[S], s_ncost[S], s_nwp[S],
-        s_guard[S], s_active[S], s_parent[S], s_nexp[S], s_order[S], s_hist[64];
-    __shared__ R s_bc0[S], s_bc1[S], s_bc2[S], s_bc3[S], s_blen[S], s_bt[S];
+    __shared__ long long s_q[S];
+    __shared__ uint32_t s_ctr[S];
+    __shared__ int s_nnodes[S], s_nchunks[S], s_it[S], s_status[S], s_nwp[S], s_nprims[S],
+        s_active[S], s_parent[S], s_nexp[S], s_order[S], s_hist[64];
+    __shared__ R s_bc0[S];
     // which time bins of each tree are non-empty (<= 128 bins): the rejection loop of the parent pick probes bins until
     // it finds one (rrt_dubins.py:123-125); testing a bit in shared memory instead of reading count[bin] from the tree's
     // workspace takes a dependent global load (and a 32-byte sector) off every probe
@@ -110,6 +115,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         NodeRow<R> *nodes = (NodeRow<R> *)(base + L.nodes);
         int *pool = (int *)(base + L.pool), *next = (int *)(base + L.next);
         int *head = (int *)(base + L.head), *tail = (int *)(base + L.tail), *count = (int *)(base + L.count);
+        TptHdr<R> *hdr = (TptHdr<R> *)(base + L.hdr);
         const int n_exp = s_nexp[slot];
         if (s_active[slot] && n_exp != -2) {
             const long long q = s_q[slot];
@@ -139,7 +145,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     s_nwp[slot] += nwp; s_nprims[slot] += n_exp;
                     if (P.trace) {
                         size_t r = (size_t)q * P.I + it;
-                        tr.parent[r] = parent; tr.safe[r] = safe ? 1 : 0; tr.nwp[r] = nwp; tr.upos[r] = s_upos[slot];
+                        tr.parent[r] = parent; tr.safe[r] = safe ? 1 : 0; tr.nwp[r] = nwp; tr.upos[r] = hdr->upos;
                         R *lf = (R *)tr.leaf + 5 * r;
                         lf[0] = x; lf[1] = y; lf[2] = th; lf[3] = t; lf[4] = len;
                     }
@@ -185,21 +191,22 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                             if (t > (R)0) { c1 = A::div(c1, t); c2 = A::div(c2, t); }
                             if (env.H != 0) c0 = A::div(A::mul(P.w1, (R)__popcll(mk)), (R)env.H);
                             const R total = py_sum3p<R>(c0, c1, c2);
-                            s_ncost[slot]++;
+                            hdr->ncost++;
                             if (total < s_bc0[slot]) {
-                                s_bc0[slot] = total; s_bc1[slot] = c0; s_bc2[slot] = c1; s_bc3[slot] = c2;
-                                s_bestnode[slot] = id; s_bestiter[slot] = it; s_blen[slot] = len; s_bt[slot] = t;
+                                s_bc0[slot] = total; hdr->bc1 = c0; hdr->bc2 = c1; hdr->bc3 = c2;
+                                hdr->bestnode = id; hdr->bestiter = it; hdr->blen = len; hdr->bt = t;
                             }
                         }
                     }
                     it++;
                     s_it[slot] = it;
-                    s_z[slot] = (unsigned long long)rng.wa | ((unsigned long long)rng.wb << 32); s_ctr[slot] = rng.ctr; s_upos[slot] = rng.ctr;
+                    s_z[slot] = (unsigned long long)rng.wa | ((unsigned long long)rng.wb << 32); s_ctr[slot] = rng.ctr;
+                    if (P.trace) hdr->upos = rng.ctr;
                 }
             }
             // ---- query finished (budget spent, or an error): chain + record, free the slot
             if (status || it >= P.I || n_exp == -1) {
-                const int best_node = s_bestnode[slot];
+                const int best_node = hdr->bestnode;
                 if (status == AUVRRT_ST_OK && best_node < 0) status = AUVRRT_ST_NO_PATH;
                 int depth = 0;
                 if (best_node >= 0) for (int n = best_node; nodes[n].parent >= 0; n = nodes[n].parent) depth++;
@@ -211,12 +218,12 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     for (int k = depth; k < P.chain_cap; k++) chain[k] = 0u;
                 }
                 auvrrt_plan_record_t rec;
-                rec.status = status; rec.n_nodes = s_nnodes[slot]; rec.best_node = best_node; rec.best_iter = s_bestiter[slot];
-                rec.depth = depth; rec.n_path = 0; rec.n_cost_evals = s_ncost[slot]; rec.n_waypoints = s_nwp[slot];
-                rec.n_uniforms = (long long)s_ctr[slot]; rec.n_primitives = s_nprims[slot];
-                rec.cost[0] = best_node >= 0 ? (double)s_bc0[slot] : 0.0; rec.cost[1] = (double)s_bc1[slot];
-                rec.cost[2] = (double)s_bc2[slot]; rec.cost[3] = (double)s_bc3[slot];
-                rec.path_length = (double)s_blen[slot]; rec.t_leaf = (double)s_bt[slot];
+                rec.status = status; rec.n_nodes = s_nnodes[slot]; rec.best_node = best_node; rec.best_iter = hdr->bestiter;
+                rec.depth = depth; rec.n_path = 0; rec.n_cost_evals = hdr->ncost; rec.n_waypoints = s_nwp[slot];
+                rec.n_uniforms = (long long)s_ctr[slot]; rec.n_primitives = (long long)s_nprims[slot];
+                rec.cost[0] = best_node >= 0 ? (double)s_bc0[slot] : 0.0; rec.cost[1] = (double)hdr->bc1;
+                rec.cost[2] = (double)hdr->bc2; rec.cost[3] = (double)hdr->bc3;
+                rec.path_length = (double)hdr->blen; rec.t_leaf = (double)hdr->bt;
                 records[q] = rec;
                 s_active[slot] = 0;
             }
@@ -240,10 +247,11 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     nodes[0] = r0;
                     head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
                     s_nonempty[slot][0] = 2u; s_nonempty[slot][1] = s_nonempty[slot][2] = s_nonempty[slot][3] = 0u;     // bin 1 holds `initial`
-                    s_z[slot] = stream_key(seeds[q]); s_ctr[slot] = 0; s_upos[slot] = 0; s_q[slot] = q; s_nprims[slot] = 0;
+                    s_z[slot] = stream_key(seeds[q]); s_ctr[slot] = 0; s_q[slot] = q; s_nprims[slot] = 0;
                     s_nnodes[slot] = 1; s_nchunks[slot] = 1; s_it[slot] = 0; s_status[slot] = AUVRRT_ST_OK;
-                    s_bestnode[slot] = -1; s_bestiter[slot] = -1; s_ncost[slot] = 0; s_nwp[slot] = 0; s_guard[slot] = 0;
-                    s_bc0[slot] = A::inf(); s_bc1[slot] = 0; s_bc2[slot] = 0; s_bc3[slot] = 0; s_blen[slot] = 0; s_bt[slot] = 0;
+                    s_nwp[slot] = 0; s_bc0[slot] = A::inf();
+                    { TptHdr<R> h0; h0.bestnode = -1; h0.bestiter = -1; h0.ncost = 0; h0.guard = 0; h0.upos = 0; h0.pad_ = 0;
+                      h0.bc1 = 0; h0.bc2 = 0; h0.bc3 = 0; h0.blen = 0; h0.bt = 0; *hdr = h0; }
                     s_active[slot] = 1;
                 }
             }
@@ -305,7 +313,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 if (status) { s_status[slot] = status; key = 62; s_nexp[slot] = -1; }    // phase B finalises it
                 if (skip) {
                     s_nexp[slot] = -2;
-                    if (++s_guard[slot] >= guard_max) { key = 62; s_nexp[slot] = -1; }
+                    if (++hdr->guard >= guard_max) { key = 62; s_nexp[slot] = -1; }
                 }
             }
             if (j == 0) key0 = key; else key1 = key;
