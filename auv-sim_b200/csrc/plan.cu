@@ -41,17 +41,19 @@ namespace auv {
                            cudaGetErrorString(e_));                                         \
     } while (0)
 
-#ifndef AUV_PLAN_THREADS
-#define AUV_PLAN_THREADS 128  // 4 warps per CTA: config 2's 4096 trees (one warp each) spread as 6-7 CTAs = 24-28 warps per SM;
-                              // with 256-thread CTAs 68 SMs held 32 warps and 80 held 24, and the kernel waited for the
-                              // fuller ones (measured 15.5 ms -> 14.7 ms)
+// CTA shape of k_plan.  Config 2's 4096 trees (one warp each) need 28 resident warps per SM to run in one wave
+// (4096 / 148 = 27.7) and get 72 registers per thread.  Every CTA stages its own copy of the world model's hot part
+// (11 KB), so fewer, larger CTAs leave more of the SM to the L1 that serves the trees, the classification grid and the
+// probability table.  Measured on B200, config 2: 128 threads x 7 CTAs 8.63 ms per step (256 x 4 in round 1: 32 / 24
+// warps per SM, the kernel waited for the fuller SMs), 224 x 4 8.45 ms, 448 x 2 8.25 ms (1.02e9 edges/s).
+// The narrower groups (16 / 8 lanes per tree) keep 128-thread CTAs: their per-group scratch would not fit.
+#ifndef AUV_PLAN_THREADS32
+#define AUV_PLAN_THREADS32 448
 #endif
-static const int PLAN_THREADS = AUV_PLAN_THREADS;
-#ifndef AUV_PLAN_MINB
-#define AUV_PLAN_MINB 7      // resident CTAs per SM the fp32 register allocation targets: 7 x 4 warps = 28 warps is what one
-                             // wave of config 2 needs (4096 trees / 148 SMs = 27.7) and leaves 72 registers per thread
-                             // (measured 14.6 ms at 8 CTAs / 64 registers, 13.7 ms at 7 / 72, 20.7 ms at 6 / 80: two waves)
+#ifndef AUV_PLAN_MINB32
+#define AUV_PLAN_MINB32 (896 / AUV_PLAN_THREADS32)
 #endif
+template <int G> struct PlanCta { static const int T = G == 32 ? AUV_PLAN_THREADS32 : 128, MINB = G == 32 ? AUV_PLAN_MINB32 : 7; };
 
 struct WsLayout {
     size_t slot_bytes;
@@ -152,7 +154,7 @@ template <typename R> struct BestPlan { R c0, c1, c2, len, t; int node, iter; };
 // the compiler otherwise places inside the hot loop -- disappears); MODE < 0 reads P.mode at run time.
 // ONE: freq <= G, every edge is a single chunk of primitives (eval_edge ONE_CHUNK)
 template <typename R, int G, bool BS, int MODE, bool ONE>
-__global__ void __launch_bounds__(PLAN_THREADS, sizeof(R) == 4 ? AUV_PLAN_MINB : (AUV_PLAN_MINB + 1) / 2)
+__global__ void __launch_bounds__(PlanCta<G>::T, sizeof(R) == 4 ? PlanCta<G>::MINB : (PlanCta<G>::MINB + 1) / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
@@ -160,9 +162,10 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     const bool VERIFY = Policy<R>::VERIFY;
     const int pick_mode = MODE >= 0 ? MODE : P.mode;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ GroupScratch<R, G> scratch[PLAN_THREADS / G];
-    __shared__ BestPlan<R> best_s[PLAN_THREADS / G];
-    __shared__ unsigned short binmeta[BS ? PLAN_THREADS / G : 1][3][BS ? AUV_BINS_SMEM : 1];
+    const int PLAN_THREADS = PlanCta<G>::T;
+    __shared__ GroupScratch<R, G> scratch[PlanCta<G>::T / G];
+    __shared__ BestPlan<R> best_s[PlanCta<G>::T / G];
+    __shared__ unsigned short binmeta[BS ? PlanCta<G>::T / G : 1][3][BS ? AUV_BINS_SMEM : 1];
     EnvView<R> env;
     {
         if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
@@ -674,7 +677,7 @@ template <typename R, int G, bool BS, int MODE, bool ONE> static int plan_geomet
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
     AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS, MODE, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE, ONE>, PLAN_THREADS, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE, ONE>, PlanCta<G>::T, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan: kernel does not fit on an SM (smem %d)", sm);
     int nsm = 0, dev = 0;
     AUV_CUDA(cudaGetDevice(&dev));
@@ -695,7 +698,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     rc = plan_geometry<R, G, BS, MODE, ONE>(env, &grid, &smem, &mode);
     if (rc) return rc;
     WsLayout L = make_layout<R>(P.cap, P.nb, P.nchunks);
-    const int gpc = PLAN_THREADS / G;
+    const int gpc = PlanCta<G>::T / G;
     int64_t need = 256 + (int64_t)grid * gpc * (int64_t)L.slot_bytes;
     if (need_bytes) { *need_bytes = need; return AUVRRT_OK; }
     if (Q <= 0) return AUVRRT_OK;
@@ -707,7 +710,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     auvrrt_plan_trace_t tr;
     if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
     EnvBlob<R> b = env_blob<R>(env);
-    k_plan<R, G, BS, MODE, ONE><<<grid, PLAN_THREADS, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+    k_plan<R, G, BS, MODE, ONE><<<grid, PlanCta<G>::T, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
                                                   (unsigned char *)workspace + 256, (unsigned long long *)workspace,
                                                   records, chain, path, tr);
     AUV_LAUNCH_CHECK2();
