@@ -36,7 +36,7 @@ static const int TPT_THREADS = AUV_TPT_THREADS;
 #endif
 static const int TPT_SLOTS = AUV_TPT_THREADS * AUV_TPT_SPT;
 
-struct TptLayout { size_t slot_bytes, nodes, pool, next, head, tail, count, hdr; };
+struct TptLayout { size_t slot_bytes, nodes, pool, next, bins, hdr; };
 
 // the part of a tree's bookkeeping that is touched rarely (a new best plan, a skipped trip, the trace): in the tree's
 // workspace, not in shared memory -- every byte of per-tree shared state costs resident warps
@@ -48,7 +48,9 @@ template <typename R> static TptLayout make_tpt_layout(int cap, int nb, int nchu
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~(size_t)127; return r; };
     L.nodes = take(sizeof(NodeRow<R>) * (size_t)cap);
     L.pool = take(4 * 32 * (size_t)nchunks); L.next = take(4 * (size_t)nchunks);
-    L.head = take(4 * (size_t)(nb + 2)); L.tail = take(4 * (size_t)(nb + 2)); L.count = take(4 * (size_t)(nb + 2));
+    // time bins: {count, head chunk, tail chunk, -} per bin in ONE 16-byte row: the pick reads count and head, the insert
+    // reads and writes all three -- one 32-byte sector each instead of three
+    L.bins = take(16 * (size_t)(nb + 2));
     L.hdr = take(sizeof(TptHdr<R>));
     L.slot_bytes = o;
     return L;
@@ -114,7 +116,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         unsigned char *base = block_ws + (size_t)slot * L.slot_bytes;
         NodeRow<R> *nodes = (NodeRow<R> *)(base + L.nodes);
         int *pool = (int *)(base + L.pool), *next = (int *)(base + L.next);
-        int *head = (int *)(base + L.head), *tail = (int *)(base + L.tail), *count = (int *)(base + L.count);
+        int4 *bins = (int4 *)(base + L.bins);
         TptHdr<R> *hdr = (TptHdr<R> *)(base + L.hdr);
         const int n_exp = s_nexp[slot];
         if (s_active[slot] && n_exp != -2) {
@@ -170,18 +172,20 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                         else if (curr_bin > P.max_traj) { if (fidx >= (R)1 && fidx <= (R)P.nb) { bidx = (int)fidx; reset = true; } }
                         else { if (fidx >= (R)1 && fidx <= (R)P.nb) bidx = (int)fidx; else status = AUVRRT_ST_KEY_ERROR; }
                         if (bidx >= 0) {
-                            const int c_old = count[bidx];
+                            int4 bm = bins[bidx];                      // x: count, y: head chunk, z: tail chunk
+                            const int c_old = bm.x;
                             const bool reuse_head = reset && c_old > 0;
                             const int c = reset ? 0 : c_old;
-                            if (reuse_head) tail[bidx] = head[bidx];
+                            if (reuse_head) bm.z = bm.y;
                             if ((c & 31) == 0 && !reuse_head) {
                                 const int nc = s_nchunks[slot]++;
                                 next[nc] = -1;
-                                if (c == 0) head[bidx] = nc; else next[tail[bidx]] = nc;
-                                tail[bidx] = nc;
+                                if (c == 0) bm.y = nc; else next[bm.z] = nc;
+                                bm.z = nc;
                             }
-                            pool[tail[bidx] * 32 + (c & 31)] = id;
-                            count[bidx] = c + 1;
+                            pool[bm.z * 32 + (c & 31)] = id;
+                            bm.x = c + 1;
+                            bins[bidx] = bm;
                             if (bin_bits) s_nonempty[slot][bidx >> 5] |= 1u << (bidx & 31);
                         }
                         if (!status && t >= P.horizon) {                                // :158-171
@@ -237,7 +241,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 if (q >= Q) queue_empty = true;
                 else {
                     // ---- init                                                           rrt_dubins.py:105-114
-                    for (int b = 0; b < P.nb + 2; b++) count[b] = 0;
+                    for (int b = 0; b < P.nb + 2; b++) bins[b] = make_int4(0, 0, 0, 0);
                     NodeRow<R> r0;
                     r0.x = starts[5 * q]; r0.y = starts[5 * q + 1]; r0.th = starts[5 * q + 2]; r0.t = starts[5 * q + 3];
                     r0.len = starts[5 * q + 4]; r0.s2 = (R)0; r0.ctr = 0; r0.parent = -1; r0.cnt = 0; r0.mask = 0ull; r0.born = 0;
@@ -245,7 +249,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                     r0.self_s2 = (c.bin >= 0 && c.cell >= 0) ? A::mul(P.w3, env.probs[(size_t)c.bin * env.C + c.cell]) : (R)0;
                     r0.self_hab = c.bin >= 0 ? c.hab : -1;
                     nodes[0] = r0;
-                    head[1] = 0; tail[1] = 0; count[1] = 1; pool[0] = 0; next[0] = -1;
+                    bins[1] = make_int4(1, 0, 0, 0); pool[0] = 0; next[0] = -1;
                     s_nonempty[slot][0] = 2u; s_nonempty[slot][1] = s_nonempty[slot][2] = s_nonempty[slot][3] = 0u;     // bin 1 holds `initial`
                     s_z[slot] = stream_key(seeds[q]); s_ctr[slot] = 0; s_q[slot] = q; s_nprims[slot] = 0;
                     s_nnodes[slot] = 1; s_nchunks[slot] = 1; s_it[slot] = 0; s_status[slot] = AUVRRT_ST_OK;
@@ -262,19 +266,19 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
                 int parent = -1, status = AUVRRT_ST_OK;
                 bool skip = false;
                 if (P.mode == 0) {                                                      // :122-127
-                    int rb = 0, cn = 0;
+                    int rb = 0, cn = 0, ch = 0;
                     for (;;) {
                         rb = (int)uniform_ab<R>((R)1, (R)(P.nb + 1), rng.next());
                         if (rb > P.nb || rb < 1) { status = AUVRRT_ST_KEY_ERROR; break; }
                         if (bin_bits && !((s_nonempty[slot][rb >> 5] >> (rb & 31)) & 1u)) continue;      // empty: draw again
-                        cn = count[rb];
+                        const int4 bm = bins[rb];
+                        cn = bm.x; ch = bm.y;
                         if (cn > 0) break;
                     }
                     if (!status) {
                         int idx = (int)uniform_ab<R>((R)0, (R)cn, rng.next());
                         if (idx >= cn) status = AUVRRT_ST_KEY_ERROR;
                         else {
-                            int ch = head[rb];
                             for (int hop = idx >> 5; hop > 0; hop--) ch = next[ch];
                             parent = pool[ch * 32 + (idx & 31)];
                         }
