@@ -568,6 +568,38 @@ def test_edges_arc_cost_vs_oracle(api, env, oworld, edge_variant):
     assert (s32[3][:, 0] != 0).sum() > 100
 
 
+def test_edges_arc_allpairs_many_circles(api, catalina_map, shark_grid, monkeypatch):
+    """config 4's world (500 random circles + the Catalina boundary, habitats and shark grid): the all-pairs variant --
+    circle quads, two waypoints per pass over the table, the rounding guard with its direct-formula fallback -- gives the
+    booleans, waypoint counts and cost terms of the grid kernel in fp32, and both give the oracle's in fp64"""
+    rs = np.random.RandomState(1234)
+    K = 500
+    circles = np.stack([rs.uniform(-467.4, 82.4, K), rs.uniform(-153.5, 191.2, K), rs.uniform(1, 5, K)], 1)
+    e = api.Env(circles=circles, boundary=catalina_map["boundary"], habitats=catalina_map["habitats"], bins=shark_grid[0],
+                cells=catalina_map["cells"], probs=shark_grid[1])
+    ow = orc.OracleWorld(circles=circles, boundary=catalina_map["boundary"], habitats=catalina_map["habitats"], bins=shark_grid[0],
+                         cells=catalina_map["cells"], probs=shark_grid[1])
+    n = 60000
+    parents = np.stack([rs.uniform(-467, 82, n), rs.uniform(-153, 191, n), rs.uniform(-np.pi, np.pi, n),
+                        rs.uniform(0, 400, n), np.zeros(n)], 1).astype(np.float32).astype(np.float64)
+    seeds = np.arange(n) + 5
+    params, w3 = [2.0, 0.5, 30.0, 0.5, 2.0], -4.0
+    monkeypatch.setenv("AUVRRT_EDGES_VARIANT", "tpe")
+    out = {}
+    for brute in ("0", "1"):
+        monkeypatch.setenv("AUVRRT_EDGES_BRUTE", brute)
+        out[brute] = api.edges_arc_cost(e, parents, seeds, params, w3, "f32")
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
+    assert 0.1 < out["0"][0].mean() < 0.6                      # a dense world: most edges collide
+    want_safe, want_nwp, _ = orc.edges_arc_batch(ow, parents[:8000], seeds[:8000], velocity=2.0)
+    for brute in ("0", "1"):
+        monkeypatch.setenv("AUVRRT_EDGES_BRUTE", brute)
+        s64 = api.edges_arc_cost(e, parents[:8000], seeds[:8000], params, w3, "f64")
+        assert np.array_equal(s64[0], want_safe) and np.array_equal(s64[1], want_nwp)
+    e.close()
+
+
 def test_edges_arc_cta_shapes_agree(api, env, monkeypatch):
     """the thread-per-edge kernel gives the same bits in every CTA shape: 256-thread CTAs (slow cells resolved in
     place) against 1024-thread CTAs (grid plane in shared memory, slow cells queued per warp and resolved after the

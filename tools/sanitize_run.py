@@ -55,6 +55,17 @@ for prec in ("f32", "f64"):
     api.collide_points(env, parents[:50, :2], prec)
     api.cost(env, [np.concatenate([parents[:40, :2], parents[:40, 3:4]], 1)], [100.0], [-3, -3, -4], precision=prec)
     api.cost_point(env, parents[:9, :2], [0] * 10, 1, [-3, -3, -4], prec)
+# round 2: the all-pairs arc variant on a dense world (circle quads, two waypoints per pass, the direct-formula fallback)
+rs = np.random.RandomState(7)
+dense = np.stack([rs.uniform(-467.4, 82.4, 300), rs.uniform(-153.5, 191.2, 300), rs.uniform(1, 5, 300)], 1)
+env_d = api.Env(circles=dense, boundary=world["boundary"], habitats=world["habitats"], bins=g["bins"], cells=world["cells"], probs=g["probs"])
+par_d = np.stack([rs.uniform(-467, 82, 3000), rs.uniform(-153, 191, 3000), rs.uniform(-3, 3, 3000), rs.uniform(0, 400, 3000), np.zeros(3000)], 1)
+os.environ["AUVRRT_EDGES_BRUTE"] = "1"
+for prec in ("f32", "f64"):
+    api.edges_arc_cost(env_d, par_d, np.arange(3000), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, prec)
+os.environ["AUVRRT_EDGES_BRUTE"] = "0"
+api.edges_arc_cost(env_d, par_d, np.arange(3000), [2.0, 0.5, 30.0, 0.5, 2.0], -4.0, "f32")
+env_d.close()
 z = np.load(os.path.join(ROOT, "tests", "golden", "occupancy.npz"))
 polys = [z["cell_xy"][z["cell_off"][i]:z["cell_off"][i + 1]] for i in range(len(z["cell_off"]) - 1)]
 toff, trk = z["c1_toff"], z["c1_trk"]
