@@ -78,7 +78,7 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
     __shared__ long long s_q[S];
     __shared__ uint32_t s_ctr[S];
     __shared__ int s_nnodes[S], s_nchunks[S], s_it[S], s_status[S], s_nwp[S], s_nprims[S],
-        s_active[S], s_parent[S], s_nexp[S], s_order[S], s_hist[64];
+        s_active[S], s_parent[S], s_nexp[S], s_order[S], s_hist[2][64];
     __shared__ R s_bc0[S];
     // which time bins of each tree are non-empty (<= 128 bins): the rejection loop of the parent pick probes bins until
     // it finds one (rrt_dubins.py:123-125); testing a bit in shared memory instead of reading count[bin] from the tree's
@@ -101,6 +101,8 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
     const int tid = threadIdx.x;
     unsigned char *block_ws = ws + (size_t)blockIdx.x * S * L.slot_bytes;
     for (int i = tid; i < S; i += T) { s_active[i] = 0; s_q[i] = -1; s_nexp[i] = -2; s_order[i] = i; }
+    if (tid < 64) { s_hist[0][tid] = 0; s_hist[1][tid] = 0; }
+    int trip = 0;
     bool queue_empty = false;
     const int guard_max = 64 * P.I + 1024;
     __syncthreads();
@@ -325,20 +327,28 @@ k_plan_tpt(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_
         }
         }   // j
         // ============================ counting sort of the slots by n_expand ======================
-        if (tid < 64) s_hist[tid] = 0;
-        __syncthreads();
-        const int rank0 = atomicAdd(&s_hist[key0], 1), rank1 = SPT == 2 ? atomicAdd(&s_hist[key1], 1) : 0;
-        __syncthreads();
-        if (tid < 32) {                       // exclusive scan of 64 buckets by one warp
-            int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1], v = a0 + a1;
+        // Two barriers per trip: the histogram alternates between two buffers (the idle one is cleared while this one is
+        // read), and every warp scans the 64 buckets for itself in registers instead of waiting for one warp to do it.
+        int *hist = s_hist[trip & 1];
+        const int rank0 = atomicAdd(&hist[key0], 1), rank1 = SPT == 2 ? atomicAdd(&hist[key1], 1) : 0;
+        __syncthreads();                          // histogram complete; every thread is past this trip's edges
+        {
+            const int lane = tid & 31;
+            const int a0 = hist[2 * lane], a1 = hist[2 * lane + 1];
+            int v = a0 + a1;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (tid >= d) v += o; }
-            s_hist[2 * tid] = v - a0 - a1; s_hist[2 * tid + 1] = v - a1;
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+            const int e0 = v - a0 - a1, e1 = v - a1;            // exclusive offsets of buckets 2 lane and 2 lane + 1
+            const int b0e = __shfl_sync(0xffffffffu, e0, key0 >> 1), b0o = __shfl_sync(0xffffffffu, e1, key0 >> 1);
+            s_order[((key0 & 1) ? b0o : b0e) + rank0] = slot0;
+            if (SPT == 2) {
+                const int b1e = __shfl_sync(0xffffffffu, e0, key1 >> 1), b1o = __shfl_sync(0xffffffffu, e1, key1 >> 1);
+                s_order[((key1 & 1) ? b1o : b1e) + rank1] = slot1;
+            }
         }
-        __syncthreads();
-        s_order[s_hist[key0] + rank0] = slot0;
-        if (SPT == 2) s_order[s_hist[key1] + rank1] = slot1;
-        if (__syncthreads_count(any_active) == 0) break;      // also publishes s_order
+        if (tid < 64) s_hist[(trip + 1) & 1][tid] = 0;
+        trip++;
+        if (__syncthreads_count(any_active) == 0) break;      // also publishes s_order and the cleared histogram
     }
 }
 
