@@ -32,10 +32,12 @@ template <typename R> struct SteerParams {
 template <int G> struct Log2 { static const int v = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : 1; };
 
 // per-group shared-memory scratch
-template <typename R, int G> struct GroupScratch {
-    R us[3 * G];                          // window of uniforms starting at the chunk's offset
+// FLAT = false (the counter stream with slot addressing: the planners) needs neither the window of uniforms nor the
+// pointer-doubling table: 396 instead of 1148 bytes per 32-lane group in fp32 -- shared memory the L1 gets back
+template <typename R, int G, bool FLAT = true> struct GroupScratch {
+    R us[FLAT ? 3 * G : 32];              // window of uniforms starting at the chunk's offset (FLAT); 32 words of scratch otherwise (k_plan mode 3)
     R wx[G + 1], wy[G + 1];               // waypoint coordinates for the circle lanes (slot G: parent)
-    unsigned char jmp[Log2<G>::v][3 * G + 4];
+    unsigned char jmp[FLAT ? Log2<G>::v : 1][FLAT ? 3 * G + 4 : 4];
 };
 
 template <typename R> struct EdgeOut {
@@ -75,8 +77,9 @@ __device__ __forceinline__ float sinc_small(float h) {
 //   doubling give each lane the offset of its primitive.
 // ONE_CHUNK: the caller guarantees n_expand <= G (freq <= G, checked on the host): the chunk loop runs at most once
 //   and its loop-carried state disappears.
-template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP, bool FLAT = false, bool ONE_CHUNK = false>
-__device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &sc, const EnvView<R> &env,
+// GRIDS: plane 0 of the classification grid is staged in shared memory (env.grid0s)
+template <typename R, int G, bool DO_COLLIDE, bool DO_COST, bool WRITE_WP, bool FLAT = false, bool ONE_CHUNK = false, bool GRIDS = false>
+__device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G, FLAT> &sc, const EnvView<R> &env,
                                           const Stream<R> &rng, uint32_t ctr, const SteerParams<R> &sp,
                                           R px, R py, R pth, R pt, R plen, R w3, int n_hab,
                                           R *wp_out, int wp_cap, EdgeOut<R> &out) {
@@ -105,7 +108,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
         // (testing it behind the draws and the steer arithmetic of the first chunk, to run those under the planner's
         // load of the parent row, was measured slower: 9.16 vs 8.75 ms per step on config 2)
         if (g.gl == 0) { sc.wx[G] = px; sc.wy[G] = py; }
-        const Cls pcl = env.classify(px, py);
+        const Cls pcl = env.template classify<GRIDS>(px, py);
         parent_clear = (pcl.code & 4u) != 0u;
         parent_many = (pcl.code & AUV_GRID_CIRC_MANY) != 0u;
         if (VERIFY || !AUV_EDGE_ONE || (pcl.code & AUV_GRID_SLOW)) {
@@ -253,7 +256,7 @@ __device__ __forceinline__ void eval_edge(const Grp<G> &g, GroupScratch<R, G> &s
         }
         // one classification-grid load per waypoint replaces most of the exact tests below
         Cls cl; cl.code = AUV_GRID_ALL_AMBIG | 4u; cl.idx = -1;
-        if ((DO_COLLIDE || DO_COST) && (is_wp || g.gl == last_valid)) cl = env.classify(x, y);
+        if ((DO_COLLIDE || DO_COST) && (is_wp || g.gl == last_valid)) cl = env.template classify<GRIDS>(x, y);
         if (DO_COLLIDE) {
             // lane = waypoint: polygon and the cell's candidate circles
             bool in = true, h1 = false;

@@ -612,9 +612,9 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? AUV_EA_MINB : 1) k_edges
                                                    R *cost_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     EnvView<R> env = load_env<R>(smem, blob, hot_bytes, total_bytes, stage_mode);
-    __shared__ GroupScratch<R, G> scratch[256 / G];
+    __shared__ GroupScratch<R, G, false> scratch[256 / G];
     Grp<G> g;
-    GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
+    GroupScratch<R, G, false> &sc = scratch[threadIdx.x / G];
     const int64_t groups = (int64_t)gridDim.x * (256 / G);
     for (int64_t i = blockIdx.x * (int64_t)(256 / G) + threadIdx.x / G; i < n; i += groups) {
         Stream<R> rng;

@@ -45,15 +45,19 @@ namespace auv {
 // (4096 / 148 = 27.7) and get 72 registers per thread.  Every CTA stages its own copy of the world model's hot part
 // (11 KB), so fewer, larger CTAs leave more of the SM to the L1 that serves the trees, the classification grid and the
 // probability table.  Measured on B200, config 2: 128 threads x 7 CTAs 8.63 ms per step (256 x 4 in round 1: 32 / 24
-// warps per SM, the kernel waited for the fuller SMs), 224 x 4 8.45 ms, 448 x 2 8.25 ms (1.02e9 edges/s).
+// warps per SM, the kernel waited for the fuller SMs), 224 x 4 8.45 ms, 448 x 2 8.25 ms, 896 x 1 7.78 ms (1.08e9 edges/s;
+// the per-group scratch of the slot-addressed stream is 396 bytes, so 28 groups fit the 48 KB of static shared memory).
 // The narrower groups (16 / 8 lanes per tree) keep 128-thread CTAs: their per-group scratch would not fit.
 #ifndef AUV_PLAN_THREADS32
-#define AUV_PLAN_THREADS32 448
+#define AUV_PLAN_THREADS32 896
 #endif
 #ifndef AUV_PLAN_MINB32
 #define AUV_PLAN_MINB32 (896 / AUV_PLAN_THREADS32)
 #endif
-template <int G> struct PlanCta { static const int T = G == 32 ? AUV_PLAN_THREADS32 : 128, MINB = G == 32 ? AUV_PLAN_MINB32 : 7; };
+// (the fp64 verification build keeps 128-thread CTAs: it needs more than the 72 registers a 896-thread CTA leaves)
+template <typename R, int G> struct PlanCta {
+    static const int T = (sizeof(R) == 4 && G == 32) ? AUV_PLAN_THREADS32 : 128, MINB = (sizeof(R) == 4 && G == 32) ? AUV_PLAN_MINB32 : 7;
+};
 
 struct WsLayout {
     size_t slot_bytes;
@@ -154,7 +158,7 @@ template <typename R> struct BestPlan { R c0, c1, c2, len, t; int node, iter; };
 // the compiler otherwise places inside the hot loop -- disappears); MODE < 0 reads P.mode at run time.
 // ONE: freq <= G, every edge is a single chunk of primitives (eval_edge ONE_CHUNK)
 template <typename R, int G, bool BS, int MODE, bool ONE>
-__global__ void __launch_bounds__(PlanCta<G>::T, sizeof(R) == 4 ? PlanCta<G>::MINB : (PlanCta<G>::MINB + 1) / 2)
+__global__ void __launch_bounds__(PlanCta<R, G>::T, sizeof(R) == 4 ? PlanCta<R, G>::MINB : (PlanCta<R, G>::MINB + 1) / 2)
 k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode, const R *starts,
        const uint64_t *seeds, long long Q, PlanP<R> P, WsLayout L, unsigned char *ws, unsigned long long *qcounter,
        auvrrt_plan_record_t *records, uint32_t *chain_out, R *path_out, auvrrt_plan_trace_t tr) {
@@ -162,24 +166,43 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
     const bool VERIFY = Policy<R>::VERIFY;
     const int pick_mode = MODE >= 0 ? MODE : P.mode;
     extern __shared__ __align__(16) unsigned char smem[];
-    const int PLAN_THREADS = PlanCta<G>::T;
-    __shared__ GroupScratch<R, G> scratch[PlanCta<G>::T / G];
-    __shared__ BestPlan<R> best_s[PlanCta<G>::T / G];
-    __shared__ unsigned short binmeta[BS ? PlanCta<G>::T / G : 1][3][BS ? AUV_BINS_SMEM : 1];
+    const int PLAN_THREADS = PlanCta<R, G>::T;
+    __shared__ GroupScratch<R, G, false> scratch[PlanCta<R, G>::T / G];
+    __shared__ BestPlan<R> best_s[PlanCta<R, G>::T / G];
+    __shared__ unsigned short binmeta[BS ? PlanCta<R, G>::T / G : 1][3][BS ? AUV_BINS_SMEM : 1];
     EnvView<R> env;
     {
         if (stage_mode == 0) { env.bind(blob, blob); env.bind_grid(blob, blob); }
-        else {
+        else if (stage_mode == 3) {
+            // one CTA per SM: the world model, the probability table and plane 0 of the classification grid (two regions,
+            // one barrier) -- every lookup of the edge evaluation is then an LDS
+            uint64_t *bar = (uint64_t *)smem;
+            const EnvHeader *gh = (const EnvHeader *)blob;
+            const int plane = (gh->gnx * gh->gny * 4 + 15) & ~15;
+            if (threadIdx.x == 0) mbar_init(bar, 1);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)(total_bytes + plane));
+                for (int o = 0; o < total_bytes; o += 65536) tma_bulk_g2s(smem + 16 + o, blob + o, (uint32_t)(total_bytes - o < 65536 ? total_bytes - o : 65536), bar);
+                const unsigned char *gsrc = blob + gh->off_grid;
+                for (int o = 0; o < plane; o += 65536) tma_bulk_g2s(smem + 16 + total_bytes + o, gsrc + o, (uint32_t)(plane - o < 65536 ? plane - o : 65536), bar);
+            }
+            mbar_wait(bar, 0);
+            env.bind(smem + 16, smem + 16);
+            env.bind_grid(blob, smem + 16);
+            env.grid0s = (const unsigned *)(smem + 16 + total_bytes);
+            __builtin_assume(__isShared(env.grid0s));
+        } else {
             uint64_t *bar = (uint64_t *)smem;
             stage_env_tma(smem + 16, blob, stage_mode == 2 ? total_bytes : hot_bytes, bar);
             env.bind(smem + 16, stage_mode == 2 ? smem + 16 : blob);
             env.bind_grid(blob, smem + 16);
         }
         // the single-chunk variant is only launched with the hot part staged (launch_plan_g): its loads are LDS
-        if (ONE) env.assume_hot_shared(false);
+        if (ONE) env.assume_hot_shared(PlanCta<R, G>::T >= 896);     // (896-thread shape: stage mode 3, the probability table is staged too)
     }
     Grp<G> g;
-    GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
+    GroupScratch<R, G, false> &sc = scratch[threadIdx.x / G];
     const int slot = blockIdx.x * (PLAN_THREADS / G) + threadIdx.x / G;
     Tree<R> T;
     T.bind(ws + (size_t)slot * L.slot_bytes, L, P.cap);
@@ -439,7 +462,7 @@ k_plan(const unsigned char *blob, int hot_bytes, int total_bytes, int stage_mode
             }
 #endif
             EdgeOut<R> o;
-            eval_edge<R, G, true, true, false, false, ONE>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
+            eval_edge<R, G, true, true, false, false, ONE, ONE && (PlanCta<R, G>::T >= 896)>(g, sc, env, rng, ctr, P.sp, ppx, ppy, ppth, ppt, pplen, P.w3, env.H,
                                                            nullptr, 0, o);
 #if AUV_PLAN_PREFETCH
             if (ONE && BS && pick_mode == 0 && spec_parent >= 0 && g.gl < 2)
@@ -616,12 +639,12 @@ template <typename R, int G>
 __global__ void __launch_bounds__(128)
 k_materialize(const unsigned char *blob, const R *starts, const uint64_t *seeds, const uint32_t *chain,
               const int32_t *depth, long long Q, PlanP<R> P, R *path_out, int32_t *n_path_out) {
-    __shared__ GroupScratch<R, G> scratch[128 / G];
+    __shared__ GroupScratch<R, G, false> scratch[128 / G];
     EnvView<R> env;
     env.bind(blob, blob);
     env.bind_grid(blob, blob);
     Grp<G> g;
-    GroupScratch<R, G> &sc = scratch[threadIdx.x / G];
+    GroupScratch<R, G, false> &sc = scratch[threadIdx.x / G];
     const long long groups = (long long)gridDim.x * (128 / G);
     for (long long q = blockIdx.x * (long long)(128 / G) + threadIdx.x / G; q < Q; q += groups) {
         Stream<R> rng;
@@ -670,14 +693,21 @@ template <typename R, int G, bool BS, int MODE, bool ONE> static int plan_geomet
     EnvBlob<R> b = env_blob<R>(env);
     // only the small hot part of the world model is staged in shared memory when it is tight: with 4
     // CTAs per SM the probability table (39 KB for Catalina) is better served by the larger L1
-    int budget = sizeof(R) == 4 ? 24 * 1024 : 110 * 1024;
+    // (one 896-thread CTA per SM: the probability table is staged too -- measured 7.79 -> 7.69 ms per step on config 2)
+    int budget = sizeof(R) == 4 ? (PlanCta<R, G>::T >= 896 ? 96 * 1024 : 24 * 1024) : 110 * 1024;
     if (const char *ev = getenv("AUVRRT_PLAN_STAGE_KB")) budget = atoi(ev) * 1024;
+    if (const char *ev = getenv("AUVRRT_PLAN_BUDGET_KB")) budget = atoi(ev) * 1024;      // (does not switch the kernel variant)
     int sm = 16, mode = 0;
     if (b.total_bytes + 16 <= budget) { sm = b.total_bytes + 16; mode = 2; }
     else if (b.hot_bytes + 16 <= budget) { sm = b.hot_bytes + 16; mode = 1; }
+    if (ONE && PlanCta<R, G>::T >= 896) {
+        // the single-chunk kernel in its one-CTA-per-SM shape reads the grid from shared memory (launch_plan_g checked the fit)
+        const EnvHeader &hd = sizeof(R) == 4 ? env->h32 : env->h64;
+        sm = b.total_bytes + 16 + ((hd.gnx * hd.gny * 4 + 15) & ~15); mode = 3;
+    }
     AUV_CUDA(cudaFuncSetAttribute(k_plan<R, G, BS, MODE, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = 0;
-    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE, ONE>, PlanCta<G>::T, sm));
+    AUV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan<R, G, BS, MODE, ONE>, PlanCta<R, G>::T, sm));
     if (per_sm < 1) return set_err(AUVRRT_ERR_CUDA, "plan: kernel does not fit on an SM (smem %d)", sm);
     int nsm = 0, dev = 0;
     AUV_CUDA(cudaGetDevice(&dev));
@@ -698,7 +728,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     rc = plan_geometry<R, G, BS, MODE, ONE>(env, &grid, &smem, &mode);
     if (rc) return rc;
     WsLayout L = make_layout<R>(P.cap, P.nb, P.nchunks);
-    const int gpc = PlanCta<G>::T / G;
+    const int gpc = PlanCta<R, G>::T / G;
     int64_t need = 256 + (int64_t)grid * gpc * (int64_t)L.slot_bytes;
     if (need_bytes) { *need_bytes = need; return AUVRRT_OK; }
     if (Q <= 0) return AUVRRT_OK;
@@ -710,7 +740,7 @@ static int launch_plan_gb(const auvrrt_env *env, const R *starts, const uint64_t
     auvrrt_plan_trace_t tr;
     if (trace) tr = *trace; else { tr.parent = nullptr; tr.safe = nullptr; tr.nwp = nullptr; tr.leaf = nullptr; tr.upos = nullptr; }
     EnvBlob<R> b = env_blob<R>(env);
-    k_plan<R, G, BS, MODE, ONE><<<grid, PlanCta<G>::T, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
+    k_plan<R, G, BS, MODE, ONE><<<grid, PlanCta<R, G>::T, smem, s>>>(b.blob, b.hot_bytes, b.total_bytes, mode, starts, seeds, (long long)Q, P, L,
                                                   (unsigned char *)workspace + 256, (unsigned long long *)workspace,
                                                   records, chain, path, tr);
     AUV_LAUNCH_CHECK2();
@@ -729,7 +759,11 @@ static int launch_plan_g(const auvrrt_env *env, const R *starts, const uint64_t 
     if constexpr (sizeof(R) == 4) {
         if (p->mode == 0 && !getenv("AUVRRT_PLAN_GENERIC")) {
             // the common shape: every edge one chunk, bins in shared memory, hot part of the world model staged
-            if (p->freq <= (double)G && bs && env->h32.hot_bytes + 16 <= 24 * 1024 && !getenv("AUVRRT_PLAN_STAGE_KB"))
+            // (896-thread shape: world model + probability table + grid plane 0 must fit next to 36 KB of static arrays)
+            const bool fits = PlanCta<R, G>::T >= 896
+                                  ? (env->h32.gnx > 0 && env->h32.total_bytes + 16 + env->h32.gnx * env->h32.gny * 4 + 16 <= 180 * 1024)
+                                  : env->h32.hot_bytes + 16 <= 24 * 1024;
+            if (p->freq <= (double)G && bs && fits && !getenv("AUVRRT_PLAN_STAGE_KB"))
                 return launch_plan_gb<R, G, true, 0, true>(AUV_PLAN_ARGS);
             return bs ? launch_plan_gb<R, G, true, 0, false>(AUV_PLAN_ARGS) : launch_plan_gb<R, G, false, 0, false>(AUV_PLAN_ARGS);
         }
